@@ -1,0 +1,25 @@
+# Build everything in-tree: harness (host, g++), oracle (gcc), device library (nvcc, sm_100a).
+PKG := 3d-dycoreplanet_b200
+NVCC := /usr/local/cuda/bin/nvcc
+CXX := g++
+CXXFLAGS := -O3 -march=x86-64-v3 -std=c++17 -fopenmp -fPIC -Wall -Wno-unused-variable
+NVFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall,-fopenmp -Xptxas -v
+CU_SRCS := $(wildcard $(PKG)/csrc/device/*.cu)
+CU_HDRS := $(wildcard $(PKG)/csrc/device/*.cuh) $(wildcard $(PKG)/csrc/device/*.h) include/dcp.h
+
+all: lib/libdcp_harness.so oracle lib/libdcp.so
+
+lib/libdcp_harness.so: $(wildcard $(PKG)/csrc/harness/*.hpp) $(PKG)/csrc/harness/harness_api.cpp include/dcp_harness.h
+	mkdir -p lib
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(PKG)/csrc/harness/harness_api.cpp
+
+oracle:
+	$(MAKE) -C oracle
+
+lib/libdcp.so: $(CU_SRCS) $(CU_HDRS)
+	mkdir -p lib build
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRCS) -lcudart > build/ptxas.log 2>&1 || (cat build/ptxas.log; false)
+
+clean:
+	rm -rf lib build oracle/_build
+.PHONY: all oracle clean

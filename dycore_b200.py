@@ -1,0 +1,11 @@
+"""Import shim: loads the package directory `3d-dycoreplanet_b200/` under the name `dycore_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "3d-dycoreplanet_b200")
+_spec = importlib.util.spec_from_file_location(
+    "dycore_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["dycore_b200"] = _mod
+_spec.loader.exec_module(_mod)
