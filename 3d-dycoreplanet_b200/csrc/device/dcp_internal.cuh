@@ -1,0 +1,156 @@
+// Internal declarations of the device library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../../include/dcp.h"
+
+#define DCP_MAXB DCP_MAX_BLOCKS
+
+void dcp_set_error(const std::string& s);
+
+#define DCP_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      dcp_set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                    std::to_string(__LINE__) + ")");                                           \
+      return DCP_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define DCP_TRY(call)            \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__ != DCP_OK) return rc__; \
+  } while (0)
+
+struct dcp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int64_t launches = 0;
+  int sm_count = 148;
+  int* d_err = nullptr;  // [4] device-side error counters (0: missing pattern entries)
+  int* h_err = nullptr;  // pinned mirror
+  // staging buffers for DCP_HOST vectors
+  double* stage[3] = {nullptr, nullptr, nullptr};
+  int64_t stage_cap[3] = {0, 0, 0};
+};
+
+// constraint lines on the device
+struct DevCs {
+  int64_t n_dofs = 0, n_lines = 0;
+  int32_t* line_of_dof = nullptr;
+  int32_t* line_ptr = nullptr;
+  int32_t* entry_dof = nullptr;
+  double* entry_w = nullptr;
+  double* inhom = nullptr;
+};
+struct CsView {
+  const int32_t* line_of_dof;
+  const int32_t* line_ptr;
+  const int32_t* entry_dof;
+  const double* entry_w;
+  const double* inhom;
+};
+
+struct DevCsr {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int64_t* rowptr = nullptr;
+  int32_t* col = nullptr;
+  double* val = nullptr;
+  bool owns_pattern = true;  // mass/stiffness/temperature matrices share one pattern
+  int lanes = 32;            // lanes per row chosen for the SpMV kernel
+};
+
+struct BlockMat {
+  int nb = 1;
+  int64_t start[DCP_MAXB + 1] = {0, 0, 0, 0};
+  DevCsr blk[DCP_MAXB][DCP_MAXB];
+  double* diag_inv[DCP_MAXB] = {nullptr, nullptr, nullptr};  // Jacobi: 1/diag of the diagonal blocks
+};
+
+// by-value kernel argument describing a block matrix for scatter
+struct BlockView {
+  int nb;
+  long long start[DCP_MAXB + 1];
+  const long long* rowptr[DCP_MAXB][DCP_MAXB];
+  const int* col[DCP_MAXB][DCP_MAXB];
+  double* val[DCP_MAXB][DCP_MAXB];
+};
+
+inline BlockView make_view(const BlockMat& M) {
+  BlockView v;
+  v.nb = M.nb;
+  for (int i = 0; i <= DCP_MAXB; ++i) v.start[i] = M.start[i < M.nb + 1 ? i : M.nb];
+  for (int i = 0; i < DCP_MAXB; ++i)
+    for (int j = 0; j < DCP_MAXB; ++j) {
+      v.rowptr[i][j] = (const long long*)M.blk[i][j].rowptr;
+      v.col[i][j] = M.blk[i][j].col;
+      v.val[i][j] = M.blk[i][j].val;
+    }
+  return v;
+}
+
+inline CsView make_view(const DevCs& c) { return CsView{c.line_of_dof, c.line_ptr, c.entry_dof, c.entry_w, c.inhom}; }
+
+struct OwnerPlan;  // row-owner tiles (assemble_th_owner.cu)
+
+struct dcp_model {
+  dcp_ctx* ctx = nullptr;
+  int dim = 3, family = 0, strategy = DCP_STRATEGY_ATOMIC;
+  int64_t n_cells = 0;
+  // spaces
+  int nse_n_local = 0, nse_nb = 2, temp_n_local = 0;
+  int64_t nse_n_dofs = 0, temp_n_dofs = 0;
+  int32_t *nse_l2g = nullptr, *temp_l2g = nullptr;
+  int32_t *nse_local_field = nullptr, *nse_local_base = nullptr;
+  std::vector<int32_t> h_local_field, h_local_base;
+  DevCs nse_cs, temp_cs;
+  // cells that hold at least one constrained dof (for the owner strategy's fix-up pass)
+  int32_t* nse_constrained_cells = nullptr;
+  int64_t n_nse_constrained_cells = 0;
+  // tables
+  int nq_nse = 0, nq_temp = 0, ndu = 0, ndp = 0, ndt = 0;
+  double *phi_u_qn = nullptr, *dphi_u_qn = nullptr, *phi_p_qn = nullptr, *phi_t_qn = nullptr;
+  double *phi_u_qt = nullptr, *phi_t_qt = nullptr, *dphi_t_qt = nullptr;
+  // mapping data
+  double *geom_qn = nullptr, *geom_qt = nullptr;
+  bool geom_shared = false;
+  // matrices and vectors
+  BlockMat nse, pre, tmass, tstiff, tmat;
+  double *nse_rhs = nullptr, *temp_rhs = nullptr;
+  bool temp_matrices_ready = false;
+  OwnerPlan* owner_nse = nullptr;
+  OwnerPlan* owner_pre = nullptr;
+};
+
+// ---- helpers implemented in context.cu -----------------------------------------------------------
+template <class T>
+int dcp_upload(dcp_ctx* ctx, T** dst, const T* src, int64_t n);
+int dcp_check_device_errors(dcp_ctx* ctx, const char* what);
+int dcp_stage_in(dcp_ctx* ctx, int slot, const double* src, int64_t n, int mem, const double** dev);
+int dcp_stage_out_alloc(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem, double** dev);
+int dcp_stage_out_finish(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem);
+
+// ---- kernels' host launchers ---------------------------------------------------------------------
+int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add);
+int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv);
+int dcp_launch_jacobi(dcp_ctx* ctx, int64_t n, const double* diag_inv, const double* x, double* y);
+int dcp_launch_axpby_values(dcp_ctx* ctx, int64_t n, const double* a, const double* b, double fb, double* out);
+int dcp_launch_fill(dcp_ctx* ctx, double* p, int64_t n, double v);
+
+int dcp_launch_th_cells(dcp_model* m, const dcp_params& p, bool system, const double* old_nse, const double* old_temp,
+                        const int32_t* cell_list, int64_t n_list, bool only_constrained_entries);
+int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p);
+int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* old_temp, const double* nse_solution);
+
+int dcp_owner_plan_build(dcp_model* m, bool system, const dcp_model_desc* desc);
+void dcp_owner_plan_free(OwnerPlan* p);
+int dcp_launch_th_owner(dcp_model* m, const dcp_params& p, bool system);
+int dcp_launch_th_rhs(dcp_model* m, const dcp_params& p, const double* old_nse, const double* old_temp);

@@ -1,0 +1,659 @@
+// Context, model object and the C ABI entry points declared in include/dcp.h.
+#include <algorithm>
+#include <cstring>
+
+#include "dcp_internal.cuh"
+
+static thread_local std::string g_dcp_err;
+void dcp_set_error(const std::string& s) { g_dcp_err = s; }
+
+template <class T>
+int dcp_upload(dcp_ctx* ctx, T** dst, const T* src, int64_t n) {
+  *dst = nullptr;
+  if (n <= 0) return DCP_OK;
+  if (src == nullptr) {
+    dcp_set_error("dcp_upload: null source for a non-empty array");
+    return DCP_ERR_ARG;
+  }
+  DCP_CUDA(cudaMalloc((void**)dst, sizeof(T) * (size_t)n));
+  DCP_CUDA(cudaMemcpyAsync(*dst, src, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  return DCP_OK;
+}
+template int dcp_upload<double>(dcp_ctx*, double**, const double*, int64_t);
+template int dcp_upload<int32_t>(dcp_ctx*, int32_t**, const int32_t*, int64_t);
+template int dcp_upload<int64_t>(dcp_ctx*, int64_t**, const int64_t*, int64_t);
+
+int dcp_check_device_errors(dcp_ctx* ctx, const char* what) {
+  DCP_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_err[0] != 0) {
+    int n = ctx->h_err[0];
+    cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
+    dcp_set_error(std::string(what) + ": " + std::to_string(n) + " scatter targets are not in the sparsity pattern");
+    return DCP_ERR_PATTERN;
+  }
+  return DCP_OK;
+}
+
+static int ensure_stage(dcp_ctx* ctx, int slot, int64_t n) {
+  if (ctx->stage_cap[slot] >= n) return DCP_OK;
+  if (ctx->stage[slot]) DCP_CUDA(cudaFree(ctx->stage[slot]));
+  ctx->stage[slot] = nullptr;
+  ctx->stage_cap[slot] = 0;
+  DCP_CUDA(cudaMalloc((void**)&ctx->stage[slot], sizeof(double) * (size_t)n));
+  ctx->stage_cap[slot] = n;
+  return DCP_OK;
+}
+
+int dcp_stage_in(dcp_ctx* ctx, int slot, const double* src, int64_t n, int mem, const double** dev) {
+  if (mem == DCP_DEVICE) {
+    *dev = src;
+    return DCP_OK;
+  }
+  DCP_TRY(ensure_stage(ctx, slot, n));
+  DCP_CUDA(cudaMemcpyAsync(ctx->stage[slot], src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  *dev = ctx->stage[slot];
+  return DCP_OK;
+}
+int dcp_stage_out_alloc(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem, double** dev) {
+  if (mem == DCP_DEVICE) {
+    *dev = dst;
+    return DCP_OK;
+  }
+  DCP_TRY(ensure_stage(ctx, slot, n));
+  *dev = ctx->stage[slot];
+  return DCP_OK;
+}
+int dcp_stage_out_finish(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem) {
+  if (mem == DCP_DEVICE) return DCP_OK;
+  DCP_CUDA(cudaMemcpyAsync(dst, ctx->stage[slot], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DCP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+static int upload_cs(dcp_ctx* ctx, const dcp_constraints_desc& d, DevCs& out) {
+  out.n_dofs = d.n_dofs;
+  out.n_lines = d.n_lines;
+  std::vector<int32_t> lod((size_t)d.n_dofs, -1);
+  for (int64_t l = 0; l < d.n_lines; ++l) {
+    if (d.line_dof[l] < 0 || d.line_dof[l] >= d.n_dofs) {
+      dcp_set_error("constraints: line_dof out of range");
+      return DCP_ERR_ARG;
+    }
+    lod[d.line_dof[l]] = (int32_t)l;
+  }
+  DCP_TRY(dcp_upload(ctx, &out.line_of_dof, lod.data(), d.n_dofs));
+  // the async copy above reads from `lod`: finish it before the vector dies
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  static const int32_t zero_ptr[1] = {0};
+  DCP_TRY(dcp_upload(ctx, &out.line_ptr, d.n_lines ? d.line_ptr : zero_ptr, d.n_lines + 1));
+  int64_t ne = d.n_lines ? d.line_ptr[d.n_lines] : 0;
+  // keep one valid element so that kernels never see a null pointer
+  static const int32_t zi[1] = {0};
+  static const double zd[1] = {0.0};
+  DCP_TRY(dcp_upload(ctx, &out.entry_dof, ne ? d.entry_dof : zi, ne ? ne : 1));
+  DCP_TRY(dcp_upload(ctx, &out.entry_w, ne ? d.entry_w : zd, ne ? ne : 1));
+  DCP_TRY(dcp_upload(ctx, &out.inhom, d.n_lines ? d.inhom : zd, d.n_lines ? d.n_lines : 1));
+  return DCP_OK;
+}
+
+static void free_cs(DevCs& c) {
+  cudaFree(c.line_of_dof);
+  cudaFree(c.line_ptr);
+  cudaFree(c.entry_dof);
+  cudaFree(c.entry_w);
+  cudaFree(c.inhom);
+  c = DevCs();
+}
+
+static int pick_lanes(int64_t n_rows, int64_t nnz) {
+  if (n_rows == 0) return 32;
+  double mean = (double)nnz / (double)n_rows;
+  if (mean <= 6) return 4;
+  if (mean <= 14) return 8;
+  if (mean <= 40) return 16;
+  return 32;
+}
+
+static int upload_csr_pattern(dcp_ctx* ctx, const dcp_csr_desc& d, DevCsr& A, bool alloc_values) {
+  A = DevCsr();
+  A.n_rows = d.n_rows;
+  A.n_cols = d.n_cols;
+  if (d.rowptr == nullptr || d.n_rows == 0) return DCP_OK;
+  A.nnz = d.rowptr[d.n_rows];
+  if (A.nnz == 0) return DCP_OK;
+  DCP_TRY(dcp_upload(ctx, &A.rowptr, d.rowptr, d.n_rows + 1));
+  DCP_TRY(dcp_upload(ctx, &A.col, d.col, A.nnz));
+  if (alloc_values) {
+    DCP_CUDA(cudaMalloc((void**)&A.val, sizeof(double) * (size_t)A.nnz));
+    DCP_CUDA(cudaMemsetAsync(A.val, 0, sizeof(double) * (size_t)A.nnz, ctx->stream));
+  }
+  A.lanes = pick_lanes(A.n_rows, A.nnz);
+  return DCP_OK;
+}
+
+static int share_csr_pattern(dcp_ctx* ctx, const DevCsr& src, DevCsr& A) {
+  A = src;
+  A.owns_pattern = false;
+  A.val = nullptr;
+  if (A.nnz) {
+    DCP_CUDA(cudaMalloc((void**)&A.val, sizeof(double) * (size_t)A.nnz));
+    DCP_CUDA(cudaMemsetAsync(A.val, 0, sizeof(double) * (size_t)A.nnz, ctx->stream));
+  }
+  return DCP_OK;
+}
+
+static void free_csr(DevCsr& A) {
+  if (A.owns_pattern) {
+    cudaFree(A.rowptr);
+    cudaFree(A.col);
+  }
+  cudaFree(A.val);
+  A = DevCsr();
+}
+
+static void free_blockmat(BlockMat& M) {
+  for (int i = 0; i < DCP_MAXB; ++i) {
+    for (int j = 0; j < DCP_MAXB; ++j) free_csr(M.blk[i][j]);
+    cudaFree(M.diag_inv[i]);
+    M.diag_inv[i] = nullptr;
+  }
+}
+
+static int zero_blockmat(dcp_ctx* ctx, BlockMat& M) {
+  for (int i = 0; i < M.nb; ++i)
+    for (int j = 0; j < M.nb; ++j)
+      if (M.blk[i][j].val) DCP_CUDA(cudaMemsetAsync(M.blk[i][j].val, 0, sizeof(double) * (size_t)M.blk[i][j].nnz, ctx->stream));
+  return DCP_OK;
+}
+
+static int refresh_jacobi(dcp_ctx* ctx, BlockMat& M) {
+  for (int b = 0; b < M.nb; ++b) {
+    DevCsr& A = M.blk[b][b];
+    if (A.nnz == 0) continue;
+    if (!M.diag_inv[b]) DCP_CUDA(cudaMalloc((void**)&M.diag_inv[b], sizeof(double) * (size_t)A.n_rows));
+    DCP_TRY(dcp_launch_extract_diag_inv(ctx, A, M.diag_inv[b]));
+  }
+  return DCP_OK;
+}
+
+static BlockMat* select_matrix(dcp_model* m, int which) {
+  switch (which) {
+    case DCP_MAT_NSE: return &m->nse;
+    case DCP_MAT_NSE_PRECOND: return &m->pre;
+    case DCP_MAT_TEMP_MASS: return &m->tmass;
+    case DCP_MAT_TEMP_STIFF: return &m->tstiff;
+    case DCP_MAT_TEMP: return &m->tmat;
+    default: return nullptr;
+  }
+}
+
+static int get_block(dcp_model* m, int which, int bi, int bj, DevCsr** out, BlockMat** bm = nullptr) {
+  BlockMat* M = select_matrix(m, which);
+  if (!M || bi < 0 || bj < 0 || bi >= M->nb || bj >= M->nb) {
+    dcp_set_error("invalid matrix / block selector");
+    return DCP_ERR_ARG;
+  }
+  *out = &M->blk[bi][bj];
+  if (bm) *bm = M;
+  return DCP_OK;
+}
+
+extern "C" {
+
+const char* dcp_last_error(void) { return g_dcp_err.c_str(); }
+
+int dcp_ctx_create(int device, dcp_ctx** out) {
+  if (!out) return DCP_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    dcp_set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                  "); this library has no CPU fallback");
+    return DCP_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    dcp_set_error("device index out of range");
+    return DCP_ERR_ARG;
+  }
+  DCP_CUDA(cudaSetDevice(device));
+  dcp_ctx* ctx = new dcp_ctx;
+  ctx->device = device;
+  DCP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  DCP_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  DCP_CUDA(cudaMalloc((void**)&ctx->d_err, 4 * sizeof(int)));
+  DCP_CUDA(cudaMemset(ctx->d_err, 0, 4 * sizeof(int)));
+  DCP_CUDA(cudaMallocHost((void**)&ctx->h_err, 4 * sizeof(int)));
+  *out = ctx;
+  return DCP_OK;
+}
+
+int dcp_ctx_destroy(dcp_ctx* ctx) {
+  if (!ctx) return DCP_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int s = 0; s < 3; ++s) cudaFree(ctx->stage[s]);
+  cudaFree(ctx->d_err);
+  cudaFreeHost(ctx->h_err);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return DCP_OK;
+}
+
+int dcp_ctx_set_stream(dcp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return DCP_ERR_ARG;
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (cuda_stream == nullptr) {
+    if (!ctx->own_stream) {
+      DCP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    return DCP_OK;
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return DCP_OK;
+}
+
+int dcp_ctx_synchronize(dcp_ctx* ctx) {
+  if (!ctx) return DCP_ERR_ARG;
+  return dcp_check_device_errors(ctx, "dcp_ctx_synchronize");
+}
+
+int64_t dcp_ctx_launch_count(const dcp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dcp_malloc(dcp_ctx* ctx, int64_t bytes, void** out) {
+  if (!ctx || !out || bytes < 0) return DCP_ERR_ARG;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  DCP_CUDA(cudaMalloc(out, (size_t)(bytes > 0 ? bytes : 1)));
+  return DCP_OK;
+}
+int dcp_free(dcp_ctx* ctx, void* p) {
+  if (!ctx) return DCP_ERR_ARG;
+  DCP_CUDA(cudaFree(p));
+  return DCP_OK;
+}
+int dcp_memcpy_h2d(dcp_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes) {
+  if (!ctx) return DCP_ERR_ARG;
+  DCP_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DCP_OK;
+}
+int dcp_memcpy_d2h(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
+  if (!ctx) return DCP_ERR_ARG;
+  DCP_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DCP_OK;
+}
+
+int dcp_model_destroy(dcp_model* m) {
+  if (!m) return DCP_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->nse_l2g);
+  cudaFree(m->temp_l2g);
+  cudaFree(m->nse_local_field);
+  cudaFree(m->nse_local_base);
+  cudaFree(m->nse_constrained_cells);
+  free_cs(m->nse_cs);
+  free_cs(m->temp_cs);
+  cudaFree(m->phi_u_qn);
+  cudaFree(m->dphi_u_qn);
+  cudaFree(m->phi_p_qn);
+  cudaFree(m->phi_t_qn);
+  cudaFree(m->phi_u_qt);
+  cudaFree(m->phi_t_qt);
+  cudaFree(m->dphi_t_qt);
+  cudaFree(m->geom_qn);
+  if (!m->geom_shared) cudaFree(m->geom_qt);
+  free_blockmat(m->nse);
+  free_blockmat(m->pre);
+  free_blockmat(m->tmass);
+  free_blockmat(m->tstiff);
+  free_blockmat(m->tmat);
+  cudaFree(m->nse_rhs);
+  cudaFree(m->temp_rhs);
+  dcp_owner_plan_free(m->owner_nse);
+  dcp_owner_plan_free(m->owner_pre);
+  delete m;
+  return DCP_OK;
+}
+
+int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
+  if (!ctx || !d || !out) return DCP_ERR_ARG;
+  *out = nullptr;
+  if (d->dim != 2 && d->dim != 3) {
+    dcp_set_error("dim must be 2 or 3");
+    return DCP_ERR_ARG;
+  }
+  if (d->family != DCP_FAMILY_CLASSIC) {
+    dcp_set_error("only DCP_FAMILY_CLASSIC is implemented by this build");
+    return DCP_ERR_ARG;
+  }
+  const int dim = d->dim;
+  const int nu = dim == 3 ? 27 : 9, np = dim == 3 ? 8 : 4;
+  if (d->ndu != nu || d->ndp != np || d->nq_nse != nu || d->nse_n_local != dim * nu + np || d->nse_n_blocks != 2) {
+    dcp_set_error("classic family expects Q2^dim x Q1 with QGauss(3): ndu=3^dim, ndp=2^dim, nq_nse=3^dim");
+    return DCP_ERR_ARG;
+  }
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  dcp_model* m = new dcp_model;
+  m->ctx = ctx;
+  m->dim = dim;
+  m->family = d->family;
+  m->n_cells = d->n_cells;
+  m->nse_n_local = d->nse_n_local;
+  m->nse_nb = d->nse_n_blocks;
+  m->temp_n_local = d->temp_n_local;
+  m->nse_n_dofs = 0;
+  for (int b = 0; b < m->nse_nb; ++b) m->nse_n_dofs += d->nse_block_size[b];
+  m->temp_n_dofs = d->temp_cs.n_dofs;
+  m->nq_nse = d->nq_nse;
+  m->nq_temp = d->nq_temp;
+  m->ndu = d->ndu;
+  m->ndp = d->ndp;
+  m->ndt = d->ndt;
+  int rc = DCP_OK;
+  auto fail = [&](int code) {
+    dcp_model_destroy(m);
+    return code;
+  };
+#define M_TRY(x)                       \
+  do {                                 \
+    rc = (x);                          \
+    if (rc != DCP_OK) return fail(rc); \
+  } while (0)
+  const int64_t nc = d->n_cells;
+  const int gs_n = d->nq_nse * (1 + dim * dim + dim), gs_t = d->nq_temp * (1 + dim * dim + dim);
+  M_TRY(dcp_upload(ctx, &m->nse_l2g, d->nse_l2g, nc * d->nse_n_local));
+  M_TRY(dcp_upload(ctx, &m->temp_l2g, d->temp_l2g, nc * d->temp_n_local));
+  M_TRY(dcp_upload(ctx, &m->nse_local_field, d->nse_local_field, d->nse_n_local));
+  M_TRY(dcp_upload(ctx, &m->nse_local_base, d->nse_local_base, d->nse_n_local));
+  m->h_local_field.assign(d->nse_local_field, d->nse_local_field + d->nse_n_local);
+  m->h_local_base.assign(d->nse_local_base, d->nse_local_base + d->nse_n_local);
+  M_TRY(upload_cs(ctx, d->nse_cs, m->nse_cs));
+  M_TRY(upload_cs(ctx, d->temp_cs, m->temp_cs));
+  if (d->nse_cs.n_dofs != m->nse_n_dofs) {
+    dcp_set_error("nse_cs.n_dofs != sum of block sizes");
+    return fail(DCP_ERR_ARG);
+  }
+  M_TRY(dcp_upload(ctx, &m->phi_u_qn, d->phi_u_qn, (int64_t)d->nq_nse * d->ndu));
+  M_TRY(dcp_upload(ctx, &m->dphi_u_qn, d->dphi_u_qn, (int64_t)d->nq_nse * d->ndu * dim));
+  M_TRY(dcp_upload(ctx, &m->phi_p_qn, d->phi_p_qn, (int64_t)d->nq_nse * d->ndp));
+  M_TRY(dcp_upload(ctx, &m->phi_t_qn, d->phi_t_qn, (int64_t)d->nq_nse * d->ndt));
+  M_TRY(dcp_upload(ctx, &m->phi_u_qt, d->phi_u_qt, (int64_t)d->nq_temp * d->ndu));
+  M_TRY(dcp_upload(ctx, &m->phi_t_qt, d->phi_t_qt, (int64_t)d->nq_temp * d->ndt));
+  M_TRY(dcp_upload(ctx, &m->dphi_t_qt, d->dphi_t_qt, (int64_t)d->nq_temp * d->ndt * dim));
+  M_TRY(dcp_upload(ctx, &m->geom_qn, d->geom_qn, nc * gs_n));
+  if (d->geom_qt == d->geom_qn && gs_n == gs_t) {
+    m->geom_qt = m->geom_qn;
+    m->geom_shared = true;
+  } else
+    M_TRY(dcp_upload(ctx, &m->geom_qt, d->geom_qt, nc * gs_t));
+
+  // matrices
+  auto setup_blocks = [&](BlockMat& M, const dcp_csr_desc pat[DCP_MAXB][DCP_MAXB]) -> int {
+    M.nb = m->nse_nb;
+    M.start[0] = 0;
+    for (int b = 0; b < M.nb; ++b) M.start[b + 1] = M.start[b] + d->nse_block_size[b];
+    for (int b = M.nb + 1; b <= DCP_MAXB; ++b) M.start[b] = M.start[M.nb];
+    for (int i = 0; i < M.nb; ++i)
+      for (int j = 0; j < M.nb; ++j) {
+        if (pat[i][j].rowptr &&
+            (pat[i][j].n_rows != d->nse_block_size[i] || pat[i][j].n_cols != d->nse_block_size[j])) {
+          dcp_set_error("block pattern shape does not match the block sizes");
+          return DCP_ERR_ARG;
+        }
+        DCP_TRY(upload_csr_pattern(ctx, pat[i][j], M.blk[i][j], true));
+        M.blk[i][j].n_rows = d->nse_block_size[i];
+        M.blk[i][j].n_cols = d->nse_block_size[j];
+      }
+    return DCP_OK;
+  };
+  M_TRY(setup_blocks(m->nse, d->nse_pattern));
+  M_TRY(setup_blocks(m->pre, d->pre_pattern));
+  m->tmass.nb = m->tstiff.nb = m->tmat.nb = 1;
+  for (BlockMat* T : {&m->tmass, &m->tstiff, &m->tmat}) {
+    T->start[0] = 0;
+    for (int b = 1; b <= DCP_MAXB; ++b) T->start[b] = m->temp_n_dofs;
+  }
+  M_TRY(upload_csr_pattern(ctx, d->temp_pattern, m->tmass.blk[0][0], true));
+  M_TRY(share_csr_pattern(ctx, m->tmass.blk[0][0], m->tstiff.blk[0][0]));
+  M_TRY(share_csr_pattern(ctx, m->tmass.blk[0][0], m->tmat.blk[0][0]));
+  rc = cudaMalloc((void**)&m->nse_rhs, sizeof(double) * (size_t)std::max<int64_t>(m->nse_n_dofs, 1)) == cudaSuccess ? DCP_OK : DCP_ERR_CUDA;
+  if (rc != DCP_OK) {
+    dcp_set_error("cudaMalloc nse_rhs failed");
+    return fail(rc);
+  }
+  rc = cudaMalloc((void**)&m->temp_rhs, sizeof(double) * (size_t)std::max<int64_t>(m->temp_n_dofs, 1)) == cudaSuccess ? DCP_OK : DCP_ERR_CUDA;
+  if (rc != DCP_OK) {
+    dcp_set_error("cudaMalloc temp_rhs failed");
+    return fail(rc);
+  }
+  // cells holding a constrained NSE dof
+  {
+    std::vector<int32_t> lod((size_t)m->nse_n_dofs, -1);
+    for (int64_t l = 0; l < d->nse_cs.n_lines; ++l) lod[d->nse_cs.line_dof[l]] = (int32_t)l;
+    std::vector<int32_t> cells;
+    for (int64_t c = 0; c < nc; ++c) {
+      const int32_t* idx = d->nse_l2g + c * d->nse_n_local;
+      bool any = false;
+      for (int i = 0; i < d->nse_n_local && !any; ++i) any = lod[idx[i]] >= 0;
+      if (any) cells.push_back((int32_t)c);
+    }
+    m->n_nse_constrained_cells = (int64_t)cells.size();
+    M_TRY(dcp_upload(ctx, &m->nse_constrained_cells, cells.data(), (int64_t)cells.size()));
+    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef M_TRY
+  *out = m;
+  return DCP_OK;
+}
+
+int dcp_model_set_strategy(dcp_model* m, int strategy) {
+  if (!m || (strategy != DCP_STRATEGY_ATOMIC && strategy != DCP_STRATEGY_OWNER)) return DCP_ERR_ARG;
+  m->strategy = strategy;
+  return DCP_OK;
+}
+
+int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old_nse, const double* old_temp, int mem) {
+  if (!m || !p || !old_nse || !old_temp) return DCP_ERR_ARG;
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  const double *d_nse, *d_temp;
+  DCP_TRY(dcp_stage_in(ctx, 0, old_nse, m->nse_n_dofs, mem, &d_nse));
+  DCP_TRY(dcp_stage_in(ctx, 1, old_temp, m->temp_n_dofs, mem, &d_temp));
+  DCP_CUDA(cudaMemsetAsync(m->nse_rhs, 0, sizeof(double) * (size_t)m->nse_n_dofs, ctx->stream));
+  if (m->strategy == DCP_STRATEGY_OWNER) {
+    DCP_TRY(dcp_launch_th_owner(m, *p, true));
+    DCP_TRY(dcp_launch_th_rhs(m, *p, d_nse, d_temp));
+    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
+  } else {
+    DCP_TRY(zero_blockmat(ctx, m->nse));
+    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, nullptr, 0, false));
+  }
+  if (mem == DCP_HOST) DCP_TRY(dcp_check_device_errors(ctx, "dcp_assemble_nse_system"));
+  return DCP_OK;
+}
+
+int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
+  if (!m || !p) return DCP_ERR_ARG;
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  if (m->strategy == DCP_STRATEGY_OWNER) {
+    DCP_TRY(dcp_launch_th_owner(m, *p, false));
+    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
+  } else {
+    DCP_TRY(zero_blockmat(ctx, m->pre));
+    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, nullptr, 0, false));
+  }
+  // build_nse_preconditioner: Jacobi of block(0,0) and block(1,1)  (boussinesq_model.tpp:531-539)
+  DCP_TRY(refresh_jacobi(ctx, m->pre));
+  return DCP_OK;
+}
+
+int dcp_assemble_temperature_matrix(dcp_model* m, const dcp_params* p) {
+  if (!m || !p) return DCP_ERR_ARG;
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  DCP_TRY(zero_blockmat(ctx, m->tmass));
+  DCP_TRY(zero_blockmat(ctx, m->tstiff));
+  DCP_TRY(dcp_launch_temperature_matrix(m, *p));
+  m->temp_matrices_ready = true;
+  return DCP_OK;
+}
+
+int dcp_assemble_temperature_rhs(dcp_model* m, const dcp_params* p, const double* old_temp, const double* nse_solution, int mem) {
+  if (!m || !p || !old_temp || !nse_solution) return DCP_ERR_ARG;
+  if (!m->temp_matrices_ready) {
+    dcp_set_error("dcp_assemble_temperature_rhs: call dcp_assemble_temperature_matrix first");
+    return DCP_ERR_STATE;
+  }
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  const double *d_temp, *d_nse;
+  DCP_TRY(dcp_stage_in(ctx, 0, nse_solution, m->nse_n_dofs, mem, &d_nse));
+  DCP_TRY(dcp_stage_in(ctx, 1, old_temp, m->temp_n_dofs, mem, &d_temp));
+  // temperature_matrix.copy_from(mass); temperature_matrix.add(dt/n, stiffness)  (:975-978)
+  DevCsr& T = m->tmat.blk[0][0];
+  DCP_TRY(dcp_launch_axpby_values(ctx, T.nnz, m->tmass.blk[0][0].val, m->tstiff.blk[0][0].val,
+                                  p->dt / p->nse_interval, T.val));
+  // T_preconditioner = Jacobi(temperature_matrix)  (:980-986)
+  DCP_TRY(refresh_jacobi(ctx, m->tmat));
+  DCP_CUDA(cudaMemsetAsync(m->temp_rhs, 0, sizeof(double) * (size_t)m->temp_n_dofs, ctx->stream));
+  DCP_TRY(dcp_launch_temperature_rhs(m, *p, d_temp, d_nse));
+  if (mem == DCP_HOST) DCP_TRY(dcp_check_device_errors(ctx, "dcp_assemble_temperature_rhs"));
+  return DCP_OK;
+}
+
+int dcp_matrix_info(const dcp_model* m, int which, int bi, int bj, int64_t* n_rows, int64_t* n_cols, int64_t* nnz) {
+  DevCsr* A;
+  DCP_TRY(get_block(const_cast<dcp_model*>(m), which, bi, bj, &A));
+  if (n_rows) *n_rows = A->n_rows;
+  if (n_cols) *n_cols = A->n_cols;
+  if (nnz) *nnz = A->nnz;
+  return DCP_OK;
+}
+
+int dcp_matrix_values_device(dcp_model* m, int which, int bi, int bj, double** out) {
+  DevCsr* A;
+  DCP_TRY(get_block(m, which, bi, bj, &A));
+  *out = A->val;
+  return DCP_OK;
+}
+
+int dcp_matrix_download(dcp_model* m, int which, int bi, int bj, double* host_values) {
+  DevCsr* A;
+  DCP_TRY(get_block(m, which, bi, bj, &A));
+  DCP_TRY(dcp_check_device_errors(m->ctx, "dcp_matrix_download"));
+  if (A->nnz == 0) return DCP_OK;
+  return dcp_memcpy_d2h(m->ctx, host_values, A->val, (int64_t)sizeof(double) * A->nnz);
+}
+
+int dcp_matrix_upload(dcp_model* m, int which, int bi, int bj, const double* host_values) {
+  DevCsr* A;
+  BlockMat* M;
+  DCP_TRY(get_block(m, which, bi, bj, &A, &M));
+  if (A->nnz == 0) return DCP_OK;
+  DCP_TRY(dcp_memcpy_h2d(m->ctx, A->val, host_values, (int64_t)sizeof(double) * A->nnz));
+  if (bi == bj) DCP_TRY(refresh_jacobi(m->ctx, *M));
+  if (which == DCP_MAT_TEMP_MASS || which == DCP_MAT_TEMP_STIFF) m->temp_matrices_ready = true;
+  return DCP_OK;
+}
+
+int dcp_vector_device(dcp_model* m, int which, double** out, int64_t* n) {
+  if (!m || !out) return DCP_ERR_ARG;
+  if (which == DCP_VEC_NSE_RHS) {
+    *out = m->nse_rhs;
+    if (n) *n = m->nse_n_dofs;
+  } else if (which == DCP_VEC_TEMP_RHS) {
+    *out = m->temp_rhs;
+    if (n) *n = m->temp_n_dofs;
+  } else
+    return DCP_ERR_ARG;
+  return DCP_OK;
+}
+
+int dcp_vector_download(dcp_model* m, int which, double* host) {
+  double* d;
+  int64_t n;
+  DCP_TRY(dcp_vector_device(m, which, &d, &n));
+  DCP_TRY(dcp_check_device_errors(m->ctx, "dcp_vector_download"));
+  return dcp_memcpy_d2h(m->ctx, host, d, (int64_t)sizeof(double) * n);
+}
+
+static int vmult_impl(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem, bool add) {
+  if (!m || !dst || !src) return DCP_ERR_ARG;
+  DevCsr* A;
+  DCP_TRY(get_block(m, which, bi, bj, &A));
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  const double* dx;
+  double* dy;
+  DCP_TRY(dcp_stage_in(ctx, 0, src, A->n_cols, mem, &dx));
+  if (add && mem == DCP_HOST) {
+    const double* tmp;
+    DCP_TRY(dcp_stage_in(ctx, 1, dst, A->n_rows, mem, &tmp));
+    dy = const_cast<double*>(tmp);
+  } else
+    DCP_TRY(dcp_stage_out_alloc(ctx, 1, dst, A->n_rows, mem, &dy));
+  DCP_TRY(dcp_launch_spmv(ctx, *A, dx, dy, add));
+  return dcp_stage_out_finish(ctx, 1, dst, A->n_rows, mem);
+}
+
+int dcp_vmult(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem) {
+  return vmult_impl(m, which, bi, bj, dst, src, mem, false);
+}
+int dcp_vmult_add(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem) {
+  return vmult_impl(m, which, bi, bj, dst, src, mem, true);
+}
+
+int dcp_block_vmult(dcp_model* m, int which, double* dst, const double* src, int mem) {
+  if (!m || !dst || !src) return DCP_ERR_ARG;
+  BlockMat* M = select_matrix(m, which);
+  if (!M) return DCP_ERR_ARG;
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = M->start[M->nb];
+  const double* dx;
+  double* dy;
+  DCP_TRY(dcp_stage_in(ctx, 0, src, n, mem, &dx));
+  DCP_TRY(dcp_stage_out_alloc(ctx, 1, dst, n, mem, &dy));
+  // BlockMatrixBase::vmult: dst.block(r) = sum_c block(r,c) * src.block(c)
+  for (int r = 0; r < M->nb; ++r) {
+    bool first = true;
+    for (int c = 0; c < M->nb; ++c) {
+      DevCsr& A = M->blk[r][c];
+      if (A.nnz == 0) continue;
+      DCP_TRY(dcp_launch_spmv(ctx, A, dx + M->start[c], dy + M->start[r], !first));
+      first = false;
+    }
+    if (first) DCP_TRY(dcp_launch_fill(ctx, dy + M->start[r], M->start[r + 1] - M->start[r], 0.0));
+  }
+  return dcp_stage_out_finish(ctx, 1, dst, n, mem);
+}
+
+int dcp_jacobi_vmult(dcp_model* m, int which, int bi, double* dst, const double* src, int mem) {
+  if (!m || !dst || !src) return DCP_ERR_ARG;
+  BlockMat* M = select_matrix(m, which);
+  if (!M || bi < 0 || bi >= M->nb || !M->diag_inv[bi]) {
+    dcp_set_error("dcp_jacobi_vmult: diagonal not available (assemble first)");
+    return DCP_ERR_STATE;
+  }
+  dcp_ctx* ctx = m->ctx;
+  const int64_t n = M->start[bi + 1] - M->start[bi];
+  const double* dx;
+  double* dy;
+  DCP_TRY(dcp_stage_in(ctx, 0, src, n, mem, &dx));
+  DCP_TRY(dcp_stage_out_alloc(ctx, 1, dst, n, mem, &dy));
+  DCP_TRY(dcp_launch_jacobi(ctx, n, M->diag_inv[bi], dx, dy));
+  return dcp_stage_out_finish(ctx, 1, dst, n, mem);
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// FP64 CSR SpMV and the small streaming kernels around it (Jacobi apply, CSR value axpy).
+//
+// Replaces Epetra_CrsMatrix::Multiply behind LA::SparseMatrix::vmult / vmult_add (call sites listed in
+// include/dcp.h).  HBM-bound: algorithmic bytes per product = nnz*(8+4) + n_rows*(8+8) + n_cols*8
+// (values + int32 columns streamed once, y written once, int64 row pointers, x read once; the x gather
+// is served from the 126 MB L2).  Values and columns are read with ld.global.nc.L1::no_allocate (they
+// have no reuse); x goes through the read-only path so that gathers hit L1/L2.
+#include "dcp_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// LANES lanes cooperate on one row; 4-way unrolled so each lane keeps 8 independent loads in flight.
+template <int LANES, bool ADD>
+__global__ void __launch_bounds__(256) spmv_csr_kernel(long long n_rows, const long long* __restrict__ rowptr,
+                                                       const int* __restrict__ col, const double* __restrict__ val,
+                                                       const double* __restrict__ x, double* __restrict__ y) {
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = gtid / LANES;
+  const int lane = threadIdx.x % LANES;
+  double sum = 0.0;
+  if (row < n_rows) {
+    const long long p0 = rowptr[row], p1 = rowptr[row + 1];
+    long long p = p0 + lane;
+    for (; p + 3 * LANES < p1; p += 4 * LANES) {
+      const int c0 = ld_stream_s32(col + p), c1 = ld_stream_s32(col + p + LANES);
+      const int c2 = ld_stream_s32(col + p + 2 * LANES), c3 = ld_stream_s32(col + p + 3 * LANES);
+      const double v0 = ld_stream_f64(val + p), v1 = ld_stream_f64(val + p + LANES);
+      const double v2 = ld_stream_f64(val + p + 2 * LANES), v3 = ld_stream_f64(val + p + 3 * LANES);
+      sum += v0 * __ldg(x + c0);
+      sum += v1 * __ldg(x + c1);
+      sum += v2 * __ldg(x + c2);
+      sum += v3 * __ldg(x + c3);
+    }
+    for (; p < p1; p += LANES) sum += ld_stream_f64(val + p) * __ldg(x + ld_stream_s32(col + p));
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (row < n_rows && lane == 0) y[row] = ADD ? y[row] + sum : sum;
+}
+
+__global__ void extract_diag_inv_kernel(long long n_rows, const long long* __restrict__ rowptr,
+                                        const int* __restrict__ col, const double* __restrict__ val,
+                                        double* __restrict__ dinv) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  long long lo = rowptr[r], hi = rowptr[r + 1];
+  const long long end = hi;
+  const int target = (int)r;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (col[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  double d = (lo < end && col[lo] == target) ? val[lo] : 0.0;
+  dinv[r] = d != 0.0 ? 1.0 / d : 0.0;
+}
+
+__global__ void jacobi_kernel(long long n, const double* __restrict__ dinv, const double* __restrict__ x,
+                              double* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = dinv[i] * x[i];
+}
+
+__global__ void axpby_values_kernel(long long n, const double* __restrict__ a, const double* __restrict__ b, double fb,
+                                    double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = a[i] + fb * b[i];
+}
+
+__global__ void fill_kernel(double* __restrict__ p, long long n, double v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+template <int LANES>
+int launch_spmv_t(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add) {
+  const int threads = 256;
+  const long long rows_per_block = threads / LANES;
+  const long long blocks = (A.n_rows + rows_per_block - 1) / rows_per_block;
+  if (blocks == 0) return DCP_OK;
+  if (add)
+    spmv_csr_kernel<LANES, true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+        A.n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
+  else
+    spmv_csr_kernel<LANES, false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+        A.n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
+  ctx->launches++;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
+}
+
+inline unsigned grid_for(dcp_ctx* ctx, long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)ctx->sm_count * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add) {
+  if (A.n_rows == 0) return DCP_OK;
+  if (A.rowptr == nullptr || A.nnz == 0) {
+    if (!add) return dcp_launch_fill(ctx, y, A.n_rows, 0.0);
+    return DCP_OK;
+  }
+  switch (A.lanes) {
+    case 4: return launch_spmv_t<4>(ctx, A, x, y, add);
+    case 8: return launch_spmv_t<8>(ctx, A, x, y, add);
+    case 16: return launch_spmv_t<16>(ctx, A, x, y, add);
+    default: return launch_spmv_t<32>(ctx, A, x, y, add);
+  }
+}
+
+int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv) {
+  if (A.n_rows == 0) return DCP_OK;
+  const int threads = 256;
+  unsigned blocks = (unsigned)((A.n_rows + threads - 1) / threads);
+  extract_diag_inv_kernel<<<blocks, threads, 0, ctx->stream>>>(A.n_rows, (const long long*)A.rowptr, A.col, A.val, diag_inv);
+  ctx->launches++;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
+}
+
+int dcp_launch_jacobi(dcp_ctx* ctx, int64_t n, const double* diag_inv, const double* x, double* y) {
+  if (n == 0) return DCP_OK;
+  jacobi_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, diag_inv, x, y);
+  ctx->launches++;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
+}
+
+int dcp_launch_axpby_values(dcp_ctx* ctx, int64_t n, const double* a, const double* b, double fb, double* out) {
+  if (n == 0) return DCP_OK;
+  axpby_values_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, a, b, fb, out);
+  ctx->launches++;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
+}
+
+int dcp_launch_fill(dcp_ctx* ctx, double* p, int64_t n, double v) {
+  if (n == 0) return DCP_OK;
+  fill_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, v);
+  ctx->launches++;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
+}

@@ -1,0 +1,206 @@
+/* dcp.h -- C ABI of the B200 device library (libdcp.so) for 3D-DyCorePlanet's data-parallel hot path:
+ * per-cell finite-element assembly of the buoyancy-Boussinesq system and the FP64 CSR SpMVs of its
+ * Krylov solves.  Plain pointers and sizes only; no C++ / torch types; every call returns an int status
+ * (0 = DCP_OK) and leaves a message retrievable with dcp_last_error().
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *
+ *   dcp_model_create            the "once per mesh" part of Standard::BoussinesqModel::setup_dofs
+ *                               (include/core/boussinesq_model.tpp:184-412): DoF maps, constraint lines
+ *                               and sparsity patterns are taken from the caller (deal.II keeps ownership
+ *                               of mesh / DoFHandler / AffineConstraints) and uploaded into SoA device
+ *                               buffers together with what FEValues::reinit would deliver per cell
+ *                               (Scratch objects, include/core/boussineq_model_assembly.tpp:18-171).
+ *   dcp_assemble_nse_system     the statement group `nse_matrix = 0; nse_rhs = 0; WorkStream::run(
+ *                               local_assemble_nse_system, copy_local_to_global_nse_system);
+ *                               compress(add)` of assemble_nse_system (boussinesq_model.tpp:691-740,
+ *                               worker :550-673, copier :677-687).  FEEC: boussineq_model_FEEC.tpp:826-875.
+ *   dcp_assemble_nse_preconditioner   assemble_nse_preconditioner (:479-514, worker :421-464, copier
+ *                               :468-476) + the Jacobi set-up of build_nse_preconditioner (:520-542).
+ *   dcp_assemble_temperature_matrix   assemble_temperature_matrix (:821-864, worker :748-800, copier :804-817).
+ *   dcp_assemble_temperature_rhs      assemble_temperature_rhs (:966-1020): temperature_matrix = M + dt/n K,
+ *                               Jacobi set-up, worker :873-952, copier :955-964 (matrix_for_bc overload).
+ *   dcp_vmult / dcp_vmult_add   LA::SparseMatrix::vmult / vmult_add on one block (Epetra Multiply), call
+ *                               sites include/linear_algebra/schur_complement.hpp:147-149,266-274,
+ *                               approximate_schur_complement.hpp:139-141, shifted_schur_complement.hpp:
+ *                               159-170, nested_schur_complement.hpp:177-179,
+ *                               block_schur_preconditioner.hpp:55,131,144, boussinesq_model.tpp:1317,1392.
+ *   dcp_block_vmult             LA::BlockSparseMatrix::vmult on nse_matrix as called by SolverFGMRES /
+ *                               SolverGMRES (boussinesq_model.tpp:1196,1225; boussineq_model_FEEC.tpp:1372-1401).
+ *   dcp_jacobi_vmult            LA::PreconditionJacobi::vmult (one sweep, omega = 1) on
+ *                               Mu_plus_A_preconditioner / Mp_preconditioner / T_preconditioner
+ *                               (boussinesq_model.tpp:531-539, 982-983).
+ *
+ * Threading: one context per GPU, calls from one host thread (the rank's main thread, where the
+ * reference calls WorkStream::run).  Not re-entrant per context.
+ * There is NO CPU fallback: every entry point fails with DCP_ERR_CUDA if no device is present.
+ */
+#ifndef DCP_H
+#define DCP_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  DCP_OK = 0,
+  DCP_ERR_CUDA = 1,     /* CUDA runtime error or no device */
+  DCP_ERR_ARG = 2,      /* invalid argument */
+  DCP_ERR_PATTERN = 3,  /* a scatter target is not in the sparsity pattern */
+  DCP_ERR_STATE = 4     /* call order (e.g. rhs before matrices) */
+};
+
+enum { DCP_HOST = 0, DCP_DEVICE = 1 }; /* where a caller-provided vector lives */
+enum { DCP_FAMILY_CLASSIC = 0, DCP_FAMILY_FEEC = 1 };
+
+/* which matrix of the model */
+enum {
+  DCP_MAT_NSE = 0,        /* nse_matrix                      (blocks) */
+  DCP_MAT_NSE_PRECOND = 1,/* nse_preconditioner_matrix       (blocks) */
+  DCP_MAT_TEMP_MASS = 2,  /* temperature_mass_matrix         (single block 0,0) */
+  DCP_MAT_TEMP_STIFF = 3, /* temperature_stiffness_matrix */
+  DCP_MAT_TEMP = 4        /* temperature_matrix = M + dt/n K */
+};
+/* which vector of the model */
+enum { DCP_VEC_NSE_RHS = 0, DCP_VEC_TEMP_RHS = 1 };
+/* assembly strategy (dcp_model_set_strategy): both give the same matrix up to summation order */
+enum {
+  DCP_STRATEGY_ATOMIC = 0, /* cell-parallel, red.global.add.f64 scatter, column positions by search */
+  DCP_STRATEGY_OWNER = 1   /* row-owner tiles: every CSR value is written exactly once, no atomics */
+};
+
+typedef struct dcp_ctx dcp_ctx;
+typedef struct dcp_model dcp_model;
+
+/* The pointwise coefficients the quadrature loops consume (boussinesq_model.tpp:564-568, 615-621, 640-650,
+ * 760-764; core_model_data.cc:88-94; core_model_data.tpp:86-118). */
+typedef struct {
+  int32_t dim;
+  int32_t cuboid;       /* parameters.cuboid_geometry: vertical gravity + Coriolis */
+  int32_t nse_interval; /* parameters.NSE_solver_interval */
+  int32_t pad;
+  double dt;            /* parameters.time_step */
+  double inv_re;        /* 1 / Reynolds */
+  double inv_pe;        /* 1 / Peclet */
+  double beta;          /* expansion coefficient */
+  double T_ref;         /* reference temperature */
+  double g_scale;       /* L / U^2 */
+  double g_const;       /* gravity constant */
+  double cor_scale;     /* L / U */
+  double omega;         /* rotation rate */
+} dcp_params;
+
+/* AffineConstraints as a CSR of lines: dof -> sum_k entry_w[k] * dof(entry_dof[k]) + inhom */
+typedef struct {
+  int64_t n_dofs;
+  int64_t n_lines;
+  const int32_t* line_dof;  /* [n_lines], ascending */
+  const int32_t* line_ptr;  /* [n_lines+1] */
+  const int32_t* entry_dof;
+  const double* entry_w;
+  const double* inhom;      /* [n_lines] */
+} dcp_constraints_desc;
+
+/* one CSR block; rowptr == NULL means "empty block" */
+typedef struct {
+  int64_t n_rows, n_cols;
+  const int64_t* rowptr; /* [n_rows+1] */
+  const int32_t* col;    /* block-local, ascending within a row */
+} dcp_csr_desc;
+
+#define DCP_MAX_BLOCKS 3
+
+/* Everything that is uploaded once per mesh.  All pointers are HOST pointers; the library copies. */
+typedef struct {
+  int32_t dim;
+  int32_t family;
+  int64_t n_cells;
+
+  /* Navier-Stokes FE space: cell -> global dof map in the block-concatenated numbering
+   * (after DoFRenumbering::component_wise, boussinesq_model.tpp:204) */
+  int32_t nse_n_local;               /* dofs per cell (classic 3-D: 89) */
+  int32_t nse_n_blocks;              /* classic 2 (u,p), FEEC 3 (w,u,p) */
+  int64_t nse_block_size[DCP_MAX_BLOCKS];
+  const int32_t* nse_l2g;            /* [n_cells][nse_n_local] */
+  const int32_t* nse_local_field;    /* [nse_n_local] vector component of each cell dof */
+  const int32_t* nse_local_base;     /* [nse_n_local] index within its scalar base element */
+  dcp_constraints_desc nse_cs;
+
+  /* temperature FE space */
+  int32_t temp_n_local;
+  int32_t pad0;
+  const int32_t* temp_l2g;
+  dcp_constraints_desc temp_cs;
+
+  /* reference-cell tables, [nq][nd] values and [nq][nd][dim] reference gradients.
+   * *_qn on the NSE rule QGauss(deg+1) (boussinesq_model.tpp:487,708), *_qt on the temperature rule
+   * QGauss(Tdeg+2) (:834,990). */
+  int32_t nq_nse, nq_temp;
+  int32_t ndu, ndp, ndt, pad1;
+  const double *phi_u_qn, *dphi_u_qn, *phi_p_qn, *phi_t_qn;
+  const double *phi_u_qt, *phi_t_qt, *dphi_t_qt;
+
+  /* mapping data per cell and rule: [n_cells][ JxW(nq) | Kinv[e][d](nq each) | xq[d](nq each) ],
+   * Kinv[e][d] = d xi_e / d x_d (inverse Jacobian of the cell mapping at the quadrature point) */
+  const double* geom_qn;
+  const double* geom_qt; /* may be == geom_qn when both rules coincide */
+
+  /* sparsity patterns as deal.II/Trilinos built them (setup_nse_matrices :79-112, setup_nse_preconditioner
+   * :116-150, setup_temperature_matrices :154-180) */
+  dcp_csr_desc nse_pattern[DCP_MAX_BLOCKS][DCP_MAX_BLOCKS];
+  dcp_csr_desc pre_pattern[DCP_MAX_BLOCKS][DCP_MAX_BLOCKS];
+  dcp_csr_desc temp_pattern;
+} dcp_model_desc;
+
+/* ---- context --------------------------------------------------------------------------------- */
+int dcp_ctx_create(int device, dcp_ctx** out);
+int dcp_ctx_destroy(dcp_ctx* ctx);
+/* run all work of this context on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int dcp_ctx_set_stream(dcp_ctx* ctx, void* cuda_stream);
+int dcp_ctx_synchronize(dcp_ctx* ctx);
+/* message of the last failing call on this thread */
+const char* dcp_last_error(void);
+/* number of kernel launches issued by this context since creation (for bench accounting) */
+int64_t dcp_ctx_launch_count(const dcp_ctx* ctx);
+/* device memory helpers for callers without a CUDA runtime of their own */
+int dcp_malloc(dcp_ctx* ctx, int64_t bytes, void** out);
+int dcp_free(dcp_ctx* ctx, void* p);
+int dcp_memcpy_h2d(dcp_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+int dcp_memcpy_d2h(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
+/* ---- model (one per mesh) -------------------------------------------------------------------- */
+int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* desc, dcp_model** out);
+int dcp_model_destroy(dcp_model* m);
+int dcp_model_set_strategy(dcp_model* m, int strategy);
+
+/* ---- assembly (one call per reference assemble_* member) ------------------------------------- */
+/* old_nse: [n_u+n_p(+..)] ghosted old_nse_solution, old_temp: [n_T] old_temperature_solution */
+int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old_nse, const double* old_temp, int mem);
+int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p);
+int dcp_assemble_temperature_matrix(dcp_model* m, const dcp_params* p);
+/* nse_solution: the NEW velocity/pressure vector (reference advects with nse_solution, :904-905) */
+int dcp_assemble_temperature_rhs(dcp_model* m, const dcp_params* p, const double* old_temp, const double* nse_solution, int mem);
+
+/* ---- results --------------------------------------------------------------------------------- */
+/* nnz / shape of block (bi,bj) of matrix `which`; nnz = 0 for an empty block */
+int dcp_matrix_info(const dcp_model* m, int which, int bi, int bj, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
+/* device pointer to the values of that block (owned by the model) */
+int dcp_matrix_values_device(dcp_model* m, int which, int bi, int bj, double** out);
+int dcp_matrix_download(dcp_model* m, int which, int bi, int bj, double* host_values);
+int dcp_matrix_upload(dcp_model* m, int which, int bi, int bj, const double* host_values);
+int dcp_vector_device(dcp_model* m, int which, double** out, int64_t* n);
+int dcp_vector_download(dcp_model* m, int which, double* host);
+
+/* ---- operators (deal.II vmult concept) ------------------------------------------------------- */
+/* dst = A(bi,bj) * src ;  dst += A(bi,bj) * src */
+int dcp_vmult(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem);
+int dcp_vmult_add(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem);
+/* dst = A * src over all blocks; vectors are block-concatenated */
+int dcp_block_vmult(dcp_model* m, int which, double* dst, const double* src, int mem);
+/* dst = diag(A(bi,bi))^-1 * src  (Jacobi, one sweep, omega 1).  Diagonals are refreshed by the assemble calls. */
+int dcp_jacobi_vmult(dcp_model* m, int which, int bi, double* dst, const double* src, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
