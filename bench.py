@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- DoFs assembled/s + SpMV GB/s (FP64) on the hypershell, classic Taylor-Hood config.
+
+One "step" = one pass of the hot path over one mesh: the four assemblers of the reference's time loop
+(assemble_nse_system, assemble_nse_preconditioner, assemble_temperature_matrix, assemble_temperature_rhs;
+/root/reference/include/core/boussinesq_model.tpp:1867-1884) followed by the SpMVs one outer Krylov iteration
+makes (full nse_matrix block vmult + temperature_matrix vmult).  `value` = DoFs (n_u+n_p+n_T) / step time with
+all inputs resident in HBM; `e2e` = the same step through the C ABI with HOST buffers (H2D of the solution
+vectors and SpMV sources, D2H of the right-hand sides and SpMV results inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--refine R] [--temperature-degree D]
+  python bench.py --impl reference ...   # the restated CPU path (oracle, OpenMP) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(P, T_deg_rule_shared=True):
+    """Per-kernel algorithmic bytes (DESIGN.md 'roofline accounting')."""
+    nc, nq, dim = P.n_cells, P.scalar("q_nse.nq"), P.dim
+    nqt = P.scalar("q_temp.nq")
+    nd, ndt = P.scalar("nse.n_local"), P.scalar("temp.n_local")
+    n_nse, n_t = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
+    geom_n = nc * nq * (1 + dim * dim + dim) * 8
+    geom_n_noxq = nc * nq * (1 + dim * dim) * 8
+    geom_t = nc * nqt * (1 + dim * dim) * 8
+    nnz_nse = sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(2) for j in range(2))
+    nnz_pre = sum(P.scalar(f"pre.b{i}{j}.nnz") for i in range(2) for j in range(2))
+    nnz_t = P.scalar("temp.pat.nnz")
+    out = {
+        "nse_system": geom_n + nc * nd * 4 + nc * ndt * 4 + n_nse * 8 + n_t * 8 + nnz_nse * 8 + n_nse * 8,
+        "nse_preconditioner": geom_n_noxq + nc * nd * 4 + nnz_pre * 8,
+        "temperature_matrix": geom_t + nc * ndt * 4 + 2 * nnz_t * 8,
+        "temperature_rhs": geom_t + nc * ndt * 4 + nc * nd * 4 + n_nse * 8 + n_t * 8 + 3 * nnz_t * 8 + n_t * 8,
+    }
+    spmv = 0
+    for i in range(2):
+        for j in range(2):
+            z = P.scalar(f"nse.b{i}{j}.nnz")
+            if z:
+                spmv += z * 12 + P.scalar(f"nse.b{i}{j}.n_rows") * 16 + P.scalar(f"nse.b{i}{j}.n_cols") * 8
+    spmv += P.scalar("nse.b00.n_rows") * 8  # block(0,1) is applied as vmult_add on the velocity rows
+    out["spmv_nse"] = spmv
+    out["spmv_temperature"] = nnz_t * 12 + n_t * 16 + n_t * 8
+    return out
+
+
+def cpu_leg(refine, temperature_degree, steps, warmup, mp):
+    """The restated CPU path (oracle, OpenMP over cells with atomic adds) on the host cores."""
+    import dycore_b200  # noqa: F401
+    from dycore_b200 import harness
+    from oracle import oracle as orc
+    from util import synthetic_fields
+    P = harness.Problem(geometry="shell", refine=refine, temperature_degree=temperature_degree)
+    u, T = synthetic_fields(P)
+    prm = orc.params_from(mp)
+    n_dofs = P.scalar("nse.n_dofs") + P.scalar("temp.n_dofs")
+    rp, col, _, _ = P.csr("nse.full")
+    rpt, colt, _, _ = P.csr("temp.pat")
+    x = np.random.default_rng(1).standard_normal(P.scalar("nse.n_dofs"))
+    xt = np.random.default_rng(2).standard_normal(P.scalar("temp.n_dofs"))
+    times, t_spmv = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        vals, _ = orc.assemble_nse_system(P, prm, u, T, use_omp=True)
+        orc.assemble_nse_preconditioner(P, prm, use_omp=True)
+        m, k = orc.assemble_temperature_matrix(P, prm, use_omp=True)
+        tm = orc.temperature_matrix_combine(m, k, mp.time_step / mp.NSE_solver_interval)
+        orc.assemble_temperature_rhs(P, prm, T, u, use_omp=True)
+        t1 = time.perf_counter()
+        orc.spmv(rp, col, vals, x, use_omp=True)
+        orc.spmv(rpt, colt, tm, xt, use_omp=True)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            times.append(t2 - t0)
+            t_spmv.append(t2 - t1)
+    ab = algorithmic_bytes(P)
+    dt = float(np.mean(times))
+    return {"value": n_dofs / dt, "unit": "DoFs/s", "cores": orc.max_threads(), "kind": "port",
+            "sample": f"hypershell classic refine={refine} ({P.n_cells} cells, {n_dofs} DoFs), {steps} step(s) "
+                      f"after {warmup} warm-up; restated CPU path (oracle), OpenMP, not the deal.II/Trilinos MPI binary",
+            "ms_per_step": dt * 1e3,
+            "spmv_gbs": (ab["spmv_nse"] + ab["spmv_temperature"]) / float(np.mean(t_spmv)) / 1e9}, n_dofs, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--refine", type=int, default=5)
+    ap.add_argument("--temperature-degree", type=int, default=1)
+    ap.add_argument("--strategy", default="auto", choices=["auto", "atomic", "owner"])
+    ap.add_argument("--cpu-refine", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import dycore_b200  # noqa: F401
+    from dycore_b200 import params
+    mp = params.NAMED["shell_3d_classic"]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        warm = min(args.warmup, 1)
+        steps = min(args.steps, 3)
+        base, n_dofs, dt = cpu_leg(args.cpu_refine, args.temperature_degree, steps, warm, mp)
+        line = {"impl": "reference", "metric": "dofs_assembled_per_s", "value": base["value"], "unit": "DoFs/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "hypershell classic (Taylor-Hood Q2/Q1 + Q1 temperature): full Boussinesq "
+                                       "assembly pass + nse_matrix/temperature_matrix SpMV",
+                           "note": "bounded sample: " + base["sample"]},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dycore_b200 import device, harness
+    from util import synthetic_fields
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- problem (weak scaling: every rank owns one mesh of the same size) --------------------------
+    t_setup = time.perf_counter()
+    P = harness.Problem(geometry="shell", refine=args.refine, temperature_degree=args.temperature_degree)
+    u, T = synthetic_fields(P)
+    n_nse, n_t = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
+    n_dofs = n_nse + n_t
+    ctx = device.Context(local_rank)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    strategy = args.strategy
+    if strategy == "auto":
+        strategy = "owner"
+    try:
+        model.set_strategy(device.STRATEGY_OWNER if strategy == "owner" else device.STRATEGY_ATOMIC)
+        if strategy == "owner":
+            model.assemble_nse_preconditioner()
+    except device.DcpError:
+        strategy = "atomic"
+        model.set_strategy(device.STRATEGY_ATOMIC)
+    t_setup = time.perf_counter() - t_setup
+
+    with torch.cuda.stream(stream):
+        d_u = torch.from_numpy(u).cuda()
+        d_T = torch.from_numpy(T).cuda()
+        rng = np.random.default_rng(1)
+        d_x = torch.from_numpy(rng.standard_normal(n_nse)).cuda()
+        d_y = torch.zeros(n_nse, dtype=torch.float64, device="cuda")
+        d_xt = torch.from_numpy(rng.standard_normal(n_t)).cuda()
+        d_yt = torch.zeros(n_t, dtype=torch.float64, device="cuda")
+    # pinned host buffers for the e2e leg
+    h_u, h_T = torch.from_numpy(u).pin_memory(), torch.from_numpy(T).pin_memory()
+    h_x, h_y = d_x.cpu().pin_memory(), torch.zeros(n_nse, dtype=torch.float64).pin_memory()
+    h_xt, h_yt = d_xt.cpu().pin_memory(), torch.zeros(n_t, dtype=torch.float64).pin_memory()
+    h_rhs, h_trhs = torch.zeros(n_nse, dtype=torch.float64).pin_memory(), torch.zeros(n_t, dtype=torch.float64).pin_memory()
+
+    phases = ["nse_system", "nse_preconditioner", "temperature_matrix", "temperature_rhs", "spmv_nse", "spmv_temperature"]
+
+    def step_device(ev=None):
+        def mark(i):
+            if ev is not None:
+                ev[i].record(stream)
+        mark(0)
+        model.assemble_nse_system(d_u, d_T)
+        mark(1)
+        model.assemble_nse_preconditioner()
+        mark(2)
+        model.assemble_temperature_matrix()
+        mark(3)
+        model.assemble_temperature_rhs(d_T, d_u)
+        mark(4)
+        model.nse_matrix.vmult(d_y, d_x)
+        mark(5)
+        model.temperature_matrix.vmult(d_yt, d_xt)
+        mark(6)
+
+    def step_host():
+        model.assemble_nse_system(h_u.numpy(), h_T.numpy())
+        model.assemble_nse_preconditioner()
+        model.assemble_temperature_matrix()
+        model.assemble_temperature_rhs(h_T.numpy(), h_u.numpy())
+        model.nse_matrix.vmult(h_y.numpy(), h_x.numpy())
+        model.temperature_matrix.vmult(h_yt.numpy(), h_xt.numpy())
+        device.check(device.lib().dcp_vector_download(model._h, device.VEC_NSE_RHS, h_rhs.data_ptr()))
+        device.check(device.lib().dcp_vector_download(model._h, device.VEC_TEMP_RHS, h_trhs.data_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_events):
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(steps)] if with_events else None
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(steps):
+            fn(evs[s]) if with_events else fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, evs
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ms, evs = timed(step_device, args.steps, True)
+    launches = (ctx.launch_count() - l0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    phase_ms = {p: float(np.mean([evs[s][i].elapsed_time(evs[s][i + 1]) for s in range(args.steps)]))
+                for i, p in enumerate(phases)}
+    for _ in range(2):
+        step_host()
+    ms_e2e, _ = timed(step_host, args.steps, False)
+    ctx.synchronize()
+
+    if rank == 0:
+        ab = algorithmic_bytes(P)
+        peak, peak_src = peaks()
+        ms_step = ms / args.steps
+        dom = max(("nse_system", "nse_preconditioner"), key=lambda k: phase_ms[k])
+        ach = ab[dom] / (phase_ms[dom] * 1e-3) / 1e9
+        asm_ms = sum(phase_ms[p] for p in phases[:4])
+        spmv_ms = phase_ms["spmv_nse"] + phase_ms["spmv_temperature"]
+        line = {
+            "metric": "dofs_assembled_per_s", "value": world * n_dofs / (ms_step * 1e-3), "unit": "DoFs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"hypershell classic refine={args.refine} (Taylor-Hood Q2/Q1 + Q{args.temperature_degree} "
+                                   f"temperature): full Boussinesq assembly pass + nse_matrix/temperature_matrix SpMV",
+                       "cells_per_gpu": P.n_cells, "dofs_per_gpu": n_dofs,
+                       "nnz_nse": sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(2) for j in range(2)),
+                       "strategy": strategy, "l2": "inputs larger than L2" if ab["nse_system"] > 4 * 126e6 else "inputs fit L2",
+                       "partition": "one mesh per GPU" if world > 1 else "single GPU", "setup_s": round(t_setup, 2)},
+            "assembly_dofs_per_s": world * n_dofs / (asm_ms * 1e-3),
+            "spmv_gbs": world * (ab["spmv_nse"] + ab["spmv_temperature"]) / (spmv_ms * 1e-3) / 1e9,
+            "phase_ms": phase_ms,
+            "phase_gbs": {p: ab[p] / (phase_ms[p] * 1e-3) / 1e9 for p in phases},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "spmv_frac": ab["spmv_nse"] / (phase_ms["spmv_nse"] * 1e-3) / 1e9 / peak},
+            "e2e": {"value": world * n_dofs / (ms_e2e / args.steps * 1e-3), "unit": "DoFs/s",
+                    "h2d_bytes_per_step": int(8 * (2 * (n_nse + n_t) + n_nse + n_t)),
+                    "d2h_bytes_per_step": int(8 * (2 * (n_nse + n_t)))},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            base, _, _ = cpu_leg(args.cpu_refine, args.temperature_degree, 1, 1, mp)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    model.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

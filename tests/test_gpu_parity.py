@@ -95,11 +95,13 @@ def test_spmv_matches_oracle(ctx, problem_factory, spec):
                 y = np.zeros(sizes[bi])
                 A.vmult(y, x)
                 yr = orc.spmv(rp, col, vals, x)
-                assert rel_err_max(y, yr) <= TOL
+                # scale = max(|A||x|): rows of B sum to ~0 on constants, so ||y|| itself can be round-off
+                scale = orc.spmv(rp, col, np.abs(vals), np.abs(x)).max()
+                assert np.abs(y - yr).max() <= TOL * scale
                 y2 = rng.standard_normal(sizes[bi])
                 y2r = orc.spmv(rp, col, vals, x, y=y2.copy(), add=True)
                 A.vmult_add(y2, x)
-                assert rel_err_max(y2, y2r) <= TOL
+                assert np.abs(y2 - y2r).max() <= TOL * max(scale, np.abs(y2r).max())
     # full block vmult and temperature matrix
     x = rng.standard_normal(n_u + n_p)
     y = np.zeros(n_u + n_p)
