@@ -100,10 +100,11 @@ inline BlockView make_view(const BlockMat& M) {
 inline CsView make_view(const DevCs& c) { return CsView{c.line_of_dof, c.line_ptr, c.entry_dof, c.entry_w, c.inhom}; }
 
 struct OwnerPlan;  // row-owner tiles (assemble_th_owner.cu)
+struct FastPlan;   // position tables (assemble_th_fast.cu)
 
 struct dcp_model {
   dcp_ctx* ctx = nullptr;
-  int dim = 3, family = 0, strategy = DCP_STRATEGY_ATOMIC;
+  int dim = 3, family = 0, strategy = DCP_STRATEGY_POSITIONS;
   int64_t n_cells = 0;
   // spaces
   int nse_n_local = 0, nse_nb = 2, temp_n_local = 0;
@@ -128,6 +129,8 @@ struct dcp_model {
   bool temp_matrices_ready = false;
   OwnerPlan* owner_nse = nullptr;
   OwnerPlan* owner_pre = nullptr;
+  FastPlan* fast_nse = nullptr;
+  FastPlan* fast_pre = nullptr;
 };
 
 // ---- helpers implemented in context.cu -----------------------------------------------------------
@@ -150,6 +153,12 @@ int dcp_launch_th_cells(dcp_model* m, const dcp_params& p, bool system, const do
 int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p);
 int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* old_temp, const double* nse_solution);
 
+int dcp_fast_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, FastPlan** out);
+void dcp_fast_plan_free(FastPlan* p);
+int64_t dcp_fast_plan_counts(const FastPlan* p, int64_t* n_general);
+const int32_t* dcp_fast_plan_general_cells(const FastPlan* p);
+int dcp_launch_th_fast(dcp_model* m, const dcp_params& p, bool system, const FastPlan* plan, const double* old_nse,
+                       const double* old_temp);
 int dcp_owner_plan_build(dcp_model* m, bool system, const dcp_model_desc* desc);
 void dcp_owner_plan_free(OwnerPlan* p);
 int dcp_launch_th_owner(dcp_model* m, const dcp_params& p, bool system);

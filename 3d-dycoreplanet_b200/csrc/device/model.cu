@@ -320,6 +320,8 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->temp_rhs);
   dcp_owner_plan_free(m->owner_nse);
   dcp_owner_plan_free(m->owner_pre);
+  dcp_fast_plan_free(m->fast_nse);
+  dcp_fast_plan_free(m->fast_pre);
   delete m;
   return DCP_OK;
 }
@@ -450,6 +452,9 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     M_TRY(dcp_upload(ctx, &m->nse_constrained_cells, cells.data(), (int64_t)cells.size()));
     DCP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  // position tables for the unconstrained cells (DCP_STRATEGY_POSITIONS)
+  M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
+  M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
   DCP_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef M_TRY
   *out = m;
@@ -457,7 +462,11 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
 }
 
 int dcp_model_set_strategy(dcp_model* m, int strategy) {
-  if (!m || (strategy != DCP_STRATEGY_ATOMIC && strategy != DCP_STRATEGY_OWNER)) return DCP_ERR_ARG;
+  if (!m || strategy < DCP_STRATEGY_SEARCH || strategy > DCP_STRATEGY_OWNER) return DCP_ERR_ARG;
+  if (strategy == DCP_STRATEGY_OWNER) {
+    dcp_set_error("DCP_STRATEGY_OWNER is not built yet");
+    return DCP_ERR_STATE;
+  }
   m->strategy = strategy;
   return DCP_OK;
 }
@@ -470,10 +479,12 @@ int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old
   DCP_TRY(dcp_stage_in(ctx, 0, old_nse, m->nse_n_dofs, mem, &d_nse));
   DCP_TRY(dcp_stage_in(ctx, 1, old_temp, m->temp_n_dofs, mem, &d_temp));
   DCP_CUDA(cudaMemsetAsync(m->nse_rhs, 0, sizeof(double) * (size_t)m->nse_n_dofs, ctx->stream));
-  if (m->strategy == DCP_STRATEGY_OWNER) {
-    DCP_TRY(dcp_launch_th_owner(m, *p, true));
-    DCP_TRY(dcp_launch_th_rhs(m, *p, d_nse, d_temp));
-    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
+  if (m->strategy == DCP_STRATEGY_POSITIONS) {
+    DCP_TRY(zero_blockmat(ctx, m->nse));
+    DCP_TRY(dcp_launch_th_fast(m, *p, true, m->fast_nse, d_nse, d_temp));
+    int64_t ng = 0;
+    dcp_fast_plan_counts(m->fast_nse, &ng);
+    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, dcp_fast_plan_general_cells(m->fast_nse), ng, false));
   } else {
     DCP_TRY(zero_blockmat(ctx, m->nse));
     DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, nullptr, 0, false));
@@ -486,9 +497,12 @@ int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
   if (!m || !p) return DCP_ERR_ARG;
   dcp_ctx* ctx = m->ctx;
   DCP_CUDA(cudaSetDevice(ctx->device));
-  if (m->strategy == DCP_STRATEGY_OWNER) {
-    DCP_TRY(dcp_launch_th_owner(m, *p, false));
-    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
+  if (m->strategy == DCP_STRATEGY_POSITIONS) {
+    DCP_TRY(zero_blockmat(ctx, m->pre));
+    DCP_TRY(dcp_launch_th_fast(m, *p, false, m->fast_pre, nullptr, nullptr));
+    int64_t ng = 0;
+    dcp_fast_plan_counts(m->fast_pre, &ng);
+    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, dcp_fast_plan_general_cells(m->fast_pre), ng, false));
   } else {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, nullptr, 0, false));

@@ -21,7 +21,7 @@ _LIB = None
 HOST, DEVICE = 0, 1
 MAT_NSE, MAT_NSE_PRECOND, MAT_TEMP_MASS, MAT_TEMP_STIFF, MAT_TEMP = 0, 1, 2, 3, 4
 VEC_NSE_RHS, VEC_TEMP_RHS = 0, 1
-STRATEGY_ATOMIC, STRATEGY_OWNER = 0, 1
+STRATEGY_SEARCH, STRATEGY_POSITIONS, STRATEGY_OWNER = 0, 1, 2
 MAXB = 3
 
 c_dp = ctypes.POINTER(ctypes.c_double)

@@ -149,7 +149,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--refine", type=int, default=5)
     ap.add_argument("--temperature-degree", type=int, default=1)
-    ap.add_argument("--strategy", default="auto", choices=["auto", "atomic", "owner"])
+    ap.add_argument("--strategy", default="auto", choices=["auto", "search", "positions", "owner"])
     ap.add_argument("--cpu-refine", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -199,16 +199,9 @@ def main():
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     model = device.BoussinesqModel.from_problem(ctx, P, mp)
-    strategy = args.strategy
-    if strategy == "auto":
-        strategy = "owner"
-    try:
-        model.set_strategy(device.STRATEGY_OWNER if strategy == "owner" else device.STRATEGY_ATOMIC)
-        if strategy == "owner":
-            model.assemble_nse_preconditioner()
-    except device.DcpError:
-        strategy = "atomic"
-        model.set_strategy(device.STRATEGY_ATOMIC)
+    strategy = "positions" if args.strategy == "auto" else args.strategy
+    model.set_strategy({"search": device.STRATEGY_SEARCH, "positions": device.STRATEGY_POSITIONS,
+                        "owner": device.STRATEGY_OWNER}[strategy])
     t_setup = time.perf_counter() - t_setup
 
     with torch.cuda.stream(stream):

@@ -63,10 +63,12 @@ enum {
 };
 /* which vector of the model */
 enum { DCP_VEC_NSE_RHS = 0, DCP_VEC_TEMP_RHS = 1 };
-/* assembly strategy (dcp_model_set_strategy): both give the same matrix up to summation order */
+/* assembly strategy (dcp_model_set_strategy): all give the same matrix up to summation order */
 enum {
-  DCP_STRATEGY_ATOMIC = 0, /* cell-parallel, red.global.add.f64 scatter, column positions by search */
-  DCP_STRATEGY_OWNER = 1   /* row-owner tiles: every CSR value is written exactly once, no atomics */
+  DCP_STRATEGY_SEARCH = 0,    /* every cell: general AffineConstraints scatter, column positions by binary search */
+  DCP_STRATEGY_POSITIONS = 1, /* unconstrained cells scatter from registers through a precomputed position table
+                                 (no search, no local matrix in shared memory); constrained cells use SEARCH */
+  DCP_STRATEGY_OWNER = 2      /* row-owner tiles: every CSR value written exactly once, no atomics (planned) */
 };
 
 typedef struct dcp_ctx dcp_ctx;
