@@ -73,6 +73,7 @@ struct BlockMat {
   int64_t start[DCP_MAXB + 1] = {0, 0, 0, 0};
   DevCsr blk[DCP_MAXB][DCP_MAXB];
   double* diag_inv[DCP_MAXB] = {nullptr, nullptr, nullptr};  // Jacobi: 1/diag of the diagonal blocks
+  int64_t owned[DCP_MAXB] = {-1, -1, -1};  // rows of each block owned by this rank (-1: all)
 };
 
 // by-value kernel argument describing a block matrix for scatter
@@ -142,7 +143,8 @@ int dcp_stage_out_alloc(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem,
 int dcp_stage_out_finish(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem);
 
 // ---- kernels' host launchers ---------------------------------------------------------------------
-int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add);
+int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit = -1);
+int dcp_launch_gather(dcp_ctx* ctx, int64_t n, const int32_t* idx, const double* src, double* dst, bool scatter);
 int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv);
 int dcp_launch_jacobi(dcp_ctx* ctx, int64_t n, const double* diag_inv, const double* x, double* y);
 int dcp_launch_axpby_values(dcp_ctx* ctx, int64_t n, const double* a, const double* b, double fb, double* out);

@@ -471,6 +471,29 @@ int dcp_model_set_strategy(dcp_model* m, int strategy) {
   return DCP_OK;
 }
 
+int dcp_model_set_owned(dcp_model* m, const int64_t* nse_owned_per_block, int64_t temp_owned) {
+  if (!m || !nse_owned_per_block) return DCP_ERR_ARG;
+  for (int b = 0; b < m->nse_nb; ++b) {
+    if (nse_owned_per_block[b] < 0 || nse_owned_per_block[b] > m->nse.start[b + 1] - m->nse.start[b]) {
+      dcp_set_error("dcp_model_set_owned: owned count exceeds the block size");
+      return DCP_ERR_ARG;
+    }
+    m->nse.owned[b] = m->pre.owned[b] = nse_owned_per_block[b];
+  }
+  if (temp_owned < 0 || temp_owned > m->temp_n_dofs) return DCP_ERR_ARG;
+  m->tmass.owned[0] = m->tstiff.owned[0] = m->tmat.owned[0] = temp_owned;
+  return DCP_OK;
+}
+
+int dcp_gather_f64(dcp_ctx* ctx, int64_t n, const int32_t* idx_dev, const double* src_dev, double* dst_dev) {
+  if (!ctx || n < 0) return DCP_ERR_ARG;
+  return dcp_launch_gather(ctx, n, idx_dev, src_dev, dst_dev, false);
+}
+int dcp_scatter_f64(dcp_ctx* ctx, int64_t n, const int32_t* idx_dev, const double* src_dev, double* dst_dev) {
+  if (!ctx || n < 0) return DCP_ERR_ARG;
+  return dcp_launch_gather(ctx, n, idx_dev, src_dev, dst_dev, true);
+}
+
 int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old_nse, const double* old_temp, int mem) {
   if (!m || !p || !old_nse || !old_temp) return DCP_ERR_ARG;
   dcp_ctx* ctx = m->ctx;
@@ -605,7 +628,8 @@ int dcp_vector_download(dcp_model* m, int which, double* host) {
 static int vmult_impl(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem, bool add) {
   if (!m || !dst || !src) return DCP_ERR_ARG;
   DevCsr* A;
-  DCP_TRY(get_block(m, which, bi, bj, &A));
+  BlockMat* BM;
+  DCP_TRY(get_block(m, which, bi, bj, &A, &BM));
   dcp_ctx* ctx = m->ctx;
   DCP_CUDA(cudaSetDevice(ctx->device));
   const double* dx;
@@ -617,7 +641,7 @@ static int vmult_impl(dcp_model* m, int which, int bi, int bj, double* dst, cons
     dy = const_cast<double*>(tmp);
   } else
     DCP_TRY(dcp_stage_out_alloc(ctx, 1, dst, A->n_rows, mem, &dy));
-  DCP_TRY(dcp_launch_spmv(ctx, *A, dx, dy, add));
+  DCP_TRY(dcp_launch_spmv(ctx, *A, dx, dy, add, BM->owned[bi]));
   return dcp_stage_out_finish(ctx, 1, dst, A->n_rows, mem);
 }
 
@@ -645,10 +669,11 @@ int dcp_block_vmult(dcp_model* m, int which, double* dst, const double* src, int
     for (int c = 0; c < M->nb; ++c) {
       DevCsr& A = M->blk[r][c];
       if (A.nnz == 0) continue;
-      DCP_TRY(dcp_launch_spmv(ctx, A, dx + M->start[c], dy + M->start[r], !first));
+      DCP_TRY(dcp_launch_spmv(ctx, A, dx + M->start[c], dy + M->start[r], !first, M->owned[r]));
       first = false;
     }
-    if (first) DCP_TRY(dcp_launch_fill(ctx, dy + M->start[r], M->start[r + 1] - M->start[r], 0.0));
+    if (first)
+      DCP_TRY(dcp_launch_fill(ctx, dy + M->start[r], M->owned[r] >= 0 ? M->owned[r] : M->start[r + 1] - M->start[r], 0.0));
   }
   return dcp_stage_out_finish(ctx, 1, dst, n, mem);
 }
@@ -666,7 +691,7 @@ int dcp_jacobi_vmult(dcp_model* m, int which, int bi, double* dst, const double*
   double* dy;
   DCP_TRY(dcp_stage_in(ctx, 0, src, n, mem, &dx));
   DCP_TRY(dcp_stage_out_alloc(ctx, 1, dst, n, mem, &dy));
-  DCP_TRY(dcp_launch_jacobi(ctx, n, M->diag_inv[bi], dx, dy));
+  DCP_TRY(dcp_launch_jacobi(ctx, M->owned[bi] >= 0 ? M->owned[bi] : n, M->diag_inv[bi], dx, dy));
   return dcp_stage_out_finish(ctx, 1, dst, n, mem);
 }
 

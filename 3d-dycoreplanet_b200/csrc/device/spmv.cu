@@ -86,17 +86,17 @@ __global__ void fill_kernel(double* __restrict__ p, long long n, double v) {
 }
 
 template <int LANES>
-int launch_spmv_t(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add) {
+int launch_spmv_t(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, long long n_rows) {
   const int threads = 256;
   const long long rows_per_block = threads / LANES;
-  const long long blocks = (A.n_rows + rows_per_block - 1) / rows_per_block;
+  const long long blocks = (n_rows + rows_per_block - 1) / rows_per_block;
   if (blocks == 0) return DCP_OK;
   if (add)
     spmv_csr_kernel<LANES, true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-        A.n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
+        n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
   else
     spmv_csr_kernel<LANES, false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-        A.n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
+        n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;
@@ -110,18 +110,42 @@ inline unsigned grid_for(dcp_ctx* ctx, long long n, int threads) {
 
 }  // namespace
 
-int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add) {
-  if (A.n_rows == 0) return DCP_OK;
+int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit) {
+  const long long n_rows = row_limit >= 0 && row_limit < A.n_rows ? row_limit : A.n_rows;
+  if (n_rows == 0) return DCP_OK;
   if (A.rowptr == nullptr || A.nnz == 0) {
-    if (!add) return dcp_launch_fill(ctx, y, A.n_rows, 0.0);
+    if (!add) return dcp_launch_fill(ctx, y, n_rows, 0.0);
     return DCP_OK;
   }
   switch (A.lanes) {
-    case 4: return launch_spmv_t<4>(ctx, A, x, y, add);
-    case 8: return launch_spmv_t<8>(ctx, A, x, y, add);
-    case 16: return launch_spmv_t<16>(ctx, A, x, y, add);
-    default: return launch_spmv_t<32>(ctx, A, x, y, add);
+    case 4: return launch_spmv_t<4>(ctx, A, x, y, add, n_rows);
+    case 8: return launch_spmv_t<8>(ctx, A, x, y, add, n_rows);
+    case 16: return launch_spmv_t<16>(ctx, A, x, y, add, n_rows);
+    default: return launch_spmv_t<32>(ctx, A, x, y, add, n_rows);
   }
+}
+
+namespace {
+template <bool SCATTER>
+__global__ void gather_scatter_kernel(long long n, const int* __restrict__ idx, const double* __restrict__ src,
+                                      double* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    if (SCATTER) dst[idx[i]] = src[i]; else dst[i] = src[idx[i]];
+  }
+}
+}  // namespace
+
+int dcp_launch_gather(dcp_ctx* ctx, int64_t n, const int32_t* idx, const double* src, double* dst, bool scatter) {
+  if (n == 0) return DCP_OK;
+  if (scatter)
+    gather_scatter_kernel<true><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, idx, src, dst);
+  else
+    gather_scatter_kernel<false><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, idx, src, dst);
+  ctx->launches++;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
 }
 
 int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv) {

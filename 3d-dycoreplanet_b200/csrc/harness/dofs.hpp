@@ -133,7 +133,10 @@ struct Constraints {
 struct DofMap {
   FESystemDesc fe;
   int64_t n_cells = 0, n_dofs = 0;
-  std::vector<int64_t> block_size;    // dofs per block
+  std::vector<int64_t> block_size;    // dofs per block (owned + ghost on this rank)
+  std::vector<int64_t> owned_size;    // dofs per block owned by this rank (numbered first within the block)
+  std::vector<int64_t> dof_key;       // [n_dofs] global key (lattice node * 8 + rank of the field on the node)
+  std::vector<int32_t> dof_owner;     // [n_dofs] owning rank
   std::vector<int32_t> l2g;           // [n_cells][n_local], block-concatenated global numbering
   std::vector<int32_t> node_first;    // [n_nodes] first (pre-renumbering) dof at lattice node or -1
   std::vector<int32_t> renumber;      // [n_dofs] pre -> final
@@ -148,7 +151,10 @@ struct DofMap {
   }
 };
 
-inline DofMap distribute_dofs(const Mesh& mesh, FESystemDesc fe) {
+// node_owner (optional): owning rank per lattice node; dofs owned by other ranks are numbered after the owned
+// ones inside each block (Trilinos-style local numbering: owned rows first, then ghost columns).
+inline DofMap distribute_dofs(const Mesh& mesh, FESystemDesc fe, const std::vector<int32_t>* node_owner = nullptr,
+                              int rank = 0) {
   DofMap dm;
   fe.dim = mesh.dim;
   fe.finalize();
@@ -188,7 +194,12 @@ inline DofMap distribute_dofs(const Mesh& mesh, FESystemDesc fe) {
   int n_blocks = 0;
   for (int b : fe.field_block) n_blocks = std::max(n_blocks, b + 1);
   dm.block_size.assign(n_blocks, 0);
-  std::vector<int8_t> pre_block((size_t)next, 0);
+  dm.owned_size.assign(n_blocks, 0);
+  dm.dof_key.assign((size_t)next, -1);
+  dm.dof_owner.assign((size_t)next, rank);
+  std::vector<int8_t> pre_block((size_t)next, 0);   // pseudo block = 2*block + is_ghost
+  std::vector<int64_t> pre_key((size_t)next, -1);
+  std::vector<int32_t> pre_owner((size_t)next, rank);
   {
     std::vector<int8_t> node_ed((size_t)mesh.n_nodes, -1);
     for (int64_t c = 0; c < mesh.n_cells; ++c) {
@@ -199,19 +210,33 @@ inline DofMap distribute_dofs(const Mesh& mesh, FESystemDesc fe) {
       int32_t f0 = dm.node_first[node];
       if (f0 < 0) continue;
       int ed = node_ed[node];
+      const int own = node_owner ? (*node_owner)[node] : rank;
       for (int f = 0; f < nf; ++f) {
         int rk = dm.field_rank[f][ed];
-        if (rk >= 0) pre_block[f0 + rk] = (int8_t)fe.field_block[f];
+        if (rk >= 0) {
+          pre_block[f0 + rk] = (int8_t)(2 * fe.field_block[f] + (own != rank ? 1 : 0));
+          pre_key[f0 + rk] = node * 8 + rk;
+          pre_owner[f0 + rk] = own;
+        }
       }
     }
   }
-  for (int64_t d = 0; d < next; ++d) dm.block_size[pre_block[d]]++;
-  std::vector<int64_t> block_start(n_blocks + 1, 0);
-  for (int b = 0; b < n_blocks; ++b) block_start[b + 1] = block_start[b] + dm.block_size[b];
+  std::vector<int64_t> pseudo_size(2 * n_blocks, 0);
+  for (int64_t d = 0; d < next; ++d) pseudo_size[pre_block[d]]++;
+  std::vector<int64_t> pseudo_start(2 * n_blocks + 1, 0);
+  for (int b = 0; b < 2 * n_blocks; ++b) pseudo_start[b + 1] = pseudo_start[b] + pseudo_size[b];
+  for (int b = 0; b < n_blocks; ++b) {
+    dm.owned_size[b] = pseudo_size[2 * b];
+    dm.block_size[b] = pseudo_size[2 * b] + pseudo_size[2 * b + 1];
+  }
   dm.renumber.resize((size_t)next);
   {
-    std::vector<int64_t> cur(block_start.begin(), block_start.end() - 1);
-    for (int64_t d = 0; d < next; ++d) dm.renumber[d] = (int32_t)cur[pre_block[d]]++;
+    std::vector<int64_t> cur(pseudo_start.begin(), pseudo_start.end() - 1);
+    for (int64_t d = 0; d < next; ++d) {
+      dm.renumber[d] = (int32_t)cur[pre_block[d]]++;
+      dm.dof_key[dm.renumber[d]] = pre_key[d];
+      dm.dof_owner[dm.renumber[d]] = pre_owner[d];
+    }
   }
   // pass 2: cell -> global
   dm.l2g.resize((size_t)mesh.n_cells * fe.n_local);

@@ -151,6 +151,7 @@ inline void demorton3(uint32_t m, uint32_t& i, uint32_t& j, uint32_t& k) {
 // ---- cubed-sphere hypershell -------------------------------------------------------------------
 struct ShellMesh3D : Mesh {
   int r, n, M;
+  int nr, Mr;  // radial layers (n * radial_factor) and radial half-step lattice size
   double R0, R1;
   int64_t n_surf = 0;
   std::vector<int32_t> sid;   // (M+1)^3 -> surface node id or -1
@@ -158,11 +159,14 @@ struct ShellMesh3D : Mesh {
   // tree frames on the integer cube [0,M]^3: P = O + a*A + b*B, A x B = outward normal
   int O[6][3], A[6][3], B[6][3];
 
-  ShellMesh3D(int refinements, double r0, double r1) : r(refinements), R0(r0), R1(r1) {
+  // radial_factor > 1 gives the "synthetic refinement" used for weak scaling: n_r = n * radial_factor layers
+  ShellMesh3D(int refinements, double r0, double r1, int radial_factor = 1) : r(refinements), R0(r0), R1(r1) {
     dim = 3;
     n = 1 << r;
     M = 2 * n;
-    n_cells = 6LL * n * n * n;
+    nr = n * radial_factor;
+    Mr = 2 * nr;
+    n_cells = 6LL * n * n * nr;
     const int o[6][3] = {{1, 0, 0}, {0, 0, 0}, {0, 1, 0}, {0, 0, 0}, {0, 0, 1}, {0, 0, 0}};
     const int a[6][3] = {{0, 1, 0}, {0, 0, 1}, {0, 0, 1}, {1, 0, 0}, {1, 0, 0}, {0, 1, 0}};
     const int b[6][3] = {{0, 0, 1}, {0, 1, 0}, {1, 0, 0}, {0, 0, 1}, {0, 1, 0}, {1, 0, 0}};
@@ -180,7 +184,7 @@ struct ShellMesh3D : Mesh {
         for (int64_t x = 0; x < L; ++x)
           if (x == 0 || x == M || y == 0 || y == M || z == 0 || z == M) sid[(size_t)((z * L + y) * L + x)] = next++;
     n_surf = next;
-    n_nodes = n_surf * L;
+    n_nodes = n_surf * (int64_t)(Mr + 1);
     build_directions();
   }
 
@@ -222,19 +226,23 @@ struct ShellMesh3D : Mesh {
     }
   }
 
+  // cell order: tree, then radial super-block (for radial_factor > 1), then Morton within the n^3 cube
   inline void decode(int64_t c, int& t, int& i, int& j, int& k) const {
-    int64_t per = (int64_t)n * n * n;
+    int64_t cube = (int64_t)n * n * n, per = cube * (nr / n);
     t = (int)(c / per);
+    int64_t rem = c % per;
+    int khi = (int)(rem / cube);
     uint32_t ii, jj, kk;
-    demorton3((uint32_t)(c % per), ii, jj, kk);
+    demorton3((uint32_t)(rem % cube), ii, jj, kk);
     i = (int)ii;
     j = (int)jj;
-    k = (int)kk;
+    k = khi * n + (int)kk;
   }
   inline int64_t encode(int t, int i, int j, int k) const {
-    return (int64_t)t * n * n * n + morton3((uint32_t)i, (uint32_t)j, (uint32_t)k);
+    int64_t cube = (int64_t)n * n * n, per = cube * (nr / n);
+    return (int64_t)t * per + (int64_t)(k / n) * cube + morton3((uint32_t)i, (uint32_t)j, (uint32_t)(k % n));
   }
-  inline double radius(int kk) const { return R0 + (R1 - R0) * ((double)kk / (double)M); }
+  inline double radius(int kk) const { return R0 + (R1 - R0) * ((double)kk / (double)Mr); }
 
   void cell_nodes(int64_t c, int64_t* ids) const override {
     int t, i, j, k;
@@ -242,7 +250,7 @@ struct ShellMesh3D : Mesh {
     for (int oz = 0; oz < 3; ++oz)
       for (int oy = 0; oy < 3; ++oy)
         for (int ox = 0; ox < 3; ++ox)
-          ids[ox + 3 * (oy + 3 * oz)] = (int64_t)surf(t, 2 * i + ox, 2 * j + oy) * (M + 1) + (2 * k + oz);
+          ids[ox + 3 * (oy + 3 * oz)] = (int64_t)surf(t, 2 * i + ox, 2 * j + oy) * (Mr + 1) + (2 * k + oz);
   }
   void cell_vertices(int64_t c, double* X) const override {
     int t, i, j, k;
@@ -260,13 +268,13 @@ struct ShellMesh3D : Mesh {
     int t, i, j, k;
     decode(c, t, i, j, k);
     if (f == 4 && k == 0) return 0;
-    if (f == 5 && k == n - 1) return 1;
+    if (f == 5 && k == nr - 1) return 1;
     return -1;
   }
   bool at_boundary(int64_t c) const override {
     int t, i, j, k;
     decode(c, t, i, j, k);
-    return k == 0 || k == n - 1;
+    return k == 0 || k == nr - 1;
   }
   void manifold_point(int64_t c, const double* xi, double* x) const override {
     int t, i, j, k;
@@ -349,6 +357,23 @@ struct CubeMesh3D : Mesh {
     if (y == M) y = 0;
     return (z * L + y) * L + x;
   }
+};
+
+// ---- a subset of the cells of a base mesh (one rank's owned + ghost cells) -------------------------------
+struct SubMesh : Mesh {
+  const Mesh& base;
+  std::vector<int64_t> cells;  // local -> base cell id
+  SubMesh(const Mesh& b, std::vector<int64_t> c) : base(b), cells(std::move(c)) {
+    dim = b.dim;
+    n_cells = (int64_t)cells.size();
+    n_nodes = b.n_nodes;
+  }
+  void cell_nodes(int64_t c, int64_t* ids) const override { base.cell_nodes(cells[c], ids); }
+  void cell_vertices(int64_t c, double* X) const override { base.cell_vertices(cells[c], X); }
+  int face_boundary_id(int64_t c, int f) const override { return base.face_boundary_id(cells[c], f); }
+  bool at_boundary(int64_t c) const override { return base.at_boundary(cells[c]); }
+  void manifold_point(int64_t c, const double* xi, double* x) const override { base.manifold_point(cells[c], xi, x); }
+  int64_t periodic_master(int64_t node) const override { return base.periodic_master(node); }
 };
 
 }  // namespace dcph

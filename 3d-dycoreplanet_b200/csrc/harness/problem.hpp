@@ -32,6 +32,8 @@ struct Spec {
   int geometry_data = 1;  // build per-cell mapping data
   int mapping_degree = 3;
   int threads = 0;
+  int radial_factor = 1;  // shell only: n_r = 2^refine * radial_factor layers (weak-scaling synthetic refinement)
+  int n_ranks = 1, rank = 0;  // contiguous partition of the (tree, Morton) cell order, one ghost-cell layer
 };
 
 inline Spec parse_spec(const std::string& s) {
@@ -54,6 +56,9 @@ inline Spec parse_spec(const std::string& s) {
     else if (k == "geometry_data") sp.geometry_data = std::stoi(v);
     else if (k == "mapping_degree") sp.mapping_degree = std::stoi(v);
     else if (k == "threads") sp.threads = std::stoi(v);
+    else if (k == "radial_factor") sp.radial_factor = std::stoi(v);
+    else if (k == "n_ranks") sp.n_ranks = std::stoi(v);
+    else if (k == "rank") sp.rank = std::stoi(v);
     else throw std::runtime_error("unknown spec key: " + k);
   }
   return sp;
@@ -197,7 +202,11 @@ inline void compute_geometry(const Mesh& mesh, int mapping_degree, const QuadRul
 
 struct Problem {
   Spec spec;
-  std::unique_ptr<Mesh> mesh;
+  std::unique_ptr<Mesh> base_mesh;  // whole mesh (only when partitioned)
+  std::unique_ptr<Mesh> mesh;       // this rank's cells: owned chunk first, then the ghost layer
+  std::vector<int64_t> cell_global;
+  std::vector<int32_t> node_owner;
+  int64_t n_owned_cells = 0;
   DofMap nse, temp;
   Constraints nse_cs, temp_cs;
   std::vector<int64_t> nse_block_start;
@@ -325,6 +334,9 @@ inline void add_periodic(const Mesh& mesh, const DofMap& dm, Constraints& cs) {
 }
 
 // compute_no_normal_flux_constraints on boundary `bid` for the vector field starting at component 0
+// `mesh` is the mesh the normals are averaged over: for a partitioned problem this is the WHOLE mesh, so that the
+// constraint of a ghost dof does not depend on which of its faces happen to be local (deal.II needs
+// AffineConstraints::is_consistent_in_parallel for the same reason); only nodes that carry local dofs get lines.
 inline void add_no_normal_flux(const Mesh& mesh, const DofMap& dm, int bid, int mapping_degree, Constraints& cs) {
   const int dim = mesh.dim, nfaces = 2 * dim;
   auto offs = hierarchical_offsets(dim);
@@ -372,6 +384,7 @@ inline void add_no_normal_flux(const Mesh& mesh, const DofMap& dm, int bid, int 
     for (int i = 1; i < dim; ++i)
       if (std::fabs(n[i]) > std::fabs(n[k])) k = i;
     int ed = node_ed[kv.first];
+    if (dm.node_first[kv.first] < 0) continue;  // node not on this rank
     int32_t dk = dm.dof_at(kv.first, ed, k);
     std::vector<std::pair<int32_t, double>> e;
     for (int i = 0; i < dim; ++i)
@@ -388,11 +401,51 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   if (sp.family != "classic") throw std::runtime_error("harness: only family=classic is implemented");
   const int dim = sp.dim;
   if (sp.geometry == "shell")
-    P->mesh = std::make_unique<ShellMesh3D>(sp.refine, sp.R0, sp.R1);
+    P->mesh = std::make_unique<ShellMesh3D>(sp.refine, sp.R0, sp.R1, sp.radial_factor);
   else if (sp.geometry == "cube")
     P->mesh = std::make_unique<CubeMesh3D>(sp.refine, true);
   else
     throw std::runtime_error("harness: unknown geometry " + sp.geometry);
+  P->n_owned_cells = P->mesh->n_cells;
+  if (sp.n_ranks > 1) {
+    // p4est-style partition (restated): rank p owns cells [floor(pN/P), floor((p+1)N/P))
+    // of the space-filling curve; a lattice node (and its dofs) belongs to the lowest rank touching it; the
+    // rank also sees the one-deep layer of ghost cells (cells sharing a node with an owned cell).
+    if (sp.geometry != "shell") throw std::runtime_error("harness: only the shell can be partitioned");
+    P->base_mesh = std::move(P->mesh);
+    const Mesh& B = *P->base_mesh;
+    const int64_t N = B.n_cells;
+    auto rank_of = [&](int64_t c) {
+      int p = (int)(((__int128)(c + 1) * sp.n_ranks - 1) / N);
+      while ((int64_t)(((__int128)p * N) / sp.n_ranks) > c) --p;
+      while ((int64_t)(((__int128)(p + 1) * N) / sp.n_ranks) <= c) ++p;
+      return p;
+    };
+    const int64_t c0 = (int64_t)(((__int128)sp.rank * N) / sp.n_ranks), c1 = (int64_t)(((__int128)(sp.rank + 1) * N) / sp.n_ranks);
+    P->node_owner.assign((size_t)B.n_nodes, INT32_MAX);
+    std::vector<uint8_t> touched((size_t)B.n_nodes, 0);
+    int64_t ids[27];
+    for (int64_t c = 0; c < N; ++c) {
+      B.cell_nodes(c, ids);
+      const int rk = rank_of(c);
+      for (int k = 0; k < 27; ++k) {
+        if (P->node_owner[ids[k]] > rk) P->node_owner[ids[k]] = rk;
+        if (c >= c0 && c < c1) touched[ids[k]] = 1;
+      }
+    }
+    std::vector<int64_t> cells;
+    for (int64_t c = c0; c < c1; ++c) cells.push_back(c);
+    for (int64_t c = 0; c < N; ++c) {
+      if (c >= c0 && c < c1) continue;
+      B.cell_nodes(c, ids);
+      bool g = false;
+      for (int k = 0; k < 27 && !g; ++k) g = touched[ids[k]];
+      if (g) cells.push_back(c);
+    }
+    P->n_owned_cells = c1 - c0;
+    P->cell_global = cells;
+    P->mesh = std::make_unique<SubMesh>(B, cells);
+  }
   const Mesh& mesh = *P->mesh;
   const bool cuboid = sp.geometry == "cube";
 
@@ -405,12 +458,13 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   }
   nse_fe.field_degree.push_back(sp.velocity_degree - 1);
   nse_fe.field_block.push_back(1);
-  P->nse = distribute_dofs(mesh, nse_fe);
+  const std::vector<int32_t>* owner = sp.n_ranks > 1 ? &P->node_owner : nullptr;
+  P->nse = distribute_dofs(mesh, nse_fe, owner, sp.rank);
   FESystemDesc t_fe;
   t_fe.dim = dim;
   t_fe.field_degree = {sp.temperature_degree};
   t_fe.field_block = {0};
-  P->temp = distribute_dofs(mesh, t_fe);
+  P->temp = distribute_dofs(mesh, t_fe, owner, sp.rank);
   P->nse_block_start = {0, P->nse.block_size[0], P->nse.block_size[0] + P->nse.block_size[1]};
 
   dof_positions(mesh, P->nse, sp.mapping_degree, P->nse_dof_xyz, &P->nse_dof_comp);
@@ -431,7 +485,7 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
                   P->temp_cs);
   } else {
     add_dirichlet(mesh, P->nse, 0, vel, nullptr, P->nse_dof_xyz, P->nse_cs);
-    add_no_normal_flux(mesh, P->nse, 1, sp.mapping_degree, P->nse_cs);
+    add_no_normal_flux(P->base_mesh ? *P->base_mesh : mesh, P->nse, 1, sp.mapping_degree, P->nse_cs);
     add_dirichlet(mesh, P->temp, 0, {0}, [&](const double* p) { return temperature_initial_shell(dim, sp.R0, sp.R1, p); },
                   P->temp_dof_xyz, P->temp_cs);
   }
@@ -477,6 +531,17 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   auto& S = P->scalars;
   S["dim"] = dim;
   S["n_cells"] = mesh.n_cells;
+  S["n_owned_cells"] = P->n_owned_cells;
+  S["n_ranks"] = sp.n_ranks;
+  S["rank"] = sp.rank;
+  S["nse.n_u_owned"] = P->nse.owned_size[0];
+  S["nse.n_p_owned"] = P->nse.owned_size[1];
+  S["temp.n_owned"] = P->temp.owned_size[0];
+  P->reg("cell_global", P->cell_global, I64);
+  P->reg("nse.dof_key", P->nse.dof_key, I64);
+  P->reg("nse.dof_owner", P->nse.dof_owner, I32);
+  P->reg("temp.dof_key", P->temp.dof_key, I64);
+  P->reg("temp.dof_owner", P->temp.dof_owner, I32);
   S["nse.n_dofs"] = P->nse.n_dofs;
   S["nse.n_u"] = P->nse.block_size[0];
   S["nse.n_p"] = P->nse.block_size[1];

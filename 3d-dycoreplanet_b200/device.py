@@ -64,7 +64,7 @@ class ModelDesc(ctypes.Structure):
 EXPORTS = [
     "dcp_ctx_create", "dcp_ctx_destroy", "dcp_ctx_set_stream", "dcp_ctx_synchronize", "dcp_last_error",
     "dcp_ctx_launch_count", "dcp_malloc", "dcp_free", "dcp_memcpy_h2d", "dcp_memcpy_d2h", "dcp_model_create",
-    "dcp_model_destroy", "dcp_model_set_strategy", "dcp_assemble_nse_system", "dcp_assemble_nse_preconditioner",
+    "dcp_model_destroy", "dcp_model_set_strategy", "dcp_model_set_owned", "dcp_gather_f64", "dcp_scatter_f64", "dcp_assemble_nse_system", "dcp_assemble_nse_preconditioner",
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
     "dcp_vmult_add", "dcp_block_vmult", "dcp_jacobi_vmult",
@@ -101,6 +101,9 @@ def lib():
         L.dcp_model_create.argtypes = [vp, ctypes.POINTER(ModelDesc), ctypes.POINTER(vp)]
         L.dcp_model_destroy.argtypes = [vp]
         L.dcp_model_set_strategy.argtypes = [vp, ctypes.c_int]
+        L.dcp_model_set_owned.argtypes = [vp, c_lp, ctypes.c_int64]
+        L.dcp_gather_f64.argtypes = [vp, ctypes.c_int64, vp, vp, vp]
+        L.dcp_scatter_f64.argtypes = [vp, ctypes.c_int64, vp, vp, vp]
         L.dcp_assemble_nse_system.argtypes = [vp, ctypes.POINTER(Params), vp, vp, ctypes.c_int]
         L.dcp_assemble_nse_preconditioner.argtypes = [vp, ctypes.POINTER(Params)]
         L.dcp_assemble_temperature_matrix.argtypes = [vp, ctypes.POINTER(Params)]
@@ -332,6 +335,10 @@ class BoussinesqModel:
 
     def set_strategy(self, s):
         check(lib().dcp_model_set_strategy(self._h, s), "dcp_model_set_strategy")
+
+    def set_owned(self, nse_owned_per_block, temp_owned):
+        arr = (ctypes.c_int64 * MAXB)(*(list(nse_owned_per_block) + [0] * (MAXB - len(nse_owned_per_block))))
+        check(lib().dcp_model_set_owned(self._h, arr, int(temp_owned)), "dcp_model_set_owned")
 
     # --- the four assemblers (boussinesq_model.h:168-180) ---------------------------------------
     def assemble_nse_system(self, old_nse_solution, old_temperature_solution):

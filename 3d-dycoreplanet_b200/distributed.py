@@ -1,0 +1,135 @@
+"""One-process-per-GPU plumbing for the partitioned hot path: ghost-dof halo exchange for SpMV.
+
+The reference shards this path over MPI ranks along the p4est curve (`LocallyOwnedCell` filter,
+/root/reference/include/core/boussinesq_model.tpp:491-494; owned / relevant index sets :241-252) and every
+`LA::SparseMatrix::vmult` hides an Epetra_Import of the off-rank x entries.  Here:
+
+  * assembly needs no collective: every rank integrates its owned cells plus the one-deep ghost layer, so
+    each owned row is complete (replaces `compress(VectorOperation::add)`, :513, 736-737);
+  * SpMV needs exactly one exchange per product: owned boundary entries are packed with the library's gather
+    kernel, moved with grouped point-to-point sends (torch.distributed, NCCL over NVLink on GPUs, gloo in the
+    CPU tests) and unpacked with the scatter kernel into the ghost slots of the source vector.
+
+torch is used for device memory, streams and the process group only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class HaloPlan:
+    """Owned/ghost maps of one vector layout on this rank.
+
+    keys[i]   : global identity of local dof i (harness `*.dof_key`; a deal.II build would use the global
+                dof index)
+    owners[i] : owning rank of local dof i
+    """
+
+    def __init__(self, keys, owners, rank, world, group=None, device=None):
+        self.rank, self.world, self.group = rank, world, group
+        keys = np.asarray(keys, dtype=np.int64)
+        owners = np.asarray(owners, dtype=np.int32)
+        self.n_local = len(keys)
+        ghost = np.flatnonzero(owners != rank)
+        order = np.argsort(owners[ghost], kind="stable")
+        ghost = ghost[order]
+        self.recv_idx = ghost.astype(np.int32)                       # local slots, grouped by owner
+        self.recv_counts = np.bincount(owners[ghost], minlength=world).astype(np.int64)
+        want = {}
+        off = 0
+        for p in range(world):
+            n = int(self.recv_counts[p])
+            if n:
+                want[p] = keys[ghost[off:off + n]]
+            off += n
+        # tell every owner which of its dofs we need, in our order
+        if world > 1:
+            all_want = [None] * world
+            dist.all_gather_object(all_want, want, group=group)
+        else:
+            all_want = [want]
+        owned = np.flatnonzero(owners == rank)
+        okeys = keys[owned]
+        srt = np.argsort(okeys)
+        okeys_sorted = okeys[srt]
+        send_idx, send_counts = [], np.zeros(world, dtype=np.int64)
+        for q in range(world):
+            wk = all_want[q].get(rank) if q != rank else None
+            if wk is None or len(wk) == 0:
+                continue
+            pos = np.searchsorted(okeys_sorted, wk)
+            if (pos >= len(okeys_sorted)).any() or (okeys_sorted[np.minimum(pos, len(okeys_sorted) - 1)] != wk).any():
+                raise RuntimeError(f"rank {rank}: rank {q} asks for dofs this rank does not own")
+            send_idx.append(owned[srt[pos]].astype(np.int32))
+            send_counts[q] = len(wk)
+        self.send_idx = np.concatenate(send_idx) if send_idx else np.zeros(0, dtype=np.int32)
+        self.send_counts = send_counts
+        self.device = device
+        dev = device if device is not None else "cpu"
+        self.t_send_idx = torch.from_numpy(self.send_idx).to(dev)
+        self.t_recv_idx = torch.from_numpy(self.recv_idx).to(dev)
+        self.send_buf = torch.zeros(max(len(self.send_idx), 1), dtype=torch.float64, device=dev)
+        self.recv_buf = torch.zeros(max(len(self.recv_idx), 1), dtype=torch.float64, device=dev)
+
+    @property
+    def bytes_per_exchange(self):
+        return 8 * int(len(self.send_idx))
+
+    def exchange(self, x, ctx=None):
+        """Refresh the ghost entries of the local vector `x` (torch tensor, CPU or CUDA) in place."""
+        if self.world == 1:
+            return
+        ns, nr = len(self.send_idx), len(self.recv_idx)
+        if x.is_cuda and ctx is not None:
+            from . import device as dv
+            if ns:
+                dv.check(dv.lib().dcp_gather_f64(ctx._h, ns, ctypes.c_void_p(self.t_send_idx.data_ptr()),
+                                                 ctypes.c_void_p(x.data_ptr()),
+                                                 ctypes.c_void_p(self.send_buf.data_ptr())), "dcp_gather_f64")
+        elif ns:
+            self.send_buf[:ns] = x[self.t_send_idx.long()]
+        ops, so, ro = [], 0, 0
+        for p in range(self.world):
+            n = int(self.send_counts[p])
+            if n:
+                ops.append(dist.P2POp(dist.isend, self.send_buf[so:so + n], p, group=self.group))
+            so += n
+        for p in range(self.world):
+            n = int(self.recv_counts[p])
+            if n:
+                ops.append(dist.P2POp(dist.irecv, self.recv_buf[ro:ro + n], p, group=self.group))
+            ro += n
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        if x.is_cuda and ctx is not None:
+            from . import device as dv
+            if nr:
+                dv.check(dv.lib().dcp_scatter_f64(ctx._h, nr, ctypes.c_void_p(self.t_recv_idx.data_ptr()),
+                                                  ctypes.c_void_p(self.recv_buf.data_ptr()),
+                                                  ctypes.c_void_p(x.data_ptr())), "dcp_scatter_f64")
+        elif nr:
+            x[self.t_recv_idx.long()] = self.recv_buf[:nr]
+
+
+class DistributedMatrix:
+    """`vmult` of a row-distributed matrix: halo exchange of the source, then the owned rows on the device."""
+
+    def __init__(self, matrix, halo, ctx):
+        self.matrix, self.halo, self.ctx = matrix, halo, ctx
+
+    def vmult(self, dst, src):
+        self.halo.exchange(src, self.ctx)
+        self.matrix.vmult(dst, src)
+
+
+def global_dot(a, b, owned_mask_or_slices, group=None):
+    """Dot product over owned entries + all-reduce (the Krylov solvers' MPI_Allreduce of one double)."""
+    s = torch.zeros(1, dtype=torch.float64, device=a.device)
+    for sl in owned_mask_or_slices:
+        s += torch.dot(a[sl], b[sl])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(s, group=group)
+    return s

@@ -189,12 +189,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # ---- problem (weak scaling: every rank owns one mesh of the same size) --------------------------
+    # ---- problem: weak scaling.  N ranks share ONE shell with N x the radial layers (synthetic refinement),
+    # partitioned along the (tree, Morton) curve like the reference's p4est partition; every rank builds only
+    # its own subdomain (owned cells + one ghost-cell layer).
     t_setup = time.perf_counter()
-    P = harness.Problem(geometry="shell", refine=args.refine, temperature_degree=args.temperature_degree)
+    spec = dict(geometry="shell", refine=args.refine, temperature_degree=args.temperature_degree)
+    if world > 1:
+        spec.update(radial_factor=world, n_ranks=world, rank=rank)
+    P = harness.Problem(**spec)
     u, T = synthetic_fields(P)
     n_nse, n_t = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
-    n_dofs = n_nse + n_t
+    n_u = P.scalar("nse.n_u")
+    owned = [P.scalar("nse.n_u_owned"), P.scalar("nse.n_p_owned")]
+    n_dofs = owned[0] + owned[1] + P.scalar("temp.n_owned")
     ctx = device.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
@@ -202,6 +209,13 @@ def main():
     strategy = "positions" if args.strategy == "auto" else args.strategy
     model.set_strategy({"search": device.STRATEGY_SEARCH, "positions": device.STRATEGY_POSITIONS,
                         "owner": device.STRATEGY_OWNER}[strategy])
+    halo_nse = halo_t = None
+    if world > 1:
+        from dycore_b200 import distributed
+        model.set_owned(owned, P.scalar("temp.n_owned"))
+        torch.cuda.set_stream(stream)
+        halo_nse = distributed.HaloPlan(P["nse.dof_key"], P["nse.dof_owner"], rank, world, device="cuda")
+        halo_t = distributed.HaloPlan(P["temp.dof_key"], P["temp.dof_owner"], rank, world, device="cuda")
     t_setup = time.perf_counter() - t_setup
 
     with torch.cuda.stream(stream):
@@ -217,6 +231,7 @@ def main():
     h_x, h_y = d_x.cpu().pin_memory(), torch.zeros(n_nse, dtype=torch.float64).pin_memory()
     h_xt, h_yt = d_xt.cpu().pin_memory(), torch.zeros(n_t, dtype=torch.float64).pin_memory()
     h_rhs, h_trhs = torch.zeros(n_nse, dtype=torch.float64).pin_memory(), torch.zeros(n_t, dtype=torch.float64).pin_memory()
+    d_rhs = torch.zeros(n_nse, dtype=torch.float64, device="cuda")
 
     phases = ["nse_system", "nse_preconditioner", "temperature_matrix", "temperature_rhs", "spmv_nse", "spmv_temperature"]
 
@@ -224,27 +239,45 @@ def main():
         def mark(i):
             if ev is not None:
                 ev[i].record(stream)
-        mark(0)
-        model.assemble_nse_system(d_u, d_T)
-        mark(1)
-        model.assemble_nse_preconditioner()
-        mark(2)
-        model.assemble_temperature_matrix()
-        mark(3)
-        model.assemble_temperature_rhs(d_T, d_u)
-        mark(4)
-        model.nse_matrix.vmult(d_y, d_x)
-        mark(5)
-        model.temperature_matrix.vmult(d_yt, d_xt)
-        mark(6)
+        with torch.cuda.stream(stream):
+            mark(0)
+            model.assemble_nse_system(d_u, d_T)
+            mark(1)
+            model.assemble_nse_preconditioner()
+            mark(2)
+            model.assemble_temperature_matrix()
+            mark(3)
+            model.assemble_temperature_rhs(d_T, d_u)
+            mark(4)
+            if halo_nse is not None:
+                halo_nse.exchange(d_x, ctx)     # Epetra_Import of the ghost columns (NCCL p2p over NVLink)
+            model.nse_matrix.vmult(d_y, d_x)
+            mark(5)
+            if halo_t is not None:
+                halo_t.exchange(d_xt, ctx)
+            model.temperature_matrix.vmult(d_yt, d_xt)
+            mark(6)
 
     def step_host():
-        model.assemble_nse_system(h_u.numpy(), h_T.numpy())
-        model.assemble_nse_preconditioner()
-        model.assemble_temperature_matrix()
-        model.assemble_temperature_rhs(h_T.numpy(), h_u.numpy())
-        model.nse_matrix.vmult(h_y.numpy(), h_x.numpy())
-        model.temperature_matrix.vmult(h_yt.numpy(), h_xt.numpy())
+        # the same step for a caller whose vectors live in host memory: H2D of the solution vectors and SpMV
+        # sources, D2H of the right-hand sides and SpMV results, all inside the timed region
+        with torch.cuda.stream(stream):
+            d_u.copy_(h_u, non_blocking=True)
+            d_T.copy_(h_T, non_blocking=True)
+            model.assemble_nse_system(d_u, d_T)
+            model.assemble_nse_preconditioner()
+            model.assemble_temperature_matrix()
+            model.assemble_temperature_rhs(d_T, d_u)
+            d_x.copy_(h_x, non_blocking=True)
+            d_xt.copy_(h_xt, non_blocking=True)
+            if halo_nse is not None:
+                halo_nse.exchange(d_x, ctx)
+            model.nse_matrix.vmult(d_y, d_x)
+            if halo_t is not None:
+                halo_t.exchange(d_xt, ctx)
+            model.temperature_matrix.vmult(d_yt, d_xt)
+            h_y.copy_(d_y, non_blocking=True)
+            h_yt.copy_(d_yt, non_blocking=True)
         device.check(device.lib().dcp_vector_download(model._h, device.VEC_NSE_RHS, h_rhs.data_ptr()))
         device.check(device.lib().dcp_vector_download(model._h, device.VEC_TEMP_RHS, h_trhs.data_ptr()))
 
@@ -285,6 +318,11 @@ def main():
     ms_e2e, _ = timed(step_host, args.steps, False)
     ctx.synchronize()
 
+    total_dofs = n_dofs
+    if world > 1:
+        t = torch.tensor([n_dofs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        total_dofs = int(t.item())
     if rank == 0:
         ab = algorithmic_bytes(P)
         peak, peak_src = peaks()
@@ -294,23 +332,25 @@ def main():
         asm_ms = sum(phase_ms[p] for p in phases[:4])
         spmv_ms = phase_ms["spmv_nse"] + phase_ms["spmv_temperature"]
         line = {
-            "metric": "dofs_assembled_per_s", "value": world * n_dofs / (ms_step * 1e-3), "unit": "DoFs/s",
+            "metric": "dofs_assembled_per_s", "value": total_dofs / (ms_step * 1e-3), "unit": "DoFs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"hypershell classic refine={args.refine} (Taylor-Hood Q2/Q1 + Q{args.temperature_degree} "
                                    f"temperature): full Boussinesq assembly pass + nse_matrix/temperature_matrix SpMV",
-                       "cells_per_gpu": P.n_cells, "dofs_per_gpu": n_dofs,
+                       "cells_per_gpu": P.scalar("n_owned_cells"), "dofs_per_gpu": n_dofs, "total_dofs": total_dofs,
+                       "ghost_cells_rank0": P.n_cells - P.scalar("n_owned_cells"),
                        "nnz_nse": sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(2) for j in range(2)),
                        "strategy": strategy, "l2": "inputs larger than L2" if ab["nse_system"] > 4 * 126e6 else "inputs fit L2",
-                       "partition": "one mesh per GPU" if world > 1 else "single GPU", "setup_s": round(t_setup, 2)},
-            "assembly_dofs_per_s": world * n_dofs / (asm_ms * 1e-3),
+                       "partition": (f"shell with {world}x radial layers cut into {world} contiguous (tree, Morton) chunks, one "
+                                     "ghost-cell layer, ghost-dof halo over NCCL p2p") if world > 1 else "single GPU", "setup_s": round(t_setup, 2)},
+            "assembly_dofs_per_s": total_dofs / (asm_ms * 1e-3),
             "spmv_gbs": world * (ab["spmv_nse"] + ab["spmv_temperature"]) / (spmv_ms * 1e-3) / 1e9,
             "phase_ms": phase_ms,
             "phase_gbs": {p: ab[p] / (phase_ms[p] * 1e-3) / 1e9 for p in phases},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                          "spmv_frac": ab["spmv_nse"] / (phase_ms["spmv_nse"] * 1e-3) / 1e9 / peak},
-            "e2e": {"value": world * n_dofs / (ms_e2e / args.steps * 1e-3), "unit": "DoFs/s",
+            "e2e": {"value": total_dofs / (ms_e2e / args.steps * 1e-3), "unit": "DoFs/s",
                     "h2d_bytes_per_step": int(8 * (2 * (n_nse + n_t) + n_nse + n_t)),
                     "d2h_bytes_per_step": int(8 * (2 * (n_nse + n_t)))},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -174,6 +174,17 @@ int dcp_memcpy_d2h(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t by
 int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* desc, dcp_model** out);
 int dcp_model_destroy(dcp_model* m);
 int dcp_model_set_strategy(dcp_model* m, int strategy);
+/* Multi-GPU (one process per GPU, cells partitioned along the p4est curve as the reference does over MPI,
+ * include/core/boussinesq_model.tpp:241-252, 491-494): the rank's local numbering puts the dofs it owns first
+ * inside every block, ghost dofs after them.  After this call the operators (vmult, vmult_add, block_vmult,
+ * jacobi_vmult) compute only the owned rows of each block -- the ghost entries of `src` must have been refreshed
+ * by the caller's halo exchange (Epetra_Import inside LA::SparseMatrix::vmult), the ghost rows of `dst` are left
+ * untouched.  Assembly still integrates every local cell (owned + one ghost layer), which makes each owned row
+ * complete without the reference's compress(VectorOperation::add) (:513, 736-737, 859-861, 1017). */
+int dcp_model_set_owned(dcp_model* m, const int64_t* nse_owned_per_block, int64_t temp_owned);
+/* halo pack / unpack: dst[i] = src[idx[i]]  and  dst[idx[i]] = src[i]  (device pointers) */
+int dcp_gather_f64(dcp_ctx* ctx, int64_t n, const int32_t* idx_dev, const double* src_dev, double* dst_dev);
+int dcp_scatter_f64(dcp_ctx* ctx, int64_t n, const int32_t* idx_dev, const double* src_dev, double* dst_dev);
 
 /* ---- assembly (one call per reference assemble_* member) ------------------------------------- */
 /* old_nse: [n_u+n_p(+..)] ghosted old_nse_solution, old_temp: [n_T] old_temperature_solution */

@@ -1,0 +1,81 @@
+"""Launched with torchrun (N ranks, one GPU each): partitioned device assembly + halo SpMV vs the oracle on the
+unpartitioned mesh.  Used by tests/test_gpu_multi.py and by hand:
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def field(k, seed):
+    return np.sin(0.37 * (k % 1000003) + seed) + 0.1 * np.cos(0.011 * (k % 7919))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import dycore_b200  # noqa: F401
+    from dycore_b200 import device, distributed, harness, params
+    from oracle import oracle as orc
+    refine = int(os.environ.get("DCP_CHECK_REFINE", "2"))
+    mp_ = params.NAMED["shell_3d_classic"]
+    P = harness.Problem(geometry="shell", refine=refine, n_ranks=world, rank=rank)
+    keys, owners = P["nse.dof_key"], P["nse.dof_owner"]
+    n_u, n_uo, n_po = P.scalar("nse.n_u"), P.scalar("nse.n_u_owned"), P.scalar("nse.n_p_owned")
+    owned = np.concatenate([np.arange(n_uo), n_u + np.arange(n_po)])
+    u = np.ascontiguousarray(field(keys, 1.0) * 0.1)
+    T = np.ascontiguousarray(2.0 + 0.2 * field(P["temp.dof_key"], 2.0))
+    ctx = device.Context(local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    torch.cuda.set_stream(stream)
+    model = device.BoussinesqModel.from_problem(ctx, P, mp_)
+    model.set_owned([n_uo, n_po], P.scalar("temp.n_owned"))
+    halo = distributed.HaloPlan(keys, owners, rank, world, device="cuda")
+    d_u, d_T = torch.from_numpy(u).cuda(), torch.from_numpy(T).cuda()
+    model.assemble_nse_system(d_u, d_T)
+    x = field(keys, 3.0)
+    xs = x.copy()
+    xs[owners != rank] = 0.0
+    d_x = torch.from_numpy(xs).cuda()
+    d_y = torch.zeros_like(d_x)
+    distributed.DistributedMatrix(model.nse_matrix, halo, ctx).vmult(d_y, d_x)
+    ctx.synchronize()
+    y = d_y.cpu().numpy()
+    rhs = model.nse_rhs
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (keys[owned], y[owned], rhs[owned]))
+    ok = True
+    if rank == 0:
+        G = harness.Problem(geometry="shell", refine=refine)
+        gk = G["nse.dof_key"]
+        prm = orc.params_from(mp_)
+        gv, grhs = orc.assemble_nse_system(G, prm, np.ascontiguousarray(field(gk, 1.0) * 0.1),
+                                           np.ascontiguousarray(2.0 + 0.2 * field(G["temp.dof_key"], 2.0)))
+        grp, gcol, _, _ = G.csr("nse.full")
+        yg = orc.spmv(grp, gcol, gv, field(gk, 3.0))
+        order = np.argsort(gk)
+        kk = np.concatenate([g[0] for g in gathered])
+        yy = np.concatenate([g[1] for g in gathered])
+        rr = np.concatenate([g[2] for g in gathered])
+        pos = np.searchsorted(gk[order], kk)
+        err_y = np.abs(yy - yg[order][pos]).max() / np.abs(yg).max()
+        err_r = np.abs(rr - grhs[order][pos]).max() / np.abs(grhs).max()
+        ok = len(kk) == len(gk) and err_y <= 1e-12 and err_r <= 1e-12
+        print(f"multi_gpu_check world={world} refine={refine}: spmv err {err_y:.2e}, rhs err {err_r:.2e} -> {'OK' if ok else 'FAIL'}")
+    model.close()
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
