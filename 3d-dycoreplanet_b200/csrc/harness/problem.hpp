@@ -32,6 +32,7 @@ struct Spec {
   int geometry_data = 1;  // build per-cell mapping data
   int mapping_degree = 3;
   int threads = 0;
+  int constraints = 1;    // 0: no boundary conditions at all (used by the oracle identity tests)
   int radial_factor = 1;  // shell only: n_r = 2^refine * radial_factor layers (weak-scaling synthetic refinement)
   int n_ranks = 1, rank = 0;  // contiguous partition of the (tree, Morton) cell order, one ghost-cell layer
 };
@@ -57,6 +58,7 @@ inline Spec parse_spec(const std::string& s) {
     else if (k == "mapping_degree") sp.mapping_degree = std::stoi(v);
     else if (k == "threads") sp.threads = std::stoi(v);
     else if (k == "radial_factor") sp.radial_factor = std::stoi(v);
+    else if (k == "constraints") sp.constraints = std::stoi(v);
     else if (k == "n_ranks") sp.n_ranks = std::stoi(v);
     else if (k == "rank") sp.rank = std::stoi(v);
     else throw std::runtime_error("unknown spec key: " + k);
@@ -473,7 +475,9 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   // --- constraints (boussinesq_model.tpp:259-387)
   std::vector<int> vel;
   for (int d = 0; d < dim; ++d) vel.push_back(d);
-  if (cuboid) {
+  if (!sp.constraints) {
+    // unconstrained spaces
+  } else if (cuboid) {
     add_periodic(mesh, P->nse, P->nse_cs);
     add_dirichlet(mesh, P->nse, 4, vel, nullptr, P->nse_dof_xyz, P->nse_cs);
     add_no_normal_flux(mesh, P->nse, 5, sp.mapping_degree, P->nse_cs);
