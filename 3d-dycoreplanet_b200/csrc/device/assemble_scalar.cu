@@ -19,6 +19,8 @@ constexpr int WARPS = 3;
 struct ScalarArgs {
   long long n_cells;
   int nd, nq;
+  int gstride;          // doubles per cell record
+  int feec;             // rhs: velocity is the Raviart-Thomas field (Piola-mapped, unsigned)
   const double* geom;
   const int* l2g;
   const double* phi;   // [nq][nd]
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(32 * WARPS) temperature_matrix_kernel(ScalarAr
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpScratch& s = scratch[wid];
   const int nd = a.nd, nn = nd * nd;
-  const int gs = a.nq * (1 + DIM * DIM + DIM);
+  const int gs = a.gstride;
   for (long long cell = (long long)blockIdx.x * WARPS + wid; cell < a.n_cells; cell += (long long)gridDim.x * WARPS) {
     const double* g = a.geom + cell * gs;
     for (int i = lane; i < nn; i += 32) {
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(32 * WARPS) temperature_rhs_kernel(ScalarArgs 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpScratch& s = scratch[wid];
   const int nd = a.nd, nn = nd * nd;
-  const int gs = a.nq * (1 + DIM * DIM + DIM);
+  const int gs = a.gstride;
   const double tau = a.prm.dt / a.prm.nse_interval;
   for (long long cell = (long long)blockIdx.x * WARPS + wid; cell < a.n_cells; cell += (long long)gridDim.x * WARPS) {
     const double* g = a.geom + cell * gs;
@@ -146,6 +148,22 @@ __global__ void __launch_bounds__(32 * WARPS) temperature_rhs_kernel(ScalarArgs 
       double pu[DIM];
 #pragma unroll
       for (int d = 0; d < DIM; ++d) pu[d] = 0.0;
+      if (a.feec) {
+        // u(q) = sum_k U_k J phi_hat_k / det J over the six face dofs (cell dofs 12..17), no face sign
+        // (get_function_values, boussineq_model_FEEC.tpp:1039-1040)
+        if (DIM == 3 && lane < 6) {
+          const double U = a.nse_solution[a.l2g_nse[cell * a.nd_nse + 12 + lane]];
+          const double det = __ldg(g + a.nq * 22 + q);
+          const double* ph = a.phi_u + ((size_t)q * 6 + lane) * 3;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            double v = 0.0;
+#pragma unroll
+            for (int e = 0; e < DIM; ++e) v += __ldg(g + a.nq * (13 + d * 3 + e) + q) * __ldg(ph + e);
+            pu[d] = U * v / det;
+          }
+        }
+      } else
       for (int k = lane; k < a.nd_nse; k += 32) {
         const int f = __ldg(a.nse_field + k);
         if (f < DIM) {
@@ -196,6 +214,7 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
   a.nd = m->temp_n_local;
   a.nq = m->nq_temp;
   a.geom = m->geom_qt;
+  a.gstride = m->gs_t;
   a.l2g = m->temp_l2g;
   a.phi = m->phi_t_qt;
   a.dphi = m->dphi_t_qt;
@@ -219,6 +238,8 @@ int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* 
   a.nd = m->temp_n_local;
   a.nq = m->nq_temp;
   a.geom = m->geom_qt;
+  a.gstride = m->gs_t;
+  a.feec = m->family == DCP_FAMILY_FEEC ? 1 : 0;
   a.l2g = m->temp_l2g;
   a.phi = m->phi_t_qt;
   a.dphi = m->dphi_t_qt;
@@ -228,7 +249,7 @@ int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* 
   a.ndu = m->ndu;
   a.nse_field = m->nse_local_field;
   a.nse_base = m->nse_local_base;
-  a.phi_u = m->phi_u_qt;
+  a.phi_u = a.feec ? m->feec_u_qt : m->phi_u_qt;
   a.old_temp = old_temp;
   a.nse_solution = nse_solution;
   a.rhs = m->temp_rhs;

@@ -124,6 +124,13 @@ struct dcp_model {
   // mapping data
   double *geom_qn = nullptr, *geom_qt = nullptr;
   bool geom_shared = false;
+  int gs_n = 0, gs_t = 0, gs_p = 0;  // doubles per cell record on the NSE / temperature / preconditioner rule
+  // FEEC family
+  int nq_pre = 0;
+  double *geom_qp = nullptr, *nse_sign = nullptr;
+  double *feec_w_qn = nullptr, *feec_c_qn = nullptr, *feec_u_qn = nullptr;
+  double *feec_w_qp = nullptr, *feec_c_qp = nullptr, *feec_u_qp = nullptr;
+  double *feec_u_qt = nullptr, *feec_div = nullptr;
   // matrices and vectors
   BlockMat nse, pre, tmass, tstiff, tmat;
   double *nse_rhs = nullptr, *temp_rhs = nullptr;
@@ -155,6 +162,7 @@ int dcp_launch_th_cells(dcp_model* m, const dcp_params& p, bool system, const do
 int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p);
 int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* old_temp, const double* nse_solution);
 
+int dcp_launch_feec(dcp_model* m, const dcp_params& p, bool system, const double* old_nse, const double* old_temp);
 int dcp_fast_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, FastPlan** out);
 void dcp_fast_plan_free(FastPlan* p);
 int64_t dcp_fast_plan_counts(const FastPlan* p, int64_t* n_general);

@@ -311,6 +311,16 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->dphi_t_qt);
   cudaFree(m->geom_qn);
   if (!m->geom_shared) cudaFree(m->geom_qt);
+  cudaFree(m->geom_qp);
+  cudaFree(m->nse_sign);
+  cudaFree(m->feec_w_qn);
+  cudaFree(m->feec_c_qn);
+  cudaFree(m->feec_u_qn);
+  cudaFree(m->feec_w_qp);
+  cudaFree(m->feec_c_qp);
+  cudaFree(m->feec_u_qp);
+  cudaFree(m->feec_u_qt);
+  cudaFree(m->feec_div);
   free_blockmat(m->nse);
   free_blockmat(m->pre);
   free_blockmat(m->tmass);
@@ -333,14 +343,21 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     dcp_set_error("dim must be 2 or 3");
     return DCP_ERR_ARG;
   }
-  if (d->family != DCP_FAMILY_CLASSIC) {
-    dcp_set_error("only DCP_FAMILY_CLASSIC is implemented by this build");
+  if (d->family != DCP_FAMILY_CLASSIC && d->family != DCP_FAMILY_FEEC) {
+    dcp_set_error("unknown element family");
     return DCP_ERR_ARG;
   }
   const int dim = d->dim;
+  const bool feec = d->family == DCP_FAMILY_FEEC;
   const int nu = dim == 3 ? 27 : 9, np = dim == 3 ? 8 : 4;
-  if (d->ndu != nu || d->ndp != np || d->nq_nse != nu || d->nse_n_local != dim * nu + np || d->nse_n_blocks != 2) {
+  if (!feec && (d->ndu != nu || d->ndp != np || d->nq_nse != nu || d->nse_n_local != dim * nu + np || d->nse_n_blocks != 2)) {
     dcp_set_error("classic family expects Q2^dim x Q1 with QGauss(3): ndu=3^dim, ndp=2^dim, nq_nse=3^dim");
+    return DCP_ERR_ARG;
+  }
+  if (feec && (dim != 3 || d->nse_n_local != 19 || d->nse_n_blocks != 3 || d->nq_nse > 27 || d->nq_pre > 27 ||
+               !d->nse_sign || !d->feec_phi_w_qn || !d->feec_curl_w_qn || !d->feec_phi_u_qn || !d->feec_phi_w_qp ||
+               !d->feec_curl_w_qp || !d->feec_phi_u_qp || !d->feec_phi_u_qt || !d->feec_div_u || !d->geom_qp)) {
+    dcp_set_error("FEEC family expects dim=3, 19 dofs per cell, 3 blocks, <=27 quadrature points and all feec_* tables");
     return DCP_ERR_ARG;
   }
   DCP_CUDA(cudaSetDevice(ctx->device));
@@ -371,7 +388,12 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     if (rc != DCP_OK) return fail(rc); \
   } while (0)
   const int64_t nc = d->n_cells;
-  const int gs_n = d->nq_nse * (1 + dim * dim + dim), gs_t = d->nq_temp * (1 + dim * dim + dim);
+  const int rec = feec ? (1 + dim * dim + dim + dim * dim + 1) : (1 + dim * dim + dim);
+  const int gs_n = d->nq_nse * rec, gs_t = d->nq_temp * rec;
+  m->gs_n = gs_n;
+  m->gs_t = gs_t;
+  m->gs_p = d->nq_pre * rec;
+  m->nq_pre = d->nq_pre;
   M_TRY(dcp_upload(ctx, &m->nse_l2g, d->nse_l2g, nc * d->nse_n_local));
   M_TRY(dcp_upload(ctx, &m->temp_l2g, d->temp_l2g, nc * d->temp_n_local));
   M_TRY(dcp_upload(ctx, &m->nse_local_field, d->nse_local_field, d->nse_n_local));
@@ -384,11 +406,24 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     dcp_set_error("nse_cs.n_dofs != sum of block sizes");
     return fail(DCP_ERR_ARG);
   }
-  M_TRY(dcp_upload(ctx, &m->phi_u_qn, d->phi_u_qn, (int64_t)d->nq_nse * d->ndu));
-  M_TRY(dcp_upload(ctx, &m->dphi_u_qn, d->dphi_u_qn, (int64_t)d->nq_nse * d->ndu * dim));
-  M_TRY(dcp_upload(ctx, &m->phi_p_qn, d->phi_p_qn, (int64_t)d->nq_nse * d->ndp));
+  if (!feec) {
+    M_TRY(dcp_upload(ctx, &m->phi_u_qn, d->phi_u_qn, (int64_t)d->nq_nse * d->ndu));
+    M_TRY(dcp_upload(ctx, &m->dphi_u_qn, d->dphi_u_qn, (int64_t)d->nq_nse * d->ndu * dim));
+    M_TRY(dcp_upload(ctx, &m->phi_p_qn, d->phi_p_qn, (int64_t)d->nq_nse * d->ndp));
+    M_TRY(dcp_upload(ctx, &m->phi_u_qt, d->phi_u_qt, (int64_t)d->nq_temp * d->ndu));
+  } else {
+    M_TRY(dcp_upload(ctx, &m->nse_sign, d->nse_sign, nc * d->nse_n_local));
+    M_TRY(dcp_upload(ctx, &m->feec_w_qn, d->feec_phi_w_qn, (int64_t)d->nq_nse * 36));
+    M_TRY(dcp_upload(ctx, &m->feec_c_qn, d->feec_curl_w_qn, (int64_t)d->nq_nse * 36));
+    M_TRY(dcp_upload(ctx, &m->feec_u_qn, d->feec_phi_u_qn, (int64_t)d->nq_nse * 18));
+    M_TRY(dcp_upload(ctx, &m->feec_w_qp, d->feec_phi_w_qp, (int64_t)d->nq_pre * 36));
+    M_TRY(dcp_upload(ctx, &m->feec_c_qp, d->feec_curl_w_qp, (int64_t)d->nq_pre * 36));
+    M_TRY(dcp_upload(ctx, &m->feec_u_qp, d->feec_phi_u_qp, (int64_t)d->nq_pre * 18));
+    M_TRY(dcp_upload(ctx, &m->feec_u_qt, d->feec_phi_u_qt, (int64_t)d->nq_temp * 18));
+    M_TRY(dcp_upload(ctx, &m->feec_div, d->feec_div_u, 6));
+    M_TRY(dcp_upload(ctx, &m->geom_qp, d->geom_qp, nc * (int64_t)m->gs_p));
+  }
   M_TRY(dcp_upload(ctx, &m->phi_t_qn, d->phi_t_qn, (int64_t)d->nq_nse * d->ndt));
-  M_TRY(dcp_upload(ctx, &m->phi_u_qt, d->phi_u_qt, (int64_t)d->nq_temp * d->ndu));
   M_TRY(dcp_upload(ctx, &m->phi_t_qt, d->phi_t_qt, (int64_t)d->nq_temp * d->ndt));
   M_TRY(dcp_upload(ctx, &m->dphi_t_qt, d->dphi_t_qt, (int64_t)d->nq_temp * d->ndt * dim));
   M_TRY(dcp_upload(ctx, &m->geom_qn, d->geom_qn, nc * gs_n));
@@ -452,9 +487,11 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     M_TRY(dcp_upload(ctx, &m->nse_constrained_cells, cells.data(), (int64_t)cells.size()));
     DCP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  // position tables for the unconstrained cells (DCP_STRATEGY_POSITIONS)
-  M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
-  M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
+  // position tables for the unconstrained cells (DCP_STRATEGY_POSITIONS; classic family)
+  if (!feec) {
+    M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
+    M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
+  }
   DCP_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef M_TRY
   *out = m;
@@ -502,7 +539,12 @@ int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old
   DCP_TRY(dcp_stage_in(ctx, 0, old_nse, m->nse_n_dofs, mem, &d_nse));
   DCP_TRY(dcp_stage_in(ctx, 1, old_temp, m->temp_n_dofs, mem, &d_temp));
   DCP_CUDA(cudaMemsetAsync(m->nse_rhs, 0, sizeof(double) * (size_t)m->nse_n_dofs, ctx->stream));
-  if (m->strategy == DCP_STRATEGY_POSITIONS) {
+  if (m->family == DCP_FAMILY_FEEC) {
+    DCP_TRY(zero_blockmat(ctx, m->nse));
+    DCP_TRY(dcp_launch_feec(m, *p, true, d_nse, d_temp));
+    // Jacobi of Mw = block(0,0) and Mu = block(1,1) used by solve_NSE_block_preconditioned (:1283-1304)
+    DCP_TRY(refresh_jacobi(ctx, m->nse));
+  } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
     DCP_TRY(zero_blockmat(ctx, m->nse));
     DCP_TRY(dcp_launch_th_fast(m, *p, true, m->fast_nse, d_nse, d_temp));
     int64_t ng = 0;
@@ -520,7 +562,10 @@ int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
   if (!m || !p) return DCP_ERR_ARG;
   dcp_ctx* ctx = m->ctx;
   DCP_CUDA(cudaSetDevice(ctx->device));
-  if (m->strategy == DCP_STRATEGY_POSITIONS) {
+  if (m->family == DCP_FAMILY_FEEC) {
+    DCP_TRY(zero_blockmat(ctx, m->pre));
+    DCP_TRY(dcp_launch_feec(m, *p, false, nullptr, nullptr));
+  } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_th_fast(m, *p, false, m->fast_pre, nullptr, nullptr));
     int64_t ng = 0;

@@ -27,6 +27,14 @@ struct FESystemDesc {
   int dim = 3;
   std::vector<int> field_degree;  // per field (= component)
   std::vector<int> field_block;   // target block per field (component_wise)
+  // 0 = continuous Lagrange of `field_degree`; lowest-order FEEC spaces (one dof per entity):
+  // 1 = Nedelec (lines), 2 = Raviart-Thomas (faces), 3 = DGQ0 (cell)
+  std::vector<int> field_kind;
+  bool present(size_t f, int ed) const {
+    const int kind = field_kind.empty() ? 0 : field_kind[f];
+    if (kind == 0) return field_degree[f] == 2 || ed == 0;
+    return ed == (kind == 1 ? 1 : (kind == 2 ? dim - 1 : dim));
+  }
   // derived
   int n_local = 0;
   std::vector<int> local_field;  // [n_local] component
@@ -43,7 +51,7 @@ struct FESystemDesc {
     for (size_t h = 0; h < offs.size(); ++h) {
       int ed = entity_dim(dim, offs[h]);
       for (size_t f = 0; f < field_degree.size(); ++f) {
-        if (field_degree[f] == 1 && ed != 0) continue;
+        if (!present(f, ed)) continue;
         local_field.push_back((int)f);
         local_lex.push_back(lex_index(dim, offs[h]));
         local_base.push_back((int)h);
@@ -166,7 +174,7 @@ inline DofMap distribute_dofs(const Mesh& mesh, FESystemDesc fe, const std::vect
   int count_by_ed[4] = {0, 0, 0, 0};
   for (int ed = 0; ed <= dim; ++ed)
     for (int f = 0; f < nf; ++f)
-      if (fe.field_degree[f] == 2 || ed == 0) dm.field_rank[f][ed] = count_by_ed[ed]++;
+      if (fe.present(f, ed)) dm.field_rank[f][ed] = count_by_ed[ed]++;
   auto offs = hierarchical_offsets(dim);
   const int n3 = dim == 3 ? 27 : 9;
   std::vector<int> lex_ed(n3);

@@ -202,6 +202,67 @@ inline void compute_geometry(const Mesh& mesh, int mapping_degree, const QuadRul
   }
 }
 
+// ---- lowest-order FEEC reference shape functions (deal.II 9.2 FE_Nedelec(0), FE_RaviartThomas(0), FE_DGQ(0);
+// restated from memory): Nedelec: unit tangential component along its own line, oriented
+// along the positive axis, phi_l = prod_{e != d} h_e(x_e) e_d ; RT: phi_f = h(x_d) e_d (normal component
+// measured along the POSITIVE axis on both faces of a pair), div = -1 / +1 ; DGQ0: 1.
+struct FeecTable {
+  int nq = 0;
+  std::vector<double> phi_w, curl_w, phi_u;  // [nq][12][3], [nq][12][3], [nq][6][3]
+  std::vector<double> div_u;                 // [6]
+};
+inline FeecTable tabulate_feec(const QuadRule& q) {
+  FeecTable t;
+  t.nq = q.nq;
+  t.phi_w.assign((size_t)q.nq * 36, 0.0);
+  t.curl_w.assign((size_t)q.nq * 36, 0.0);
+  t.phi_u.assign((size_t)q.nq * 18, 0.0);
+  t.div_u.assign(6, 0.0);
+  auto offs = hierarchical_offsets(3);
+  auto h = [](int o, double x) { return o == 0 ? 1.0 - x : x; };
+  auto dh = [](int o) { return o == 0 ? -1.0 : 1.0; };
+  for (int iq = 0; iq < q.nq; ++iq) {
+    const double* x = &q.pts[iq * 3];
+    for (int l = 0; l < 12; ++l) {
+      const auto& o = offs[8 + l];
+      int d = o[0] == 1 ? 0 : (o[1] == 1 ? 1 : 2);
+      int e1 = (d + 1) % 3, e2 = (d + 2) % 3;
+      double f = h(o[e1], x[e1]) * h(o[e2], x[e2]);
+      double grad[3] = {0, 0, 0};
+      grad[e1] = dh(o[e1]) * h(o[e2], x[e2]);
+      grad[e2] = h(o[e1], x[e1]) * dh(o[e2]);
+      t.phi_w[((size_t)iq * 12 + l) * 3 + d] = f;
+      // curl(f e_d) = grad f x e_d : component e1 = -(d_e2 f) ... with (d,e1,e2) cyclic:
+      //   (grad f x e_d)_{e1} = grad_{e2} f,  (grad f x e_d)_{e2} = -grad_{e1} f
+      t.curl_w[((size_t)iq * 12 + l) * 3 + e1] = grad[e2];
+      t.curl_w[((size_t)iq * 12 + l) * 3 + e2] = -grad[e1];
+    }
+    for (int f = 0; f < 6; ++f) {
+      int d = f / 2, side = f % 2;
+      t.phi_u[((size_t)iq * 6 + f) * 3 + d] = side ? x[d] : 1.0 - x[d];
+    }
+  }
+  for (int f = 0; f < 6; ++f) t.div_u[f] = (f % 2) ? 1.0 : -1.0;
+  return t;
+}
+
+// extended record for the Piola transforms: [JxW | Kinv[e][d] | xq[d] | J[i][j] | detJ], nq entries each
+inline int geom_stride_ext(int dim, int nq) { return nq * (1 + dim * dim + dim + dim * dim + 1); }
+inline void compute_geometry_ext(const Mesh& mesh, int mapping_degree, const QuadRule& q, std::vector<double>& out) {
+  const int dim = mesh.dim, nq = q.nq;
+  std::vector<double> base, jac;
+  compute_geometry(mesh, mapping_degree, q, base, true, &jac);
+  const int s0 = geom_stride(dim, nq), s1 = geom_stride_ext(dim, nq), nj = dim * dim + 1;
+  out.resize((size_t)mesh.n_cells * s1);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < mesh.n_cells; ++c) {
+    double* g = &out[(size_t)c * s1];
+    std::copy(&base[(size_t)c * s0], &base[(size_t)c * s0] + s0, g);
+    for (int iq = 0; iq < nq; ++iq)
+      for (int e = 0; e < nj; ++e) g[s0 + e * nq + iq] = jac[((size_t)c * nq + iq) * nj + e];
+  }
+}
+
 struct Problem {
   Spec spec;
   std::unique_ptr<Mesh> base_mesh;  // whole mesh (only when partitioned)
@@ -225,6 +286,11 @@ struct Problem {
   std::vector<double> nse_dof_xyz, temp_dof_xyz;
   std::vector<int8_t> nse_dof_comp;
   std::vector<int32_t> nse_coupling, pre_coupling;
+  // FEEC family
+  QuadRule q_pre;
+  FeecTable feec_qn, feec_qp, feec_qt;
+  std::vector<double> geom_qp, nse_sign;
+  Csr nse_b3[3][3], pre_b3[3][3];
   std::map<std::string, ArrayRef> arrays;
   std::map<std::string, int64_t> scalars;
 
@@ -395,12 +461,177 @@ inline void add_no_normal_flux(const Mesh& mesh, const DofMap& dm, int bid, int 
   }
 }
 
+// FEEC model: FESystem(FE_Nedelec(0), FE_RaviartThomas(0), FE_DGQ(0)) + Q1 temperature
+// (include/core/boussineq_model_FEEC.tpp:14-55, setup_dofs :231-478, setup_nse_matrices :79-130,
+// setup_nse_preconditioner :133-198).  Deviations that cannot matter to the kernels: no Cuthill-McKee pass
+// (:243, tie-breaking unverifiable) -- dofs keep first-visit order inside each block (block_wise, :245).
+inline void build_feec(Problem* P, const Spec& sp) {
+  const Mesh& mesh = *P->mesh;
+  const int dim = 3;
+  const bool cuboid = sp.geometry == "cube";
+  if (sp.n_ranks > 1) throw std::runtime_error("harness: FEEC family is not partitioned yet");
+  FESystemDesc fe;
+  fe.dim = dim;
+  fe.field_degree = {0, 0, 0};
+  fe.field_block = {0, 1, 2};
+  fe.field_kind = {1, 2, 3};
+  P->nse = distribute_dofs(mesh, fe, nullptr, 0);
+  FESystemDesc t_fe;
+  t_fe.dim = dim;
+  t_fe.field_degree = {sp.temperature_degree};
+  t_fe.field_block = {0};
+  P->temp = distribute_dofs(mesh, t_fe, nullptr, 0);
+  P->nse_block_start = {0, P->nse.block_size[0], P->nse.block_size[0] + P->nse.block_size[1],
+                        P->nse.block_size[0] + P->nse.block_size[1] + P->nse.block_size[2]};
+  const int mdeg = 1;  // FEValues without a mapping argument (boussineq_model_assembly_FEEC.tpp:24,67,160); T: MappingQ(1)
+  dof_positions(mesh, P->nse, mdeg, P->nse_dof_xyz, &P->nse_dof_comp);
+  dof_positions(mesh, P->temp, mdeg, P->temp_dof_xyz, nullptr);
+
+  // constraints (:308-478): zero tangential (Nedelec) and zero normal (RT) boundary dofs on both boundaries
+  if (sp.constraints) {
+    if (cuboid) {
+      add_periodic(mesh, P->nse, P->nse_cs);
+      for (int bid : {4, 5}) add_dirichlet(mesh, P->nse, bid, {0, 1}, nullptr, P->nse_dof_xyz, P->nse_cs);
+      add_periodic(mesh, P->temp, P->temp_cs);
+      double center[3] = {0.5, 0.5, 0.5};
+      double diam = std::sqrt(3.0);
+      add_dirichlet(mesh, P->temp, 4, {0}, [&](const double* p) { return temperature_initial_cuboid(dim, center, diam, p); },
+                    P->temp_dof_xyz, P->temp_cs);
+    } else {
+      for (int bid : {0, 1}) add_dirichlet(mesh, P->nse, bid, {0, 1}, nullptr, P->nse_dof_xyz, P->nse_cs);
+      add_dirichlet(mesh, P->temp, 0, {0}, [&](const double* p) { return temperature_initial_shell(dim, sp.R0, sp.R1, p); },
+                    P->temp_dof_xyz, P->temp_cs);
+    }
+  }
+  P->nse_cs.close(P->nse.n_dofs);
+  P->temp_cs.close(P->temp.n_dofs);
+
+  // face sign (source/base/utilities.cc:20-46): -1 on the RT dof of an interior face the cell sees in
+  // non-standard orientation.  Here: the first cell (in cell order) that meets a face defines its normal; a
+  // later cell that sees the face on the same side (both as a "0" face or both as a "1" face, which only
+  // happens across the seams of the six trees) has the opposite local normal.
+  {
+    const int nl = P->nse.fe.n_local;
+    P->nse_sign.assign((size_t)mesh.n_cells * nl, 1.0);
+    auto offs = hierarchical_offsets(dim);
+    std::vector<int8_t> first_side((size_t)mesh.n_nodes, -1);
+    int64_t ids[27];
+    for (int64_t c = 0; c < mesh.n_cells; ++c) {
+      mesh.cell_nodes(c, ids);
+      for (int f = 0; f < 6; ++f) {
+        if (mesh.face_boundary_id(c, f) >= 0) continue;
+        int64_t node = ids[lex_index(dim, offs[20 + f])];
+        int side = f % 2;
+        if (first_side[node] < 0)
+          first_side[node] = (int8_t)side;
+        else if (first_side[node] == side)
+          P->nse_sign[(size_t)c * nl + 12 + f] = -1.0;
+      }
+    }
+  }
+
+  // rules: system QGauss(deg+2) (:843), preconditioner QGauss(deg+1) (:595), temperature QGauss(Tdeg+2) (:969,1125)
+  const int deg = 1;  // "nse velocity degree" of the FEEC configs
+  P->q_nse = qgauss(dim, deg + 2);
+  P->q_pre = qgauss(dim, deg + 1);
+  P->q_temp = qgauss(dim, sp.temperature_degree + 2);
+  P->feec_qn = tabulate_feec(P->q_nse);
+  P->feec_qp = tabulate_feec(P->q_pre);
+  P->feec_qt = tabulate_feec(P->q_temp);
+  P->tab_t_qn = tabulate_scalar(dim, sp.temperature_degree, P->q_nse);
+  P->tab_t_qt = tabulate_scalar(dim, sp.temperature_degree, P->q_temp);
+  if (sp.geometry_data) {
+    compute_geometry_ext(mesh, mdeg, P->q_nse, P->geom_qn);
+    compute_geometry_ext(mesh, mdeg, P->q_pre, P->geom_qp);
+    if (P->q_temp.n1 != P->q_nse.n1) compute_geometry_ext(mesh, mdeg, P->q_temp, P->geom_qt);
+  }
+  // block couplings through the first nonzero component of each (non-primitive) shape function
+  // (setup_nse_matrices :94-118, setup_nse_preconditioner :151-184): blocks w=0, u=1, p=2
+  P->nse_coupling = {1, 1, 0, 1, 1, 1, 0, 1, 0};
+  P->pre_coupling = {1, 1, 0, 1, 1, 0, 1, 0, 1};
+  P->nse_adj = build_row_adjacency(P->nse, P->nse_cs);
+  P->temp_adj = build_row_adjacency(P->temp, P->temp_cs);
+  if (sp.patterns) {
+    std::vector<int> cn(P->nse_coupling.begin(), P->nse_coupling.end()), cp(P->pre_coupling.begin(), P->pre_coupling.end());
+    P->nse_full = make_sparsity_pattern(P->nse, P->nse_cs, cn, P->nse_adj);
+    P->pre_full = make_sparsity_pattern(P->nse, P->nse_cs, cp, P->nse_adj);
+    P->temp_pat = make_sparsity_pattern(P->temp, P->temp_cs, {1}, P->temp_adj);
+    for (int bi = 0; bi < 3; ++bi)
+      for (int bj = 0; bj < 3; ++bj) {
+        P->nse_b3[bi][bj] = extract_block(P->nse_full, P->nse_block_start, bi, bj);
+        P->pre_b3[bi][bj] = extract_block(P->pre_full, P->nse_block_start, bi, bj);
+      }
+  }
+  auto& S = P->scalars;
+  S["dim"] = dim;
+  S["feec"] = 1;
+  S["n_cells"] = mesh.n_cells;
+  S["n_owned_cells"] = mesh.n_cells;
+  S["n_ranks"] = 1;
+  S["rank"] = 0;
+  S["nse.n_dofs"] = P->nse.n_dofs;
+  S["nse.n_w"] = P->nse.block_size[0];
+  S["nse.n_u"] = P->nse.block_size[1];
+  S["nse.n_p"] = P->nse.block_size[2];
+  S["nse.n_local"] = P->nse.fe.n_local;
+  S["temp.n_dofs"] = P->temp.n_dofs;
+  S["temp.n_local"] = P->temp.fe.n_local;
+  S["temp.n_owned"] = P->temp.n_dofs;
+  S["q_nse.nq"] = P->q_nse.nq;
+  S["q_pre.nq"] = P->q_pre.nq;
+  S["q_temp.nq"] = P->q_temp.nq;
+  S["geom_shared"] = (P->q_temp.n1 == P->q_nse.n1) ? 1 : 0;
+  S["cuboid"] = cuboid ? 1 : 0;
+  P->reg("nse.l2g", P->nse.l2g, I32);
+  P->reg("temp.l2g", P->temp.l2g, I32);
+  P->reg("nse.local_field", P->nse.fe.local_field, I32);
+  P->reg("nse.local_base", P->nse.fe.local_base, I32);
+  P->reg("nse.sign", P->nse_sign, F64);
+  P->reg("nse.dof_xyz", P->nse_dof_xyz, F64);
+  P->reg("temp.dof_xyz", P->temp_dof_xyz, F64);
+  P->reg("nse.dof_comp", P->nse_dof_comp, I8);
+  P->reg("nse.dof_key", P->nse.dof_key, I64);
+  P->reg("temp.dof_key", P->temp.dof_key, I64);
+  P->reg_cs("nse.cs", P->nse_cs);
+  P->reg_cs("temp.cs", P->temp_cs);
+  P->reg("q_nse.w", P->q_nse.w, F64);
+  P->reg("q_pre.w", P->q_pre.w, F64);
+  P->reg("q_temp.w", P->q_temp.w, F64);
+  auto reg_feec = [&](const std::string& n, const FeecTable& t) {
+    P->reg(n + ".phi_w", t.phi_w, F64);
+    P->reg(n + ".curl_w", t.curl_w, F64);
+    P->reg(n + ".phi_u", t.phi_u, F64);
+    P->reg(n + ".div_u", t.div_u, F64);
+  };
+  reg_feec("feec.qn", P->feec_qn);
+  reg_feec("feec.qp", P->feec_qp);
+  reg_feec("feec.qt", P->feec_qt);
+  P->reg_tab("tab.t_qn", P->tab_t_qn);
+  P->reg_tab("tab.t_qt", P->tab_t_qt);
+  P->reg("geom.qn", P->geom_qn, F64);
+  P->reg("geom.qp", P->geom_qp, F64);
+  P->reg("geom.qt", P->q_temp.n1 == P->q_nse.n1 ? P->geom_qn : P->geom_qt, F64);
+  P->reg("nse.coupling", P->nse_coupling, I32);
+  P->reg("pre.coupling", P->pre_coupling, I32);
+  if (sp.patterns) {
+    P->reg_csr("nse.full", P->nse_full);
+    P->reg_csr("pre.full", P->pre_full);
+    P->reg_csr("temp.pat", P->temp_pat);
+    for (int bi = 0; bi < 3; ++bi)
+      for (int bj = 0; bj < 3; ++bj) {
+        std::string t = std::to_string(bi) + std::to_string(bj);
+        P->reg_csr("nse.b" + t, P->nse_b3[bi][bj]);
+        P->reg_csr("pre.b" + t, P->pre_b3[bi][bj]);
+      }
+  }
+}
+
 inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   if (sp.threads > 0) omp_set_num_threads(sp.threads);
   auto P = std::make_unique<Problem>();
   P->spec = sp;
   if (sp.dim != 3) throw std::runtime_error("harness: only dim=3 is implemented");
-  if (sp.family != "classic") throw std::runtime_error("harness: only family=classic is implemented");
+  if (sp.family != "classic" && sp.family != "feec") throw std::runtime_error("harness: unknown family " + sp.family);
   const int dim = sp.dim;
   if (sp.geometry == "shell")
     P->mesh = std::make_unique<ShellMesh3D>(sp.refine, sp.R0, sp.R1, sp.radial_factor);
@@ -447,6 +678,10 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
     P->n_owned_cells = c1 - c0;
     P->cell_global = cells;
     P->mesh = std::make_unique<SubMesh>(B, cells);
+  }
+  if (sp.family == "feec") {
+    build_feec(P.get(), sp);
+    return P;
   }
   const Mesh& mesh = *P->mesh;
   const bool cuboid = sp.geometry == "cube";

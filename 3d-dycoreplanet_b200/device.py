@@ -58,6 +58,11 @@ class ModelDesc(ctypes.Structure):
         ("phi_u_qt", c_dp), ("phi_t_qt", c_dp), ("dphi_t_qt", c_dp),
         ("geom_qn", c_dp), ("geom_qt", c_dp),
         ("nse_pattern", (CsrDesc * MAXB) * MAXB), ("pre_pattern", (CsrDesc * MAXB) * MAXB), ("temp_pattern", CsrDesc),
+        # FEEC family
+        ("nq_pre", ctypes.c_int32), ("pad2", ctypes.c_int32), ("nse_sign", c_dp),
+        ("feec_phi_w_qn", c_dp), ("feec_curl_w_qn", c_dp), ("feec_phi_u_qn", c_dp),
+        ("feec_phi_w_qp", c_dp), ("feec_curl_w_qp", c_dp), ("feec_phi_u_qp", c_dp),
+        ("feec_phi_u_qt", c_dp), ("feec_div_u", c_dp), ("geom_qp", c_dp),
     ]
 
 
@@ -282,16 +287,37 @@ def model_desc_from_problem(P):
     """Fill a dcp_model_desc from a harness Problem (the stand-in for deal.II's objects)."""
     keep = []
     d = ModelDesc()
-    d.dim, d.family, d.n_cells = P.dim, 0, P.n_cells
-    d.nse_n_local, d.nse_n_blocks = P.scalar("nse.n_local"), 2
-    d.nse_block_size[0], d.nse_block_size[1] = P.scalar("nse.n_u"), P.scalar("nse.n_p")
-    for name, field, ct in [("nse.l2g", "nse_l2g", c_ip), ("nse.local_field", "nse_local_field", c_ip),
-                            ("nse.local_base", "nse_local_base", c_ip), ("temp.l2g", "temp_l2g", c_ip),
-                            ("tab.u_qn.phi", "phi_u_qn", c_dp), ("tab.u_qn.dphi", "dphi_u_qn", c_dp),
-                            ("tab.p_qn.phi", "phi_p_qn", c_dp), ("tab.t_qn.phi", "phi_t_qn", c_dp),
-                            ("tab.u_qt.phi", "phi_u_qt", c_dp), ("tab.t_qt.phi", "phi_t_qt", c_dp),
-                            ("tab.t_qt.dphi", "dphi_t_qt", c_dp), ("geom.qn", "geom_qn", c_dp),
-                            ("geom.qt", "geom_qt", c_dp)]:
+    feec = "feec" in P.spec.get("family", "classic")
+    d.dim, d.family, d.n_cells = P.dim, (1 if feec else 0), P.n_cells
+    d.nse_n_local = P.scalar("nse.n_local")
+    if feec:
+        d.nse_n_blocks = 3
+        d.nse_block_size[0], d.nse_block_size[1], d.nse_block_size[2] = \
+            P.scalar("nse.n_w"), P.scalar("nse.n_u"), P.scalar("nse.n_p")
+        names = [("nse.l2g", "nse_l2g", c_ip), ("nse.local_field", "nse_local_field", c_ip),
+                 ("nse.local_base", "nse_local_base", c_ip), ("temp.l2g", "temp_l2g", c_ip),
+                 ("tab.t_qn.phi", "phi_t_qn", c_dp), ("tab.t_qt.phi", "phi_t_qt", c_dp),
+                 ("tab.t_qt.dphi", "dphi_t_qt", c_dp), ("geom.qn", "geom_qn", c_dp), ("geom.qt", "geom_qt", c_dp),
+                 ("geom.qp", "geom_qp", c_dp), ("nse.sign", "nse_sign", c_dp),
+                 ("feec.qn.phi_w", "feec_phi_w_qn", c_dp), ("feec.qn.curl_w", "feec_curl_w_qn", c_dp),
+                 ("feec.qn.phi_u", "feec_phi_u_qn", c_dp), ("feec.qp.phi_w", "feec_phi_w_qp", c_dp),
+                 ("feec.qp.curl_w", "feec_curl_w_qp", c_dp), ("feec.qp.phi_u", "feec_phi_u_qp", c_dp),
+                 ("feec.qt.phi_u", "feec_phi_u_qt", c_dp), ("feec.qn.div_u", "feec_div_u", c_dp)]
+        d.nq_pre = P.scalar("q_pre.nq")
+        d.ndu, d.ndp, d.ndt = 0, 0, P.scalar("tab.t_qn.nd")
+        nb = 3
+    else:
+        d.nse_n_blocks = 2
+        d.nse_block_size[0], d.nse_block_size[1] = P.scalar("nse.n_u"), P.scalar("nse.n_p")
+        names = [("nse.l2g", "nse_l2g", c_ip), ("nse.local_field", "nse_local_field", c_ip),
+                 ("nse.local_base", "nse_local_base", c_ip), ("temp.l2g", "temp_l2g", c_ip),
+                 ("tab.u_qn.phi", "phi_u_qn", c_dp), ("tab.u_qn.dphi", "dphi_u_qn", c_dp),
+                 ("tab.p_qn.phi", "phi_p_qn", c_dp), ("tab.t_qn.phi", "phi_t_qn", c_dp),
+                 ("tab.u_qt.phi", "phi_u_qt", c_dp), ("tab.t_qt.phi", "phi_t_qt", c_dp),
+                 ("tab.t_qt.dphi", "dphi_t_qt", c_dp), ("geom.qn", "geom_qn", c_dp), ("geom.qt", "geom_qt", c_dp)]
+        d.ndu, d.ndp, d.ndt = P.scalar("tab.u_qn.nd"), P.scalar("tab.p_qn.nd"), P.scalar("tab.t_qn.nd")
+        nb = 2
+    for name, field, ct in names:
         a = P[name]
         keep.append(a)
         setattr(d, field, _ptr(a, ct))
@@ -299,9 +325,8 @@ def model_desc_from_problem(P):
     d.temp_cs = _cs_desc(P, "temp.cs", keep)
     d.temp_n_local = P.scalar("temp.n_local")
     d.nq_nse, d.nq_temp = P.scalar("q_nse.nq"), P.scalar("q_temp.nq")
-    d.ndu, d.ndp, d.ndt = P.scalar("tab.u_qn.nd"), P.scalar("tab.p_qn.nd"), P.scalar("tab.t_qn.nd")
-    for i in range(2):
-        for j in range(2):
+    for i in range(nb):
+        for j in range(nb):
             d.nse_pattern[i][j] = _csr_desc(P, f"nse.b{i}{j}", keep)
             d.pre_pattern[i][j] = _csr_desc(P, f"pre.b{i}{j}", keep)
     d.temp_pattern = _csr_desc(P, "temp.pat", keep)

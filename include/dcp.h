@@ -152,6 +152,20 @@ typedef struct {
   dcp_csr_desc nse_pattern[DCP_MAX_BLOCKS][DCP_MAX_BLOCKS];
   dcp_csr_desc pre_pattern[DCP_MAX_BLOCKS][DCP_MAX_BLOCKS];
   dcp_csr_desc temp_pattern;
+
+  /* ---- FEEC family only (family == DCP_FAMILY_FEEC; ExteriorCalculus::BoussinesqModel<3>,
+   * include/core/boussineq_model_FEEC.tpp).  FESystem(FE_Nedelec(0), FE_RaviartThomas(0), FE_DGQ(0)): cell dofs
+   * 0..11 vorticity (lines), 12..17 velocity (faces), 18 pressure; three blocks (w,u,p).  The mapping records of
+   * this family carry the Jacobian for the Piola transforms: [JxW | Kinv | xq | J[i][j] | detJ], nq entries each.
+   * The Lagrange velocity/pressure tables above are unused; the temperature tables are used as in the classic family. */
+  int32_t nq_pre;            /* preconditioner rule QGauss(deg+1) (:595) */
+  int32_t pad2;
+  const double* nse_sign;    /* [n_cells][19] face sign of Tools::get_face_sign_change_raviart_thomas (utilities.cc:20-46) */
+  const double *feec_phi_w_qn, *feec_curl_w_qn, *feec_phi_u_qn; /* reference values [nq_nse][12|12|6][3] */
+  const double *feec_phi_w_qp, *feec_curl_w_qp, *feec_phi_u_qp; /* ... on the preconditioner rule */
+  const double* feec_phi_u_qt;                                   /* RT values on the temperature rule */
+  const double* feec_div_u;                                      /* [6] reference divergence of the RT functions */
+  const double* geom_qp;                                         /* mapping records on the preconditioner rule */
 } dcp_model_desc;
 
 /* ---- context --------------------------------------------------------------------------------- */

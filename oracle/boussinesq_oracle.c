@@ -30,45 +30,13 @@
 #include <omp.h>
 #endif
 
-#define ORC_MAXD 96 /* max dofs per cell handled by the stack buffers (classic 3D: 89) */
-
-typedef struct {
-  int32_t dim;
-  int32_t cuboid;        /* parameters.cuboid_geometry */
-  int32_t nse_interval;  /* parameters.NSE_solver_interval */
-  int32_t pad;
-  double dt;             /* parameters.time_step */
-  double inv_re;         /* 1/Re, boussinesq_model.tpp:564-568 */
-  double inv_pe;         /* 1/Pe, :760-764 */
-  double beta;           /* expansion_coefficient */
-  double T_ref;          /* reference_quantities.temperature_ref */
-  double g_scale;        /* L/U^2, :640-643 */
-  double g_const;        /* physical_constants.gravity_constant */
-  double cor_scale;      /* L/U, :615-621 */
-  double omega;          /* physical_constants.omega */
-} orc_params;
-
-typedef struct {
-  int64_t n_dofs;
-  const int32_t* line_of_dof; /* [n_dofs] -> line or -1 */
-  const int32_t* line_ptr;
-  const int32_t* entry_dof;
-  const double* entry_w;
-  const double* inhom;
-} orc_constraints;
-
-typedef struct {
-  int64_t n_rows;
-  const int64_t* rowptr;
-  const int32_t* col;
-  double* val;
-} orc_csr;
+#include "oracle_common.h"
 
 static int g_orc_missing = 0; /* counts scatter targets that are not in the pattern */
 int orc_missing_entries(void) { return g_orc_missing; }
 void orc_reset_missing(void) { g_orc_missing = 0; }
 
-static inline void csr_add(const orc_csr* A, int64_t r, int32_t c, double v, int atomic) {
+void orc_csr_add(const orc_csr* A, int64_t r, int32_t c, double v, int atomic) {
   const int32_t* b = A->col + A->rowptr[r];
   int64_t lo = 0, hi = A->rowptr[r + 1] - A->rowptr[r];
   while (lo < hi) {
@@ -88,7 +56,7 @@ static inline void csr_add(const orc_csr* A, int64_t r, int32_t c, double v, int
     *p += v;
 }
 
-static inline void vec_add(double* b, int64_t i, double v, int atomic) {
+void orc_vec_add(double* b, int64_t i, double v, int atomic) {
   if (atomic) {
 #pragma omp atomic
     b[i] += v;
@@ -98,7 +66,7 @@ static inline void vec_add(double* b, int64_t i, double v, int atomic) {
 
 /* AffineConstraints::distribute_local_to_global(local_matrix[, local_vector], indices, A[, b]).
  * Call sites: boussinesq_model.tpp:473-475 (matrix only), :682-686 (matrix+rhs), :809-816. */
-static void distribute_matrix(const orc_constraints* cs, int n, const double* L, const double* l, const int32_t* idx,
+void orc_distribute_matrix(const orc_constraints* cs, int n, const double* L, const double* l, const int32_t* idx,
                               const orc_csr* A, double* b, int atomic) {
   int any_constrained = 0;
   for (int i = 0; i < n; ++i) {
@@ -120,18 +88,18 @@ static void distribute_matrix(const orc_constraints* cs, int n, const double* L,
       if (v == 0.0) continue;
       int32_t gj = idx[j], lj = cs->line_of_dof[gj];
       if (lj < 0) {
-        for (int a = 0; a < nr; ++a) csr_add(A, rd[a], gj, rw[a] * v, atomic);
+        for (int a = 0; a < nr; ++a) orc_csr_add(A, rd[a], gj, rw[a] * v, atomic);
       } else {
         int nc = cs->line_ptr[lj + 1] - cs->line_ptr[lj];
         const int32_t* cd = cs->entry_dof + cs->line_ptr[lj];
         const double* cw = cs->entry_w + cs->line_ptr[lj];
         for (int a = 0; a < nr; ++a)
-          for (int e = 0; e < nc; ++e) csr_add(A, rd[a], cd[e], rw[a] * cw[e] * v, atomic);
+          for (int e = 0; e < nc; ++e) orc_csr_add(A, rd[a], cd[e], rw[a] * cw[e] * v, atomic);
         if (l) rhs_i -= v * cs->inhom[lj];
       }
     }
     if (b)
-      for (int a = 0; a < nr; ++a) vec_add(b, rd[a], rw[a] * rhs_i, atomic);
+      for (int a = 0; a < nr; ++a) orc_vec_add(b, rd[a], rw[a] * rhs_i, atomic);
   }
   if (any_constrained) {
     double avg = 0;
@@ -141,19 +109,19 @@ static void distribute_matrix(const orc_constraints* cs, int n, const double* L,
       int32_t gi = idx[i];
       if (cs->line_of_dof[gi] < 0) continue;
       double d = fabs(L[i * n + i]);
-      csr_add(A, gi, gi, d != 0.0 ? d : avg, atomic);
+      orc_csr_add(A, gi, gi, d != 0.0 ? d : avg, atomic);
     }
   }
 }
 
 /* AffineConstraints::distribute_local_to_global(local_vector, indices, global_vector, local_matrix)
  * -- the "matrix_for_bc" overload used at boussinesq_model.tpp:960-963. */
-static void distribute_vector_bc(const orc_constraints* cs, int n, const double* l, const double* Lbc,
+void orc_distribute_vector_bc(const orc_constraints* cs, int n, const double* l, const double* Lbc,
                                  const int32_t* idx, double* b, int atomic) {
   for (int i = 0; i < n; ++i) {
     int32_t gi = idx[i], li = cs->line_of_dof[gi];
     if (li < 0) {
-      vec_add(b, gi, l[i], atomic);
+      orc_vec_add(b, gi, l[i], atomic);
       continue;
     }
     double val = cs->inhom[li];
@@ -161,21 +129,21 @@ static void distribute_vector_bc(const orc_constraints* cs, int n, const double*
       for (int j = 0; j < n; ++j) {
         int32_t gj = idx[j], lj = cs->line_of_dof[gj];
         if (lj < 0) {
-          vec_add(b, gj, -val * Lbc[j * n + i], atomic);
+          orc_vec_add(b, gj, -val * Lbc[j * n + i], atomic);
           continue;
         }
         double m = Lbc[j * n + i];
         if (m == 0.0) continue;
         for (int32_t e = cs->line_ptr[lj]; e < cs->line_ptr[lj + 1]; ++e)
-          vec_add(b, cs->entry_dof[e], -val * cs->entry_w[e] * m, atomic);
+          orc_vec_add(b, cs->entry_dof[e], -val * cs->entry_w[e] * m, atomic);
       }
     for (int32_t e = cs->line_ptr[li]; e < cs->line_ptr[li + 1]; ++e)
-      vec_add(b, cs->entry_dof[e], l[i] * cs->entry_w[e], atomic);
+      orc_vec_add(b, cs->entry_dof[e], l[i] * cs->entry_w[e], atomic);
   }
 }
 
 /* CoreModelData::gravity_vector / vertical_gravity_vector (include/model_data/core_model_data.tpp:86-106) */
-static void gravity(const orc_params* P, const double* x, double* g) {
+void orc_gravity(const orc_params* P, const double* x, double* g) {
   int dim = P->dim;
   if (P->cuboid) {
     for (int d = 0; d < dim; ++d) g[d] = 0;
@@ -282,7 +250,7 @@ void orc_assemble_nse_system(const orc_params* P, int64_t n_cells, int nd, int n
         /* gravity, coriolis (:615-621, 640-650) */
         double xq[3] = {0, 0, 0}, grav[3] = {0, 0, 0}, cor[3] = {0, 0, 0};
         for (int d = 0; d < dim; ++d) xq[d] = g[nq * (1 + dim * dim + d) + q];
-        gravity(P, xq, grav);
+        orc_gravity(P, xq, grav);
         for (int d = 0; d < dim; ++d) grav[d] *= P->g_scale;
         if (P->cuboid) cor[dim - 1] = P->cor_scale * P->omega; /* L * coriolis_vector / U */
         /* advection: old_velocity * transpose(grad u)  ->  (u . grad) u  (:599-600, 660) */
@@ -310,7 +278,7 @@ void orc_assemble_nse_system(const orc_params* P, int64_t n_cells, int nd, int n
           l[i] += (a1 + P->dt * density_scaling * a2 - P->dt * a3 - P->dt * a4) * JxW;
         }
       }
-      distribute_matrix(cs, nd, L, l, idx, A, rhs, use_omp);
+      orc_distribute_matrix(cs, nd, L, l, idx, A, rhs, use_omp);
     }
     free(L);
   }
@@ -361,7 +329,7 @@ void orc_assemble_nse_preconditioner(const orc_params* P, int64_t n_cells, int n
             L[i * nd + j] += (uu + P->dt * P->inv_re * gg + phip[i] * phip[j]) * JxW;
           }
       }
-      distribute_matrix(cs, nd, L, NULL, idx, A, NULL, use_omp);
+      orc_distribute_matrix(cs, nd, L, NULL, idx, A, NULL, use_omp);
     }
     free(L);
   }
@@ -399,8 +367,8 @@ void orc_assemble_temperature_matrix(const orc_params* P, int64_t n_cells, int n
             LK[i * nd + j] += P->inv_pe * gg * g[q];
           }
       }
-      distribute_matrix(cs, nd, LM, NULL, l2g + (size_t)c * nd, Mass, NULL, use_omp);
-      distribute_matrix(cs, nd, LK, NULL, l2g + (size_t)c * nd, Stiff, NULL, use_omp);
+      orc_distribute_matrix(cs, nd, LM, NULL, l2g + (size_t)c * nd, Mass, NULL, use_omp);
+      orc_distribute_matrix(cs, nd, LK, NULL, l2g + (size_t)c * nd, Stiff, NULL, use_omp);
     }
     free(LM);
     free(LK);
@@ -463,7 +431,7 @@ void orc_assemble_temperature_rhs(const orc_params* P, int64_t n_cells, int nd, 
             }
         }
       }
-      distribute_vector_bc(cs, nd, l, Lbc, idx, rhs, use_omp);
+      orc_distribute_vector_bc(cs, nd, l, Lbc, idx, rhs, use_omp);
     }
     free(Lbc);
   }

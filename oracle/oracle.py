@@ -177,3 +177,69 @@ def params_from(mp):
                   dt=mp.time_step, inv_re=mp.inv_re, inv_pe=mp.inv_pe, beta=mp.expansion_coefficient,
                   T_ref=mp.ref_temperature, g_scale=mp.g_scale, g_const=mp.gravity_constant, cor_scale=mp.cor_scale,
                   omega=mp.omega)
+
+
+# ---- FEEC family (oracle/feec_oracle.c) ------------------------------------------------------------------
+def _feec_tabs(P, rule):
+    return [_dp(P[f"feec.{rule}.{n}"]) for n in ("phi_w", "curl_w", "phi_u", "div_u")]
+
+
+def feec_assemble_nse_system(P, prm, old_nse, old_temp, use_omp=False):
+    rowptr, col, n, _ = P.csr("nse.full")
+    val = np.zeros(len(col))
+    rhs = np.zeros(n)
+    A = make_csr(rowptr, col, val)
+    cs = make_cs(P, "nse.cs")
+    tw, tc, tu, td = _feec_tabs(P, "qn")
+    lib().orc_feec_assemble_nse_system(
+        ctypes.byref(prm), ctypes.c_int64(P.n_cells), P.scalar("q_nse.nq"), P.scalar("tab.t_qn.nd"), tw, tc, tu, td,
+        _dp(P["tab.t_qn.phi"]), _dp(P["geom.qn"]), _dp(P["nse.sign"]), _ip(P["nse.l2g"]), _ip(P["temp.l2g"]),
+        _dp(old_nse), _dp(old_temp), ctypes.byref(cs), ctypes.byref(A), _dp(rhs), ctypes.c_int64(n), int(use_omp))
+    _check_missing("feec nse_system")
+    return val, rhs
+
+
+def feec_assemble_nse_preconditioner(P, prm, use_omp=False):
+    rowptr, col, n, _ = P.csr("pre.full")
+    val = np.zeros(len(col))
+    A = make_csr(rowptr, col, val)
+    cs = make_cs(P, "nse.cs")
+    tw, tc, tu, td = _feec_tabs(P, "qp")
+    lib().orc_feec_assemble_nse_preconditioner(
+        ctypes.byref(prm), ctypes.c_int64(P.n_cells), P.scalar("q_pre.nq"), tw, tc, tu, td, _dp(P["geom.qp"]),
+        _dp(P["nse.sign"]), _ip(P["nse.l2g"]), ctypes.byref(cs), ctypes.byref(A), int(use_omp))
+    _check_missing("feec nse_preconditioner")
+    return val
+
+
+def feec_compact_geometry(P, name):
+    """First 13 rows (JxW, Kinv, xq) of the extended FEEC record, for the classic temperature-matrix oracle."""
+    nq = P.scalar("q_temp.nq" if name == "geom.qt" else "q_nse.nq")
+    return np.ascontiguousarray(P[name].reshape(P.n_cells, 23, nq)[:, :13, :])
+
+
+def feec_assemble_temperature_matrix(P, prm, use_omp=False):
+    rowptr, col, n, _ = P.csr("temp.pat")
+    m = np.zeros(len(col))
+    k = np.zeros(len(col))
+    M, K = make_csr(rowptr, col, m), make_csr(rowptr, col, k)
+    cs = make_cs(P, "temp.cs")
+    g13 = feec_compact_geometry(P, "geom.qt")
+    lib().orc_assemble_temperature_matrix(
+        ctypes.byref(prm), ctypes.c_int64(P.n_cells), P.scalar("temp.n_local"), P.scalar("q_temp.nq"),
+        _dp(P["tab.t_qt.phi"]), _dp(P["tab.t_qt.dphi"]), _dp(g13), _ip(P["temp.l2g"]), ctypes.byref(cs),
+        ctypes.byref(M), ctypes.byref(K), int(use_omp))
+    _check_missing("feec temperature_matrix")
+    return m, k
+
+
+def feec_assemble_temperature_rhs(P, prm, old_temp, nse_solution, use_omp=False):
+    n = P.scalar("temp.n_dofs")
+    rhs = np.zeros(n)
+    cs = make_cs(P, "temp.cs")
+    lib().orc_feec_assemble_temperature_rhs(
+        ctypes.byref(prm), ctypes.c_int64(P.n_cells), P.scalar("temp.n_local"), P.scalar("q_temp.nq"),
+        _dp(P["tab.t_qt.phi"]), _dp(P["tab.t_qt.dphi"]), _dp(P["feec.qt.phi_u"]), _dp(P["geom.qt"]),
+        _ip(P["temp.l2g"]), _ip(P["nse.l2g"]), _dp(old_temp), _dp(nse_solution), ctypes.byref(cs), _dp(rhs),
+        ctypes.c_int64(n), int(use_omp))
+    return rhs

@@ -21,6 +21,8 @@ CASES = {
     "shell_r2_classic": dict(spec=dict(geometry="shell", refine=2), params="shell_3d_classic"),
     "cube_r2_classic": dict(spec=dict(geometry="cube", refine=2), params="cube_3d"),
     "shell_r1_classic_Tq2": dict(spec=dict(geometry="shell", refine=1, temperature_degree=2), params="shell_3d_classic"),
+    "shell_r2_feec": dict(spec=dict(geometry="shell", refine=2, family="feec"), params="shell_3d_feec"),
+    "cube_r2_feec": dict(spec=dict(geometry="cube", refine=2, family="feec"), params="cube_3d"),
 }
 
 
@@ -46,6 +48,8 @@ def build(case):
     P = harness.Problem(**case["spec"])
     mp = params.NAMED[case["params"]]
     prm = orc.params_from(mp)
+    if case["spec"].get("family") == "feec":
+        return build_feec(P, mp, prm)
     u, T = synthetic_fields(P)
     rng = np.random.default_rng(7)
     out = {"n_cells": P.n_cells, "n_u": P.scalar("nse.n_u"), "n_p": P.scalar("nse.n_p"), "n_T": P.scalar("temp.n_dofs")}
@@ -72,6 +76,38 @@ def build(case):
     xt = np.random.default_rng(2).standard_normal(P.scalar("temp.n_dofs"))
     rp, col, _, _ = P.csr("temp.pat")
     summarize("spmv.temp", orc.spmv(rp, col, tm, xt), rng, out)
+    return out
+
+
+def feec_fields(P):
+    rng = np.random.default_rng(20261018)
+    u = np.ascontiguousarray(0.1 * rng.uniform(-1, 1, P.scalar("nse.n_dofs")) + 0.05)
+    T = np.ascontiguousarray(2.0 + 0.3 * rng.uniform(-1, 1, P.scalar("temp.n_dofs")))
+    return u, T
+
+
+def build_feec(P, mp, prm):
+    from oracle import oracle as orc
+    u, T = feec_fields(P)
+    rng = np.random.default_rng(7)
+    out = {"n_cells": P.n_cells, "n_w": P.scalar("nse.n_w"), "n_u": P.scalar("nse.n_u"), "n_p": P.scalar("nse.n_p"),
+           "n_T": P.scalar("temp.n_dofs")}
+    for pat in ("nse.full", "pre.full", "temp.pat"):
+        out[pat + ".nnz"] = P.scalar(pat + ".nnz")
+        out[pat + ".sha"] = sha(P[pat + ".rowptr"]) + sha(P[pat + ".col"])
+    out["nse.l2g.sha"] = sha(P["nse.l2g"])
+    out["nse.sign.sha"] = sha(P["nse.sign"])
+    vals, rhs = orc.feec_assemble_nse_system(P, prm, u, T)
+    summarize("nse.full", vals, rng, out)
+    summarize("nse.rhs", rhs, rng, out)
+    summarize("pre.full", orc.feec_assemble_nse_preconditioner(P, prm), rng, out)
+    m, k = orc.feec_assemble_temperature_matrix(P, prm)
+    summarize("temp.mass", m, rng, out)
+    summarize("temp.stiff", k, rng, out)
+    summarize("temp.rhs", orc.feec_assemble_temperature_rhs(P, prm, T, u), rng, out)
+    x = np.random.default_rng(1).standard_normal(P.scalar("nse.n_dofs"))
+    rp, col, _, _ = P.csr("nse.full")
+    summarize("spmv.nse", orc.spmv(rp, col, vals, x), rng, out)
     return out
 
 

@@ -94,3 +94,76 @@ def test_cuda_path_matches_golden(problem_factory, case):
     _check("spmv.temp", yt, G, 1e-11)
     model.close()
     ctx.close()
+
+
+FEEC_CASES = {"shell_r2_feec": (dict(geometry="shell", refine=2, family="feec"), "shell_3d_feec"),
+              "cube_r2_feec": (dict(geometry="cube", refine=2, family="feec"), "cube_3d")}
+
+
+def _feec_fields(P):
+    rng = np.random.default_rng(20261018)
+    return (np.ascontiguousarray(0.1 * rng.uniform(-1, 1, P.scalar("nse.n_dofs")) + 0.05),
+            np.ascontiguousarray(2.0 + 0.3 * rng.uniform(-1, 1, P.scalar("temp.n_dofs"))))
+
+
+def _full_from_blocks(P, model_matrix, prefix):
+    """Device blocks -> values in `<prefix>.full` order (three blocks)."""
+    rp, col = P[prefix + ".full.rowptr"], P[prefix + ".full.col"]
+    n, nw, nu = P.scalar("nse.n_dofs"), P.scalar("nse.n_w"), P.scalar("nse.n_u")
+    start = [0, nw, nw + nu, n]
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    out = np.zeros(len(col))
+    for bi in range(3):
+        for bj in range(3):
+            m = (rows >= start[bi]) & (rows < start[bi + 1]) & (col >= start[bj]) & (col < start[bj + 1])
+            out[m] = model_matrix.block(bi, bj).values()
+    return out
+
+
+@pytest.mark.parametrize("case", sorted(FEEC_CASES))
+def test_feec_oracle_and_harness_match_golden(problem_factory, case):
+    from dycore_b200 import params
+    from oracle import oracle as orc
+    spec, pname = FEEC_CASES[case]
+    G = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    P = problem_factory(**spec)
+    prm = orc.params_from(params.NAMED[pname])
+    assert (P.n_cells, P.scalar("nse.n_w"), P.scalar("nse.n_u"), P.scalar("nse.n_p")) == \
+        (int(G["n_cells"]), int(G["n_w"]), int(G["n_u"]), int(G["n_p"]))
+    for pat in ("nse.full", "pre.full", "temp.pat"):
+        assert _sha(P[pat + ".rowptr"]) + _sha(P[pat + ".col"]) == str(G[pat + ".sha"])
+    assert _sha(P["nse.l2g"]) == str(G["nse.l2g.sha"]) and _sha(P["nse.sign"]) == str(G["nse.sign.sha"])
+    u, T = _feec_fields(P)
+    vals, rhs = orc.feec_assemble_nse_system(P, prm, u, T)
+    _check("nse.full", vals, G, 1e-13)
+    _check("nse.rhs", rhs, G, 1e-13)
+    _check("pre.full", orc.feec_assemble_nse_preconditioner(P, prm), G, 1e-13)
+    _check("temp.rhs", orc.feec_assemble_temperature_rhs(P, prm, T, u), G, 1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(FEEC_CASES))
+def test_feec_cuda_path_matches_golden(problem_factory, case):
+    from dycore_b200 import device, params
+    spec, pname = FEEC_CASES[case]
+    G = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    P = problem_factory(**spec)
+    u, T = _feec_fields(P)
+    ctx = device.Context(0)
+    model = device.BoussinesqModel.from_problem(ctx, P, params.NAMED[pname])
+    model.assemble_nse_system(u, T)
+    _check("nse.full", _full_from_blocks(P, model.nse_matrix, "nse"), G, 1e-12)
+    _check("nse.rhs", model.nse_rhs, G, 1e-12)
+    model.assemble_nse_preconditioner()
+    _check("pre.full", _full_from_blocks(P, model.nse_preconditioner_matrix, "pre"), G, 1e-12)
+    model.assemble_temperature_matrix()
+    _check("temp.mass", model.temperature_mass_matrix.values(), G, 1e-12)
+    _check("temp.stiff", model.temperature_stiffness_matrix.values(), G, 1e-12)
+    model.assemble_temperature_rhs(T, u)
+    _check("temp.rhs", model.temperature_rhs, G, 1e-12)
+    n = P.scalar("nse.n_dofs")
+    y = np.zeros(n)
+    model.nse_matrix.vmult(y, np.random.default_rng(1).standard_normal(n))
+    _check("spmv.nse", y, G, 1e-11)
+    model.close()
+    ctx.close()

@@ -123,3 +123,66 @@ def test_spmv_matches_oracle(ctx, problem_factory, spec):
     Tm = sp.csr_matrix((model.temperature_matrix.values(), col, rp), shape=(n_t, n_t))
     assert rel_err_max(d, xt / Tm.diagonal()) <= TOL
     model.close()
+
+
+def split_blocks3(P, prefix, vals):
+    """FEEC: values on `<prefix>.full` -> {(bi,bj)} for the three blocks (w,u,p)."""
+    rp, col = P[prefix + ".full.rowptr"], P[prefix + ".full.col"]
+    n = P.scalar("nse.n_dofs")
+    nw, nu = P.scalar("nse.n_w"), P.scalar("nse.n_u")
+    start = [0, nw, nw + nu, n]
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    out = {}
+    for bi in range(3):
+        for bj in range(3):
+            m = (rows >= start[bi]) & (rows < start[bi + 1]) & (col >= start[bj]) & (col < start[bj + 1])
+            out[(bi, bj)] = vals[m]
+    return out
+
+
+FEEC_CASES = [(dict(geometry="shell", refine=1, family="feec"), "shell_3d_feec"),
+              (dict(geometry="shell", refine=3, family="feec"), "shell_3d_feec"),
+              (dict(geometry="cube", refine=2, family="feec"), "cube_3d")]
+
+
+@pytest.mark.parametrize("spec,pname", FEEC_CASES, ids=["shell-r1", "shell-r3-named", "cube-r2"])
+def test_feec_assembly_and_spmv_match_oracle(ctx, problem_factory, spec, pname):
+    from dycore_b200 import device, params
+    from oracle import oracle as orc
+    P = problem_factory(**spec)
+    mp = params.NAMED[pname]
+    oprm = orc.params_from(mp)
+    n, nT = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
+    rng = np.random.default_rng(20261018)
+    u = np.ascontiguousarray(0.1 * rng.uniform(-1, 1, n) + 0.05)
+    T = np.ascontiguousarray(2.0 + 0.3 * rng.uniform(-1, 1, nT))
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    model.assemble_nse_system(u, T)
+    ref_vals, ref_rhs = orc.feec_assemble_nse_system(P, oprm, u, T)
+    for (bi, bj), rv in split_blocks3(P, "nse", ref_vals).items():
+        assert rel_err_max(model.nse_matrix.block(bi, bj).values(), rv) <= TOL, f"feec nse block {bi}{bj}"
+    assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
+    model.assemble_nse_preconditioner()
+    for (bi, bj), rv in split_blocks3(P, "pre", orc.feec_assemble_nse_preconditioner(P, oprm)).items():
+        assert rel_err_max(model.nse_preconditioner_matrix.block(bi, bj).values(), rv) <= TOL, f"feec pre block {bi}{bj}"
+    model.assemble_temperature_matrix()
+    rm, rk = orc.feec_assemble_temperature_matrix(P, oprm)
+    assert rel_err_max(model.temperature_mass_matrix.values(), rm) <= TOL
+    assert rel_err_max(model.temperature_stiffness_matrix.values(), rk) <= TOL
+    model.assemble_temperature_rhs(T, u)
+    assert rel_err_max(model.temperature_rhs, orc.feec_assemble_temperature_rhs(P, oprm, T, u)) <= TOL
+    # 3x3-block vmult as called by SolverGMRES (boussineq_model_FEEC.tpp:1372-1401) and the leaves of the FEEC
+    # preconditioner (block_schur_preconditioner.hpp:131,144)
+    x = rng.standard_normal(n)
+    y = np.zeros(n)
+    model.nse_matrix.vmult(y, x)
+    rp, col, _, _ = P.csr("nse.full")
+    scale = orc.spmv(rp, col, np.abs(ref_vals), np.abs(x)).max()
+    assert np.abs(y - orc.spmv(rp, col, ref_vals, x)).max() <= 1e-12 * scale
+    nw, nu = P.scalar("nse.n_w"), P.scalar("nse.n_u")
+    A10 = model.nse_matrix.block(1, 0)
+    y10 = np.zeros(nu)
+    A10.vmult(y10, np.ascontiguousarray(x[:nw]))
+    rp10, col10, _, _ = P.csr("nse.b10")
+    assert np.abs(y10 - orc.spmv(rp10, col10, A10.values(), np.ascontiguousarray(x[:nw]))).max() <= 1e-12 * scale
+    model.close()
