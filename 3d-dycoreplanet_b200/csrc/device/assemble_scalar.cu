@@ -2,11 +2,17 @@
 //
 // Replaces local_assemble_temperature_matrix + copier (/root/reference/include/core/boussinesq_model.tpp:
 // 748-817) and local_assemble_temperature_rhs + copier (:873-964); identical integrands are used by the
-// FEEC model (include/core/boussineq_model_FEEC.tpp:883-952, 1008-1099).
+// FEEC model (include/core/boussineq_model_FEEC.tpp:883-952, 1008-1099; there the advecting velocity is the
+// Raviart-Thomas field, Piola-mapped and without the face sign).
 //   M[i,j] += phi_i phi_j JxW,   K[i,j] += (1/Pe) grad phi_i . grad phi_j JxW      (:786-797)
 //   r[i]   += (phi_i T_old - tau phi_i (u_new . grad T_old) - tau*0*phi_i) JxW,  tau = dt/n   (:928-937)
 //   matrix_for_bc(j,i) = (phi_i phi_j + tau/Pe grad phi_i . grad phi_j) JxW  for inhomogeneous i (:939-949)
-// One warp per cell: 8..27 dofs per cell make these kernels HBM/latency bound, not FLOP bound.
+//
+// One warp per cell.  Quadrature points are processed 32 at a time with ONE POINT PER LANE: the lane reads its
+// column of the cell's mapping record (coalesced), maps all shape functions of its point and parks
+// (phi, d_x phi, d_y phi, d_z phi) in a shared-memory row S[lane][.] of odd stride (conflict-free for the
+// writer "lane = point" and for the readers "lane = matrix entry").  Lanes then own the symmetric local
+// matrix entries.  8..27 dofs per cell: these kernels are HBM/latency bound, not FLOP bound.
 #include "scatter.cuh"
 
 namespace {
@@ -14,7 +20,6 @@ namespace {
 using namespace dcpdev;
 
 constexpr int MAX_ND = 27;
-constexpr int WARPS = 3;
 
 struct ScalarArgs {
   long long n_cells;
@@ -31,174 +36,236 @@ struct ScalarArgs {
   int nd_nse, ndu;
   const int* nse_field;
   const int* nse_base;
-  const double* phi_u;  // [nq][ndu] velocity base element on the temperature rule
+  const double* phi_u;  // classic: [nq][ndu] velocity base element on the temperature rule; FEEC: [nq][6][3]
   const double* old_temp;
   const double* nse_solution;
   double* rhs;
 };
 
-struct WarpScratch {
-  double A[MAX_ND * MAX_ND];
-  double B[MAX_ND * MAX_ND];
-  double g[MAX_ND * 3];
-  double ph[MAX_ND];
-  double l[MAX_ND];
-  double T[MAX_ND];
-  int idx[MAX_ND + 1];
-  int lines[MAX_ND + 1];
+// per-warp shared scratch, carved from dynamic shared memory
+struct ScalarLayout {
+  int sv;        // stride of S rows (4*nd rounded up to odd)
+  int doubles;   // doubles per warp
+  int o_S, o_A, o_B, o_c, o_l, o_T, o_U, o_idx;
 };
+__host__ __device__ inline ScalarLayout scalar_layout(int nd, int nd_nse) {
+  ScalarLayout L;
+  L.sv = (4 * nd) | 1;
+  int o = 0;
+  L.o_S = o; o += 32 * L.sv;
+  L.o_A = o; o += nd * nd;
+  L.o_B = o; o += nd * nd;
+  L.o_c = o; o += 32 * 2;          // per point: weight, rhs coefficient
+  L.o_l = o; o += MAX_ND + 1;
+  L.o_T = o; o += MAX_ND + 1;
+  L.o_U = o; o += nd_nse + 1;      // velocity dofs of the cell (rhs)
+  L.o_idx = o; o += MAX_ND + 5;    // ints: idx[nd], lines[nd] (2 ints per double slot)
+  L.doubles = o;
+  return L;
+}
 
+// lane = quadrature point q: map all shape functions at q into row[k*4 + {0:phi,1..3:grad}]
 template <int DIM>
-__device__ __forceinline__ void point_shapes(const ScalarArgs& a, const double* g, int q, int lane, WarpScratch& s) {
-  if (lane < a.nd) {
-    const double* dr = a.dphi + ((size_t)q * a.nd + lane) * DIM;
+__device__ __forceinline__ void map_point(const ScalarArgs& a, const double* g, int q, double* row) {
+  double K[DIM][DIM];
+#pragma unroll
+  for (int e = 0; e < DIM; ++e)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) K[e][d] = g[a.nq * (1 + e * DIM + d) + q];
+  for (int k = 0; k < a.nd; ++k) {
+    const double* dr = a.dphi + ((size_t)q * a.nd + k) * DIM;
     double r[DIM];
 #pragma unroll
     for (int e = 0; e < DIM; ++e) r[e] = __ldg(dr + e);
+    row[k * 4] = __ldg(a.phi + (size_t)q * a.nd + k);
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       double v = 0.0;
 #pragma unroll
-      for (int e = 0; e < DIM; ++e) v += __ldg(g + a.nq * (1 + e * DIM + d) + q) * r[e];
-      s.g[lane * 3 + d] = v;
+      for (int e = 0; e < DIM; ++e) v += K[e][d] * r[e];
+      row[k * 4 + 1 + d] = v;
     }
-    s.ph[lane] = __ldg(a.phi + (size_t)q * a.nd + lane);
+    if (DIM == 2) row[k * 4 + 3] = 0.0;
   }
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(32 * WARPS) temperature_matrix_kernel(ScalarArgs a, CsView cs, BlockView Mass,
-                                                                        BlockView Stiff, int* err) {
-  __shared__ WarpScratch scratch[WARPS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  WarpScratch& s = scratch[wid];
-  const int nd = a.nd, nn = nd * nd;
-  const int gs = a.gstride;
-  for (long long cell = (long long)blockIdx.x * WARPS + wid; cell < a.n_cells; cell += (long long)gridDim.x * WARPS) {
-    const double* g = a.geom + cell * gs;
-    for (int i = lane; i < nn; i += 32) {
-      s.A[i] = 0.0;
-      s.B[i] = 0.0;
-    }
-    if (lane < nd) s.idx[lane] = a.l2g[cell * nd + lane];
-    __syncwarp();
-    for (int q = 0; q < a.nq; ++q) {
-      point_shapes<DIM>(a, g, q, lane, s);
+__global__ void __launch_bounds__(128) temperature_matrix_kernel(ScalarArgs a, CsView cs, BlockView Mass, BlockView Stiff,
+                                                                 int* err) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const ScalarLayout L = scalar_layout(a.nd, 0);
+  double* base = smem_d + (size_t)wid * L.doubles;
+  double* S = base + L.o_S;
+  double* A = base + L.o_A;
+  double* B = base + L.o_B;
+  double* wq = base + L.o_c;
+  int* idx = reinterpret_cast<int*>(base + L.o_idx);
+  int* lines = idx + MAX_ND + 1;
+  const int nd = a.nd, nsym = nd * (nd + 1) / 2;
+  for (long long cell = (long long)blockIdx.x * nwarps + wid; cell < a.n_cells; cell += (long long)gridDim.x * nwarps) {
+    const double* g = a.geom + cell * a.gstride;
+    if (lane < nd) idx[lane] = a.l2g[cell * nd + lane];
+    for (int q0 = 0; q0 < a.nq; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < a.nq) {
+        map_point<DIM>(a, g, q, S + lane * L.sv);
+        wq[lane] = g[q];
+      }
       __syncwarp();
-      const double w = __ldg(g + q);
-      for (int e = lane; e < nn; e += 32) {
-        const int i = e / nd, j = e - i * nd;
-        double gg = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) gg += s.g[i * 3 + d] * s.g[j * 3 + d];
-        s.A[e] += s.ph[i] * s.ph[j] * w;
-        s.B[e] += a.prm.inv_pe * gg * w;
+      const int nqc = min(32, a.nq - q0);
+      for (int e = lane; e < nsym; e += 32) {
+        int i = 0, r = e;
+        while (r >= nd - i) { r -= nd - i; ++i; }
+        const int j = i + r;
+        double m = 0.0, k = 0.0;
+        for (int p = 0; p < nqc; ++p) {
+          const double* si = S + p * L.sv + i * 4;
+          const double* sj = S + p * L.sv + j * 4;
+          const double w = wq[p];
+          m += w * si[0] * sj[0];
+          k += w * (si[1] * sj[1] + si[2] * sj[2] + si[3] * sj[3]);
+        }
+        k *= a.prm.inv_pe;
+        if (q0 == 0) {
+          A[i * nd + j] = m;
+          B[i * nd + j] = k;
+        } else {
+          A[i * nd + j] += m;
+          B[i * nd + j] += k;
+        }
       }
       __syncwarp();
     }
-    distribute_local_matrix<true>(cs, nd, nd, s.A, nullptr, s.idx, s.lines, Mass, nullptr, lane, 32, false, err);
+    for (int e = lane; e < nd * nd; e += 32) {
+      const int i = e / nd, j = e - i * nd;
+      if (i > j) {
+        A[e] = A[j * nd + i];
+        B[e] = B[j * nd + i];
+      }
+    }
     __syncwarp();
-    distribute_local_matrix<true>(cs, nd, nd, s.B, nullptr, s.idx, s.lines, Stiff, nullptr, lane, 32, false, err);
+    distribute_local_matrix<true>(cs, nd, nd, A, nullptr, idx, lines, Mass, nullptr, lane, 32, false, err);
+    __syncwarp();
+    distribute_local_matrix<true>(cs, nd, nd, B, nullptr, idx, lines, Stiff, nullptr, lane, 32, false, err);
     __syncwarp();
   }
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 template <int DIM>
-__global__ void __launch_bounds__(32 * WARPS) temperature_rhs_kernel(ScalarArgs a, CsView cs) {
-  __shared__ WarpScratch scratch[WARPS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  WarpScratch& s = scratch[wid];
+__global__ void __launch_bounds__(128) temperature_rhs_kernel(ScalarArgs a, CsView cs) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const ScalarLayout L = scalar_layout(a.nd, a.nd_nse);
+  double* base = smem_d + (size_t)wid * L.doubles;
+  double* S = base + L.o_S;
+  double* A = base + L.o_A;
+  double* cq = base + L.o_c;  // [32][2]: weight, rhs coefficient
+  double* l = base + L.o_l;
+  double* T = base + L.o_T;
+  double* U = base + L.o_U;
+  int* idx = reinterpret_cast<int*>(base + L.o_idx);
+  int* lines = idx + MAX_ND + 1;
   const int nd = a.nd, nn = nd * nd;
-  const int gs = a.gstride;
   const double tau = a.prm.dt / a.prm.nse_interval;
-  for (long long cell = (long long)blockIdx.x * WARPS + wid; cell < a.n_cells; cell += (long long)gridDim.x * WARPS) {
-    const double* g = a.geom + cell * gs;
+  for (long long cell = (long long)blockIdx.x * nwarps + wid; cell < a.n_cells; cell += (long long)gridDim.x * nwarps) {
+    const double* g = a.geom + cell * a.gstride;
     bool inhom = false;
     if (lane < nd) {
       const int gi = a.l2g[cell * nd + lane];
-      s.idx[lane] = gi;
-      s.T[lane] = a.old_temp[gi];
-      s.l[lane] = 0.0;
+      idx[lane] = gi;
+      T[lane] = a.old_temp[gi];
+      l[lane] = 0.0;
       const int li = cs.line_of_dof[gi];
-      s.lines[lane] = li;
+      lines[lane] = li;
       inhom = li >= 0 && cs.inhom[li] != 0.0;
     }
     const bool need_bc = __any_sync(0xffffffffu, inhom);
+    for (int k = lane; k < a.nd_nse; k += 32) U[k] = a.nse_solution[a.l2g_nse[cell * a.nd_nse + k]];
     if (need_bc)
-      for (int i = lane; i < nn; i += 32) s.A[i] = 0.0;
-    // velocity dofs of this cell held in registers, strided over lanes
+      for (int i = lane; i < nn; i += 32) A[i] = 0.0;
     __syncwarp();
-    for (int q = 0; q < a.nq; ++q) {
-      point_shapes<DIM>(a, g, q, lane, s);
-      __syncwarp();
-      double pT = 0.0, pg[DIM];
+    for (int q0 = 0; q0 < a.nq; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < a.nq) {
+        double* row = S + lane * L.sv;
+        map_point<DIM>(a, g, q, row);
+        double oldT = 0.0, gT[3] = {0.0, 0.0, 0.0}, u[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < nd; ++k) {
+          oldT += T[k] * row[k * 4];
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) pg[d] = 0.0;
-      if (lane < nd) {
-        pT = s.T[lane] * s.ph[lane];
+          for (int d = 0; d < DIM; ++d) gT[d] += T[k] * row[k * 4 + 1 + d];
+        }
+        if (a.feec) {
+          // u(q) = sum_k U_k J phi_hat_k / det J over the six face dofs (cell dofs 12..17), no face sign
+          // (get_function_values, boussineq_model_FEEC.tpp:1039-1040)
+          const double det = g[a.nq * 22 + q];
+          for (int k = 0; k < 6; ++k) {
+            const double* ph = a.phi_u + ((size_t)q * 6 + k) * 3;
+            const double p0 = __ldg(ph), p1 = __ldg(ph + 1), p2 = __ldg(ph + 2), Uk = U[12 + k];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) pg[d] = s.T[lane] * s.g[lane * 3 + d];
-      }
-      double pu[DIM];
+            for (int d = 0; d < 3; ++d)
+              u[d] += Uk * ((g[a.nq * (13 + d * 3) + q] * p0 + g[a.nq * (14 + d * 3) + q] * p1 +
+                             g[a.nq * (15 + d * 3) + q] * p2) / det);
+          }
+        } else {
+          for (int k = 0; k < a.nd_nse; ++k) {
+            const int f = __ldg(a.nse_field + k);
+            if (f < DIM) {
+              const double v = U[k] * __ldg(a.phi_u + (size_t)q * a.ndu + __ldg(a.nse_base + k));
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) pu[d] = 0.0;
-      if (a.feec) {
-        // u(q) = sum_k U_k J phi_hat_k / det J over the six face dofs (cell dofs 12..17), no face sign
-        // (get_function_values, boussineq_model_FEEC.tpp:1039-1040)
-        if (DIM == 3 && lane < 6) {
-          const double U = a.nse_solution[a.l2g_nse[cell * a.nd_nse + 12 + lane]];
-          const double det = __ldg(g + a.nq * 22 + q);
-          const double* ph = a.phi_u + ((size_t)q * 6 + lane) * 3;
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) {
-            double v = 0.0;
-#pragma unroll
-            for (int e = 0; e < DIM; ++e) v += __ldg(g + a.nq * (13 + d * 3 + e) + q) * __ldg(ph + e);
-            pu[d] = U * v / det;
+              for (int d = 0; d < DIM; ++d)
+                if (d == f) u[d] += v;
+            }
           }
         }
-      } else
-      for (int k = lane; k < a.nd_nse; k += 32) {
-        const int f = __ldg(a.nse_field + k);
-        if (f < DIM) {
-          const double v = a.nse_solution[a.l2g_nse[cell * a.nd_nse + k]] * __ldg(a.phi_u + (size_t)q * a.ndu + __ldg(a.nse_base + k));
+        double ugT = 0.0;
 #pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            if (d == f) pu[d] += v;
-        }
+        for (int d = 0; d < DIM; ++d) ugT += u[d] * gT[d];
+        const double w = g[q];
+        const double gamma = 0.0;  // heat source multiplied by literal 0 in the reference (:922-926)
+        cq[lane * 2] = w;
+        cq[lane * 2 + 1] = (oldT - tau * ugT - tau * gamma) * w;
       }
-      const double oldT = warp_sum(pT);
-      double ugT = 0.0;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) ugT += warp_sum(pu[d]) * warp_sum(pg[d]);
-      const double w = __ldg(g + q);
-      const double gamma = 0.0;  // heat source multiplied by literal 0 in the reference (:922-926)
-      if (lane < nd) s.l[lane] += (s.ph[lane] * oldT - tau * s.ph[lane] * ugT - tau * gamma * s.ph[lane]) * w;
+      __syncwarp();
+      const int nqc = min(32, a.nq - q0);
+      if (lane < nd) {
+        double s = 0.0;
+        for (int p = 0; p < nqc; ++p) s += S[p * L.sv + lane * 4] * cq[p * 2 + 1];
+        l[lane] += s;
+      }
       if (need_bc)
         for (int e = lane; e < nn; e += 32) {
           const int j = e / nd, i = e - j * nd;
-          double gg = 0.0;
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) gg += s.g[i * 3 + d] * s.g[j * 3 + d];
-          s.A[e] += (s.ph[i] * s.ph[j] + tau * a.prm.inv_pe * gg) * w;
+          double s = 0.0;
+          for (int p = 0; p < nqc; ++p) {
+            const double* si = S + p * L.sv + i * 4;
+            const double* sj = S + p * L.sv + j * 4;
+            s += cq[p * 2] * (si[0] * sj[0] + tau * a.prm.inv_pe * (si[1] * sj[1] + si[2] * sj[2] + si[3] * sj[3]));
+          }
+          A[e] += s;
         }
       __syncwarp();
     }
-    distribute_local_vector_bc<true>(cs, nd, nd, s.l, s.A, s.idx, s.lines, a.rhs, lane, 32);
+    distribute_local_vector_bc<true>(cs, nd, nd, l, A, idx, lines, a.rhs, lane, 32);
     __syncwarp();
   }
 }
 
-unsigned scalar_grid(dcp_ctx* ctx, long long n_cells) {
-  long long b = (n_cells + WARPS - 1) / WARPS;
-  long long cap = (long long)ctx->sm_count * 8;
-  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+struct ScalarLaunch {
+  int warps;
+  size_t smem;
+  unsigned grid;
+};
+ScalarLaunch scalar_launch(dcp_ctx* ctx, long long n_cells, int nd, int nd_nse) {
+  const ScalarLayout L = scalar_layout(nd, nd_nse);
+  ScalarLaunch s;
+  s.warps = nd <= 8 ? 4 : 2;
+  s.smem = (size_t)L.doubles * sizeof(double) * s.warps;
+  long long b = (n_cells + s.warps - 1) / s.warps;
+  long long cap = (long long)ctx->sm_count * 12;
+  s.grid = (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+  return s;
 }
 
 }  // namespace
@@ -220,12 +287,16 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
   a.dphi = m->dphi_t_qt;
   a.prm = p;
   if (m->n_cells == 0) return DCP_OK;
-  if (m->dim == 3)
-    temperature_matrix_kernel<3><<<scalar_grid(ctx, m->n_cells), 32 * WARPS, 0, ctx->stream>>>(
+  const ScalarLaunch s = scalar_launch(ctx, m->n_cells, a.nd, 0);
+  if (m->dim == 3) {
+    DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
+    temperature_matrix_kernel<3><<<s.grid, 32 * s.warps, s.smem, ctx->stream>>>(
         a, make_view(m->temp_cs), make_view(m->tmass), make_view(m->tstiff), ctx->d_err);
-  else
-    temperature_matrix_kernel<2><<<scalar_grid(ctx, m->n_cells), 32 * WARPS, 0, ctx->stream>>>(
+  } else {
+    DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
+    temperature_matrix_kernel<2><<<s.grid, 32 * s.warps, s.smem, ctx->stream>>>(
         a, make_view(m->temp_cs), make_view(m->tmass), make_view(m->tstiff), ctx->d_err);
+  }
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;
@@ -254,10 +325,14 @@ int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* 
   a.nse_solution = nse_solution;
   a.rhs = m->temp_rhs;
   if (m->n_cells == 0) return DCP_OK;
-  if (m->dim == 3)
-    temperature_rhs_kernel<3><<<scalar_grid(ctx, m->n_cells), 32 * WARPS, 0, ctx->stream>>>(a, make_view(m->temp_cs));
-  else
-    temperature_rhs_kernel<2><<<scalar_grid(ctx, m->n_cells), 32 * WARPS, 0, ctx->stream>>>(a, make_view(m->temp_cs));
+  const ScalarLaunch s = scalar_launch(ctx, m->n_cells, a.nd, a.nd_nse);
+  if (m->dim == 3) {
+    DCP_CUDA(cudaFuncSetAttribute(temperature_rhs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
+    temperature_rhs_kernel<3><<<s.grid, 32 * s.warps, s.smem, ctx->stream>>>(a, make_view(m->temp_cs));
+  } else {
+    DCP_CUDA(cudaFuncSetAttribute(temperature_rhs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
+    temperature_rhs_kernel<2><<<s.grid, 32 * s.warps, s.smem, ctx->stream>>>(a, make_view(m->temp_cs));
+  }
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;

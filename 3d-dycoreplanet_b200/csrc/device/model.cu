@@ -491,6 +491,17 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
   if (!feec) {
     M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
     M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
+    // row-owner tiles (DCP_STRATEGY_OWNER): optional -- a numbering that is not node-blocked keeps POSITIONS
+    if (dim == 3) {
+      rc = dcp_owner_plan_build(m, true, d);
+      if (rc == DCP_OK) rc = dcp_owner_plan_build(m, false, d);
+      if (rc == DCP_ERR_CUDA) return fail(rc);
+      if (rc != DCP_OK) {
+        dcp_owner_plan_free(m->owner_nse);
+        dcp_owner_plan_free(m->owner_pre);
+        m->owner_nse = m->owner_pre = nullptr;
+      }
+    }
   }
   DCP_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef M_TRY
@@ -500,8 +511,8 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
 
 int dcp_model_set_strategy(dcp_model* m, int strategy) {
   if (!m || strategy < DCP_STRATEGY_SEARCH || strategy > DCP_STRATEGY_OWNER) return DCP_ERR_ARG;
-  if (strategy == DCP_STRATEGY_OWNER) {
-    dcp_set_error("DCP_STRATEGY_OWNER is not built yet");
+  if (strategy == DCP_STRATEGY_OWNER && (!m->owner_nse || !m->owner_pre)) {
+    dcp_set_error("DCP_STRATEGY_OWNER is not available for this model (classic 3-D family with node-blocked numbering only)");
     return DCP_ERR_STATE;
   }
   m->strategy = strategy;
@@ -544,6 +555,11 @@ int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old
     DCP_TRY(dcp_launch_feec(m, *p, true, d_nse, d_temp));
     // Jacobi of Mw = block(0,0) and Mu = block(1,1) used by solve_NSE_block_preconditioned (:1283-1304)
     DCP_TRY(refresh_jacobi(ctx, m->nse));
+  } else if (m->strategy == DCP_STRATEGY_OWNER) {
+    // every CSR value written once by its owning tile; then rhs (all cells) and the constrained-dof fix-up
+    DCP_TRY(dcp_launch_th_owner(m, *p, true));
+    DCP_TRY(dcp_launch_th_rhs(m, *p, d_nse, d_temp));
+    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
   } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
     DCP_TRY(zero_blockmat(ctx, m->nse));
     DCP_TRY(dcp_launch_th_fast(m, *p, true, m->fast_nse, d_nse, d_temp));
@@ -565,6 +581,9 @@ int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
   if (m->family == DCP_FAMILY_FEEC) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_feec(m, *p, false, nullptr, nullptr));
+  } else if (m->strategy == DCP_STRATEGY_OWNER) {
+    DCP_TRY(dcp_launch_th_owner(m, *p, false));
+    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
   } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_th_fast(m, *p, false, m->fast_pre, nullptr, nullptr));

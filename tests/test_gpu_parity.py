@@ -31,7 +31,7 @@ def _params(spec):
 
 
 @pytest.mark.parametrize("spec", CASES, ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
-@pytest.mark.parametrize("strategy", [0, 1], ids=["search", "positions"])
+@pytest.mark.parametrize("strategy", [0, 1, 2], ids=["search", "positions", "owner"])
 def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy):
     from dycore_b200 import device
     from oracle import oracle as orc
