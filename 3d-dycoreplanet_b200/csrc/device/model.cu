@@ -492,7 +492,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
     M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
     // row-owner tiles (DCP_STRATEGY_OWNER): optional -- a numbering that is not node-blocked keeps POSITIONS
-    if (dim == 3) {
+    if (dim == 3 && d->build_owner_plan) {
       rc = dcp_owner_plan_build(m, true, d);
       if (rc == DCP_OK) rc = dcp_owner_plan_build(m, false, d);
       if (rc == DCP_ERR_CUDA) return fail(rc);
@@ -512,7 +512,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
 int dcp_model_set_strategy(dcp_model* m, int strategy) {
   if (!m || strategy < DCP_STRATEGY_SEARCH || strategy > DCP_STRATEGY_OWNER) return DCP_ERR_ARG;
   if (strategy == DCP_STRATEGY_OWNER && (!m->owner_nse || !m->owner_pre)) {
-    dcp_set_error("DCP_STRATEGY_OWNER is not available for this model (classic 3-D family with node-blocked numbering only)");
+    dcp_set_error("DCP_STRATEGY_OWNER is not available for this model (needs dcp_model_desc.build_owner_plan, classic 3-D family, node-blocked numbering)");
     return DCP_ERR_STATE;
   }
   m->strategy = strategy;

@@ -341,25 +341,31 @@ inline Csr make_sparsity_pattern(const DofMap& dm, const Constraints& cs, const 
     std::sort(out.begin(), out.end());
     out.erase(std::unique(out.begin(), out.end()), out.end());
   };
+  // one pass: every thread appends the rows it computes to its own arena, then the arenas are gathered
+  const int nthreads = omp_get_max_threads();
+  std::vector<std::vector<int32_t>> arena(nthreads);
+  std::vector<int64_t> row_off((size_t)dm.n_dofs);
+  std::vector<uint8_t> row_thr((size_t)dm.n_dofs);
 #pragma omp parallel
   {
+    const int t = omp_get_thread_num();
     std::vector<int32_t> tmp;
-#pragma omp for schedule(dynamic, 1024)
+    std::vector<int32_t>& mine = arena[t];
+#pragma omp for schedule(dynamic, 4096)
     for (int64_t g = 0; g < dm.n_dofs; ++g) {
       row_cols(g, tmp);
       A.rowptr[g + 1] = (int64_t)tmp.size();
+      row_off[g] = (int64_t)mine.size();
+      row_thr[g] = (uint8_t)t;
+      mine.insert(mine.end(), tmp.begin(), tmp.end());
     }
   }
   for (int64_t g = 0; g < dm.n_dofs; ++g) A.rowptr[g + 1] += A.rowptr[g];
   A.col.resize((size_t)A.rowptr.back());
-#pragma omp parallel
-  {
-    std::vector<int32_t> tmp;
-#pragma omp for schedule(dynamic, 1024)
-    for (int64_t g = 0; g < dm.n_dofs; ++g) {
-      row_cols(g, tmp);
-      std::memcpy(&A.col[(size_t)A.rowptr[g]], tmp.data(), tmp.size() * sizeof(int32_t));
-    }
+#pragma omp parallel for schedule(static)
+  for (int64_t g = 0; g < dm.n_dofs; ++g) {
+    const int64_t len = A.rowptr[g + 1] - A.rowptr[g];
+    if (len) std::memcpy(&A.col[(size_t)A.rowptr[g]], &arena[row_thr[g]][(size_t)row_off[g]], (size_t)len * sizeof(int32_t));
   }
   return A;
 }

@@ -53,7 +53,7 @@ class ModelDesc(ctypes.Structure):
         ("nse_l2g", c_ip), ("nse_local_field", c_ip), ("nse_local_base", c_ip), ("nse_cs", ConstraintsDesc),
         ("temp_n_local", ctypes.c_int32), ("pad0", ctypes.c_int32), ("temp_l2g", c_ip), ("temp_cs", ConstraintsDesc),
         ("nq_nse", ctypes.c_int32), ("nq_temp", ctypes.c_int32), ("ndu", ctypes.c_int32), ("ndp", ctypes.c_int32),
-        ("ndt", ctypes.c_int32), ("pad1", ctypes.c_int32),
+        ("ndt", ctypes.c_int32), ("build_owner_plan", ctypes.c_int32),
         ("phi_u_qn", c_dp), ("dphi_u_qn", c_dp), ("phi_p_qn", c_dp), ("phi_t_qn", c_dp),
         ("phi_u_qt", c_dp), ("phi_t_qt", c_dp), ("dphi_t_qt", c_dp),
         ("geom_qn", c_dp), ("geom_qt", c_dp),
@@ -283,10 +283,11 @@ def _cs_desc(P, prefix, keep):
     return d
 
 
-def model_desc_from_problem(P):
+def model_desc_from_problem(P, owner_plan=False):
     """Fill a dcp_model_desc from a harness Problem (the stand-in for deal.II's objects)."""
     keep = []
     d = ModelDesc()
+    d.build_owner_plan = 1 if owner_plan else 0
     feec = "feec" in P.spec.get("family", "classic")
     d.dim, d.family, d.n_cells = P.dim, (1 if feec else 0), P.n_cells
     d.nse_n_local = P.scalar("nse.n_local")
@@ -355,8 +356,8 @@ class BoussinesqModel:
         self.T_preconditioner = PreconditionJacobi(self, MAT_TEMP, 0)
 
     @classmethod
-    def from_problem(cls, ctx, P, parameters):
-        return cls(ctx, model_desc_from_problem(P), parameters)
+    def from_problem(cls, ctx, P, parameters, owner_plan=False):
+        return cls(ctx, model_desc_from_problem(P, owner_plan), parameters)
 
     def set_strategy(self, s):
         check(lib().dcp_model_set_strategy(self._h, s), "dcp_model_set_strategy")

@@ -207,8 +207,8 @@ def main():
     ctx = device.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    model = device.BoussinesqModel.from_problem(ctx, P, mp)
     strategy = "positions" if args.strategy == "auto" else args.strategy
+    model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == "owner"))
     model.set_strategy({"search": device.STRATEGY_SEARCH, "positions": device.STRATEGY_POSITIONS,
                         "owner": device.STRATEGY_OWNER}[strategy])
     halo_nse = halo_t = None

@@ -140,7 +140,8 @@ typedef struct {
    * *_qn on the NSE rule QGauss(deg+1) (boussinesq_model.tpp:487,708), *_qt on the temperature rule
    * QGauss(Tdeg+2) (:834,990). */
   int32_t nq_nse, nq_temp;
-  int32_t ndu, ndp, ndt, pad1;
+  int32_t ndu, ndp, ndt;
+  int32_t build_owner_plan; /* != 0: also build the row-owner tile plan (DCP_STRATEGY_OWNER) at create time */
   const double *phi_u_qn, *dphi_u_qn, *phi_p_qn, *phi_t_qn;
   const double *phi_u_qt, *phi_t_qt, *dphi_t_qt;
 

@@ -38,7 +38,7 @@ def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy):
     P = problem_factory(**spec)
     mp = _params(spec)
     u, T = synthetic_fields(P)
-    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == 2))
     model.set_strategy(strategy)
     oprm = orc.params_from(mp)
 
