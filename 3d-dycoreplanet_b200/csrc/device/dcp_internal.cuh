@@ -40,6 +40,8 @@ struct dcp_ctx {
   // staging buffers for DCP_HOST vectors
   double* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_cap[3] = {0, 0, 0};
+  double* dot_scratch = nullptr;  // partial sums of dcp_vec_dot
+  double* dot_host = nullptr;     // pinned result
 };
 
 // constraint lines on the device

@@ -239,6 +239,8 @@ int dcp_ctx_destroy(dcp_ctx* ctx) {
   for (int s = 0; s < 3; ++s) cudaFree(ctx->stage[s]);
   cudaFree(ctx->d_err);
   cudaFreeHost(ctx->h_err);
+  cudaFree(ctx->dot_scratch);
+  cudaFreeHost(ctx->dot_host);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return DCP_OK;

@@ -72,7 +72,8 @@ EXPORTS = [
     "dcp_model_destroy", "dcp_model_set_strategy", "dcp_model_set_owned", "dcp_gather_f64", "dcp_scatter_f64", "dcp_assemble_nse_system", "dcp_assemble_nse_preconditioner",
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
-    "dcp_vmult_add", "dcp_block_vmult", "dcp_jacobi_vmult",
+    "dcp_vmult_add", "dcp_block_vmult", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
+    "dcp_vec_scale", "dcp_vec_copy",
 ]
 
 
@@ -123,6 +124,11 @@ def lib():
         L.dcp_vmult_add.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_block_vmult.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_jacobi_vmult.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.dcp_vec_dot.argtypes = [vp, ctypes.c_int64, vp, vp, c_dp]
+        L.dcp_vec_axpy.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp, vp]
+        L.dcp_vec_sadd.argtypes = [vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, vp, vp]
+        L.dcp_vec_scale.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
+        L.dcp_vec_copy.argtypes = [vp, ctypes.c_int64, vp, vp]
         _LIB = L
     return _LIB
 

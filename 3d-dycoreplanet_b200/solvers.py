@@ -1,0 +1,322 @@
+"""Krylov solvers and operator compositions that CALL the hot path -- host-side mirror of
+
+  * deal.II SolverCG / SolverGMRES / SolverFGMRES as the reference uses them
+    (/root/reference/include/core/boussinesq_model.tpp:1165-1199 FGMRES(30) on nse_matrix, :1426-1440 CG on
+    temperature_matrix; include/linear_algebra/block_schur_preconditioner.hpp:46-51 inner GMRES),
+  * LinearAlgebra::SchurComplement (schur_complement.hpp:143-150) and
+    LinearAlgebra::BlockSchurPreconditioner::vmult (block_schur_preconditioner.hpp:41-70),
+  * Standard::BoussinesqModel::solve_NSE_block_preconditioned (:1131-1246, incl. the double pressure scaling,
+    quirk Q7) and solve_temperature (:1417-1447).
+
+The algorithms are written once against a tiny vector backend, so the same code drives
+  - `DeviceBackend`: vectors are torch CUDA tensors (device memory only), every operation is a libdcp kernel
+    (dcp_vec_dot / axpy / sadd / scale / copy, dcp_vmult, dcp_jacobi_vmult) -- vectors never leave HBM, only the
+    scalars of the dot products travel, like the reference's MPI_Allreduce;
+  - `NumpyBackend` (tests only): numpy vectors and scipy matrices built from the CPU oracle.
+deal.II's solver internals are un-vendored; what is restated (from memory, medium confidence):
+CG stops on ||r||_2 <= tol (absolute); GMRES = restarted, modified Gram-Schmidt + Givens, default 30 temporary
+vectors (restart length 28), left preconditioning, stops on the Givens residual estimate; FGMRES = flexible
+right-preconditioned GMRES with the given basis size, same stopping rule.  `SolverControl` semantics: the check
+happens before the first step (step 0) and after every step; `last_step` is returned.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+
+class NoConvergence(RuntimeError):
+    def __init__(self, last_step, last_residual):
+        super().__init__(f"no convergence after {last_step} steps, residual {last_residual:.3e}")
+        self.last_step, self.last_residual = last_step, last_residual
+
+
+# ---- backends -------------------------------------------------------------------------------------------
+class NumpyBackend:
+    """CPU vectors (tests only)."""
+
+    def zeros(self, n):
+        return np.zeros(n)
+
+    def copy(self, x):
+        return x.copy()
+
+    def assign(self, dst, src):
+        dst[...] = src
+
+    def dot(self, x, y):
+        return float(np.dot(x, y))
+
+    def axpy(self, a, x, y):
+        y += a * x
+
+    def sadd(self, s, a, x, y):
+        y *= s
+        y += a * x
+
+    def scale(self, a, y):
+        y *= a
+
+    def to_numpy(self, x):
+        return np.array(x)
+
+
+class DeviceBackend:
+    """Vectors in HBM (torch CUDA float64 tensors as plain device memory); all math through libdcp."""
+
+    def __init__(self, ctx):
+        import torch
+        from . import device
+        self.torch, self.dv, self.ctx = torch, device, ctx
+        self._res = ctypes.c_double()
+
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def zeros(self, n):
+        return self.torch.zeros(n, dtype=self.torch.float64, device="cuda")
+
+    def copy(self, x):
+        y = self.torch.empty_like(x)
+        self.assign(y, x)
+        return y
+
+    def assign(self, dst, src):
+        self.dv.check(self.dv.lib().dcp_vec_copy(self.ctx._h, dst.numel(), self._p(src), self._p(dst)), "dcp_vec_copy")
+
+    def dot(self, x, y):
+        self.dv.check(self.dv.lib().dcp_vec_dot(self.ctx._h, x.numel(), self._p(x), self._p(y), ctypes.byref(self._res)),
+                      "dcp_vec_dot")
+        return self._res.value
+
+    def axpy(self, a, x, y):
+        self.dv.check(self.dv.lib().dcp_vec_axpy(self.ctx._h, x.numel(), float(a), self._p(x), self._p(y)), "dcp_vec_axpy")
+
+    def sadd(self, s, a, x, y):
+        self.dv.check(self.dv.lib().dcp_vec_sadd(self.ctx._h, x.numel(), float(s), float(a), self._p(x), self._p(y)),
+                      "dcp_vec_sadd")
+
+    def scale(self, a, y):
+        self.dv.check(self.dv.lib().dcp_vec_scale(self.ctx._h, y.numel(), float(a), self._p(y)), "dcp_vec_scale")
+
+    def to_numpy(self, x):
+        self.ctx.synchronize()
+        return x.cpu().numpy()
+
+
+# ---- operators --------------------------------------------------------------------------------------------
+class Identity:
+    def vmult(self, dst, src, B):
+        B.assign(dst, src)
+
+
+class Wrap:
+    """Adapts any object with vmult(dst, src) (device SparseMatrix / PreconditionJacobi, or a callable)."""
+
+    def __init__(self, op):
+        self.op = op
+
+    def vmult(self, dst, src, B):
+        if callable(self.op):
+            self.op(dst, src)
+        else:
+            self.op.vmult(dst, src)
+
+
+# ---- deal.II solvers -----------------------------------------------------------------------------------------
+def solver_cg(B, A, x, b, P, tol, max_steps):
+    """SolverCG<Vector>::solve(A, x, b, P) with SolverControl(max_steps, tol).  Returns last_step."""
+    n = len(b) if hasattr(b, "__len__") else b.numel()
+    r, z, p, Ap = B.zeros(n), B.zeros(n), B.zeros(n), B.zeros(n)
+    A.vmult(r, x, B)
+    B.sadd(-1.0, 1.0, b, r)                      # r = b - A x
+    res = math.sqrt(B.dot(r, r))
+    if res <= tol:
+        return 0
+    P.vmult(z, r, B)
+    B.assign(p, z)
+    rz = B.dot(r, z)
+    for it in range(1, max_steps + 1):
+        A.vmult(Ap, p, B)
+        alpha = rz / B.dot(p, Ap)
+        B.axpy(alpha, p, x)
+        B.axpy(-alpha, Ap, r)
+        res = math.sqrt(B.dot(r, r))
+        if res <= tol:
+            return it
+        P.vmult(z, r, B)
+        rz_new = B.dot(r, z)
+        B.sadd(rz_new / rz, 1.0, z, p)            # p = z + beta p
+        rz = rz_new
+    raise NoConvergence(max_steps, res)
+
+
+def _givens(h, cs, sn, gamma, col):
+    """Apply the stored rotations to column `col` of the Hessenberg matrix and create the new one."""
+    for i in range(col):
+        t = cs[i] * h[i] + sn[i] * h[i + 1]
+        h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1]
+        h[i] = t
+    s = math.hypot(h[col], h[col + 1])
+    cs[col], sn[col] = h[col] / s, h[col + 1] / s
+    h[col] = s
+    h[col + 1] = 0.0
+    gamma[col + 1] = -sn[col] * gamma[col]
+    gamma[col] = cs[col] * gamma[col]
+
+
+def _solve_upper(H, gamma, k):
+    y = np.zeros(k)
+    for i in range(k - 1, -1, -1):
+        y[i] = (gamma[i] - sum(H[i][j] * y[j] for j in range(i + 1, k))) / H[i][i]
+    return y
+
+
+def solver_gmres(B, A, x, b, P, tol, max_steps, restart=28, flexible=False):
+    """SolverGMRES (left preconditioned, restart = max_n_tmp_vectors - 2) or, with flexible=True,
+    SolverFGMRES(max_basis_size = restart) (right preconditioned, stores the preconditioned basis)."""
+    n = b.numel() if hasattr(b, "numel") else len(b)
+    V = [B.zeros(n) for _ in range(restart + 1)]
+    Z = [B.zeros(n) for _ in range(restart)] if flexible else None
+    w, t = B.zeros(n), B.zeros(n)
+    steps = 0
+    while True:
+        A.vmult(t, x, B)
+        B.sadd(-1.0, 1.0, b, t)                  # t = b - A x
+        if flexible:
+            B.assign(V[0], t)
+        else:
+            P.vmult(V[0], t, B)                  # left preconditioning: residual of P^-1 A x = P^-1 b
+        beta = math.sqrt(B.dot(V[0], V[0]))
+        if beta <= tol:
+            return steps
+        if steps >= max_steps:
+            raise NoConvergence(steps, beta)
+        B.scale(1.0 / beta, V[0])
+        H = [[0.0] * restart for _ in range(restart + 1)]
+        cs, sn = [0.0] * restart, [0.0] * restart
+        gamma = [0.0] * (restart + 1)
+        gamma[0] = beta
+        k_done = 0
+        converged = False
+        for k in range(restart):
+            if flexible:
+                P.vmult(Z[k], V[k], B)
+                A.vmult(w, Z[k], B)
+            else:
+                A.vmult(t, V[k], B)
+                P.vmult(w, t, B)
+            h = [0.0] * (k + 2)
+            for i in range(k + 1):               # modified Gram-Schmidt
+                h[i] = B.dot(w, V[i])
+                B.axpy(-h[i], V[i], w)
+            h[k + 1] = math.sqrt(B.dot(w, w))
+            if h[k + 1] != 0.0:
+                B.assign(V[k + 1], w)
+                B.scale(1.0 / h[k + 1], V[k + 1])
+            _givens(h, cs, sn, gamma, k)
+            for i in range(k + 2):
+                H[i][k] = h[i]
+            steps += 1
+            k_done = k + 1
+            res = abs(gamma[k + 1])
+            if res <= tol:
+                converged = True
+                break
+            if steps >= max_steps:
+                break
+        y = _solve_upper(H, gamma, k_done)
+        basis = Z if flexible else V
+        for i in range(k_done):
+            B.axpy(float(y[i]), basis[i], x)
+        if converged:
+            return steps
+        if steps >= max_steps:
+            raise NoConvergence(steps, abs(gamma[k_done]))
+
+
+# ---- LinearAlgebra::* compositions of the classic block solve ---------------------------------------------------
+class SchurComplement:
+    """B * inverse * B^T on the pressure space (schur_complement.hpp:143-150)."""
+
+    def __init__(self, block_01, block_10, inverse, n_u, B):
+        self.b01, self.b10, self.inv = block_01, block_10, inverse
+        self.tmp1, self.tmp2 = B.zeros(n_u), B.zeros(n_u)
+
+    def vmult(self, dst, src, B):
+        self.b01.vmult(self.tmp1, src, B)
+        self.inv.vmult(self.tmp2, self.tmp1, B)
+        self.b10.vmult(dst, self.tmp2, B)
+
+
+class BlockSchurPreconditioner:
+    """block_schur_preconditioner.hpp:17-86 with do_solve_A = false: note that the Schur complement is built with
+    the A-preconditioner as its "inverse" (:32-35) and mp_preconditioner is never applied."""
+
+    def __init__(self, blocks, a_preconditioner, n_u, n_p, B):
+        self.blocks, self.a_prec, self.n_u, self.n_p = blocks, a_preconditioner, n_u, n_p
+        self.schur = SchurComplement(blocks[(0, 1)], blocks[(1, 0)], a_preconditioner, n_u, B)
+        self.utmp = B.zeros(n_u)
+        self.inner_iterations = []
+
+    def vmult(self, dst, src, B):
+        n_u = self.n_u
+        du, dp = dst[:n_u], dst[n_u:]
+        su, sp = src[:n_u], src[n_u:]
+        B.scale(0.0, dp)                       # deal.II hands a fresh (zero) dst to the preconditioner
+        tol = 1e-6 * math.sqrt(B.dot(sp, sp))
+        its = solver_gmres(B, self.schur, dp, sp, Identity(), tol, 5000)     # :46-51
+        self.inner_iterations.append(its)
+        B.scale(-1.0, dp)
+        self.blocks[(0, 1)].vmult(self.utmp, dp, B)                          # :55-57
+        B.sadd(-1.0, 1.0, su, self.utmp)
+        self.a_prec.vmult(du, self.utmp, B)                                  # :69
+
+
+class BlockOperator:
+    """LA::BlockSparseMatrix::vmult from its blocks (used with the numpy backend; the device has dcp_block_vmult)."""
+
+    def __init__(self, blocks, n_u, B):
+        self.blocks, self.n_u = blocks, n_u
+        self.tmp = None
+
+    def vmult(self, dst, src, B):
+        n_u = self.n_u
+        self.blocks[(0, 0)].vmult(dst[:n_u], src[:n_u], B)
+        if self.tmp is None:
+            self.tmp = B.zeros(n_u)
+        self.blocks[(0, 1)].vmult(self.tmp, src[n_u:], B)
+        B.axpy(1.0, self.tmp, dst[:n_u])
+        self.blocks[(1, 0)].vmult(dst[n_u:], src[:n_u], B)
+
+
+def distribute(B, cs_lines, x_np):
+    """AffineConstraints::distribute on a host copy: x[line] = sum w x[master] + inhom."""
+    line_dof, line_ptr, entry_dof, entry_w, inhom = cs_lines
+    for l, g in enumerate(line_dof):
+        sl = slice(line_ptr[l], line_ptr[l + 1])
+        x_np[g] = float(np.dot(entry_w[sl], x_np[entry_dof[sl]])) + inhom[l]
+    return x_np
+
+
+def solve_nse_block_preconditioned(B, nse_matrix, blocks, a_preconditioner, nse_rhs, nse_solution, n_u, n_p, dt,
+                                   constrained_pressure_mask=None):
+    """boussinesq_model.tpp:1131-1246 up to (not including) constraints.distribute.  Returns
+    (solution vector with the SCALED pressure, outer iterations, inner iteration list)."""
+    x = B.copy(nse_solution)
+    B.scale(dt, x[n_u:])                                  # :1151
+    # zero constrained pressure dofs (:1160-1162) -- there are none in the named configs
+    tol = 1e-8 * math.sqrt(B.dot(nse_rhs, nse_rhs))       # :1165
+    B.scale(dt, x[n_u:])                                  # :1177 (quirk Q7: scaled twice)
+    P = BlockSchurPreconditioner(blocks, a_preconditioner, n_u, n_p, B)
+    its = solver_gmres(B, nse_matrix, x, nse_rhs, P, tol, 40, restart=30, flexible=True)   # :1191-1199
+    return x, its, P.inner_iterations
+
+
+def solve_temperature(B, temperature_matrix, t_preconditioner, temperature_rhs, temperature_solution):
+    """boussinesq_model.tpp:1417-1440.  Returns (solution, CG iterations)."""
+    x = B.copy(temperature_solution)
+    n = x.numel() if hasattr(x, "numel") else len(x)
+    tol = 1e-12 * math.sqrt(B.dot(temperature_rhs, temperature_rhs))
+    its = solver_cg(B, temperature_matrix, x, temperature_rhs, t_preconditioner, tol, n)
+    return x, its

@@ -142,7 +142,19 @@ def cpu_leg(refine, temperature_degree, steps, warmup, mp):
             "spmv_gbs": (ab["spmv_nse"] + ab["spmv_temperature"]) / float(np.mean(t_spmv)) / 1e9}, n_dofs, dt
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -177,7 +189,7 @@ def main():
                            "note": "bounded sample: " + base["sample"]},
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -364,7 +376,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             base, _, _ = cpu_leg(args.cpu_refine, args.temperature_degree, 1, 1, mp)
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        emit(line)
     model.close()
     ctx.close()
     if world > 1:

@@ -230,6 +230,16 @@ int dcp_block_vmult(dcp_model* m, int which, double* dst, const double* src, int
 /* dst = diag(A(bi,bi))^-1 * src  (Jacobi, one sweep, omega 1).  Diagonals are refreshed by the assemble calls. */
 int dcp_jacobi_vmult(dcp_model* m, int which, int bi, double* dst, const double* src, int mem);
 
+/* ---- device-resident vector algebra for the Krylov solvers around the SpMVs (all pointers DEVICE) -----------
+ * Trilinos vector ops inside deal.II SolverCG / SolverGMRES / SolverFGMRES (boussinesq_model.tpp:1165,1191-1199,
+ * 1426-1440; inverse_matrix.hpp:99-113): operator* / l2_norm (dot, bit-reproducible two-stage tree; the scalar
+ * is returned to the host like the reference's MPI_Allreduce), add (axpy), sadd (y = s*y + a*x), scale, equ. */
+int dcp_vec_dot(dcp_ctx* ctx, int64_t n, const double* x_dev, const double* y_dev, double* result_host);
+int dcp_vec_axpy(dcp_ctx* ctx, int64_t n, double a, const double* x_dev, double* y_dev);
+int dcp_vec_sadd(dcp_ctx* ctx, int64_t n, double s, double a, const double* x_dev, double* y_dev);
+int dcp_vec_scale(dcp_ctx* ctx, int64_t n, double a, double* y_dev);
+int dcp_vec_copy(dcp_ctx* ctx, int64_t n, const double* x_dev, double* y_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,98 @@
+"""Helpers for the solver-level parity tests: one Boussinesq time step on either backend."""
+import math
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def initial_temperature(P, mp):
+    """TemperatureInitialValues<3> (boussinesq_model_data.tpp:92-147) interpolated at the temperature support points
+    (the reference projects it, boussinesq_model.tpp:1802-1829; the input vector is the same for both backends)."""
+    dim = P.dim
+    x = P["temp.dof_xyz"].reshape(-1, dim)
+    R0, R1 = mp.R0_scaled, mp.R1_scaled
+    cov = 20.0 / ((R1 - R0) / 2.0)
+    c1 = np.zeros(dim)
+    c2 = np.zeros(dim)
+    c1[0] = R0 + (R1 - R0) * 0.35
+    c2[1] = R0 + (R1 - R0) * 0.65
+    nrm = math.sqrt((2 * math.pi) ** dim)
+    det = cov ** dim
+    q1 = cov * ((x - c1) ** 2).sum(axis=1)
+    q2 = cov * ((x - c2) ** 2).sum(axis=1)
+    return np.ascontiguousarray(math.sqrt(det) * (np.exp(-0.5 * q1) + np.exp(-0.5 * q2)) / nrm)
+
+
+def cs_lines(P, prefix):
+    return (P[prefix + ".line_dof"], P[prefix + ".line_ptr"], P[prefix + ".entry_dof"], P[prefix + ".entry_w"],
+            P[prefix + ".inhom"])
+
+
+def cpu_time_step(P, mp, u0, T0):
+    """Reference-order time step (boussinesq_model.tpp:1867-1905) on the CPU: oracle assembly + numpy solvers."""
+    from dycore_b200 import solvers as S
+    from oracle import oracle as orc
+    prm = orc.params_from(mp)
+    B = S.NumpyBackend()
+    n, nT = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
+    n_u, n_p = P.scalar("nse.n_u"), P.scalar("nse.n_p")
+    vals, rhs = orc.assemble_nse_system(P, prm, u0, T0)
+    pv = orc.assemble_nse_preconditioner(P, prm)
+    m, k = orc.assemble_temperature_matrix(P, prm)
+    tm = orc.temperature_matrix_combine(m, k, mp.time_step / mp.NSE_solver_interval)
+    trhs = orc.assemble_temperature_rhs(P, prm, T0, u0)
+    rp, col, _, _ = P.csr("nse.full")
+    A = sp.csr_matrix((vals, col, rp), shape=(n, n))
+    rp, col, _, _ = P.csr("pre.full")
+    Pm = sp.csr_matrix((pv, col, rp), shape=(n, n))
+    rp, col, _, _ = P.csr("temp.pat")
+    Tm = sp.csr_matrix((tm, col, rp), shape=(nT, nT))
+
+    def mat(M):
+        return S.Wrap(lambda dst, src, M=M: dst.__setitem__(slice(None), M @ src))
+
+    def jac(M):
+        d = M.diagonal()
+        dinv = np.where(d != 0.0, 1.0 / np.where(d != 0.0, d, 1.0), 0.0)
+        return S.Wrap(lambda dst, src, dinv=dinv: dst.__setitem__(slice(None), dinv * src))
+    blocks = {(0, 0): mat(A[:n_u, :n_u]), (0, 1): mat(A[:n_u, n_u:]), (1, 0): mat(A[n_u:, :n_u])}
+    x, its, inner = S.solve_nse_block_preconditioned(B, mat(A), blocks, jac(Pm[:n_u, :n_u]), rhs, u0, n_u, n_p, mp.time_step)
+    x = S.distribute(B, cs_lines(P, "nse.cs"), x)
+    x[n_u:] /= mp.time_step
+    t, cg = S.solve_temperature(B, mat(Tm), jac(Tm), trhs, T0)
+    t = S.distribute(B, cs_lines(P, "temp.cs"), t)
+    return dict(nse=x, temp=t, fgmres=its, inner=inner, cg=cg)
+
+
+def gpu_time_step(ctx, P, mp, u0, T0):
+    """The same step with every operator on the device; vectors stay in HBM until the final download."""
+    import torch
+    from dycore_b200 import device
+    from dycore_b200 import solvers as S
+    B = S.DeviceBackend(ctx)
+    n_u, n_p = P.scalar("nse.n_u"), P.scalar("nse.n_p")
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    d_u, d_T = torch.from_numpy(u0).cuda(), torch.from_numpy(T0).cuda()
+    torch.cuda.synchronize()
+    model.assemble_nse_system(d_u, d_T)
+    model.build_nse_preconditioner()
+    model.assemble_temperature_matrix()
+    model.assemble_temperature_rhs(d_T, d_u)
+    ptr, nn = __import__("ctypes").c_void_p(), __import__("ctypes").c_int64()
+
+    def dev_vec(which, n):
+        device.check(device.lib().dcp_vector_device(model._h, which, __import__("ctypes").byref(ptr), __import__("ctypes").byref(nn)))
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        device.check(device.lib().dcp_vec_copy(ctx._h, n, ptr, __import__("ctypes").c_void_p(out.data_ptr())))
+        return out
+    rhs = dev_vec(device.VEC_NSE_RHS, n_u + n_p)
+    trhs = dev_vec(device.VEC_TEMP_RHS, P.scalar("temp.n_dofs"))
+    blocks = {(i, j): S.Wrap(model.nse_matrix.block(i, j)) for (i, j) in ((0, 0), (0, 1), (1, 0))}
+    x, its, inner = S.solve_nse_block_preconditioned(B, S.Wrap(model.nse_matrix), blocks, S.Wrap(model.Mu_plus_A_preconditioner),
+                                                     rhs, d_u, n_u, n_p, mp.time_step)
+    xh = S.distribute(B, cs_lines(P, "nse.cs"), B.to_numpy(x))
+    xh[n_u:] /= mp.time_step
+    t, cg = S.solve_temperature(B, S.Wrap(model.temperature_matrix), S.Wrap(model.T_preconditioner), trhs, d_T)
+    th = S.distribute(B, cs_lines(P, "temp.cs"), B.to_numpy(t))
+    model.close()
+    return dict(nse=xh, temp=th, fgmres=its, inner=inner, cg=cg)
