@@ -1,0 +1,34 @@
+"""Solver-level parity (north_star: Krylov iteration counts within +-1, fields after one time step within 1e-8):
+one time step of the named shell-classic config (boussinesq_model.tpp:1867-1905: assemble_nse_system,
+build_nse_preconditioner, assemble_temperature_matrix/_rhs, solve_NSE_block_preconditioned, solve_temperature)
+with every operator on the device and the Krylov vectors resident in HBM, against the same step on the CPU
+(oracle assembly + the same restated deal.II solvers on numpy vectors)."""
+import numpy as np
+import pytest
+
+import krylov_util as K
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("refine", [1, 2])
+def test_one_time_step_matches_cpu(problem_factory, refine):
+    from dycore_b200 import device, params
+    mp = params.NAMED["shell_3d_classic"]
+    P = problem_factory(geometry="shell", refine=refine)
+    u0 = np.zeros(P.scalar("nse.n_dofs"))
+    T0 = K.initial_temperature(P, mp)
+    ref = K.cpu_time_step(P, mp, u0, T0)
+    ctx = device.Context(0)
+    got = K.gpu_time_step(ctx, P, mp, u0, T0)
+    ctx.close()
+    assert abs(got["fgmres"] - ref["fgmres"]) <= 1, (got["fgmres"], ref["fgmres"])
+    assert abs(got["cg"] - ref["cg"]) <= 1, (got["cg"], ref["cg"])
+    assert abs(len(got["inner"]) - len(ref["inner"])) <= 1
+    for a, b in zip(got["inner"], ref["inner"]):
+        assert abs(a - b) <= 1, (got["inner"], ref["inner"])
+    n_u = P.scalar("nse.n_u")
+    for name, g, r in (("velocity", got["nse"][:n_u], ref["nse"][:n_u]), ("pressure", got["nse"][n_u:], ref["nse"][n_u:]),
+                       ("temperature", got["temp"], ref["temp"])):
+        err = np.abs(g - r).max() / np.abs(r).max()
+        assert err <= 1e-8, (name, err)
