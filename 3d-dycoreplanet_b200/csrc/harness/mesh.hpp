@@ -359,6 +359,97 @@ struct CubeMesh3D : Mesh {
   }
 };
 
+// ---- 2-D annulus: GridGenerator::hyper_shell<2>(tria, 0, R0, R1, 12, colorize=true) + refine_global(r) -------
+// (planet_geometry.tpp:63-68 with dim == 2).  On the polar manifold every refinement halves angle and radius
+// increments, so the refined mesh is the uniform polar grid: position(a, k) = r_k (cos th_a, sin th_a).
+// Orientation chosen here (deal.II's vertex lists are not reproducible): local x = radial (outward), local
+// y = counter-clockwise, which is right-handed.  Boundary ids: inner 0 (face 0), outer 1 (face 1).
+inline uint32_t morton2(uint32_t i, uint32_t j) {
+  auto spread = [](uint32_t v) {
+    v &= 0xffff;
+    v = (v | (v << 8)) & 0x00ff00ff;
+    v = (v | (v << 4)) & 0x0f0f0f0f;
+    v = (v | (v << 2)) & 0x33333333;
+    v = (v | (v << 1)) & 0x55555555;
+    return v;
+  };
+  return spread(i) | (spread(j) << 1);
+}
+inline void demorton2(uint32_t m, uint32_t& i, uint32_t& j) {
+  auto compact = [](uint32_t v) {
+    v &= 0x55555555;
+    v = (v | (v >> 1)) & 0x33333333;
+    v = (v | (v >> 2)) & 0x0f0f0f0f;
+    v = (v | (v >> 4)) & 0x00ff00ff;
+    v = (v | (v >> 8)) & 0x0000ffff;
+    return v;
+  };
+  i = compact(m);
+  j = compact(m >> 1);
+}
+
+struct AnnulusMesh2D : Mesh {
+  int r, n, Mr, Ma;  // n = 2^r cells per coarse cell edge; radial / angular half-step lattice sizes
+  double R0, R1;
+  AnnulusMesh2D(int refinements, double r0, double r1) : r(refinements), R0(r0), R1(r1) {
+    dim = 2;
+    n = 1 << r;
+    Mr = 2 * n;
+    Ma = 2 * 12 * n;
+    n_cells = 12LL * n * n;
+    n_nodes = (int64_t)(Mr + 1) * Ma;
+  }
+  // cell = (tree t in 0..11, i radial, j angular within the tree), Morton inside the tree
+  inline void decode(int64_t c, int& t, int& i, int& j) const {
+    int64_t per = (int64_t)n * n;
+    t = (int)(c / per);
+    uint32_t ii, jj;
+    demorton2((uint32_t)(c % per), ii, jj);
+    i = (int)ii;
+    j = (int)jj;
+  }
+  inline double radius(int k) const { return R0 + (R1 - R0) * ((double)k / (double)Mr); }
+  inline double angle(int a) const { return 2.0 * M_PI * ((double)a / (double)Ma); }
+  void cell_nodes(int64_t c, int64_t* ids) const override {
+    int t, i, j;
+    decode(c, t, i, j);
+    for (int oy = 0; oy < 3; ++oy)
+      for (int ox = 0; ox < 3; ++ox) {
+        int k = 2 * i + ox, a = (2 * (t * n + j) + oy) % Ma;
+        ids[ox + 3 * oy] = (int64_t)k * Ma + a;
+      }
+  }
+  void cell_vertices(int64_t c, double* X) const override {
+    int t, i, j;
+    decode(c, t, i, j);
+    for (int v = 0; v < 4; ++v) {
+      int k = 2 * (i + (v & 1)), a = 2 * (t * n + j + ((v >> 1) & 1));
+      X[2 * v + 0] = radius(k) * std::cos(angle(a));
+      X[2 * v + 1] = radius(k) * std::sin(angle(a));
+    }
+  }
+  int face_boundary_id(int64_t c, int f) const override {
+    int t, i, j;
+    decode(c, t, i, j);
+    if (f == 0 && i == 0) return 0;
+    if (f == 1 && i == n - 1) return 1;
+    return -1;
+  }
+  bool at_boundary(int64_t c) const override {
+    int t, i, j;
+    decode(c, t, i, j);
+    return i == 0 || i == n - 1;
+  }
+  void manifold_point(int64_t c, const double* xi, double* x) const override {
+    int t, i, j;
+    decode(c, t, i, j);
+    double rr = (1.0 - xi[0]) * radius(2 * i) + xi[0] * radius(2 * i + 2);
+    double th = (1.0 - xi[1]) * angle(2 * (t * n + j)) + xi[1] * angle(2 * (t * n + j + 1));
+    x[0] = rr * std::cos(th);
+    x[1] = rr * std::sin(th);
+  }
+};
+
 // ---- a subset of the cells of a base mesh (one rank's owned + ghost cells) -------------------------------
 struct SubMesh : Mesh {
   const Mesh& base;

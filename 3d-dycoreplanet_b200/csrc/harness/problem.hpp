@@ -630,13 +630,16 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   if (sp.threads > 0) omp_set_num_threads(sp.threads);
   auto P = std::make_unique<Problem>();
   P->spec = sp;
-  if (sp.dim != 3) throw std::runtime_error("harness: only dim=3 is implemented");
+  if (sp.dim != 3 && !(sp.dim == 2 && sp.geometry == "annulus" && sp.family == "classic"))
+    throw std::runtime_error("harness: dim=2 is implemented for geometry=annulus, family=classic only");
   if (sp.family != "classic" && sp.family != "feec") throw std::runtime_error("harness: unknown family " + sp.family);
   const int dim = sp.dim;
   if (sp.geometry == "shell")
     P->mesh = std::make_unique<ShellMesh3D>(sp.refine, sp.R0, sp.R1, sp.radial_factor);
   else if (sp.geometry == "cube")
     P->mesh = std::make_unique<CubeMesh3D>(sp.refine, true);
+  else if (sp.geometry == "annulus")
+    P->mesh = std::make_unique<AnnulusMesh2D>(sp.refine, sp.R0, sp.R1);
   else
     throw std::runtime_error("harness: unknown geometry " + sp.geometry);
   P->n_owned_cells = P->mesh->n_cells;

@@ -21,6 +21,8 @@ CASES = {
     "shell_r2_classic": dict(spec=dict(geometry="shell", refine=2), params="shell_3d_classic"),
     "cube_r2_classic": dict(spec=dict(geometry="cube", refine=2), params="cube_3d"),
     "shell_r1_classic_Tq2": dict(spec=dict(geometry="shell", refine=1, temperature_degree=2), params="shell_3d_classic"),
+    "annulus_r3_classic_2d": dict(spec=dict(geometry="annulus", dim=2, refine=3, R0=10.0, R1=30.0, temperature_degree=2),
+                                  params="annulus_2d"),
     "shell_r2_feec": dict(spec=dict(geometry="shell", refine=2, family="feec"), params="shell_3d_feec"),
     "cube_r2_feec": dict(spec=dict(geometry="cube", refine=2, family="feec"), params="cube_3d"),
 }

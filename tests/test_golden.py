@@ -13,6 +13,7 @@ CASES = {
     "shell_r2_classic": (dict(geometry="shell", refine=2), "shell_3d_classic"),
     "cube_r2_classic": (dict(geometry="cube", refine=2), "cube_3d"),
     "shell_r1_classic_Tq2": (dict(geometry="shell", refine=1, temperature_degree=2), "shell_3d_classic"),
+    "annulus_r3_classic_2d": (dict(geometry="annulus", dim=2, refine=3, R0=10.0, R1=30.0, temperature_degree=2), "annulus_2d"),
 }
 
 
