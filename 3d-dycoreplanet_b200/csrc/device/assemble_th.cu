@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(256) th_cell_kernel(ThArgs a, CsView cs, Block
   }
   __syncthreads();
   const double nu = a.prm.dt * a.prm.inv_re;
-  const long long n_work = a.cell_list ? a.n_list : a.n_cells;
+  const long long n_work = a.n_list >= 0 ? a.n_list : a.n_cells;  // n_list < 0: every cell
 
   for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
-    const long long cell = a.cell_list ? a.cell_list[w] : w;
+    const long long cell = a.n_list >= 0 ? a.cell_list[w] : w;
     const double* g = a.geom + cell * GS;
     for (int i = tid; i < GS; i += nt) sgeo[i] = g[i];
     for (int i = tid; i < ND; i += nt) {
@@ -283,7 +283,7 @@ int launch_th(dcp_model* m, const ThArgs& args, const BlockMat& mat) {
     DCP_CUDA(cudaFuncSetAttribute(th_cell_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[DIM] = true;
   }
-  const long long n_work = args.cell_list ? args.n_list : args.n_cells;
+  const long long n_work = args.n_list >= 0 ? args.n_list : args.n_cells;
   if (n_work == 0) return DCP_OK;
   int per_sm = 1;
   DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, th_cell_kernel<DIM>, 256, smem));
@@ -331,7 +331,7 @@ int dcp_launch_th_rhs(dcp_model* m, const dcp_params& p, const double* old_nse, 
   ThArgs a;
   a.n_cells = m->n_cells;
   a.cell_list = nullptr;
-  a.n_list = 0;
+  a.n_list = -1;
   a.geom = m->geom_qn;
   a.l2g = m->nse_l2g;
   a.l2g_t = m->temp_l2g;

@@ -15,14 +15,6 @@
 
 #include "scatter.cuh"
 
-struct FastPlan {
-  int64_t n_fast = 0, n_general = 0;
-  int32_t* fast_cells = nullptr;
-  int32_t* general_cells = nullptr;
-  uint16_t* pos = nullptr;  // [n_fast][NE*NE], NE = NU + NP
-  int ne = 0;
-};
-
 namespace {
 
 using namespace dcpdev;

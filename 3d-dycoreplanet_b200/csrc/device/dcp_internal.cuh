@@ -103,7 +103,25 @@ inline BlockView make_view(const BlockMat& M) {
 inline CsView make_view(const DevCs& c) { return CsView{c.line_of_dof, c.line_ptr, c.entry_dof, c.entry_w, c.inhom}; }
 
 struct OwnerPlan;  // row-owner tiles (assemble_th_owner.cu)
-struct FastPlan;   // position tables (assemble_th_fast.cu)
+// position tables of the cells without constrained dofs (built in assemble_th_fast.cu)
+struct FastPlan {
+  int64_t n_fast = 0, n_general = 0;
+  int32_t* fast_cells = nullptr;
+  int32_t* general_cells = nullptr;
+  uint16_t* pos = nullptr;  // [n_fast][NE*NE], NE = NU + NP
+  int ne = 0;
+};
+
+// masked position tables for the DMMA path (assemble_th_mma.cu): every node-blocked cell, constrained or not
+struct MaskedPlan {
+  int64_t n = 0, n_other = 0, n_wide = 0;
+  int32_t* cells = nullptr;
+  int32_t* other_cells = nullptr;  // cells that failed the layout check: general kernel, full mode
+  uint16_t* pos = nullptr;         // [n][35*35]
+  uint8_t* nmask = nullptr;        // [n][36]
+  int32_t* wide_idx = nullptr;     // [n] preconditioner: -1 or row of pos_wide
+  uint16_t* pos_wide = nullptr;    // [n_wide][3][27][27]
+};
 
 struct dcp_model {
   dcp_ctx* ctx = nullptr;
@@ -141,6 +159,8 @@ struct dcp_model {
   OwnerPlan* owner_pre = nullptr;
   FastPlan* fast_nse = nullptr;
   FastPlan* fast_pre = nullptr;
+  MaskedPlan* masked_nse = nullptr;
+  MaskedPlan* masked_pre = nullptr;
 };
 
 // ---- helpers implemented in context.cu -----------------------------------------------------------
@@ -171,6 +191,10 @@ int64_t dcp_fast_plan_counts(const FastPlan* p, int64_t* n_general);
 const int32_t* dcp_fast_plan_general_cells(const FastPlan* p);
 int dcp_launch_th_fast(dcp_model* m, const dcp_params& p, bool system, const FastPlan* plan, const double* old_nse,
                        const double* old_temp);
+int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, MaskedPlan** out);
+void dcp_masked_plan_free(MaskedPlan* p);
+int dcp_launch_th_mma(dcp_model* m, const dcp_params& p, bool system, const MaskedPlan* plan, const double* old_nse,
+                      const double* old_temp);
 int dcp_owner_plan_build(dcp_model* m, bool system, const dcp_model_desc* desc);
 void dcp_owner_plan_free(OwnerPlan* p);
 int dcp_launch_th_owner(dcp_model* m, const dcp_params& p, bool system);

@@ -334,6 +334,8 @@ int dcp_model_destroy(dcp_model* m) {
   dcp_owner_plan_free(m->owner_pre);
   dcp_fast_plan_free(m->fast_nse);
   dcp_fast_plan_free(m->fast_pre);
+  dcp_masked_plan_free(m->masked_nse);
+  dcp_masked_plan_free(m->masked_pre);
   delete m;
   return DCP_OK;
 }
@@ -491,8 +493,13 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
   }
   // position tables for the unconstrained cells (DCP_STRATEGY_POSITIONS; classic family)
   if (!feec) {
-    M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
-    M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
+    if (dim == 3) {
+      M_TRY(dcp_masked_plan_build(m, d, true, &m->masked_nse));
+      M_TRY(dcp_masked_plan_build(m, d, false, &m->masked_pre));
+    } else {
+      M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
+      M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
+    }
     // row-owner tiles (DCP_STRATEGY_OWNER): optional -- a numbering that is not node-blocked keeps POSITIONS
     if (dim == 3 && d->build_owner_plan) {
       rc = dcp_owner_plan_build(m, true, d);
@@ -564,13 +571,21 @@ int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old
     DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
   } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
     DCP_TRY(zero_blockmat(ctx, m->nse));
-    DCP_TRY(dcp_launch_th_fast(m, *p, true, m->fast_nse, d_nse, d_temp));
-    int64_t ng = 0;
-    dcp_fast_plan_counts(m->fast_nse, &ng);
-    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, dcp_fast_plan_general_cells(m->fast_nse), ng, false));
+    if (m->dim == 3) {
+      // every cell of the plan on the tensor cores, Dirichlet / no-normal-flux lines resolved in the epilogue; cells
+      // with other constraint kinds (periodic, inhomogeneous, ...) or an unverified layout take the general kernel
+      DCP_TRY(dcp_launch_th_mma(m, *p, true, m->masked_nse, d_nse, d_temp));
+      if (m->masked_nse->n_other > 0)
+        DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, m->masked_nse->other_cells, m->masked_nse->n_other, false));
+    } else {
+      DCP_TRY(dcp_launch_th_fast(m, *p, true, m->fast_nse, d_nse, d_temp));
+      int64_t ng = 0;
+      dcp_fast_plan_counts(m->fast_nse, &ng);
+      if (ng > 0) DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, dcp_fast_plan_general_cells(m->fast_nse), ng, false));
+    }
   } else {
     DCP_TRY(zero_blockmat(ctx, m->nse));
-    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, nullptr, 0, false));
+    DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, nullptr, -1, false));
   }
   if (mem == DCP_HOST) DCP_TRY(dcp_check_device_errors(ctx, "dcp_assemble_nse_system"));
   return DCP_OK;
@@ -588,13 +603,19 @@ int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
     DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
   } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
-    DCP_TRY(dcp_launch_th_fast(m, *p, false, m->fast_pre, nullptr, nullptr));
-    int64_t ng = 0;
-    dcp_fast_plan_counts(m->fast_pre, &ng);
-    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, dcp_fast_plan_general_cells(m->fast_pre), ng, false));
+    if (m->dim == 3) {
+      DCP_TRY(dcp_launch_th_mma(m, *p, false, m->masked_pre, nullptr, nullptr));
+      if (m->masked_pre->n_other > 0)
+        DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->masked_pre->other_cells, m->masked_pre->n_other, false));
+    } else {
+      DCP_TRY(dcp_launch_th_fast(m, *p, false, m->fast_pre, nullptr, nullptr));
+      int64_t ng = 0;
+      dcp_fast_plan_counts(m->fast_pre, &ng);
+      if (ng > 0) DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, dcp_fast_plan_general_cells(m->fast_pre), ng, false));
+    }
   } else {
     DCP_TRY(zero_blockmat(ctx, m->pre));
-    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, nullptr, 0, false));
+    DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, nullptr, -1, false));
   }
   // build_nse_preconditioner: Jacobi of block(0,0) and block(1,1)  (boussinesq_model.tpp:531-539)
   DCP_TRY(refresh_jacobi(ctx, m->pre));
