@@ -28,6 +28,7 @@ struct ScalarArgs {
   int feec;             // rhs: velocity is the Raviart-Thomas field (Piola-mapped, unsigned)
   const double* geom;
   const int* l2g;
+  const unsigned short* tpos;  // [n_cells][nd*nd] positions inside the row, tpos[cell][0] == 0xffff: general scatter
   const double* phi;   // [nq][nd]
   const double* dphi;  // [nq][nd][dim]
   dcp_params prm;
@@ -145,9 +146,20 @@ __global__ void __launch_bounds__(128) temperature_matrix_kernel(ScalarArgs a, C
       }
     }
     __syncwarp();
-    distribute_local_matrix<true>(cs, nd, nd, A, nullptr, idx, lines, Mass, nullptr, lane, 32, false, err);
-    __syncwarp();
-    distribute_local_matrix<true>(cs, nd, nd, B, nullptr, idx, lines, Stiff, nullptr, lane, 32, false, err);
+    const unsigned short* tp = a.tpos + cell * (long long)(nd * nd);
+    if (tp[0] != 0xffffu) {
+      // no constrained dof in this cell: both matrices share one pattern, positions were found once per mesh
+      const long long* rp = Mass.rowptr[0][0];
+      for (int e = lane; e < nd * nd; e += 32) {
+        const long long at = rp[idx[e / nd]] + tp[e];
+        red_add_f64(Mass.val[0][0] + at, A[e]);
+        red_add_f64(Stiff.val[0][0] + at, B[e]);
+      }
+    } else {
+      distribute_local_matrix<true>(cs, nd, nd, A, nullptr, idx, lines, Mass, nullptr, lane, 32, false, err);
+      __syncwarp();
+      distribute_local_matrix<true>(cs, nd, nd, B, nullptr, idx, lines, Stiff, nullptr, lane, 32, false, err);
+    }
     __syncwarp();
   }
 }
@@ -181,7 +193,15 @@ __global__ void __launch_bounds__(128) temperature_rhs_kernel(ScalarArgs a, CsVi
       inhom = li >= 0 && cs.inhom[li] != 0.0;
     }
     const bool need_bc = __any_sync(0xffffffffu, inhom);
-    for (int k = lane; k < a.nd_nse; k += 32) U[k] = a.nse_solution[a.l2g_nse[cell * a.nd_nse + k]];
+    for (int k = lane; k < a.nd_nse; k += 32) {
+      const double v = a.nse_solution[a.l2g_nse[cell * a.nd_nse + k]];
+      if (a.feec)
+        U[k] = v;
+      else {  // classic: store component-major, U[c * ndu + node]
+        const int f = __ldg(a.nse_field + k);
+        if (f < DIM) U[f * a.ndu + __ldg(a.nse_base + k)] = v;
+      }
+    }
     if (need_bc)
       for (int i = lane; i < nn; i += 32) A[i] = 0.0;
     __syncwarp();
@@ -209,14 +229,11 @@ __global__ void __launch_bounds__(128) temperature_rhs_kernel(ScalarArgs a, CsVi
                              g[a.nq * (15 + d * 3) + q] * p2) / det);
           }
         } else {
-          for (int k = 0; k < a.nd_nse; ++k) {
-            const int f = __ldg(a.nse_field + k);
-            if (f < DIM) {
-              const double v = U[k] * __ldg(a.phi_u + (size_t)q * a.ndu + __ldg(a.nse_base + k));
+          const double* pu = a.phi_u + (size_t)q * a.ndu;
+          for (int n = 0; n < a.ndu; ++n) {
+            const double ph = __ldg(pu + n);
 #pragma unroll
-              for (int d = 0; d < DIM; ++d)
-                if (d == f) u[d] += v;
-            }
+            for (int d = 0; d < DIM; ++d) u[d] += U[d * a.ndu + n] * ph;
           }
         }
         double ugT = 0.0;
@@ -283,6 +300,7 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
   a.geom = m->geom_qt;
   a.gstride = m->gs_t;
   a.l2g = m->temp_l2g;
+  a.tpos = m->temp_pos;
   a.phi = m->phi_t_qt;
   a.dphi = m->dphi_t_qt;
   a.prm = p;

@@ -27,10 +27,10 @@ namespace {
 using namespace dcpdev;
 
 constexpr int NU = 27, NP = 8, NQ = 27, ND = 89, NE = 35, GS = NQ * 13;
-constexpr int LDB = 132;        // row stride of X (132 mod 16 == 4: conflict-free fragment loads)
+constexpr int LDB = 148;        // row stride of X (148 mod 16 == 4: conflict-free fragment loads)
 constexpr int KQ = 28;          // quadrature points padded to a multiple of 4
-constexpr int PSI0 = 112;       // first psi column (node columns 0..107, 108..111 padding)
-constexpr int MTHREADS = 256;
+constexpr int PSI0 = 128;       // first psi column (node columns 32*alpha + b, b < 32)
+constexpr int MTHREADS = 128;    // 4 warps per CTA, 4 CTAs per SM: several cells in flight per SM hide the per-cell load latency
 
 struct MmaArgs {
   long long n_fast;
@@ -62,17 +62,25 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
+// shared by the node x node and node x psi epilogues: constraint data of one velocity node
+struct NodeCs {
+  int mask;   // free components
+  int k;      // component constrained with masters (no-normal-flux), 3 = none
+  double w0, w1, w2;
+};
+
 template <bool SYSTEM>
-__global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockView A, CsView cs) {
+__global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockView A, CsView cs) {
   extern __shared__ __align__(16) double smem[];
-  double* X = smem;                     // KQ * LDB
+  double* X = smem;                     // KQ * LDB, column = 32*alpha + node (alpha: d_0, d_1, d_2, value), psi at PSI0
   double* wq = X + KQ * LDB;            // KQ (+4)
   double* sgeo = wq + 32;               // GS
   double* sF = sgeo + GS;               // NQ*3
   double* sU = sF + NQ * 3;             // ND
   double* sT = sU + ND + 1;             // 32
-  double* swt_ = sT + 32;                      // 3*NU master weights of the constrained component
-  long long* rb00 = (long long*)(swt_ + 3 * NU + 1);  // 3*NU
+  double* swt = sT + 32;                // 3*NU master weights of the constrained component
+  double* sGU = swt + 3 * NU + 1;       // NQ*12 old velocity / gradient at the quadrature points
+  long long* rb00 = (long long*)(sGU + NQ * 12);  // 3*NU
   long long* rb01 = rb00 + 3 * NU;          // 3*NU
   long long* rb10 = rb01 + 3 * NU;          // NP
   int* sidx = (int*)(rb10 + NP);            // ND
@@ -81,16 +89,14 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
   unsigned short* spos = (unsigned short*)(sys_p + NP);  // NE*NE
   unsigned short* swide = spos + NE * NE + 1;              // 3*NU*NU (preconditioner, non-uniform cells)
   unsigned char* snm = (unsigned char*)(swide + (SYSTEM ? 0 : 3 * NU * NU) + 1);  // 36
-  unsigned char* skc = snm + 36;   // 28: component of the node that is constrained WITH masters (no-normal-flux), 3 = none
-  double* swt = swt_;
+  unsigned char* skc = snm + 36;            // 28
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
   for (int i = tid; i < ND; i += nt) {
     const int f = a.local_field[i], bs = a.local_base[i];
     if (f < 3) sys_u[f * NU + bs] = i; else sys_p[bs] = i;
   }
-  for (int i = tid; i < LDB; i += nt) X[(KQ - 1) * LDB + i] = 0.0;   // padded quadrature point
-  for (int i = tid; i < KQ * 4; i += nt) X[(i >> 2) * LDB + 108 + (i & 3)] = 0.0;  // padding node columns
+  for (int i = tid; i < KQ * LDB; i += nt) X[i] = 0.0;   // padding nodes 27..31, padded point 27 stay zero
   if (tid < 4) wq[NQ + tid] = 0.0;
   __syncthreads();
   const double nu = a.prm.dt * a.prm.inv_re;
@@ -101,6 +107,16 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
   double* v00 = A.val[0][0];
   double* v01 = A.val[0][1];
   double* v10 = SYSTEM ? A.val[1][0] : A.val[1][1];
+
+  auto node_cs = [&](int n) {
+    NodeCs c;
+    c.mask = snm[n];
+    c.k = skc[n];
+    c.w0 = swt[3 * n];
+    c.w1 = swt[3 * n + 1];
+    c.w2 = swt[3 * n + 2];
+    return c;
+  };
 
   for (long long w = blockIdx.x; w < a.n_fast; w += gridDim.x) {
     const long long cell = a.cells[w];
@@ -116,27 +132,6 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
       for (int i = tid; i < NE * NE; i += nt) spos[i] = p[i];
       if (tid < 36) snm[tid] = a.nmask[w * 36 + tid];
     }
-    const int cflag = a.nmask[w * 36 + 35];  // 1: the cell holds constrained velocity dofs
-    __syncthreads();
-    if (tid < NU) {
-      // no-normal-flux lines: u_k = sum_{c != k} w_c u_c on the same node (verified when the plan was built)
-      int kc = 3;
-      double wv[3] = {0.0, 0.0, 0.0};
-      if (cflag && snm[tid] != 7) {
-        const int g0 = sidx[sys_u[tid]];
-        for (int c = 0; c < 3; ++c) {
-          const int li = cs.line_of_dof[g0 + c];
-          if (li >= 0 && cs.line_ptr[li + 1] > cs.line_ptr[li]) {
-            kc = c;
-            for (int k = cs.line_ptr[li]; k < cs.line_ptr[li + 1]; ++k) wv[cs.entry_dof[k] - g0] = cs.entry_w[k];
-          }
-        }
-      }
-      skc[tid] = (unsigned char)kc;
-      swt[tid * 3] = wv[0];
-      swt[tid * 3 + 1] = wv[1];
-      swt[tid * 3 + 2] = wv[2];
-    }
     int wide = -1;
     if (!SYSTEM) {
       wide = a.wide_idx[w];
@@ -145,7 +140,31 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
         for (int i = tid; i < 3 * NU * NU; i += nt) swide[i] = p[i];
       }
     }
+    const int cflag = a.nmask[w * 36 + 35];  // 1: the cell holds constrained velocity dofs
     __syncthreads();
+    if (tid < NU) {
+      // no-normal-flux lines: u_k = sum_{c != k} w_c u_c on the same node (verified when the plan was built)
+      int kc = 3;
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+      if (cflag && snm[tid] != 7) {
+        const int g0 = sidx[sys_u[tid]];
+        for (int c = 0; c < 3; ++c) {
+          const int li = cs.line_of_dof[g0 + c];
+          if (li >= 0 && cs.line_ptr[li + 1] > cs.line_ptr[li]) {
+            kc = c;
+            for (int k = cs.line_ptr[li]; k < cs.line_ptr[li + 1]; ++k) {
+              const int mc = cs.entry_dof[k] - g0;
+              const double wv = cs.entry_w[k];
+              if (mc == 0) w0 = wv; else if (mc == 1) w1 = wv; else w2 = wv;
+            }
+          }
+        }
+      }
+      skc[tid] = (unsigned char)kc;
+      swt[tid * 3] = w0;
+      swt[tid * 3 + 1] = w1;
+      swt[tid * 3 + 2] = w2;
+    }
     for (int i = tid; i < 3 * NU; i += nt) {
       const int gi = sidx[sys_u[i]];
       rb00[i] = rp00[gi];
@@ -153,129 +172,159 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
     }
     for (int i = tid; i < NP; i += nt) rb10[i] = rp10[sidx[sys_p[i]] - a.n_u];
     if (tid < NQ) wq[tid] = sgeo[tid];
-    // operand table: physical gradients and values of the Q2 functions, then the Q1 pressure functions
+    // operand table: physical gradients and values of the Q2 functions (component-major), then the Q1 functions
     for (int i = tid; i < NQ * NU; i += nt) {
       const int q = i / NU, b = i - q * NU;
       const double r0 = __ldg(a.dphi_u + i * 3), r1 = __ldg(a.dphi_u + i * 3 + 1), r2 = __ldg(a.dphi_u + i * 3 + 2);
-      double* x = X + q * LDB + 4 * b;
+      double* x = X + q * LDB + b;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) x[d] = sgeo[NQ * (1 + d) + q] * r0 + sgeo[NQ * (4 + d) + q] * r1 + sgeo[NQ * (7 + d) + q] * r2;
-      x[3] = __ldg(a.phi_u + i);
+      for (int d = 0; d < 3; ++d)
+        x[32 * d] = sgeo[NQ * (1 + d) + q] * r0 + sgeo[NQ * (4 + d) + q] * r1 + sgeo[NQ * (7 + d) + q] * r2;
+      x[96] = __ldg(a.phi_u + i);
     }
     for (int i = tid; i < NQ * NP; i += nt) X[(i / NP) * LDB + PSI0 + (i % NP)] = __ldg(a.phi_p + i);
     __syncthreads();
 
-    // ---- Gram matrix on the tensor cores: 14 node row tiles x (14 node + 1 psi) column tiles, 7 k-steps
-    // task = (row tile mt, group of 5 column tiles); preconditioner adds the psi row tile against the psi column tile
-    const int n_tasks = SYSTEM ? 42 : 43;
-    for (int t = warp; t < n_tasks; t += nwarps) {
-      const int mt = t < 42 ? t / 3 : 14, nt0 = t < 42 ? (t % 3) * 5 : 14, ntn = t < 42 ? 5 : 1;
-      double acc[5][2];
+    // ---- Gram blocks on the tensor cores.  Task (ta <= tb): 8 row nodes x 8 column nodes, all 16 (alpha,beta)
+    // tiles in one warp, so every lane ends up with the complete 4x4 block of two node pairs (symmetric half only:
+    // the transposed block is added from the same registers).  The preconditioner needs the 4 diagonal tiles only.
+    const int frow = lane >> 2, fk = lane & 3;
+    for (int t = warp; t < 10 + (SYSTEM ? 4 : 1); t += nwarps) {
+      if (t < 10) {
+        int ta = 0, r = t;
+        while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
+        const int tb = ta + r;
+        double acc[4][4][2];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) acc[j][0] = acc[j][1] = 0.0;
-      const int frow = lane >> 2, fk = lane & 3;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int ks = 0; ks < KQ / 4; ++ks) {
-        const int q = 4 * ks + fk;
-        const double* xr = X + q * LDB;
-        const double av = wq[q] * xr[8 * mt + frow];
+          for (int k = 0; k < 4; ++k) acc[i][k][0] = acc[i][k][1] = 0.0;
 #pragma unroll
-        for (int j = 0; j < 5; ++j)
-          if (j < ntn) dmma(acc[j][0], acc[j][1], av, xr[8 * (nt0 + j) + frow]);
-      }
-      // ---- epilogue: lane holds D[row = lane/4][col = 2*(lane%4) + {0,1}] of every tile
-      const int alpha = (lane >> 2) & 3, na = 2 * mt + (lane >> 4);
+        for (int ks = 0; ks < KQ / 4; ++ks) {
+          const int q = 4 * ks + fk;
+          const double* xr = X + q * LDB;
+          const double wv = wq[q];
+          double af[4], bf[4];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        if (j >= ntn) continue;
-        const int ntile = nt0 + j;
-        if (ntile < 14 && mt < 14) {
-          const int nb = 2 * ntile + ((lane >> 1) & 1);
-          // diag_ab = D[phi,phi] + nu * trace, gathered over the 8 lanes that share the node pair (a,b)
-          const double own = (alpha & 1) ? acc[j][1] : acc[j][0];
-          double dg = ((lane & 1) == (alpha >> 1)) ? own * (alpha < 3 ? nu : 1.0) : 0.0;
-          dg += __shfl_xor_sync(0xffffffffu, dg, 1);
-          dg += __shfl_xor_sync(0xffffffffu, dg, 4);
-          dg += __shfl_xor_sync(0xffffffffu, dg, 8);
-          const bool validp = na < NU && nb < NU;
-          const int ma = validp ? snm[na] : 7, mb = validp ? snm[nb] : 7;
-          if (SYSTEM) {
-            const int ka = validp ? skc[na] : 3, kb = validp ? skc[nb] : 3;
-            // full block value F = L[(a, c = beta_jj), (b, d = alpha)] before constraints
-            double F[2];
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-              const int beta = 2 * (lane & 1) + jj;
-              F[jj] = (alpha < 3 && beta < 3) ? nu * acc[j][jj] + (alpha == beta ? dg : 0.0) : 0.0;
-            }
-            if (__any_sync(0xffffffffu, ka != 3 || kb != 3)) {
-              // rows / columns of a constrained component are redistributed to the other components of the same node:
-              // R[c][d] = F[c][d] + wa_c F[ka][d] + wb_d F[c][kb] + wa_c wb_d F[ka][kb]   (C^T L C on the 3x3 block)
-              const int kas = ka == 3 ? 0 : ka, kbs = kb == 3 ? 0 : kb;
-              const int srcA = (lane & 0x1e) | (kas >> 1), srcB = (lane & 0x13) | (kbs << 2);
-              const int srcC = (lane & 0x12) | (kbs << 2) | (kas >> 1);
-              const double a0 = __shfl_sync(0xffffffffu, F[0], srcA), a1 = __shfl_sync(0xffffffffu, F[1], srcA);
-              const double b0 = __shfl_sync(0xffffffffu, F[0], srcB), b1 = __shfl_sync(0xffffffffu, F[1], srcB);
-              const double c0 = __shfl_sync(0xffffffffu, F[0], srcC), c1 = __shfl_sync(0xffffffffu, F[1], srcC);
-              const double FA = (kas & 1) ? a1 : a0, FC = (kas & 1) ? c1 : c0;
-              const double wb = (kb != 3 && alpha < 3) ? swt[nb * 3 + alpha] : 0.0;
-#pragma unroll
-              for (int jj = 0; jj < 2; ++jj) {
-                const int beta = 2 * (lane & 1) + jj;
-                const double wa = (ka != 3 && beta < 3) ? swt[na * 3 + beta] : 0.0;
-                F[jj] += wa * FA + wb * (jj ? b1 : b0) + wa * wb * FC;
-              }
-            }
-            if (validp && alpha < 3) {
-              const long long off = (long long)spos[na * NE + nb] + __popc(mb & ((1 << alpha) - 1));
-#pragma unroll
-              for (int jj = 0; jj < 2; ++jj) {
-                const int beta = 2 * (lane & 1) + jj;
-                if (beta >= 3) continue;
-                if ((ma & (1 << beta)) && (mb & (1 << alpha)))
-                  red_add_f64(v00 + rb00[beta * NU + na] + off, F[jj]);
-                else if (na == nb && alpha == beta && !(ma & (1 << alpha)))
-                  // constrained dof: |L_ii| on its own diagonal (the row holds nothing else)
-                  red_add_f64(v00 + rb00[alpha * NU + na], fabs(nu * acc[j][jj] + dg));
-              }
-            }
-          } else if (validp && alpha < 3 && (lane & 1) == 0) {
-            if (ma & mb & (1 << alpha)) {
-              const unsigned off = wide >= 0 ? swide[(alpha * NU + na) * NU + nb] : spos[na * NE + nb];
-              if (off != 0xffffu) red_add_f64(v00 + rb00[alpha * NU + na] + off, dg);
-            } else if (na == nb && !(ma & (1 << alpha)))
-              red_add_f64(v00 + rb00[alpha * NU + na], fabs(dg));
+          for (int i = 0; i < 4; ++i) {
+            af[i] = wv * xr[32 * i + 8 * ta + frow];
+            bf[i] = xr[32 * i + 8 * tb + frow];
           }
-        } else if (ntile == 14 && mt < 14) {
-          if (SYSTEM) {
-            const bool va = na < NU;
-            const int ma = va ? snm[na] : 7, ka = va ? skc[na] : 3;
-            double sv[2] = {-acc[j][0], -acc[j][1]};
-            if (__any_sync(0xffffffffu, ka != 3)) {
-              const int src = (lane & 0x13) | ((ka == 3 ? 0 : ka) << 2);
-              const double k0 = __shfl_sync(0xffffffffu, sv[0], src), k1 = __shfl_sync(0xffffffffu, sv[1], src);
-              const double wa = (ka != 3 && alpha < 3) ? swt[na * 3 + alpha] : 0.0;
-              sv[0] += wa * k0;
-              sv[1] += wa * k1;
-            }
-            if (va && alpha < 3 && (ma & (1 << alpha))) {
-              const int rank = __popc(ma & ((1 << alpha) - 1));
 #pragma unroll
-              for (int jj = 0; jj < 2; ++jj) {
-                const int pb = 2 * (lane & 3) + jj;
-                if (!snm[NU + pb]) continue;
-                red_add_f64(v01 + rb01[alpha * NU + na] + spos[na * NE + NU + pb], sv[jj]);
-                red_add_f64(v10 + rb10[pb] + spos[(NU + pb) * NE + na] + rank, sv[jj]);
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (SYSTEM || i == k) dmma(acc[i][k][0], acc[i][k][1], af[i], bf[k]);
+        }
+        const int na = 8 * ta + frow;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int nb = 8 * tb + 2 * fk + jj;
+          if (na >= NU || nb >= NU) continue;
+          const NodeCs ca = node_cs(na), cb = node_cs(nb);
+          const double dg = acc[3][3][jj] + nu * (acc[0][0][jj] + acc[1][1][jj] + acc[2][2][jj]);
+          if (SYSTEM) {
+            // F[c][d] = L[(a,c),(b,d)] = nu * D[(a,d),(b,c)] + delta_cd diag     (acc[alpha][beta] = D[(a,alpha),(b,beta)])
+            double F[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int d = 0; d < 3; ++d) F[c][d] = nu * acc[d][c][jj] + (c == d ? dg : 0.0);
+            const double d00 = fabs(F[0][0]), d11 = fabs(F[1][1]), d22 = fabs(F[2][2]);
+            if (ca.k != 3 || cb.k != 3) {
+              // C^T F C on the 3x3 block: R[c][d] = F[c][d] + wa_c F[ka][d] + wb_d F[c][kb] + wa_c wb_d F[ka][kb]
+              const double wa[3] = {ca.w0, ca.w1, ca.w2}, wb[3] = {cb.w0, cb.w1, cb.w2};
+              double Fa[3], Fb[3], Fab;  // F[ka][d], F[c][kb], F[ka][kb]
+#pragma unroll
+              for (int d = 0; d < 3; ++d) Fa[d] = ca.k == 0 ? F[0][d] : (ca.k == 1 ? F[1][d] : (ca.k == 2 ? F[2][d] : 0.0));
+#pragma unroll
+              for (int c = 0; c < 3; ++c) Fb[c] = cb.k == 0 ? F[c][0] : (cb.k == 1 ? F[c][1] : (cb.k == 2 ? F[c][2] : 0.0));
+              Fab = cb.k == 0 ? Fa[0] : (cb.k == 1 ? Fa[1] : (cb.k == 2 ? Fa[2] : 0.0));
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) F[c][d] += wa[c] * Fa[d] + wb[d] * Fb[c] + wa[c] * wb[d] * Fab;
+            }
+            const long long off_ab = spos[na * NE + nb], off_ba = spos[nb * NE + na];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (!(ca.mask & (1 << c))) continue;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                if (!(cb.mask & (1 << d))) continue;
+                red_add_f64(v00 + rb00[c * NU + na] + off_ab + __popc(cb.mask & ((1 << d) - 1)), F[c][d]);
+                if (ta != tb)  // transposed block L[(b,d),(a,c)]
+                  red_add_f64(v00 + rb00[d * NU + nb] + off_ba + __popc(ca.mask & ((1 << c) - 1)), F[c][d]);
               }
+            }
+            if (na == nb) {  // constrained dofs keep |L_ii| on their own diagonal (the row holds nothing else)
+              if (!(ca.mask & 1)) red_add_f64(v00 + rb00[na], d00);
+              if (!(ca.mask & 2)) red_add_f64(v00 + rb00[NU + na], d11);
+              if (!(ca.mask & 4)) red_add_f64(v00 + rb00[2 * NU + na], d22);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (ca.mask & cb.mask & (1 << c)) {
+                const unsigned o1 = wide >= 0 ? swide[(c * NU + na) * NU + nb] : spos[na * NE + nb];
+                if (o1 != 0xffffu) red_add_f64(v00 + rb00[c * NU + na] + o1, dg);
+                if (ta != tb) {
+                  const unsigned o2 = wide >= 0 ? swide[(c * NU + nb) * NU + na] : spos[nb * NE + na];
+                  if (o2 != 0xffffu) red_add_f64(v00 + rb00[c * NU + nb] + o2, dg);
+                }
+              } else if (na == nb && !(ca.mask & (1 << c)))
+                red_add_f64(v00 + rb00[c * NU + na], fabs(dg));
             }
           }
-        } else if (ntile == 14 && mt == 14 && !SYSTEM) {
-          const int pa = lane >> 2;
+        }
+      } else if (SYSTEM) {
+        // velocity-pressure coupling: rows (a, alpha < 3) of row block ta against the 8 psi columns
+        const int ta = t - 10;
+        double acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+        for (int ks = 0; ks < KQ / 4; ++ks) {
+          const int q = 4 * ks + fk;
+          const double* xr = X + q * LDB;
+          const double wv = wq[q], bf = xr[PSI0 + frow];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) dmma(acc[i][0], acc[i][1], wv * xr[32 * i + 8 * ta + frow], bf);
+        }
+        const int na = 8 * ta + frow;
+        if (na < NU) {
+          const NodeCs ca = node_cs(na);
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
-            const int pb = 2 * (lane & 3) + jj;
-            if (snm[NU + pa] && snm[NU + pb]) red_add_f64(v10 + rb10[pa] + spos[(NU + pa) * NE + NU + pb], acc[j][jj]);
+            const int pb = 2 * fk + jj;
+            if (!snm[NU + pb]) continue;
+            double sv[3] = {-acc[0][jj], -acc[1][jj], -acc[2][jj]};
+            if (ca.k != 3) {
+              const double sk = ca.k == 0 ? sv[0] : (ca.k == 1 ? sv[1] : sv[2]);
+              sv[0] += ca.w0 * sk;
+              sv[1] += ca.w1 * sk;
+              sv[2] += ca.w2 * sk;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (ca.mask & (1 << c)) {
+                red_add_f64(v01 + rb01[c * NU + na] + spos[na * NE + NU + pb], sv[c]);
+                red_add_f64(v10 + rb10[pb] + spos[(NU + pb) * NE + na] + __popc(ca.mask & ((1 << c) - 1)), sv[c]);
+              }
           }
+        }
+      } else {
+        // preconditioner: pressure mass matrix, psi x psi
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KQ / 4; ++ks) {
+          const int q = 4 * ks + fk;
+          const double* xr = X + q * LDB;
+          dmma(c0, c1, wq[q] * xr[PSI0 + frow], xr[PSI0 + frow]);
+        }
+        const int pa = frow;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int pb = 2 * fk + jj;
+          if (snm[NU + pa] && snm[NU + pb]) red_add_f64(v10 + rb10[pa] + spos[(NU + pa) * NE + NU + pb], jj ? c1 : c0);
         }
       }
     }
@@ -286,17 +335,22 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
         sT[q] = tq;
       }
       __syncthreads();
+      // old velocity and its gradient at the quadrature points: 27 x 3 x (3 gradients + value) dot products
+      for (int i = tid; i < NQ * 12; i += nt) {
+        const int q = i / 12, r = i - q * 12, c = r >> 2, e = r & 3;
+        const double* x = X + q * LDB + 32 * e;   // e < 3: d_e phi_n, e == 3: phi_n
+        double sacc = 0.0;
+        for (int n = 0; n < NU; ++n) sacc += sU[sys_u[c * NU + n]] * x[n];
+        sGU[i] = sacc;
+      }
+      __syncthreads();
       for (int q = tid; q < NQ; q += nt) {
-        double u[3] = {0, 0, 0}, gu[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        for (int n = 0; n < NU; ++n) {
-          const double* x = X + q * LDB + 4 * n;
+        double u[3], gu[3][3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const double U = sU[sys_u[c * NU + n]];
-            u[c] += U * x[3];
+        for (int c = 0; c < 3; ++c) {
+          u[c] = sGU[q * 12 + c * 4 + 3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) gu[c][d] += U * x[d];
-          }
+          for (int d = 0; d < 3; ++d) gu[c][d] = sGU[q * 12 + c * 4 + d];
         }
         double xq[3], grav[3];
 #pragma unroll
@@ -323,7 +377,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
       for (int i = tid; i < 3 * NU; i += nt) {
         const int c = i / NU, n = i - c * NU;
         double s = 0.0;
-        for (int q = 0; q < NQ; ++q) s += X[q * LDB + 4 * n + 3] * sF[q * 3 + c];
+        for (int q = 0; q < NQ; ++q) s += X[q * LDB + 96 + n] * sF[q * 3 + c];
         const int gi = sidx[sys_u[i]];
         if (snm[n] & (1 << c))
           red_add_f64(a.rhs + gi, s);
@@ -338,7 +392,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) th_mma_kernel(MmaArgs a, BlockVie
 }
 
 constexpr size_t mma_smem_bytes(bool system) {
-  return sizeof(double) * (KQ * LDB + 32 + GS + NQ * 3 + ND + 1 + 32 + 3 * NU + 1) + sizeof(long long) * (6 * NU + NP) +
+  return sizeof(double) * (KQ * LDB + 32 + GS + NQ * 3 + ND + 1 + 32 + 3 * NU + 1 + NQ * 12) + sizeof(long long) * (6 * NU + NP) +
          sizeof(int) * (ND + 3 * NU + NP) + sizeof(unsigned short) * (NE * NE + 2 + (system ? 0 : 3 * NU * NU)) + 36 + 28 + 32;
 }
 

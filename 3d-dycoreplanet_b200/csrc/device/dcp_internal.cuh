@@ -131,6 +131,7 @@ struct dcp_model {
   int nse_n_local = 0, nse_nb = 2, temp_n_local = 0;
   int64_t nse_n_dofs = 0, temp_n_dofs = 0;
   int32_t *nse_l2g = nullptr, *temp_l2g = nullptr;
+  uint16_t* temp_pos = nullptr;  // [n_cells][nd*nd] scatter positions of the temperature matrices (0xffff row: general)
   int32_t *nse_local_field = nullptr, *nse_local_base = nullptr;
   std::vector<int32_t> h_local_field, h_local_base;
   DevCs nse_cs, temp_cs;

@@ -22,6 +22,7 @@ int dcp_upload(dcp_ctx* ctx, T** dst, const T* src, int64_t n) {
 template int dcp_upload<double>(dcp_ctx*, double**, const double*, int64_t);
 template int dcp_upload<int32_t>(dcp_ctx*, int32_t**, const int32_t*, int64_t);
 template int dcp_upload<int64_t>(dcp_ctx*, int64_t**, const int64_t*, int64_t);
+template int dcp_upload<uint16_t>(dcp_ctx*, uint16_t**, const uint16_t*, int64_t);
 
 int dcp_check_device_errors(dcp_ctx* ctx, const char* what) {
   DCP_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -299,6 +300,7 @@ int dcp_model_destroy(dcp_model* m) {
   cudaStreamSynchronize(m->ctx->stream);
   cudaFree(m->nse_l2g);
   cudaFree(m->temp_l2g);
+  cudaFree(m->temp_pos);
   cudaFree(m->nse_local_field);
   cudaFree(m->nse_local_base);
   cudaFree(m->nse_constrained_cells);
@@ -475,6 +477,35 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
   if (rc != DCP_OK) {
     dcp_set_error("cudaMalloc temp_rhs failed");
     return fail(rc);
+  }
+  // temperature matrices: scatter positions for the cells without constrained temperature dofs
+  {
+    const int nd = d->temp_n_local;
+    std::vector<int32_t> lod((size_t)m->temp_n_dofs, -1);
+    for (int64_t l = 0; l < d->temp_cs.n_lines; ++l) lod[d->temp_cs.line_dof[l]] = (int32_t)l;
+    std::vector<uint16_t> tp((size_t)nc * nd * nd, 0xffff);
+    const int64_t* rp = d->temp_pattern.rowptr;
+    const int32_t* col = d->temp_pattern.col;
+    if (rp && col) {
+#pragma omp parallel for schedule(static)
+      for (int64_t c = 0; c < nc; ++c) {
+        const int32_t* idx = d->temp_l2g + c * nd;
+        bool ok = true;
+        for (int i = 0; i < nd && ok; ++i) ok = lod[idx[i]] < 0;
+        uint16_t* out = &tp[(size_t)c * nd * nd];
+        for (int i = 0; i < nd && ok; ++i)
+          for (int j = 0; j < nd && ok; ++j) {
+            const int32_t* b = col + rp[idx[i]];
+            const int32_t* e = col + rp[idx[i] + 1];
+            const int32_t* p = std::lower_bound(b, e, idx[j]);
+            ok = p != e && *p == idx[j] && (p - b) < 0xffff;
+            if (ok) out[i * nd + j] = (uint16_t)(p - b);
+          }
+        if (!ok) out[0] = 0xffff;
+      }
+    }
+    M_TRY(dcp_upload(ctx, &m->temp_pos, tp.data(), (int64_t)tp.size()));
+    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   // cells holding a constrained NSE dof
   {

@@ -31,18 +31,22 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(long long n_rows, const l
   double sum = 0.0;
   if (row < n_rows) {
     const long long p0 = rowptr[row], p1 = rowptr[row + 1];
-    long long p = p0 + lane;
-    for (; p + 3 * LANES < p1; p += 4 * LANES) {
-      const int c0 = ld_stream_s32(col + p), c1 = ld_stream_s32(col + p + LANES);
-      const int c2 = ld_stream_s32(col + p + 2 * LANES), c3 = ld_stream_s32(col + p + 3 * LANES);
-      const double v0 = ld_stream_f64(val + p), v1 = ld_stream_f64(val + p + LANES);
-      const double v2 = ld_stream_f64(val + p + 2 * LANES), v3 = ld_stream_f64(val + p + 3 * LANES);
+    // 4 x LANES entries per trip, every load predicated: the whole row (mean 200 nnz) is in flight after <= 2 trips
+    for (long long p = p0 + lane; p < p1; p += 4 * LANES) {
+      const bool k1 = p + LANES < p1, k2 = p + 2 * LANES < p1, k3 = p + 3 * LANES < p1;
+      const int c0 = ld_stream_s32(col + p);
+      const int c1 = k1 ? ld_stream_s32(col + p + LANES) : 0;
+      const int c2 = k2 ? ld_stream_s32(col + p + 2 * LANES) : 0;
+      const int c3 = k3 ? ld_stream_s32(col + p + 3 * LANES) : 0;
+      const double v0 = ld_stream_f64(val + p);
+      const double v1 = k1 ? ld_stream_f64(val + p + LANES) : 0.0;
+      const double v2 = k2 ? ld_stream_f64(val + p + 2 * LANES) : 0.0;
+      const double v3 = k3 ? ld_stream_f64(val + p + 3 * LANES) : 0.0;
       sum += v0 * __ldg(x + c0);
       sum += v1 * __ldg(x + c1);
       sum += v2 * __ldg(x + c2);
       sum += v3 * __ldg(x + c3);
     }
-    for (; p < p1; p += LANES) sum += ld_stream_f64(val + p) * __ldg(x + ld_stream_s32(col + p));
   }
 #pragma unroll
   for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
