@@ -131,6 +131,9 @@ struct dcp_model {
   int nse_n_local = 0, nse_nb = 2, temp_n_local = 0;
   int64_t nse_n_dofs = 0, temp_n_dofs = 0;
   int32_t *nse_l2g = nullptr, *temp_l2g = nullptr;
+  int32_t* vel_dof = nullptr;       // [dim][ndu] cell dof of (velocity component, node), classic family
+  double* cell_vertices = nullptr;  // [n_cells][2^dim][dim] (optional)
+  int64_t n_owned_cells = 0;
   uint16_t* temp_pos = nullptr;  // [n_cells][nd*nd] scatter positions of the temperature matrices (0xffff row: general)
   int32_t *nse_local_field = nullptr, *nse_local_base = nullptr;
   std::vector<int32_t> h_local_field, h_local_base;
@@ -179,6 +182,8 @@ int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv)
 int dcp_launch_jacobi(dcp_ctx* ctx, int64_t n, const double* diag_inv, const double* x, double* y);
 int dcp_launch_axpby_values(dcp_ctx* ctx, int64_t n, const double* a, const double* b, double fb, double* out);
 int dcp_launch_fill(dcp_ctx* ctx, double* p, int64_t n, double v);
+int dcp_launch_velocity_extrema(dcp_model* m, const double* nse_solution, double* out2_dev);
+int dcp_launch_distribute(dcp_ctx* ctx, const DevCs& cs, double* x);
 
 int dcp_launch_th_cells(dcp_model* m, const dcp_params& p, bool system, const double* old_nse, const double* old_temp,
                         const int32_t* cell_list, int64_t n_list, bool only_constrained_entries);

@@ -301,6 +301,8 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->nse_l2g);
   cudaFree(m->temp_l2g);
   cudaFree(m->temp_pos);
+  cudaFree(m->vel_dof);
+  cudaFree(m->cell_vertices);
   cudaFree(m->nse_local_field);
   cudaFree(m->nse_local_base);
   cudaFree(m->nse_constrained_cells);
@@ -366,6 +368,10 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     dcp_set_error("FEEC family expects dim=3, 19 dofs per cell, 3 blocks, <=27 quadrature points and all feec_* tables");
     return DCP_ERR_ARG;
   }
+  if (!d->geom_qn || !d->geom_qt) {
+    dcp_set_error("geom_qn / geom_qt missing (host records, or device records from dcp_geometry_create)");
+    return DCP_ERR_ARG;
+  }
   DCP_CUDA(cudaSetDevice(ctx->device));
   dcp_model* m = new dcp_model;
   m->ctx = ctx;
@@ -385,6 +391,10 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
   m->ndt = d->ndt;
   int rc = DCP_OK;
   auto fail = [&](int code) {
+    if (d->geom_on_device) {  // device mapping buffers stay the caller's unless the create succeeds
+      m->geom_qn = m->geom_qt = m->geom_qp = nullptr;
+      m->geom_shared = false;
+    }
     dcp_model_destroy(m);
     return code;
   };
@@ -427,16 +437,24 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     M_TRY(dcp_upload(ctx, &m->feec_u_qp, d->feec_phi_u_qp, (int64_t)d->nq_pre * 18));
     M_TRY(dcp_upload(ctx, &m->feec_u_qt, d->feec_phi_u_qt, (int64_t)d->nq_temp * 18));
     M_TRY(dcp_upload(ctx, &m->feec_div, d->feec_div_u, 6));
-    M_TRY(dcp_upload(ctx, &m->geom_qp, d->geom_qp, nc * (int64_t)m->gs_p));
+    if (d->geom_on_device)
+      m->geom_qp = const_cast<double*>(d->geom_qp);
+    else
+      M_TRY(dcp_upload(ctx, &m->geom_qp, d->geom_qp, nc * (int64_t)m->gs_p));
   }
   M_TRY(dcp_upload(ctx, &m->phi_t_qn, d->phi_t_qn, (int64_t)d->nq_nse * d->ndt));
   M_TRY(dcp_upload(ctx, &m->phi_t_qt, d->phi_t_qt, (int64_t)d->nq_temp * d->ndt));
   M_TRY(dcp_upload(ctx, &m->dphi_t_qt, d->dphi_t_qt, (int64_t)d->nq_temp * d->ndt * dim));
-  M_TRY(dcp_upload(ctx, &m->geom_qn, d->geom_qn, nc * gs_n));
+  if (d->geom_on_device)
+    m->geom_qn = const_cast<double*>(d->geom_qn);
+  else
+    M_TRY(dcp_upload(ctx, &m->geom_qn, d->geom_qn, nc * gs_n));
   if (d->geom_qt == d->geom_qn && gs_n == gs_t) {
     m->geom_qt = m->geom_qn;
     m->geom_shared = true;
-  } else
+  } else if (d->geom_on_device)
+    m->geom_qt = const_cast<double*>(d->geom_qt);
+  else
     M_TRY(dcp_upload(ctx, &m->geom_qt, d->geom_qt, nc * gs_t));
 
   // matrices
@@ -477,6 +495,15 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
   if (rc != DCP_OK) {
     dcp_set_error("cudaMalloc temp_rhs failed");
     return fail(rc);
+  }
+  m->n_owned_cells = d->n_owned_cells;
+  if (d->cell_vertices) M_TRY(dcp_upload(ctx, &m->cell_vertices, d->cell_vertices, nc * (int64_t)(dim << dim)));
+  if (!feec) {
+    std::vector<int32_t> vd((size_t)dim * d->ndu, 0);
+    for (int k = 0; k < d->nse_n_local; ++k)
+      if (d->nse_local_field[k] < dim) vd[(size_t)d->nse_local_field[k] * d->ndu + d->nse_local_base[k]] = k;
+    M_TRY(dcp_upload(ctx, &m->vel_dof, vd.data(), (int64_t)vd.size()));
+    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   // temperature matrices: scatter positions for the cells without constrained temperature dofs
   {
@@ -684,6 +711,42 @@ int dcp_assemble_temperature_rhs(dcp_model* m, const dcp_params* p, const double
   DCP_CUDA(cudaMemsetAsync(m->temp_rhs, 0, sizeof(double) * (size_t)m->temp_n_dofs, ctx->stream));
   DCP_TRY(dcp_launch_temperature_rhs(m, *p, d_temp, d_nse));
   if (mem == DCP_HOST) DCP_TRY(dcp_check_device_errors(ctx, "dcp_assemble_temperature_rhs"));
+  return DCP_OK;
+}
+
+int dcp_velocity_extrema(dcp_model* m, const double* nse_solution, int mem, double* result_host) {
+  if (!m || !nse_solution || !result_host) return DCP_ERR_ARG;
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  if (m->family == DCP_FAMILY_FEEC && !m->cell_vertices) {
+    dcp_set_error("dcp_velocity_extrema: the FEEC family needs desc.cell_vertices");
+    return DCP_ERR_STATE;
+  }
+  const double* d_nse = nullptr;
+  DCP_TRY(dcp_stage_in(ctx, 0, nse_solution, m->nse_n_dofs, mem, &d_nse));
+  double* d_out = nullptr;
+  DCP_TRY(dcp_stage_out_alloc(ctx, 2, nullptr, 2, DCP_HOST, &d_out));
+  DCP_TRY(dcp_launch_velocity_extrema(m, d_nse, d_out));
+  DCP_CUDA(cudaMemcpyAsync(result_host, d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!m->cell_vertices) result_host[1] = -1.0;  // no diameters: CFL not available
+  return DCP_OK;
+}
+
+int dcp_constraints_distribute(dcp_model* m, int space, double* x, int mem) {
+  if (!m || !x || (space != 0 && space != 1)) return DCP_ERR_ARG;
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  const DevCs& cs = space == 0 ? m->nse_cs : m->temp_cs;
+  const int64_t n = space == 0 ? m->nse_n_dofs : m->temp_n_dofs;
+  const double* in = nullptr;
+  DCP_TRY(dcp_stage_in(ctx, 0, x, n, mem, &in));
+  double* dx = const_cast<double*>(in);
+  DCP_TRY(dcp_launch_distribute(ctx, cs, dx));
+  if (mem == DCP_HOST) {
+    DCP_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   return DCP_OK;
 }
 

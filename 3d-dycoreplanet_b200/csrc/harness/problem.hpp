@@ -263,6 +263,14 @@ inline void compute_geometry_ext(const Mesh& mesh, int mapping_degree, const Qua
   }
 }
 
+
+inline void collect_cell_vertices(const Mesh& mesh, std::vector<double>& out) {
+  const int nv = 1 << mesh.dim;
+  out.resize((size_t)mesh.n_cells * nv * mesh.dim);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < mesh.n_cells; ++c) mesh.cell_vertices(c, &out[(size_t)c * nv * mesh.dim]);
+}
+
 struct Problem {
   Spec spec;
   std::unique_ptr<Mesh> base_mesh;  // whole mesh (only when partitioned)
@@ -278,6 +286,12 @@ struct Problem {
   ScalarTable tab_u_qn, tab_p_qn, tab_t_qn;  // on the NSE rule (system, preconditioner)
   ScalarTable tab_u_qt, tab_t_qt;            // on the temperature rule (T matrices, T rhs)
   std::vector<double> geom_qn, geom_qt;
+  std::vector<double> cell_vertices;  // [n_cells][2^dim][dim]
+  // input of the device-side mapping evaluation (dcp_geometry_create)
+  std::vector<int64_t> map_ptr;       // [n_cells+1] offsets into map_points
+  std::vector<double> map_points;     // support points of each cell's mapping
+  std::map<std::string, MappingTable> map_tables;
+  std::map<std::string, std::vector<double>> map_weights;
   // patterns
   Csr nse_full, pre_full, temp_pat;
   Csr nse_b[2][2], pre_b[2][2];
@@ -312,6 +326,33 @@ struct Problem {
     reg(name + ".entry_w", c.entry_w, F64);
     reg(name + ".inhom", c.inhom, F64);
     reg(name + ".line_of_dof", c.line_of_dof, I32);
+  }
+  // mapping support points of every cell and the mapping basis on one quadrature rule
+  void collect_mapping(const Mesh& mesh, int mapping_degree) {
+    CellMapper mapper(mesh, mapping_degree);
+    const int dim = mesh.dim, nlow = 1 << dim;
+    int nhigh = 1;
+    for (int d = 0; d < dim; ++d) nhigh *= mapping_degree + 1;
+    map_ptr.assign((size_t)mesh.n_cells + 1, 0);
+    for (int64_t c = 0; c < mesh.n_cells; ++c)
+      map_ptr[c + 1] = map_ptr[c] + ((mapping_degree == 1 || !mesh.at_boundary(c)) ? nlow : nhigh);
+    map_points.resize((size_t)map_ptr.back() * dim);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t c = 0; c < mesh.n_cells; ++c) mapper.support_points(c, &map_points[(size_t)map_ptr[c] * dim]);
+    reg("map.ptr", map_ptr, I64);
+    reg("map.points", map_points, F64);
+    scalars["map.n_low"] = nlow;
+    scalars["map.n_high"] = nhigh;
+  }
+  void reg_map(const std::string& name, int dim, int mapping_degree, const QuadRule& q) {
+    map_tables[name + ".low"] = tabulate_mapping(dim, 1, q);
+    map_tables[name + ".high"] = tabulate_mapping(dim, std::max(1, mapping_degree), q);
+    map_weights[name] = q.w;
+    reg(name + ".N_low", map_tables[name + ".low"].N, F64);
+    reg(name + ".dN_low", map_tables[name + ".low"].dN, F64);
+    reg(name + ".N_high", map_tables[name + ".high"].N, F64);
+    reg(name + ".dN_high", map_tables[name + ".high"].dN, F64);
+    reg(name + ".w", map_weights[name], F64);
   }
   void reg_tab(const std::string& name, const ScalarTable& t) {
     reg(name + ".phi", t.phi, F64);
@@ -608,6 +649,12 @@ inline void build_feec(Problem* P, const Spec& sp) {
   reg_feec("feec.qt", P->feec_qt);
   P->reg_tab("tab.t_qn", P->tab_t_qn);
   P->reg_tab("tab.t_qt", P->tab_t_qt);
+  collect_cell_vertices(mesh, P->cell_vertices);
+  P->reg("cell_vertices", P->cell_vertices, F64);
+  P->collect_mapping(mesh, mdeg);
+  P->reg_map("map.qn", mesh.dim, mdeg, P->q_nse);
+  P->reg_map("map.qt", mesh.dim, mdeg, P->q_temp);
+  P->reg_map("map.qp", mesh.dim, mdeg, P->q_pre);
   P->reg("geom.qn", P->geom_qn, F64);
   P->reg("geom.qp", P->geom_qp, F64);
   P->reg("geom.qt", P->q_temp.n1 == P->q_nse.n1 ? P->geom_qn : P->geom_qt, F64);
@@ -813,6 +860,11 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   P->reg_tab("tab.t_qn", P->tab_t_qn);
   P->reg_tab("tab.u_qt", P->tab_u_qt);
   P->reg_tab("tab.t_qt", P->tab_t_qt);
+  collect_cell_vertices(mesh, P->cell_vertices);
+  P->reg("cell_vertices", P->cell_vertices, F64);
+  P->collect_mapping(mesh, sp.mapping_degree);
+  P->reg_map("map.qn", mesh.dim, sp.mapping_degree, P->q_nse);
+  P->reg_map("map.qt", mesh.dim, sp.mapping_degree, P->q_temp);
   P->reg("geom.qn", P->geom_qn, F64);
   P->reg("geom.qt", P->q_temp.n1 == P->q_nse.n1 ? P->geom_qn : P->geom_qt, F64);
   P->reg("nse.coupling", P->nse_coupling, I32);

@@ -63,6 +63,18 @@ class ModelDesc(ctypes.Structure):
         ("feec_phi_w_qn", c_dp), ("feec_curl_w_qn", c_dp), ("feec_phi_u_qn", c_dp),
         ("feec_phi_w_qp", c_dp), ("feec_curl_w_qp", c_dp), ("feec_phi_u_qp", c_dp),
         ("feec_phi_u_qt", c_dp), ("feec_div_u", c_dp), ("geom_qp", c_dp),
+        # optional diagnostics inputs
+        ("cell_vertices", c_dp), ("n_owned_cells", ctypes.c_int64),
+        ("geom_on_device", ctypes.c_int32), ("pad3", ctypes.c_int32),
+    ]
+
+
+class MappingDesc(ctypes.Structure):
+    _fields_ = [
+        ("dim", ctypes.c_int32), ("nq", ctypes.c_int32), ("extended", ctypes.c_int32), ("n_low", ctypes.c_int32),
+        ("n_high", ctypes.c_int32), ("pad", ctypes.c_int32), ("n_cells", ctypes.c_int64),
+        ("support_ptr", c_lp), ("support_points", c_dp), ("N_low", c_dp), ("dN_low", c_dp), ("N_high", c_dp),
+        ("dN_high", c_dp), ("weights", c_dp),
     ]
 
 
@@ -73,7 +85,8 @@ EXPORTS = [
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
     "dcp_vmult_add", "dcp_block_vmult", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
-    "dcp_vec_scale", "dcp_vec_copy",
+    "dcp_vec_scale", "dcp_vec_copy", "dcp_velocity_extrema", "dcp_constraints_distribute",
+    "dcp_geometry_create",
 ]
 
 
@@ -129,6 +142,9 @@ def lib():
         L.dcp_vec_sadd.argtypes = [vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, vp, vp]
         L.dcp_vec_scale.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
         L.dcp_vec_copy.argtypes = [vp, ctypes.c_int64, vp, vp]
+        L.dcp_geometry_create.argtypes = [vp, ctypes.POINTER(MappingDesc), ctypes.POINTER(vp)]
+        L.dcp_velocity_extrema.argtypes = [vp, vp, ctypes.c_int, c_dp]
+        L.dcp_constraints_distribute.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
         _LIB = L
     return _LIB
 
@@ -176,6 +192,15 @@ class Context:
 
     def synchronize(self):
         check(lib().dcp_ctx_synchronize(self._h), "dcp_ctx_synchronize")
+
+    def download_f64(self, dev_ptr, n):
+        """n doubles from a device pointer of this context (dcp_memcpy_d2h)."""
+        out = np.empty(n)
+        check(lib().dcp_memcpy_d2h(self._h, ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(dev_ptr), 8 * n), "dcp_memcpy_d2h")
+        return out
+
+    def free(self, dev_ptr):
+        check(lib().dcp_free(self._h, ctypes.c_void_p(dev_ptr)), "dcp_free")
 
     def launch_count(self):
         return int(lib().dcp_ctx_launch_count(self._h))
@@ -289,8 +314,26 @@ def _cs_desc(P, prefix, keep):
     return d
 
 
-def model_desc_from_problem(P, owner_plan=False):
-    """Fill a dcp_model_desc from a harness Problem (the stand-in for deal.II's objects)."""
+def geometry_create(ctx, P, rule):
+    """Mapping records of quadrature rule `rule` ("qn", "qt" or "qp") evaluated on the device from the cells'
+    mapping support points (dcp_geometry_create).  Returns the device pointer (int)."""
+    feec = "feec" in P.spec.get("family", "classic")
+    md = MappingDesc()
+    md.dim, md.nq, md.extended = P.dim, P[f"map.{rule}.w"].size, (1 if feec else 0)
+    md.n_low, md.n_high, md.n_cells = P.scalar("map.n_low"), P.scalar("map.n_high"), P.n_cells
+    keep = [P["map.ptr"], P["map.points"]] + [P[f"map.{rule}.{k}"] for k in ("N_low", "dN_low", "N_high", "dN_high", "w")]
+    md.support_ptr, md.support_points = _ptr(keep[0], c_lp), _ptr(keep[1], c_dp)
+    md.N_low, md.dN_low, md.N_high, md.dN_high, md.weights = (_ptr(a, c_dp) for a in keep[2:])
+    out = ctypes.c_void_p()
+    check(lib().dcp_geometry_create(ctx._h, ctypes.byref(md), ctypes.byref(out)), "dcp_geometry_create")
+    return out.value
+
+
+def model_desc_from_problem(P, owner_plan=False, device_geometry=None):
+    """Fill a dcp_model_desc from a harness Problem (the stand-in for deal.II's objects).
+
+    device_geometry: a Context -> the mapping records are evaluated on that device from the support points
+    (dcp_geometry_create) and adopted by the model instead of uploading the host records."""
     keep = []
     d = ModelDesc()
     d.build_owner_plan = 1 if owner_plan else 0
@@ -325,9 +368,18 @@ def model_desc_from_problem(P, owner_plan=False):
         d.ndu, d.ndp, d.ndt = P.scalar("tab.u_qn.nd"), P.scalar("tab.p_qn.nd"), P.scalar("tab.t_qn.nd")
         nb = 2
     for name, field, ct in names:
+        if name.startswith("geom.") and device_geometry is not None:
+            continue
         a = P[name]
         keep.append(a)
         setattr(d, field, _ptr(a, ct))
+    if device_geometry is not None:
+        gn = geometry_create(device_geometry, P, "qn")
+        gt = gn if P.scalar("geom_shared") else geometry_create(device_geometry, P, "qt")
+        d.geom_qn, d.geom_qt = ctypes.cast(gn, c_dp), ctypes.cast(gt, c_dp)
+        if feec:
+            d.geom_qp = ctypes.cast(geometry_create(device_geometry, P, "qp"), c_dp)
+        d.geom_on_device = 1
     d.nse_cs = _cs_desc(P, "nse.cs", keep)
     d.temp_cs = _cs_desc(P, "temp.cs", keep)
     d.temp_n_local = P.scalar("temp.n_local")
@@ -337,6 +389,11 @@ def model_desc_from_problem(P, owner_plan=False):
             d.nse_pattern[i][j] = _csr_desc(P, f"nse.b{i}{j}", keep)
             d.pre_pattern[i][j] = _csr_desc(P, f"pre.b{i}{j}", keep)
     d.temp_pattern = _csr_desc(P, "temp.pat", keep)
+    if "cell_vertices" in P.names():
+        a = P["cell_vertices"]
+        keep.append(a)
+        d.cell_vertices = _ptr(a, c_dp)
+    d.n_owned_cells = P.scalar("n_owned_cells")
     d._keep = keep
     return d
 
@@ -362,8 +419,8 @@ class BoussinesqModel:
         self.T_preconditioner = PreconditionJacobi(self, MAT_TEMP, 0)
 
     @classmethod
-    def from_problem(cls, ctx, P, parameters, owner_plan=False):
-        return cls(ctx, model_desc_from_problem(P, owner_plan), parameters)
+    def from_problem(cls, ctx, P, parameters, owner_plan=False, device_geometry=False):
+        return cls(ctx, model_desc_from_problem(P, owner_plan, ctx if device_geometry else None), parameters)
 
     def set_strategy(self, s):
         check(lib().dcp_model_set_strategy(self._h, s), "dcp_model_set_strategy")
@@ -392,6 +449,30 @@ class BoussinesqModel:
         b, mb = _vec_arg(nse_solution)
         assert ma == mb
         check(lib().dcp_assemble_temperature_rhs(self._h, ctypes.byref(self.prm), a, b, ma), "assemble_temperature_rhs")
+
+    # --- passes next to the solves -----------------------------------------------------------------
+    def velocity_extrema(self, nse_solution):
+        """(get_maximal_velocity(), get_cfl_number()) of boussinesq_model.tpp:1023-1098, rank-local values."""
+        a, ma = _vec_arg(nse_solution)
+        out = (ctypes.c_double * 2)()
+        check(lib().dcp_velocity_extrema(self._h, a, ma, out), "dcp_velocity_extrema")
+        return float(out[0]), float(out[1])
+
+    def get_maximal_velocity(self, nse_solution):
+        return self.velocity_extrema(nse_solution)[0]
+
+    def get_cfl_number(self, nse_solution):
+        return self.velocity_extrema(nse_solution)[1]
+
+    def distribute_nse_constraints(self, x):
+        """nse_constraints.distribute(x) (boussinesq_model.tpp:1233), in place."""
+        a, ma = _vec_arg(x)
+        check(lib().dcp_constraints_distribute(self._h, 0, a, ma), "dcp_constraints_distribute")
+
+    def distribute_temperature_constraints(self, x):
+        """temperature_constraints.distribute(x) (boussinesq_model.tpp:1442), in place."""
+        a, ma = _vec_arg(x)
+        check(lib().dcp_constraints_distribute(self._h, 1, a, ma), "dcp_constraints_distribute")
 
     # --- results --------------------------------------------------------------------------------
     def vector(self, which):

@@ -26,6 +26,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 
+FP64_DMMA_PEAK_TFLOPS = 37.0
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -336,6 +339,31 @@ def main():
     ms_e2e, _ = timed(step_host, args.steps, False)
     ctx.synchronize()
 
+    # (M2) the operators the Krylov solves apply one by one: block(0,0), block(0,1), block(1,0) of nse_matrix and
+    # temperature_matrix, each timed alone (single rank only: block products need no extra exchange pattern here)
+    spmv_blocks = {}
+    if world == 1:
+        n_p = n_nse - n_u
+        views = {"b00": (d_y[:n_u], d_x[:n_u]), "b01": (d_y[:n_u], d_x[n_u:]), "b10": (d_y[n_u:], d_x[:n_u])}
+        reps = 5
+        for name, (dst, src) in views.items():
+            A = model.nse_matrix.block(int(name[1]), int(name[2]))
+            nnz = P.scalar(f"nse.{name}.nnz")
+            nbytes = nnz * 12 + A.m() * 16 + A.n() * 8
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    A.vmult(dst, src)
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record(stream)
+                for _ in range(reps):
+                    A.vmult(dst, src)
+                b1.record(stream)
+            torch.cuda.synchronize()
+            t_ms = b0.elapsed_time(b1) / reps
+            spmv_blocks[name] = {"ms": t_ms, "gbs": nbytes / (t_ms * 1e-3) / 1e9, "nnz": int(nnz),
+                                 "l2_resident": bool(nbytes < 126e6)}
+        assert n_p == model.nse_matrix.block(1, 0).m()
+
     total_dofs = n_dofs
     if world > 1:
         t = torch.tensor([n_dofs], dtype=torch.float64, device="cuda")
@@ -365,6 +393,13 @@ def main():
             "spmv_gbs": world * (ab["spmv_nse"] + ab["spmv_temperature"]) / (spmv_ms * 1e-3) / 1e9,
             "phase_ms": phase_ms,
             "phase_gbs": {p: ab[p] / (phase_ms[p] * 1e-3) / 1e9 for p in phases},
+            "spmv_blocks": spmv_blocks,
+            # FP64 roofline of the local-matrix contraction (0.60 MFLOP/cell, unsymmetrised structure-
+            # exploiting count) against the DMMA peak measured by benchmarks/fp64_peaks.cu on this pool
+            "fp64_roofline": {"kernel": "nse_system", "flop_per_cell": 0.60e6, "peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+                              "achieved_tflops": 0.60e6 * P.n_cells / (phase_ms["nse_system"] * 1e-3) / 1e12,
+                              "frac": 0.60e6 * P.n_cells / (phase_ms["nse_system"] * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                              "peak_source": "profiles/r01_fp64_peaks.json (mma.sync m8n8k4 f64, measured)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                          "spmv_frac": ab["spmv_nse"] / (phase_ms["spmv_nse"] * 1e-3) / 1e9 / peak},

@@ -146,7 +146,9 @@ typedef struct {
   const double *phi_u_qt, *phi_t_qt, *dphi_t_qt;
 
   /* mapping data per cell and rule: [n_cells][ JxW(nq) | Kinv[e][d](nq each) | xq[d](nq each) ],
-   * Kinv[e][d] = d xi_e / d x_d (inverse Jacobian of the cell mapping at the quadrature point) */
+   * Kinv[e][d] = d xi_e / d x_d (inverse Jacobian of the cell mapping at the quadrature point).
+   * With geom_on_device != 0 (last field) these are DEVICE buffers made by dcp_geometry_create, which the model
+   * adopts (it frees them in dcp_model_destroy; pass the same pointer twice when two rules coincide). */
   const double* geom_qn;
   const double* geom_qt; /* may be == geom_qn when both rules coincide */
 
@@ -169,7 +171,30 @@ typedef struct {
   const double* feec_phi_u_qt;                                   /* RT values on the temperature rule */
   const double* feec_div_u;                                      /* [6] reference divergence of the RT functions */
   const double* geom_qp;                                         /* mapping records on the preconditioner rule */
+
+  /* ---- optional, for the time-step diagnostics (dcp_velocity_extrema) */
+  const double* cell_vertices; /* [n_cells][2^dim][dim] vertex coordinates, deal.II (lexicographic) vertex order; may be NULL */
+  int64_t n_owned_cells;       /* cells [0, n_owned_cells) are locally owned (cell->is_locally_owned()); 0 = all */
+  int32_t geom_on_device;      /* != 0: geom_qn / geom_qt / geom_qp are device buffers from dcp_geometry_create */
+  int32_t pad3;
 } dcp_model_desc;
+
+/* Input of the device-side mapping evaluation (what FEValues::reinit computes with update_JxW_values |
+ * update_inverse_jacobians | update_quadrature_points (| update_jacobians for the Piola transforms),
+ * boussineq_model_assembly.tpp:25,69-73).  MappingQ(p) as the reference constructs it (boussinesq_model.tpp:20):
+ * cells with boundary lines carry n_high = (p+1)^dim support points, all others their n_low = 2^dim vertices. */
+typedef struct {
+  int32_t dim, nq;
+  int32_t extended;              /* != 0: FEEC records [.. | J[i][j] | detJ] */
+  int32_t n_low, n_high;
+  int32_t pad;
+  int64_t n_cells;
+  const int64_t* support_ptr;    /* [n_cells+1] offsets, in points, into support_points */
+  const double* support_points;  /* [..][dim], lexicographic (x fastest) within a cell */
+  const double *N_low, *dN_low;  /* mapping basis at the quadrature points: [nq][n_low], [nq][n_low][dim] */
+  const double *N_high, *dN_high;/* same for the high-order cells; may be NULL when no cell uses it */
+  const double* weights;         /* [nq] quadrature weights */
+} dcp_mapping_desc;
 
 /* ---- context --------------------------------------------------------------------------------- */
 int dcp_ctx_create(int device, dcp_ctx** out);
@@ -186,6 +211,11 @@ int dcp_malloc(dcp_ctx* ctx, int64_t bytes, void** out);
 int dcp_free(dcp_ctx* ctx, void* p);
 int dcp_memcpy_h2d(dcp_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
 int dcp_memcpy_d2h(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
+/* ---- mapping data on the device ------------------------------------------------------- */
+/* Evaluates the records of one quadrature rule for all cells into a new device buffer (*geom_dev).  Hand it to
+ * dcp_model_create through geom_q* with geom_on_device = 1 (the model then owns it) or release it with dcp_free. */
+int dcp_geometry_create(dcp_ctx* ctx, const dcp_mapping_desc* desc, double** geom_dev);
 
 /* ---- model (one per mesh) -------------------------------------------------------------------- */
 int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* desc, dcp_model** out);
@@ -229,6 +259,17 @@ int dcp_vmult_add(dcp_model* m, int which, int bi, int bj, double* dst, const do
 int dcp_block_vmult(dcp_model* m, int which, double* dst, const double* src, int mem);
 /* dst = diag(A(bi,bi))^-1 * src  (Jacobi, one sweep, omega 1).  Diagonals are refreshed by the assemble calls. */
 int dcp_jacobi_vmult(dcp_model* m, int which, int bi, double* dst, const double* src, int mem);
+
+/* ---- passes next to the solves ---------------------------------------------------------
+ * get_maximal_velocity and get_cfl_number in one sweep over the locally owned cells (boussinesq_model.tpp:1023-1061
+ * and :1064-1098; FEEC boussineq_model_FEEC.tpp:1158-1240): result_host[0] = max_q |u(x_q)| over the
+ * QIterated(QTrapez, degree) points, result_host[1] = max_cell max(1e-10, max_q |u|) / cell->diameter().
+ * The values are rank-local; with several ranks the caller takes the maximum (Utilities::MPI::max, :1048, 1093).
+ * Without desc.cell_vertices result_host[1] is set to -1 (classic) and the FEEC family fails with DCP_ERR_STATE. */
+int dcp_velocity_extrema(dcp_model* m, const double* nse_solution, int mem, double* result_host);
+/* AffineConstraints::distribute on a solution vector (nse_constraints.distribute :1233, temperature_constraints
+ * .distribute :1442): x[line] = sum_k w_k x[master_k] + inhomogeneity.  space: 0 = NSE, 1 = temperature. */
+int dcp_constraints_distribute(dcp_model* m, int space, double* x, int mem);
 
 /* ---- device-resident vector algebra for the Krylov solvers around the SpMVs (all pointers DEVICE) -----------
  * Trilinos vector ops inside deal.II SolverCG / SolverGMRES / SolverFGMRES (boussinesq_model.tpp:1165,1191-1199,

@@ -243,3 +243,64 @@ def feec_assemble_temperature_rhs(P, prm, old_temp, nse_solution, use_omp=False)
         _ip(P["temp.l2g"]), _ip(P["nse.l2g"]), _dp(old_temp), _dp(nse_solution), ctypes.byref(cs), _dp(rhs),
         ctypes.c_int64(n), int(use_omp))
     return rhs
+
+
+# ---- passes next to the solves, numpy restatements -----------------------------------------
+def cell_diameters(P):
+    """cell->diameter(): the longest diagonal between opposite vertices (deal.II TriaAccessor::diameter)."""
+    X = P["cell_vertices"].reshape(P.n_cells, 1 << P.dim, P.dim)
+    nv = 1 << P.dim
+    d = [np.linalg.norm(X[:, nv - 1 - v] - X[:, v], axis=1) for v in range(nv // 2)]
+    return np.max(np.stack(d, axis=1), axis=1)
+
+
+def velocity_extrema(P, nse_solution):
+    """(get_maximal_velocity, get_cfl_number) over the locally owned cells.
+
+    Classic: boussinesq_model.tpp:1023-1061, 1064-1098 -- the QIterated(QTrapez, degree) points are the Lagrange
+    nodes of the velocity element, the values there are the nodal values.  FEEC: boussineq_model_FEEC.tpp:1158-1240
+    -- the 8 vertices, default Q1 mapping, Raviart-Thomas component mapped by J u_hat / det J, no face signs."""
+    dim, nc = P.dim, P.scalar("n_owned_cells") or P.n_cells
+    l2g = P["nse.l2g"].reshape(P.n_cells, -1)[:nc]
+    feec = "feec" in P.spec.get("family", "classic")
+    if not feec:
+        field, base = P["nse.local_field"], P["nse.local_base"]
+        ndu = 3 ** dim
+        U = np.zeros((nc, ndu, dim))
+        for k in range(l2g.shape[1]):
+            if field[k] < dim:
+                U[:, base[k], field[k]] = nse_solution[l2g[:, k]]
+        speed = np.linalg.norm(U, axis=2).max(axis=1)
+    else:
+        X = P["cell_vertices"].reshape(P.n_cells, 8, 3)[:nc]
+        Uf = nse_solution[l2g[:, 12:18]]
+        speed = np.zeros(nc)
+        for v in range(8):
+            b = [(v >> k) & 1 for k in range(3)]
+            J = np.zeros((nc, 3, 3))
+            for s in range(8):
+                t = [(s >> k) & 1 for k in range(3)]
+                for j in range(3):
+                    g = 1.0 if t[j] else -1.0
+                    for k in range(3):
+                        if k != j and t[k] != b[k]:
+                            g = 0.0
+                    if g != 0.0:
+                        J[:, :, j] += g * X[:, s, :]
+            uh = np.stack([Uf[:, 0 + b[0]], Uf[:, 2 + b[1]], Uf[:, 4 + b[2]]], axis=1)
+            u = np.einsum("cij,cj->ci", J, uh) / np.linalg.det(J)[:, None]
+            speed = np.maximum(speed, np.linalg.norm(u, axis=1))
+    cfl = (np.maximum(speed, 1e-10) / cell_diameters(P)[:nc]).max()
+    return float(speed.max()), float(cfl)
+
+
+def constraints_distribute(P, prefix, x):
+    """AffineConstraints::distribute: x[line] = sum_k w_k x[master_k] + inhomogeneity (boussinesq_model.tpp:1233, 1442)."""
+    x = x.copy()
+    line_dof, line_ptr = P[prefix + ".line_dof"], P[prefix + ".line_ptr"]
+    entry_dof, entry_w, inhom = P[prefix + ".entry_dof"], P[prefix + ".entry_w"], P[prefix + ".inhom"]
+    src = x.copy()
+    for l, g in enumerate(line_dof):
+        sl = slice(line_ptr[l], line_ptr[l + 1])
+        x[g] = float(np.dot(entry_w[sl], src[entry_dof[sl]])) + inhom[l]
+    return x

@@ -189,3 +189,81 @@ def test_feec_assembly_and_spmv_match_oracle(ctx, problem_factory, spec, pname):
     rp10, col10, _, _ = P.csr("nse.b10")
     assert np.abs(y10 - orc.spmv(rp10, col10, A10.values(), np.ascontiguousarray(x[:nw]))).max() <= 1e-12 * scale
     model.close()
+
+
+DIAG_CASES = [(dict(geometry="shell", refine=2), "shell_3d_classic"), (dict(geometry="cube", refine=2), "cube_3d"),
+              (dict(refine=3, **ANNULUS), "annulus_2d"), (dict(geometry="shell", refine=2, family="feec"), "shell_3d_feec"),
+              (dict(geometry="cube", refine=2, family="feec"), "cube_3d")]
+
+
+@pytest.mark.parametrize("spec,pname", DIAG_CASES, ids=["shell", "cube", "annulus", "shell-feec", "cube-feec"])
+def test_velocity_extrema_and_distribute_match_oracle(ctx, problem_factory, spec, pname):
+    """get_maximal_velocity / get_cfl_number (boussinesq_model.tpp:1023-1098) and AffineConstraints::distribute
+    (:1233, 1442) on the device vs the numpy restatement; host and device vector arguments."""
+    import torch
+    from dycore_b200 import device, params
+    from oracle import oracle as orc
+    P = problem_factory(**spec)
+    n, nT = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
+    rng = np.random.default_rng(7)
+    x = np.ascontiguousarray(rng.uniform(-1, 1, n))
+    model = device.BoussinesqModel.from_problem(ctx, P, params.NAMED[pname])
+    vmax, cfl = model.velocity_extrema(x)
+    rv, rc = orc.velocity_extrema(P, x)
+    assert abs(vmax - rv) <= 1e-13 * rv and abs(cfl - rc) <= 1e-13 * rc
+    dx = torch.from_numpy(x).cuda()
+    assert model.velocity_extrema(dx) == (vmax, cfl)
+    assert model.get_maximal_velocity(np.zeros(n)) == 0.0
+    # distribute: masters keep their value, constrained entries are overwritten
+    y = x.copy()
+    model.distribute_nse_constraints(y)
+    assert np.abs(y - orc.constraints_distribute(P, "nse.cs", x)).max() <= 1e-15
+    model.distribute_nse_constraints(dx)
+    assert np.array_equal(dx.cpu().numpy(), y)
+    t = np.ascontiguousarray(rng.uniform(-1, 1, nT))
+    t2 = t.copy()
+    model.distribute_temperature_constraints(t2)
+    assert np.abs(t2 - orc.constraints_distribute(P, "temp.cs", t)).max() <= 1e-15
+    model.close()
+
+
+GEOM_CASES = [(dict(geometry="shell", refine=2), "shell_3d_classic"), (dict(geometry="shell", refine=1, temperature_degree=2), "shell_3d_classic"),
+              (dict(refine=3, **ANNULUS), "annulus_2d"), (dict(geometry="shell", refine=2, family="feec"), "shell_3d_feec")]
+
+
+@pytest.mark.parametrize("spec,pname", GEOM_CASES, ids=["shell", "shell-Tq2", "annulus", "shell-feec"])
+def test_device_geometry_matches_host_mapping(ctx, problem_factory, spec, pname):
+    """dcp_geometry_create (MappingQ(3) on boundary cells, Q1 elsewhere; JxW, inverse Jacobian, x_q, J, det J) vs the
+    harness' host evaluation of the same mapping, and an assembly pass running on the device-made records."""
+    from dycore_b200 import device, params
+    from oracle import oracle as orc
+    P = problem_factory(**spec)
+    feec = spec.get("family") == "feec"
+    for rule, name in (("qn", "geom.qn"), ("qt", "geom.qt")) + ((("qp", "geom.qp"),) if feec else ()):
+        ptr = device.geometry_create(ctx, P, rule)
+        host = P[name]
+        dev = ctx.download_f64(ptr, host.size)
+        ctx.free(ptr)
+        nq = P[f"map.{rule}.w"].size
+        h, d = host.reshape(P.n_cells, -1, nq), dev.reshape(P.n_cells, -1, nq)
+        for f in range(h.shape[1]):   # field by field: JxW, K entries, x, ...
+            scale = np.abs(h[:, f]).max()
+            assert np.abs(h[:, f] - d[:, f]).max() <= 1e-13 * max(scale, 1e-300), f"{rule} field {f}"
+    mp = params.NAMED[pname]
+    model = device.BoussinesqModel.from_problem(ctx, P, mp, device_geometry=True)
+    oprm = orc.params_from(mp)
+    if feec:
+        n, nT = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
+        rng = np.random.default_rng(3)
+        u, T = np.ascontiguousarray(0.1 * rng.uniform(-1, 1, n)), np.ascontiguousarray(2 + 0.3 * rng.uniform(-1, 1, nT))
+        ref_vals, ref_rhs = orc.feec_assemble_nse_system(P, oprm, u, T)
+        blocks = split_blocks3(P, "nse", ref_vals)
+    else:
+        u, T = synthetic_fields(P)
+        ref_vals, ref_rhs = orc.assemble_nse_system(P, oprm, u, T)
+        blocks = split_blocks(P, "nse", ref_vals)
+    model.assemble_nse_system(u, T)
+    for (bi, bj), rv in blocks.items():
+        assert rel_err_max(model.nse_matrix.block(bi, bj).values(), rv) <= TOL
+    assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
+    model.close()

@@ -118,3 +118,26 @@ def test_temperature_rhs_manufactured_on_cube(problem_factory):
     tau = mp.time_step / mp.NSE_solver_interval
     # sum_i r_i = int ( T - tau u.grad T ) = int (1 + 2x - z) - tau int (2y - x z) = 1.5 - tau (1 - 1/4)
     assert abs(r.sum() - (1.5 - tau * 0.75)) <= 1e-13
+
+
+def test_velocity_extrema_restatement_on_known_fields(problem_factory):
+    """A constant velocity (1,2,2): max |u| = 3 and CFL = 3 / (smallest cell diameter); the cube's cells are
+    identical boxes whose diameter is the box diagonal."""
+    from oracle import oracle as orc
+    P = problem_factory(geometry="cube", refine=2)
+    n = P.scalar("nse.n_dofs")
+    comp = P["nse.dof_comp"]
+    x = np.zeros(n)
+    for c, v in enumerate((1.0, 2.0, 2.0)):
+        x[comp == c] = v
+    vmax, cfl = orc.velocity_extrema(P, x)
+    d = orc.cell_diameters(P)
+    X = P["cell_vertices"].reshape(P.n_cells, 8, 3)
+    assert np.allclose(d, np.linalg.norm(X[:, 7] - X[:, 0], axis=1))
+    assert abs(vmax - 3.0) < 1e-14 and abs(cfl - 3.0 / d.min()) < 1e-13
+    # distribute leaves unconstrained entries alone and is idempotent
+    y = orc.constraints_distribute(P, "nse.cs", x)
+    free = np.ones(n, bool)
+    free[P["nse.cs.line_dof"]] = False
+    assert np.array_equal(y[free], x[free])
+    assert np.array_equal(orc.constraints_distribute(P, "nse.cs", y), y)
