@@ -163,10 +163,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--refine", type=int, default=5)
+    ap.add_argument("--refine", type=int, default=0,
+                    help="global refinements of the 6-tree shell; 0 = 6 (41.2 M DoFs, the largest that fits one B200) "
+                         "when the box has the host and device memory for it, else 5")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N>1: strong = the same shell cut into N chunks; weak = N x the radial layers")
     ap.add_argument("--temperature-degree", type=int, default=1)
     ap.add_argument("--strategy", default="auto", choices=["auto", "search", "positions", "owner"])
-    ap.add_argument("--cpu-refine", type=int, default=3)
+    ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the CPU sample (4: ~3 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -186,7 +190,7 @@ def main():
         base, n_dofs, dt = cpu_leg(args.cpu_refine, args.temperature_degree, steps, warm, mp)
         line = {"impl": "reference", "metric": "dofs_assembled_per_s", "value": base["value"], "unit": "DoFs/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "hypershell classic (Taylor-Hood Q2/Q1 + Q1 temperature): full Boussinesq "
                                        "assembly pass + nse_matrix/temperature_matrix SpMV",
                            "note": "bounded sample: " + base["sample"]},
@@ -205,14 +209,24 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # ---- problem: weak scaling.  N ranks share ONE shell with N x the radial layers (synthetic refinement),
-    # partitioned along the (tree, Morton) curve like the reference's p4est partition; every rank builds only
-    # its own subdomain (owned cells + one ghost-cell layer).
+    # ---- problem.  N ranks share ONE shell, partitioned along the (tree, Morton) curve like the reference's p4est
+    # partition; every rank builds only its own subdomain (owned cells + one ghost-cell layer).  strong: the shell
+    # of the N=1 run; weak: N x the radial layers (synthetic refinement), i.e. fixed cells per GPU.
+    refine = args.refine
+    if refine == 0:
+        host_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 1e9
+        dev_gb = torch.cuda.mem_get_info(local_rank)[1] / 1e9
+        # refine 6 needs ~105 GB of host memory for the sparsity patterns and ~150 GB of HBM in total; under weak
+        # scaling every rank would need that much host memory, so N > 1 weak runs use refine 5 per GPU
+        shared = world == 1 or args.scaling == "strong"
+        refine = 6 if (shared and host_gb >= 150 and dev_gb * world >= 170) else 5
     t_setup = time.perf_counter()
-    spec = dict(geometry="shell", refine=args.refine, temperature_degree=args.temperature_degree,
+    spec = dict(geometry="shell", refine=refine, temperature_degree=args.temperature_degree, geometry_data=0,
                 threads=max(1, (os.cpu_count() or 1) // world))  # torchrun pins OMP_NUM_THREADS=1
     if world > 1:
-        spec.update(radial_factor=world, n_ranks=world, rank=rank)
+        spec.update(n_ranks=world, rank=rank)
+        if args.scaling == "weak":
+            spec.update(radial_factor=world)
     P = harness.Problem(**spec)
     u, T = synthetic_fields(P)
     n_nse, n_t = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
@@ -223,7 +237,7 @@ def main():
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     strategy = "positions" if args.strategy == "auto" else args.strategy
-    model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == "owner"))
+    model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == "owner"), device_geometry=True)
     model.set_strategy({"search": device.STRATEGY_SEARCH, "positions": device.STRATEGY_POSITIONS,
                         "owner": device.STRATEGY_OWNER}[strategy])
     halo_nse = halo_t = None
@@ -380,15 +394,19 @@ def main():
         line = {
             "metric": "dofs_assembled_per_s", "value": total_dofs / (ms_step * 1e-3), "unit": "DoFs/s",
             "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"hypershell classic refine={args.refine} (Taylor-Hood Q2/Q1 + Q{args.temperature_degree} "
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"hypershell classic refine={refine} (Taylor-Hood Q2/Q1 + Q{args.temperature_degree} "
                                    f"temperature): full Boussinesq assembly pass + nse_matrix/temperature_matrix SpMV",
                        "cells_per_gpu": P.scalar("n_owned_cells"), "dofs_per_gpu": n_dofs, "total_dofs": total_dofs,
                        "ghost_cells_rank0": P.n_cells - P.scalar("n_owned_cells"),
                        "nnz_nse": sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(2) for j in range(2)),
                        "strategy": strategy, "l2": "inputs larger than L2" if ab["nse_system"] > 4 * 126e6 else "inputs fit L2",
-                       "partition": (f"shell with {world}x radial layers cut into {world} contiguous (tree, Morton) chunks, one "
-                                     "ghost-cell layer, ghost-dof halo over NCCL p2p") if world > 1 else "single GPU", "setup_s": round(t_setup, 2)},
+                       "partition": ((f"shell with {world}x radial layers" if args.scaling == "weak" else "the same shell")
+                                     + f" cut into {world} contiguous (tree, Morton) chunks, one ghost-cell layer, "
+                                     "ghost-dof halo over NCCL p2p") if world > 1 else "single GPU",
+                       "mapping_data": "evaluated on the device from support points (dcp_geometry_create)",
+                       "device_mem_gb_rank0": round((torch.cuda.mem_get_info(local_rank)[1] - torch.cuda.mem_get_info(local_rank)[0]) / 1e9, 1),
+                       "setup_s": round(t_setup, 2)},
             "assembly_dofs_per_s": total_dofs / (asm_ms * 1e-3),
             "spmv_gbs": world * (ab["spmv_nse"] + ab["spmv_temperature"]) / (spmv_ms * 1e-3) / 1e9,
             "phase_ms": phase_ms,
@@ -409,7 +427,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            base, _, _ = cpu_leg(args.cpu_refine, args.temperature_degree, 1, 1, mp)
+            base, _, _ = cpu_leg(args.cpu_refine, args.temperature_degree, 3, 1, mp)
             line["cpu_baseline"] = base
         emit(line)
     model.close()
