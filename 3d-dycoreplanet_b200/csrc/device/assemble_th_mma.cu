@@ -1,24 +1,34 @@
-// Classic 3-D Taylor-Hood NSE system / preconditioner on the cells without constrained dofs: the per-cell
-// contraction on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA), scatter through the position table.
+// Classic 3-D Taylor-Hood NSE system / preconditioner: the per-cell contraction on the FP64 tensor cores
+// (mma.sync.m8n8k4.f64, SASS DMMA), constraints resolved in the epilogue, scatter through a per-cell plan.
 //
-// Same integrals as assemble_th_fast.cu (reference: include/core/boussinesq_model.tpp:421-464, 550-687).  ncu of
-// the DFMA version showed the kernel bound by shared-memory operand traffic (MIO throttle: 8 LDS per 10 DFMA);
-// B200's DMMA runs at the full FP64 rate (37.0 vs 33.9 TFLOP/s DFMA, profiles/r01_fp64_peaks.json) and needs one
-// operand double per lane per 256 FMA, so the contraction moves to the tensor pipe:
+// Same integrals as assemble_th.cu (reference: include/core/boussinesq_model.tpp:421-464, 550-687).  ncu of the
+// DFMA position-table kernel (assemble_th_fast.cu) showed it bound by shared-memory operand traffic (MIO throttle:
+// 8 LDS per 10 DFMA); B200's DMMA runs at the full FP64 rate (37.0 vs 33.9 TFLOP/s DFMA,
+// profiles/r01_fp64_peaks.json) and needs one operand double per lane per 256 FMA, so the contraction moves to the
+// tensor pipe:
 //
-//   X[q][4b+beta] = (d_0 phi_b, d_1 phi_b, d_2 phi_b, phi_b)(x_q)  for the 27 Q2 nodes b, then the 8 psi_b'(x_q)
-//   D = X^T diag(w) X      (116 x 116 Gram matrix, K = 27 quadrature points padded to 28)
+//   X[q][32*alpha + b] = (d_0 phi_b, d_1 phi_b, d_2 phi_b, phi_b)(x_q), alpha = 0..3, for the 27 Q2 nodes b (padded
+//   to 32), then the 8 psi_b'(x_q) at column PSI0;  K = 27 quadrature points padded to 28
+//   D[(a,alpha),(b,beta)] = sum_q w_q X[q][32 alpha + a] X[q][32 beta + b]
 //
-// One 8x8 DMMA tile holds complete 4x4 blocks of 2x2 node pairs, so the epilogue is local to 8 lanes:
-//   diag_ab = D[(a,3),(b,3)] + nu * sum_e D[(a,e),(b,e)]                         (three xor-shuffles)
+// A warp takes an 8x8 block of node pairs (row block ta <= column block tb: the matrix is symmetric, the transposed
+// block is added from the same registers) and keeps all 16 (alpha,beta) tiles, so every lane owns the complete 4x4
+// block of its two node pairs and the epilogue is lane-local:
+//   diag_ab = D[(a,3),(b,3)] + nu * sum_e D[(a,e),(b,e)]
 //   L[(a,c),(b,d)] = nu * D[(a,d),(b,c)] + delta_cd diag_ab                      (:626-632)
 //   L[(a,c),p_b'] = L[p_b',(a,c)] = -D[(a,c),psi_b']                             (:633-635)
 //   preconditioner: L[(a,c),(b,c)] = diag_ab, L[p_a,p_b] = D[psi_a,psi_b]        (:455-462)
-// The 6 of 16 cross terms (phi_a d phi_b) of each block are computed and dropped: the tensor pipe has the
-// headroom, the scatter (red.global.add.f64, ~240 G/s per-lane issue bound) is what limits this strategy.
+// Homogeneous Dirichlet lines mask rows/columns and keep |L_ii| on the diagonal; no-normal-flux lines (one
+// component of a node expressed by the other two) are applied as C^T F C on the 3x3 block -- exactly what
+// AffineConstraints::distribute_local_to_global does entry by entry (:677-687).  The 6 of 16 cross terms
+// (phi_a d phi_b) of each block are computed and dropped: the tensor pipe has the headroom, the L1TEX pipe (global
+// reductions, one lane per clock when the addresses are scattered, plus the shared-memory operand loads) is what
+// limits the kernel (ncu: L1TEX 74 % busy, DMMA pipe 23 %).
 #include <omp.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "scatter.cuh"
 
@@ -30,14 +40,17 @@ constexpr int NU = 27, NP = 8, NQ = 27, ND = 89, NE = 35, GS = NQ * 13;
 constexpr int LDB = 148;        // row stride of X (148 mod 16 == 4: conflict-free fragment loads)
 constexpr int KQ = 28;          // quadrature points padded to a multiple of 4
 constexpr int PSI0 = 128;       // first psi column (node columns 32*alpha + b, b < 32)
+constexpr int PSTR = 1228;       // plan row: NE*NE offsets padded to a multiple of 8 bytes (cp.async granularity)
+constexpr int MSTR = 40;         // mask row: 27 node masks, 8 pressure flags, cell flag, int32 index of the wide table
+constexpr int IDS = 92;          // dof index buffer stride
 constexpr int MTHREADS = 128;    // 4 warps per CTA, 4 CTAs per SM: several cells in flight per SM hide the per-cell load latency
 
 struct MmaArgs {
   long long n_fast;
   const int* cells;
   const unsigned short* pos;
-  const unsigned char* nmask;       // [n][36]: unconstrained-component mask of the 27 velocity nodes, 8 pressure flags
-  const int* wide_idx;              // preconditioner: -1 or index into pos_wide
+  const unsigned char* nmask;       // [n][MSTR]: unconstrained-component mask of the 27 velocity nodes, 8 pressure flags,
+                                    // cell flag, then (preconditioner) int32: -1 or index into pos_wide
   const unsigned short* pos_wide;   // [n_wide][3][27][27]
   const double* geom;
   const int* l2g;
@@ -69,27 +82,48 @@ struct NodeCs {
   double w0, w1, w2;
 };
 
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Per-cell inputs (mapping record, dof indices, plan row, masks) are copied with cp.async; the gathers that depend
+// on the dof indices (row starts, old solution values) are cp.async gathers issued before the operand table is built
+// and awaited after it.  A cross-cell double buffer (prefetching cell n+1 while cell n is processed) was measured
+// and gave nothing at refine 5 and 6: the kernel is bound by the L1TEX pipe (reductions + shared-memory operands),
+// not by the latency of these loads.
 template <bool SYSTEM>
 __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockView A, CsView cs) {
   extern __shared__ __align__(16) double smem[];
   double* X = smem;                     // KQ * LDB, column = 32*alpha + node (alpha: d_0, d_1, d_2, value), psi at PSI0
   double* wq = X + KQ * LDB;            // KQ (+4)
-  double* sgeo = wq + 32;               // GS
-  double* sF = sgeo + GS;               // NQ*3
+  double* sgeo2 = wq + 32;              // GS
+  double* swt = sgeo2 + GS + 1;         // 3*NU master weights of the constrained component
+  double* sF = swt + 3 * NU + 1;        // NQ*3   (sF .. sGU: right-hand side only, i.e. unused by the preconditioner)
   double* sU = sF + NQ * 3;             // ND
-  double* sT = sU + ND + 1;             // 32
-  double* swt = sT + 32;                // 3*NU master weights of the constrained component
-  double* sGU = swt + 3 * NU + 1;       // NQ*12 old velocity / gradient at the quadrature points
+  double* sT = sU + ND + 1;             // 32: old temperature at the quadrature points
+  double* sTn = sT + 32;                // 28: nodal old temperature
+  double* sGU = sTn + 28;               // NQ*12 old velocity / gradient at the quadrature points
   long long* rb00 = (long long*)(sGU + NQ * 12);  // 3*NU
   long long* rb01 = rb00 + 3 * NU;          // 3*NU
   long long* rb10 = rb01 + 3 * NU;          // NP
-  int* sidx = (int*)(rb10 + NP);            // ND
-  int* sys_u = sidx + ND;                   // 3*NU
-  int* sys_p = sys_u + 3 * NU;              // NP
-  unsigned short* spos = (unsigned short*)(sys_p + NP);  // NE*NE
-  unsigned short* swide = spos + NE * NE + 1;              // 3*NU*NU (preconditioner, non-uniform cells)
-  unsigned char* snm = (unsigned char*)(swide + (SYSTEM ? 0 : 3 * NU * NU) + 1);  // 36
-  unsigned char* skc = snm + 36;            // 28
+  unsigned short* spos2 = (unsigned short*)(rb10 + NP);       // PSTR
+  unsigned char* snm2 = (unsigned char*)(spos2 + PSTR);       // MSTR
+  int* sidx2 = (int*)(snm2 + MSTR);                           // IDS
+  int* sidt2 = sidx2 + IDS;                                   // 28
+  int* sys_u = sidt2 + 28;                                    // 3*NU
+  int* sys_p = sys_u + 3 * NU;                                // NP
+  unsigned char* skc = (unsigned char*)(sys_p + NP);          // 28
+  // preconditioner, cells whose offsets differ between the components: 3*NU*NU offsets in the right-hand-side scratch
+  unsigned short* swide = (unsigned short*)sF;
+  static_assert(sizeof(double) * (NQ * 3 + ND + 1 + 32 + 28 + NQ * 12) >= sizeof(unsigned short) * 3 * NU * NU, "swide alias");
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
   for (int i = tid; i < ND; i += nt) {
@@ -98,7 +132,6 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
   }
   for (int i = tid; i < KQ * LDB; i += nt) X[i] = 0.0;   // padding nodes 27..31, padded point 27 stay zero
   if (tid < 4) wq[NQ + tid] = 0.0;
-  __syncthreads();
   const double nu = a.prm.dt * a.prm.inv_re;
   const bool do_rhs = SYSTEM && a.rhs != nullptr;
   const long long* rp00 = A.rowptr[0][0];
@@ -108,6 +141,11 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
   double* v01 = A.val[0][1];
   double* v10 = SYSTEM ? A.val[1][0] : A.val[1][1];
 
+  const double* sgeo = sgeo2;
+  const unsigned short* spos = spos2;
+  const unsigned char* snm = snm2;
+  const int* sidx = sidx2;
+  const int* sidt = sidt2;
   auto node_cs = [&](int n) {
     NodeCs c;
     c.mask = snm[n];
@@ -117,31 +155,41 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
     c.w2 = swt[3 * n + 2];
     return c;
   };
+  auto issue_raw = [&](long long w, long long cell) {
+    const double* g = a.geom + cell * GS;
+    for (int i = tid; i < GS; i += nt) cp_async8(sgeo2 + i, g + i);
+    const unsigned short* p = a.pos + w * PSTR;
+    for (int i = tid; i < PSTR / 4; i += nt) cp_async8(spos2 + 4 * i, p + 4 * i);
+    if (tid < MSTR / 8) cp_async8(snm2 + 8 * tid, a.nmask + w * MSTR + 8 * tid);
+    for (int i = tid; i < ND; i += nt) cp_async4(sidx2 + i, a.l2g + cell * ND + i);
+    if (do_rhs)
+      for (int i = tid; i < a.ndt; i += nt) cp_async4(sidt2 + i, a.l2g_t + cell * a.ndt + i);
+  };
 
   for (long long w = blockIdx.x; w < a.n_fast; w += gridDim.x) {
-    const long long cell = a.cells[w];
-    const double* g = a.geom + cell * GS;
-    for (int i = tid; i < GS; i += nt) sgeo[i] = g[i];
-    for (int i = tid; i < ND; i += nt) {
-      const int gi = a.l2g[cell * ND + i];
-      sidx[i] = gi;
-      if (do_rhs) sU[i] = a.old_nse[gi];
-    }
-    {
-      const unsigned short* p = a.pos + w * (NE * NE);
-      for (int i = tid; i < NE * NE; i += nt) spos[i] = p[i];
-      if (tid < 36) snm[tid] = a.nmask[w * 36 + tid];
-    }
-    int wide = -1;
-    if (!SYSTEM) {
-      wide = a.wide_idx[w];
-      if (wide >= 0) {
-        const unsigned short* p = a.pos_wide + (size_t)wide * (3 * NU * NU);
-        for (int i = tid; i < 3 * NU * NU; i += nt) swide[i] = p[i];
-      }
-    }
-    const int cflag = a.nmask[w * 36 + 35];  // 1: the cell holds constrained velocity dofs
+    __syncthreads();  // every warp is done with the previous cell
+    issue_raw(w, a.cells[w]);
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
+    // gathers through the dof indices: row starts, old solution
+    for (int i = tid; i < 3 * NU; i += nt) {
+      const int gi = sidx[sys_u[i]];
+      cp_async8(rb00 + i, rp00 + gi);
+      if (SYSTEM) cp_async8(rb01 + i, rp01 + gi);
+    }
+    for (int i = tid; i < NP; i += nt) cp_async8(rb10 + i, rp10 + (sidx[sys_p[i]] - a.n_u));
+    if (do_rhs) {
+      for (int i = tid; i < ND; i += nt) cp_async8(sU + i, a.old_nse + sidx[i]);
+      for (int i = tid; i < a.ndt; i += nt) cp_async8(sTn + i, a.old_temp + sidt[i]);
+    }
+    cp_async_commit();
+    const int wide = SYSTEM ? -1 : *reinterpret_cast<const int*>(snm + 36);
+    if (!SYSTEM && wide >= 0) {
+      const unsigned short* p = a.pos_wide + (size_t)wide * (3 * NU * NU);
+      for (int i = tid; i < 3 * NU * NU; i += nt) swide[i] = p[i];
+    }
+    const int cflag = snm[35];  // 1: the cell holds constrained velocity dofs
     if (tid < NU) {
       // no-normal-flux lines: u_k = sum_{c != k} w_c u_c on the same node (verified when the plan was built)
       int kc = 3;
@@ -165,12 +213,6 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
       swt[tid * 3 + 1] = w1;
       swt[tid * 3 + 2] = w2;
     }
-    for (int i = tid; i < 3 * NU; i += nt) {
-      const int gi = sidx[sys_u[i]];
-      rb00[i] = rp00[gi];
-      if (SYSTEM) rb01[i] = rp01[gi];
-    }
-    for (int i = tid; i < NP; i += nt) rb10[i] = rp10[sidx[sys_p[i]] - a.n_u];
     if (tid < NQ) wq[tid] = sgeo[tid];
     // operand table: physical gradients and values of the Q2 functions (component-major), then the Q1 functions
     for (int i = tid; i < NQ * NU; i += nt) {
@@ -183,6 +225,7 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
       x[96] = __ldg(a.phi_u + i);
     }
     for (int i = tid; i < NQ * NP; i += nt) X[(i / NP) * LDB + PSI0 + (i % NP)] = __ldg(a.phi_p + i);
+    cp_async_wait<0>();  // the gathers
     __syncthreads();
 
     // ---- Gram blocks on the tensor cores.  Task (ta <= tb): 8 row nodes x 8 column nodes, all 16 (alpha,beta)
@@ -331,7 +374,7 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
     if (do_rhs) {
       for (int q = tid; q < NQ; q += nt) {
         double tq = 0.0;
-        for (int k = 0; k < a.ndt; ++k) tq += a.old_temp[a.l2g_t[cell * a.ndt + k]] * __ldg(a.phi_t + q * a.ndt + k);
+        for (int k = 0; k < a.ndt; ++k) tq += sTn[k] * __ldg(a.phi_t + q * a.ndt + k);
         sT[q] = tq;
       }
       __syncthreads();
@@ -387,13 +430,13 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
         }
       }
     }
-    __syncthreads();
   }
 }
 
 constexpr size_t mma_smem_bytes(bool system) {
-  return sizeof(double) * (KQ * LDB + 32 + GS + NQ * 3 + ND + 1 + 32 + 3 * NU + 1 + NQ * 12) + sizeof(long long) * (6 * NU + NP) +
-         sizeof(int) * (ND + 3 * NU + NP) + sizeof(unsigned short) * (NE * NE + 2 + (system ? 0 : 3 * NU * NU)) + 36 + 28 + 32;
+  (void)system;
+  return sizeof(double) * (KQ * LDB + 32 + GS + 1 + NQ * 3 + ND + 1 + 32 + 28 + 3 * NU + 1 + NQ * 12) + sizeof(long long) * (6 * NU + NP) +
+         sizeof(unsigned short) * PSTR + MSTR + sizeof(int) * (IDS + 28 + 3 * NU + NP) + 28 + 36;
 }
 
 }  // namespace
@@ -598,12 +641,13 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
     } else
       wide_idx.push_back(-1);
   }
-  pos.resize(cells.size() * (size_t)(NE * NE));
-  nmask.resize(cells.size() * (size_t)36);
+  pos.resize(cells.size() * (size_t)PSTR, 0xFFFF);
+  nmask.resize(cells.size() * (size_t)MSTR, 0);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)cells.size(); ++i) {
-    std::copy(&pos_all[(size_t)cells[i] * NE * NE], &pos_all[(size_t)cells[i] * NE * NE] + NE * NE, &pos[(size_t)i * NE * NE]);
-    std::copy(&mask_all[(size_t)cells[i] * 36], &mask_all[(size_t)cells[i] * 36] + 36, &nmask[(size_t)i * 36]);
+    std::copy(&pos_all[(size_t)cells[i] * NE * NE], &pos_all[(size_t)cells[i] * NE * NE] + NE * NE, &pos[(size_t)i * PSTR]);
+    std::copy(&mask_all[(size_t)cells[i] * 36], &mask_all[(size_t)cells[i] * 36] + 36, &nmask[(size_t)i * MSTR]);
+    std::memcpy(&nmask[(size_t)i * MSTR + 36], &wide_idx[i], sizeof(int32_t));
   }
   MaskedPlan* P = new MaskedPlan;
   P->n = (int64_t)cells.size();
@@ -633,7 +677,6 @@ int dcp_launch_th_mma(dcp_model* m, const dcp_params& p, bool system, const Mask
   a.cells = plan->cells;
   a.pos = plan->pos;
   a.nmask = plan->nmask;
-  a.wide_idx = plan->wide_idx;
   a.pos_wide = plan->pos_wide;
   a.geom = m->geom_qn;
   a.l2g = m->nse_l2g;
@@ -652,25 +695,21 @@ int dcp_launch_th_mma(dcp_model* m, const dcp_params& p, bool system, const Mask
   a.prm = p;
   if (a.n_fast == 0) return DCP_OK;
   const size_t smem = mma_smem_bytes(system);
-  static bool attr = false;
-  if (!attr) {
-    DCP_CUDA(cudaFuncSetAttribute(th_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem_bytes(true)));
-    DCP_CUDA(cudaFuncSetAttribute(th_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem_bytes(false)));
-    attr = true;
-  }
-  int per_sm = 1;
+  auto launch = [&](auto kernel) -> int {
+    DCP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MTHREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > a.n_fast) grid = a.n_fast;
+    const BlockMat& mat = system ? m->nse : m->pre;
+    kernel<<<(unsigned)grid, MTHREADS, smem, ctx->stream>>>(a, make_view(mat), make_view(m->nse_cs));
+    return DCP_OK;
+  };
   if (system)
-    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, th_mma_kernel<true>, MTHREADS, smem));
+    DCP_TRY(launch(th_mma_kernel<true>));
   else
-    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, th_mma_kernel<false>, MTHREADS, smem));
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)ctx->sm_count * per_sm;
-  if (grid > a.n_fast) grid = a.n_fast;
-  const BlockMat& mat = system ? m->nse : m->pre;
-  if (system)
-    th_mma_kernel<true><<<(unsigned)grid, MTHREADS, smem, ctx->stream>>>(a, make_view(mat), make_view(m->nse_cs));
-  else
-    th_mma_kernel<false><<<(unsigned)grid, MTHREADS, smem, ctx->stream>>>(a, make_view(mat), make_view(m->nse_cs));
+    DCP_TRY(launch(th_mma_kernel<false>));
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;
