@@ -7,7 +7,7 @@
 
 struct dcph_problem {
   std::unique_ptr<dcph::Problem> P;
-  std::vector<std::string> names;
+  std::vector<std::string> names, scalar_names;
 };
 
 static thread_local std::string g_err;
@@ -19,6 +19,7 @@ dcph_problem* dcph_create(const char* spec) {
     auto* h = new dcph_problem;
     h->P = dcph::build_problem(dcph::parse_spec(spec ? spec : ""));
     for (auto& kv : h->P->arrays) h->names.push_back(kv.first);
+    for (auto& kv : h->P->scalars) h->scalar_names.push_back(kv.first);
     return h;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -51,5 +52,7 @@ int64_t dcph_scalar(const dcph_problem* p, const char* name) {
 
 int dcph_n_arrays(const dcph_problem* p) { return (int)p->names.size(); }
 const char* dcph_array_name(const dcph_problem* p, int i) { return p->names[i].c_str(); }
+int dcph_n_scalars(const dcph_problem* p) { return (int)p->scalar_names.size(); }
+const char* dcph_scalar_name(const dcph_problem* p, int i) { return p->scalar_names[i].c_str(); }
 const char* dcph_last_error(void) { return g_err.c_str(); }
 }

@@ -35,6 +35,10 @@ def lib():
         L.dcph_n_arrays.argtypes = [ctypes.c_void_p]
         L.dcph_array_name.restype = ctypes.c_char_p
         L.dcph_array_name.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.dcph_n_scalars.restype = ctypes.c_int
+        L.dcph_n_scalars.argtypes = [ctypes.c_void_p]
+        L.dcph_scalar_name.restype = ctypes.c_char_p
+        L.dcph_scalar_name.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.dcph_last_error.restype = ctypes.c_char_p
         _LIB = L
     return _LIB
@@ -66,6 +70,10 @@ class Problem:
     def names(self):
         L = lib()
         return [L.dcph_array_name(self._h, i).decode() for i in range(L.dcph_n_arrays(self._h))]
+
+    def scalar_names(self):
+        L = lib()
+        return [L.dcph_scalar_name(self._h, i).decode() for i in range(L.dcph_n_scalars(self._h))]
 
     def has(self, name):
         return name in self.names()

@@ -7,7 +7,7 @@ NVFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xco
 CU_SRCS := $(wildcard $(PKG)/csrc/device/*.cu)
 CU_HDRS := $(wildcard $(PKG)/csrc/device/*.cuh) $(wildcard $(PKG)/csrc/device/*.h) include/dcp.h
 
-all: lib/libdcp_harness.so oracle lib/libdcp.so
+all: lib/libdcp_harness.so oracle lib/libdcp.so tests/cpp/host_mirror_test
 
 lib/libdcp_harness.so: $(wildcard $(PKG)/csrc/harness/*.hpp) $(PKG)/csrc/harness/harness_api.cpp include/dcp_harness.h
 	mkdir -p lib
@@ -20,6 +20,11 @@ lib/libdcp.so: $(CU_SRCS) $(CU_HDRS)
 	mkdir -p lib build
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRCS) -lcudart > build/ptxas.log 2>&1 || (cat build/ptxas.log; false)
 
+# C++ host mirror (include/dcp.hpp) checked against the oracle; the oracle is linked as the checker only
+tests/cpp/host_mirror_test: tests/cpp/host_mirror_test.cpp include/dcp.hpp include/dcp.h include/dcp_harness.h lib/libdcp.so lib/libdcp_harness.so oracle
+	$(CXX) -std=c++17 -O2 -Wall -Wextra -I include -o $@ tests/cpp/host_mirror_test.cpp -L lib -ldcp -ldcp_harness -L oracle/_build -loracle \
+	  -Wl,-rpath,'$$ORIGIN/../../lib' -Wl,-rpath,'$$ORIGIN/../../oracle/_build'
+
 clean:
-	rm -rf lib build oracle/_build
+	rm -rf lib build oracle/_build tests/cpp/host_mirror_test
 .PHONY: all oracle clean

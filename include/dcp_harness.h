@@ -34,6 +34,9 @@ int64_t dcph_scalar(const dcph_problem* p, const char* name);
 /* number of registered arrays / name of the i-th (for enumeration) */
 int dcph_n_arrays(const dcph_problem* p);
 const char* dcph_array_name(const dcph_problem* p, int i);
+/* same for the scalars */
+int dcph_n_scalars(const dcph_problem* p);
+const char* dcph_scalar_name(const dcph_problem* p, int i);
 const char* dcph_last_error(void);
 
 #ifdef __cplusplus
