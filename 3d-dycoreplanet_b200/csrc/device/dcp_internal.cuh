@@ -165,6 +165,7 @@ struct dcp_model {
   FastPlan* fast_pre = nullptr;
   MaskedPlan* masked_nse = nullptr;
   MaskedPlan* masked_pre = nullptr;
+  std::vector<struct dcp_ilu*> ilus;  // live ILU handles of this model (destroyed with it)
 };
 
 // ---- helpers implemented in context.cu -----------------------------------------------------------
@@ -174,6 +175,9 @@ int dcp_check_device_errors(dcp_ctx* ctx, const char* what);
 int dcp_stage_in(dcp_ctx* ctx, int slot, const double* src, int64_t n, int mem, const double** dev);
 int dcp_stage_out_alloc(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem, double** dev);
 int dcp_stage_out_finish(dcp_ctx* ctx, int slot, double* dst, int64_t n, int mem);
+
+BlockMat* dcp_select_matrix(dcp_model* m, int which);
+extern "C" int dcp_ilu_destroy(struct dcp_ilu* p);
 
 // ---- kernels' host launchers ---------------------------------------------------------------------
 int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit = -1);

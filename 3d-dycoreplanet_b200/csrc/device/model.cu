@@ -190,6 +190,8 @@ static BlockMat* select_matrix(dcp_model* m, int which) {
   }
 }
 
+BlockMat* dcp_select_matrix(dcp_model* m, int which) { return select_matrix(m, which); }
+
 static int get_block(dcp_model* m, int which, int bi, int bj, DevCsr** out, BlockMat** bm = nullptr) {
   BlockMat* M = select_matrix(m, which);
   if (!M || bi < 0 || bj < 0 || bi >= M->nb || bj >= M->nb) {
@@ -298,6 +300,7 @@ int dcp_model_destroy(dcp_model* m) {
   if (!m) return DCP_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  while (!m->ilus.empty()) dcp_ilu_destroy(m->ilus.back());  // handles that outlived their model's owner
   cudaFree(m->nse_l2g);
   cudaFree(m->temp_l2g);
   cudaFree(m->temp_pos);

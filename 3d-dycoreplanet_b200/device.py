@@ -86,7 +86,7 @@ EXPORTS = [
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
     "dcp_vmult_add", "dcp_block_vmult", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
     "dcp_vec_scale", "dcp_vec_copy", "dcp_velocity_extrema", "dcp_constraints_distribute",
-    "dcp_geometry_create",
+    "dcp_geometry_create", "dcp_ilu_create", "dcp_ilu_refactor", "dcp_ilu_vmult", "dcp_ilu_levels", "dcp_ilu_destroy",
 ]
 
 
@@ -143,6 +143,11 @@ def lib():
         L.dcp_vec_scale.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
         L.dcp_vec_copy.argtypes = [vp, ctypes.c_int64, vp, vp]
         L.dcp_geometry_create.argtypes = [vp, ctypes.POINTER(MappingDesc), ctypes.POINTER(vp)]
+        L.dcp_ilu_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        L.dcp_ilu_refactor.argtypes = [vp]
+        L.dcp_ilu_vmult.argtypes = [vp, vp, vp, ctypes.c_int]
+        L.dcp_ilu_levels.argtypes = [vp, c_lp, c_lp]
+        L.dcp_ilu_destroy.argtypes = [vp]
         L.dcp_velocity_extrema.argtypes = [vp, vp, ctypes.c_int, c_dp]
         L.dcp_constraints_distribute.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
         _LIB = L
@@ -188,7 +193,13 @@ class Context:
         self.device = device
 
     def set_stream(self, cuda_stream_ptr):
-        check(lib().dcp_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)), "dcp_ctx_set_stream")
+        """Run the library's work on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream).  Handle 0 is
+        torch's default stream = the legacy default stream, passed as cudaStreamLegacy (1); None = the own stream."""
+        if cuda_stream_ptr is None:
+            ptr = None
+        else:
+            ptr = 1 if int(cuda_stream_ptr) == 0 else int(cuda_stream_ptr)
+        check(lib().dcp_ctx_set_stream(self._h, ctypes.c_void_p(ptr)), "dcp_ctx_set_stream")
 
     def synchronize(self):
         check(lib().dcp_ctx_synchronize(self._h), "dcp_ctx_synchronize")
@@ -287,6 +298,40 @@ class PreconditionJacobi:
         s, ms = _vec_arg(src)
         assert md == ms
         check(lib().dcp_jacobi_vmult(self._m._h, self.which, self.bi, d, s, md), "jacobi vmult")
+
+
+class PreconditionILU:
+    """LA::PreconditionILU (Ifpack ILU(0), deal.II defaults) of a diagonal block, factorised on the device."""
+
+    def __init__(self, model, which, bi):
+        self._m = model
+        self._h = ctypes.c_void_p()
+        check(lib().dcp_ilu_create(model._h, which, bi, ctypes.byref(self._h)), "dcp_ilu_create")
+
+    def refactor(self):
+        check(lib().dcp_ilu_refactor(self._h), "dcp_ilu_refactor")
+
+    def levels(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        check(lib().dcp_ilu_levels(self._h, ctypes.byref(a), ctypes.byref(b)), "dcp_ilu_levels")
+        return a.value, b.value
+
+    def vmult(self, dst, src):
+        d, md = _vec_arg(dst)
+        s, ms = _vec_arg(src)
+        assert md == ms
+        check(lib().dcp_ilu_vmult(self._h, d, s, md), "dcp_ilu_vmult")
+
+    def close(self):
+        if self._h and self._m._h:      # a closed model has already destroyed its ILU handles
+            lib().dcp_ilu_destroy(self._h)
+        self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _csr_desc(P, name, keep):

@@ -69,6 +69,9 @@ class DeviceBackend:
         from . import device
         self.torch, self.dv, self.ctx = torch, device, ctx
         self._res = ctypes.c_double()
+        # the library's own stream is non-blocking: run it on torch's current stream so that tensor creation
+        # (torch.zeros, .cuda()) and the library's kernels on the same memory are ordered
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr())
@@ -249,6 +252,48 @@ class SchurComplement:
         self.b10.vmult(dst, self.tmp2, B)
 
 
+class InverseMatrix:
+    """LinearAlgebra::InverseMatrix::vmult (inverse_matrix.hpp:90-121): CG to 1e-6 |src| with the given
+    preconditioner, at most max(n, 1000) steps, dst starts from zero."""
+
+    def __init__(self, matrix, preconditioner):
+        self.matrix, self.preconditioner = matrix, preconditioner
+        self.iterations = []
+
+    def vmult(self, dst, src, B):
+        n = len(src)
+        tol = 1e-6 * math.sqrt(B.dot(src, src))
+        B.scale(0.0, dst)
+        self.iterations.append(solver_cg(B, self.matrix, dst, src, self.preconditioner, tol, max(n, 1000)))
+
+
+class ApproximateInverseMatrix(InverseMatrix):
+    """approximate_inverse.hpp:97-128: the same CG with SolverControl(n_iter, 1e-6 |src|); the reference passes
+    numbers::invalid_unsigned_int for n_iter (boussinesq_model.tpp:1359-1372), i.e. no effective step limit."""
+
+    def __init__(self, matrix, preconditioner, n_iter=4294967295):
+        super().__init__(matrix, preconditioner)
+        self.n_iter = n_iter
+
+    def vmult(self, dst, src, B):
+        tol = 1e-6 * math.sqrt(B.dot(src, src))
+        B.scale(0.0, dst)
+        self.iterations.append(solver_cg(B, self.matrix, dst, src, self.preconditioner, tol, self.n_iter))
+
+
+class ApproximateSchurComplement:
+    """approximate_schur_complement.hpp:129-142: block(1,0) * P(block(0,0)) * block(0,1) with P = PreconditionILU."""
+
+    def __init__(self, block_01, block_10, preconditioner, n_u, B):
+        self.b01, self.b10, self.prec = block_01, block_10, preconditioner
+        self.tmp1, self.tmp2 = B.zeros(n_u), B.zeros(n_u)
+
+    def vmult(self, dst, src, B):
+        self.b01.vmult(self.tmp1, src, B)
+        self.prec.vmult(self.tmp2, self.tmp1, B)
+        self.b10.vmult(dst, self.tmp2, B)
+
+
 class BlockSchurPreconditioner:
     """block_schur_preconditioner.hpp:17-86 with do_solve_A = false: note that the Schur complement is built with
     the A-preconditioner as its "inverse" (:32-35) and mp_preconditioner is never applied."""
@@ -311,6 +356,37 @@ def solve_nse_block_preconditioned(B, nse_matrix, blocks, a_preconditioner, nse_
     P = BlockSchurPreconditioner(blocks, a_preconditioner, n_u, n_p, B)
     its = solver_gmres(B, nse_matrix, x, nse_rhs, P, tol, 40, restart=30, flexible=True)   # :1191-1199
     return x, its, P.inner_iterations
+
+
+def solve_nse_schur_complement(B, blocks, ilu_00, nse_rhs, nse_solution, n_u, n_p, dt, distribute_fn,
+                               constrained_pressure=None):
+    """solve_NSE_Schur_complement (boussinesq_model.tpp:1248-1414), the path of data/aqua_planet_test_2d.prm.
+    blocks: {(i,j): operator}; ilu_00: PreconditionILU of block(0,0) (inner_schur_preconditioner and the one inside
+    ApproximateSchurComplement are both ILU(0) of the same block); distribute_fn(x) applies nse_constraints.distribute
+    in place.  Returns (solution with the pressure scaled back, GMRES iterations, [inner CG iteration lists])."""
+    x = B.copy(nse_solution)
+    xu, xp = x[:n_u], x[n_u:]
+    B.scale(dt, xp)                                                     # :1283
+    if constrained_pressure is not None and len(constrained_pressure):  # :1291-1293
+        xp[constrained_pressure] = 0.0
+    block_inverse = InverseMatrix(blocks[(0, 0)], ilu_00)               # :1271-1275
+    schur = SchurComplement(blocks[(0, 1)], blocks[(1, 0)], block_inverse, n_u, B)   # :1299-1305
+    tmp = B.zeros(n_u)
+    schur_rhs = B.zeros(n_p)
+    block_inverse.vmult(tmp, nse_rhs[:n_u], B)                          # :1315
+    blocks[(1, 0)].vmult(schur_rhs, tmp, B)                             # :1316
+    B.axpy(-1.0, nse_rhs[n_u:], schur_rhs)                              # :1317
+    approx_schur = ApproximateSchurComplement(blocks[(0, 1)], blocks[(1, 0)], ilu_00, n_u, B)   # :1342-1347
+    prec = ApproximateInverseMatrix(approx_schur, Identity())           # :1359-1372
+    tol = 1e-6 * math.sqrt(B.dot(schur_rhs, schur_rhs))                 # :1332-1333
+    its = solver_gmres(B, schur, xp, schur_rhs, prec, tol, n_u + n_p)   # :1374-1377
+    distribute_fn(x)                                                    # :1384
+    blocks[(0, 1)].vmult(tmp, xp, B)                                    # :1396-1398
+    B.sadd(-1.0, 1.0, nse_rhs[:n_u], tmp)
+    block_inverse.vmult(xu, tmp, B)                                     # :1401
+    distribute_fn(x)                                                    # :1406
+    B.scale(1.0 / dt, xp)                                               # :1412
+    return x, its, (block_inverse.iterations, prec.iterations)
 
 
 def solve_temperature(B, temperature_matrix, t_preconditioner, temperature_rhs, temperature_solution):

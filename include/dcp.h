@@ -199,7 +199,8 @@ typedef struct {
 /* ---- context --------------------------------------------------------------------------------- */
 int dcp_ctx_create(int device, dcp_ctx** out);
 int dcp_ctx_destroy(dcp_ctx* ctx);
-/* run all work of this context on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+/* run all work of this context on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's
+ * own non-blocking stream; the legacy default stream is cudaStreamLegacy, i.e. (void*)1 */
 int dcp_ctx_set_stream(dcp_ctx* ctx, void* cuda_stream);
 int dcp_ctx_synchronize(dcp_ctx* ctx);
 /* message of the last failing call on this thread */
@@ -270,6 +271,24 @@ int dcp_velocity_extrema(dcp_model* m, const double* nse_solution, int mem, doub
 /* AffineConstraints::distribute on a solution vector (nse_constraints.distribute :1233, temperature_constraints
  * .distribute :1442): x[line] = sum_k w_k x[master_k] + inhomogeneity.  space: 0 = NSE, 1 = temperature. */
 int dcp_constraints_distribute(dcp_model* m, int space, double* x, int mem);
+
+/* ---- ILU(0) -------------------------------------------------------------------------------
+ * LA::PreconditionILU = Ifpack ILU with deal.II's defaults (ilu_fill 0, ilu_atol 0, ilu_rtol 1, overlap 0) of the
+ * diagonal block (bi,bi) of matrix `which`: the inner preconditioner of the classic Schur-complement solve
+ * (`inner_schur_preconditioner->initialize(nse_matrix.block(0,0), data)`, boussinesq_model.tpp:1265-1275;
+ * preconditioner.h:36-42) and the PreconditionILU inside ApproximateSchurComplement
+ * (approximate_schur_complement.hpp:118-141).  dcp_ilu_create analyses the pattern (dependency levels) and
+ * factorises the current values; dcp_ilu_refactor repeats the numeric part after a re-assembly; dcp_ilu_vmult is
+ * PreconditionILU::vmult (forward + backward substitution).  After dcp_model_set_owned only the rank-local square
+ * block is factorised, as Ifpack does with overlap 0.  dcp_model_destroy also destroys the handles still alive
+ * (do not use or destroy them afterwards). */
+typedef struct dcp_ilu dcp_ilu;
+int dcp_ilu_create(dcp_model* m, int which, int bi, dcp_ilu** out);
+int dcp_ilu_refactor(dcp_ilu* p);
+int dcp_ilu_vmult(dcp_ilu* p, double* dst, const double* src, int mem);
+/* number of dependency levels of the two substitutions (= kernel launches per vmult) */
+int dcp_ilu_levels(const dcp_ilu* p, int64_t* n_lower, int64_t* n_upper);
+int dcp_ilu_destroy(dcp_ilu* p);
 
 /* ---- device-resident vector algebra for the Krylov solvers around the SpMVs (all pointers DEVICE) -----------
  * Trilinos vector ops inside deal.II SolverCG / SolverGMRES / SolverFGMRES (boussinesq_model.tpp:1165,1191-1199,

@@ -304,3 +304,23 @@ def constraints_distribute(P, prefix, x):
         sl = slice(line_ptr[l], line_ptr[l + 1])
         x[g] = float(np.dot(entry_w[sl], src[entry_dof[sl]])) + inhom[l]
     return x
+
+
+# ---- ILU(0) (oracle/ilu_oracle.c) -----------------------------------------------------------------------------------
+def ilu0_factor(rowptr, col, val, n=None):
+    """ILU(0) factors on the pattern of A (strict lower part L with unit diagonal, rest U)."""
+    n = len(rowptr) - 1 if n is None else n
+    lu = np.zeros(len(col))
+    L = lib()
+    L.orc_ilu0_factor.restype = ctypes.c_int
+    rc = L.orc_ilu0_factor(ctypes.c_int64(n), _lp(rowptr), _ip(col), _dp(val), _dp(lu))
+    if rc:
+        raise RuntimeError(f"ilu0: row {rc - 1} has no diagonal entry")
+    return lu
+
+
+def ilu0_solve(rowptr, col, lu, x, n=None):
+    n = len(rowptr) - 1 if n is None else n
+    y = np.zeros(n)
+    lib().orc_ilu0_solve(ctypes.c_int64(n), _lp(rowptr), _ip(col), _dp(lu), _dp(np.ascontiguousarray(x[:n])), _dp(y))
+    return y

@@ -96,3 +96,58 @@ def gpu_time_step(ctx, P, mp, u0, T0):
     th = S.distribute(B, cs_lines(P, "temp.cs"), B.to_numpy(t))
     model.close()
     return dict(nse=xh, temp=th, fgmres=its, inner=inner, cg=cg)
+
+
+# ---- classic Schur-complement path (data/aqua_planet_test_2d.prm: use_schur_complement_solver = true) -------------
+def cpu_schur_step(P, mp, u0, T0):
+    """assemble_nse_system + solve_NSE_Schur_complement (boussinesq_model.tpp:1867-1870, 1248-1414) on the CPU:
+    oracle assembly, oracle ILU(0), numpy Krylov vectors."""
+    from dycore_b200 import solvers as S
+    from oracle import oracle as orc
+    prm = orc.params_from(mp)
+    B = S.NumpyBackend()
+    n = P.scalar("nse.n_dofs")
+    n_u, n_p = P.scalar("nse.n_u"), P.scalar("nse.n_p")
+    vals, rhs = orc.assemble_nse_system(P, prm, u0, T0)
+    rp, col, _, _ = P.csr("nse.full")
+    A = sp.csr_matrix((vals, col, rp), shape=(n, n))
+    A00 = A[:n_u, :n_u].tocsr()
+    A00.sort_indices()
+    rp0, col0 = A00.indptr.astype(np.int64), A00.indices.astype(np.int32)
+    assert np.array_equal(rp0, P["nse.b00.rowptr"]) and np.array_equal(col0, P["nse.b00.col"])
+    lu = orc.ilu0_factor(rp0, col0, np.ascontiguousarray(A00.data))
+
+    def mat(M):
+        return S.Wrap(lambda dst, src, M=M: dst.__setitem__(slice(None), M @ src))
+    ilu = S.Wrap(lambda dst, src: dst.__setitem__(slice(None), orc.ilu0_solve(rp0, col0, lu, np.ascontiguousarray(src))))
+    blocks = {(0, 0): mat(A00), (0, 1): mat(A[:n_u, n_u:]), (1, 0): mat(A[n_u:, :n_u])}
+    lines = cs_lines(P, "nse.cs")
+    x, its, inner = S.solve_nse_schur_complement(B, blocks, ilu, rhs, u0, n_u, n_p, mp.time_step,
+                                                 lambda v: S.distribute(B, lines, v))
+    return dict(nse=x, gmres=its, inner=inner)
+
+
+def gpu_schur_step(ctx, P, mp, u0, T0):
+    """The same with assembly, ILU(0), SpMVs and Krylov vectors on the device."""
+    import ctypes
+    import torch
+    from dycore_b200 import device
+    from dycore_b200 import solvers as S
+    B = S.DeviceBackend(ctx)
+    n_u, n_p = P.scalar("nse.n_u"), P.scalar("nse.n_p")
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    d_u, d_T = torch.from_numpy(u0).cuda(), torch.from_numpy(T0).cuda()
+    torch.cuda.synchronize()
+    model.assemble_nse_system(d_u, d_T)
+    ptr, nn = ctypes.c_void_p(), ctypes.c_int64()
+    device.check(device.lib().dcp_vector_device(model._h, device.VEC_NSE_RHS, ctypes.byref(ptr), ctypes.byref(nn)))
+    rhs = torch.empty(n_u + n_p, dtype=torch.float64, device="cuda")
+    device.check(device.lib().dcp_vec_copy(ctx._h, n_u + n_p, ptr, ctypes.c_void_p(rhs.data_ptr())))
+    ilu = device.PreconditionILU(model, device.MAT_NSE, 0)
+    blocks = {(i, j): S.Wrap(model.nse_matrix.block(i, j)) for (i, j) in ((0, 0), (0, 1), (1, 0))}
+    x, its, inner = S.solve_nse_schur_complement(B, blocks, S.Wrap(ilu), rhs, d_u, n_u, n_p, mp.time_step,
+                                                 model.distribute_nse_constraints)
+    out = dict(nse=B.to_numpy(x), gmres=its, inner=inner)
+    ilu.close()
+    model.close()
+    return out

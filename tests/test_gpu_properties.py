@@ -21,6 +21,7 @@ def setup():
     from util import synthetic_fields
     P = harness.Problem(geometry="shell", refine=REFINE)
     ctx = device.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)   # torch's generators / fills and the library share one stream
     mp = params.NAMED["shell_3d_classic"]
     model = device.BoussinesqModel.from_problem(ctx, P, mp, device_geometry=True)
     u, T = synthetic_fields(P)
