@@ -107,6 +107,55 @@ __global__ void __launch_bounds__(128) temperature_matrix_kernel(ScalarArgs a, C
   for (long long cell = (long long)blockIdx.x * nwarps + wid; cell < a.n_cells; cell += (long long)gridDim.x * nwarps) {
     const double* g = a.geom + cell * a.gstride;
     if (lane < nd) idx[lane] = a.l2g[cell * nd + lane];
+    const unsigned short* tp = a.tpos + cell * (long long)(nd * nd);
+    if (DIM == 3 && nd == 8 && a.nq <= 28) {
+      // Q1 temperature: the two 8x8 local matrices are Gram matrices over the quadrature points -> 28 DMMA per cell
+      // instead of 36 entries x 27 points x 9 shared-memory loads (the shared-memory pipe bounded the loop below)
+      if (lane < 28) {
+        if (lane < a.nq) {
+          map_point<DIM>(a, g, lane, S + lane * L.sv);
+          wq[lane] = g[lane];
+        } else {
+          for (int k = 0; k < 32; ++k) S[lane * L.sv + k] = 0.0;
+          wq[lane] = 0.0;
+        }
+      }
+      __syncwarp();
+      const int frow = lane >> 2, fk = lane & 3;
+      double m0 = 0.0, m1 = 0.0, k0 = 0.0, k1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 7; ++ks) {
+        const int q = 4 * ks + fk;
+        const double* sp = S + q * L.sv + frow * 4;
+        const double w = wq[q], x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3];
+        dmma_m8n8k4(m0, m1, w * x0, x0);
+        dmma_m8n8k4(k0, k1, w * x1, x1);
+        dmma_m8n8k4(k0, k1, w * x2, x2);
+        dmma_m8n8k4(k0, k1, w * x3, x3);
+      }
+      k0 *= a.prm.inv_pe;
+      k1 *= a.prm.inv_pe;
+      const int e0 = frow * 8 + 2 * fk;
+      if (tp[0] != 0xffffu) {
+        const long long r0 = Mass.rowptr[0][0][idx[frow]];
+        const long long at0 = r0 + tp[e0], at1 = r0 + tp[e0 + 1];
+        red_add_f64(Mass.val[0][0] + at0, m0);
+        red_add_f64(Mass.val[0][0] + at1, m1);
+        red_add_f64(Stiff.val[0][0] + at0, k0);
+        red_add_f64(Stiff.val[0][0] + at1, k1);
+      } else {
+        A[e0] = m0;
+        A[e0 + 1] = m1;
+        B[e0] = k0;
+        B[e0 + 1] = k1;
+        __syncwarp();
+        distribute_local_matrix<true>(cs, nd, nd, A, nullptr, idx, lines, Mass, nullptr, lane, 32, false, err);
+        __syncwarp();
+        distribute_local_matrix<true>(cs, nd, nd, B, nullptr, idx, lines, Stiff, nullptr, lane, 32, false, err);
+      }
+      __syncwarp();
+      continue;
+    }
     for (int q0 = 0; q0 < a.nq; q0 += 32) {
       const int q = q0 + lane;
       if (q < a.nq) {
@@ -146,7 +195,6 @@ __global__ void __launch_bounds__(128) temperature_matrix_kernel(ScalarArgs a, C
       }
     }
     __syncwarp();
-    const unsigned short* tp = a.tpos + cell * (long long)(nd * nd);
     if (tp[0] != 0xffffu) {
       // no constrained dof in this cell: both matrices share one pattern, positions were found once per mesh
       const long long* rp = Mass.rowptr[0][0];
