@@ -626,7 +626,9 @@ int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old
     // Jacobi of Mw = block(0,0) and Mu = block(1,1) used by solve_NSE_block_preconditioned (:1283-1304)
     DCP_TRY(refresh_jacobi(ctx, m->nse));
   } else if (m->strategy == DCP_STRATEGY_OWNER) {
-    // every CSR value written once by its owning tile; then rhs (all cells) and the constrained-dof fix-up
+    // every CSR value of an unconstrained row is written once by its owning tile; then rhs (all cells) and the
+    // constrained-dof fix-up, which accumulates: those entries must start from zero on every pass
+    DCP_TRY(zero_blockmat(ctx, m->nse));
     DCP_TRY(dcp_launch_th_owner(m, *p, true));
     DCP_TRY(dcp_launch_th_rhs(m, *p, d_nse, d_temp));
     DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
@@ -660,6 +662,7 @@ int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_feec(m, *p, false, nullptr, nullptr));
   } else if (m->strategy == DCP_STRATEGY_OWNER) {
+    DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_th_owner(m, *p, false));
     DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
   } else if (m->strategy == DCP_STRATEGY_POSITIONS) {

@@ -69,8 +69,9 @@ enum {
   DCP_STRATEGY_POSITIONS = 1, /* unconstrained cells scatter from registers through a precomputed position table
                                  (no search, no local matrix in shared memory); constrained cells use SEARCH */
   DCP_STRATEGY_OWNER = 2      /* row-owner tiles: a CTA owns a contiguous row range, accumulates in shared memory and
-                                 writes every CSR value exactly once (no atomics, no zero-fill); contributions of
-                                 constrained dofs are added afterwards by SEARCH on the constrained cells */
+                                 writes every CSR value of an unconstrained row exactly once (no atomics);
+                                 contributions of constrained dofs are added afterwards by SEARCH on the constrained
+                                 cells */
 };
 
 typedef struct dcp_ctx dcp_ctx;

@@ -61,6 +61,15 @@ def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy):
         gv = model.nse_preconditioner_matrix.block(bi, bj).values()
         assert rel_err_max(gv, rv) <= TOL, f"pre block {bi}{bj}"
 
+    # every time step re-assembles (quirk Q16): a second pass must not accumulate onto the first
+    model.assemble_nse_system(u, T)
+    model.assemble_nse_preconditioner()
+    for (bi, bj), rv in split_blocks(P, "nse", ref_vals).items():
+        assert rel_err_max(model.nse_matrix.block(bi, bj).values(), rv) <= TOL, f"second pass, nse block {bi}{bj}"
+    assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
+    for (bi, bj), rv in ref_blocks.items():
+        assert rel_err_max(model.nse_preconditioner_matrix.block(bi, bj).values(), rv) <= TOL, f"second pass, pre block {bi}{bj}"
+
     # temperature matrices, combined matrix and rhs
     model.assemble_temperature_matrix()
     rm, rk = orc.assemble_temperature_matrix(P, oprm)
