@@ -13,9 +13,15 @@
 //   L[w_i,w_j] = sum w phi_w_i.phi_w_j            L[w_i,u_j] = -sum w curl_w_i.u_j
 //   L[u_i,u_j] = sum w u_i.u_j                    L[u_j,w_i] = +dt/Re sum w u_j.curl_w_i   (:753-769)
 //   L[u_i,p] = L[p,u_i] = -sum w div u_i
-// and the scatter is the general AffineConstraints path of scatter.cuh.
+// Scatter: cells without constrained dofs add their nonzero entries at `row start + position`, positions found once per
+// mesh (19 x 19 uint16 per cell and matrix); the binary searches of the general path cost ~9 dependent global loads
+// per entry and dominated the first version of this kernel.  Cells with constrained dofs take the general
+// AffineConstraints path of scatter.cuh.
 // Preconditioner (quirk Q5, :558-569): JxW multiplies only p*p; dt/Re curl.curl and the sign(u.w) terms are
 // summed unweighted over the 8 points.
+#include <algorithm>
+#include <vector>
+
 #include "scatter.cuh"
 
 namespace {
@@ -23,11 +29,10 @@ namespace {
 using namespace dcpdev;
 
 constexpr int NW = 12, NU = 6, ND = 19;
-constexpr int SV = 97;    // values per quadrature point (96) padded to an odd stride
+constexpr int SV = 97;      // preconditioner: values per quadrature point (96) padded to an odd stride
+constexpr int SV_SYS = 61;  // system: the larger of the two table halves (36 + 18 + 6) padded to an odd stride
 constexpr int NQMAX = 27;
-constexpr int FWARPS = 2;
-// offsets inside S[q][.]
-constexpr int O_W = 0, O_C = 36, O_U = 72, O_D = 90;
+constexpr int FWARPS = 1;   // one warp per CTA: the scratch of one warp (19 kB system, 11 kB preconditioner) is the occupancy unit
 
 struct FeecArgs {
   long long n_cells;
@@ -41,31 +46,85 @@ struct FeecArgs {
   const double* old_nse;
   const double* old_temp;
   double* rhs;
+  const unsigned short* pos;  // [n_cells][19*19] position of entry (i,j) inside row i of its block; pos[cell][0] == 0xfffe: general path
   dcp_params prm;
 };
 
+template <int NQM, int STRIDE>
 struct FeecScratch {
-  double S[NQMAX * SV];
+  double S[NQM * STRIDE];
   double L[ND * ND];
   double l[ND];
-  double F[NQMAX * 4];  // rhs integrand per point: A[3] (dotted with u_i) and B (times div u_i), JxW folded in
-  double wq[NQMAX];
+  double F[NQM * 4];    // rhs integrand per point: A[3] (dotted with u_i) and B (times div u_i), JxW folded in
+  double wq[NQM];
   double U[ND];
   double sg[ND];
   int idx[ND + 1];
   int lines[ND + 1];
+  long long rs[ND * 3];  // start of local row i inside column block bj
+  double Tn[28];         // nodal old temperature of the cell
+  unsigned short pos[ND * ND + 3];
 };
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-template <bool SYSTEM>
+// NQM: capacity of the per-warp table (27 for the system rule QGauss(3), 8 for the preconditioner rule QGauss(2)).
+// Shared memory per warp decides how many warps an SM holds, and this kernel is latency-bound (ncu: 12 % occupancy,
+// long-scoreboard + fixed-latency stalls), so the system pass builds its table in two halves that share one buffer:
+// first the vorticity values (for the w-w block), then curl / velocity / divergence (for everything else).
+template <bool SYSTEM, int NQM>
 __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs, BlockView A, int* err) {
   extern __shared__ __align__(16) unsigned char raw_smem[];
-  FeecScratch* all = reinterpret_cast<FeecScratch*>(raw_smem);
+  using Scratch = FeecScratch<NQM, SYSTEM ? SV_SYS : SV>;
+  Scratch* all = reinterpret_cast<Scratch*>(raw_smem);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  FeecScratch& s = all[wid];
+  Scratch& s = all[wid];
+  constexpr int ST = SYSTEM ? SV_SYS : SV;                  // row stride of S
+  constexpr int P_W = 0;                                    // vorticity values (system: first half)
+  constexpr int P_C = SYSTEM ? 0 : 36;                      // curls (system: second half)
+  constexpr int P_U = SYSTEM ? 36 : 72;                     // velocity values
+  constexpr int P_D = SYSTEM ? 54 : 90;                     // divergences
   const int nq = a.nq;
   const double nu = a.prm.dt * a.prm.inv_re;
+  // Local matrix by 3 x 3 register tiles: one lane owns a block of three row functions x three column functions and
+  // loads their 18 mapped components once per quadrature point (2 shared-memory loads per entry and point instead
+  // of 6; all tiles of a stage run in one round of the warp).
+  auto tile = [&](int orow, int ocol, bool weighted, bool sign_only, double acc[3][3]) {
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+      for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      const double* ra = s.S + q * ST + orow;
+      const double* rb = s.S + q * ST + ocol;
+      double va[9], vb[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        va[k] = ra[k];
+        vb[k] = rb[k];
+      }
+      const double w = weighted ? s.wq[q] : 1.0;
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) {
+          const double dt3 = va[3 * x] * vb[3 * y] + va[3 * x + 1] * vb[3 * y + 1] + va[3 * x + 2] * vb[3 * y + 2];
+          if (sign_only)
+            acc[x][y] += fabs(dt3) > 1.0e-9 ? (signbit(dt3) ? -1.0 : 1.0) : 0.0;
+          else
+            acc[x][y] += w * dt3;
+        }
+    }
+  };
+  // upper-triangular block pairs (I <= J) of an n x n block grid, t-th pair
+  auto sym_pair = [](int t, int n, int& I, int& J) {
+    I = 0;
+    while (t >= n - I) {
+      t -= n - I;
+      ++I;
+    }
+    J = I + t;
+  };
   for (long long cell = (long long)blockIdx.x * FWARPS + wid; cell < a.n_cells; cell += (long long)gridDim.x * FWARPS) {
     const double* g = a.geom + cell * a.gstride;
     if (lane < ND) {
@@ -74,11 +133,18 @@ __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs
       s.sg[lane] = a.sign[cell * ND + lane];
       if (SYSTEM) s.U[lane] = a.old_nse[gi];
     }
+    if (SYSTEM && lane < a.ndt) s.Tn[lane] = a.old_temp[a.l2g_t[cell * a.ndt + lane]];
+    {  // the plan row, staged now so that its latency overlaps the quadrature loop
+      const unsigned short* pp = a.pos + cell * (long long)(ND * ND);
+      for (int i = lane; i < ND * ND; i += 32) s.pos[i] = pp[i];
+    }
     for (int i = lane; i < ND * ND; i += 32) s.L[i] = 0.0;
     __syncwarp();
-    if (lane < nq) {
-      const int q = lane;
-      double J[3][3], K[3][3];
+    // ---- mapping at this lane's quadrature point (kept in registers across the two table halves)
+    const int q = lane;
+    const bool has_q = lane < nq;
+    double J[3][3], K[3][3], idet = 0.0, ow[3] = {0, 0, 0}, ou[3] = {0, 0, 0};
+    if (has_q) {
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -86,39 +152,62 @@ __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs
           K[i][j] = g[nq * (1 + i * 3 + j) + q];
           J[i][j] = g[nq * (13 + i * 3 + j) + q];
         }
-      const double det = g[nq * 22 + q], idet = 1.0 / det, w = g[q];
-      double* row = s.S + q * SV;
-      double ow[3] = {0, 0, 0}, ou[3] = {0, 0, 0};
+      idet = 1.0 / g[nq * 22 + q];
+      s.wq[q] = g[q];
+      // vorticity functions: covariant map K^T phi_hat
+      double* row = s.S + q * ST;
       for (int k = 0; k < NW; ++k) {
         const double* ph = a.tw + ((size_t)q * NW + k) * 3;
-        const double* ch = a.tc + ((size_t)q * NW + k) * 3;
         const double p0 = __ldg(ph), p1 = __ldg(ph + 1), p2 = __ldg(ph + 2);
-        const double c0 = __ldg(ch), c1 = __ldg(ch + 1), c2 = __ldg(ch + 2);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           const double vw = K[0][d] * p0 + K[1][d] * p1 + K[2][d] * p2;
-          row[O_W + k * 3 + d] = vw;
-          row[O_C + k * 3 + d] = (J[d][0] * c0 + J[d][1] * c1 + J[d][2] * c2) / det;
+          row[P_W + k * 3 + d] = vw;
           if (SYSTEM) ow[d] += s.U[k] * vw;
         }
       }
-      for (int k = 0; k < NU; ++k) {
+    }
+    double acc[3][3];
+    if (SYSTEM) {
+      __syncwarp();
+      if (lane < 10) {  // (w,w) tiles
+        int I, Jb;
+        sym_pair(lane, 4, I, Jb);
+        tile(P_W + 9 * I, P_W + 9 * Jb, true, false, acc);
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+#pragma unroll
+          for (int y = 0; y < 3; ++y) {
+            s.L[(3 * I + x) * ND + 3 * Jb + y] = acc[x][y];
+            s.L[(3 * Jb + y) * ND + 3 * I + x] = acc[x][y];
+          }
+      }
+      __syncwarp();  // the second half of the table overwrites the vorticity values
+    }
+    if (has_q) {
+      double* row = s.S + q * ST;
+      for (int k = 0; k < NW; ++k) {  // curls: J c_hat / det
+        const double* ch = a.tc + ((size_t)q * NW + k) * 3;
+        const double c0 = __ldg(ch), c1 = __ldg(ch + 1), c2 = __ldg(ch + 2);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) row[P_C + k * 3 + d] = (J[d][0] * c0 + J[d][1] * c1 + J[d][2] * c2) * idet;
+      }
+      for (int k = 0; k < NU; ++k) {  // velocity functions: contravariant Piola J phi_hat / det, times the face sign
         const double* ph = a.tu + ((size_t)q * NU + k) * 3;
         const double p0 = __ldg(ph), p1 = __ldg(ph + 1), p2 = __ldg(ph + 2);
         const double sgk = s.sg[NW + k];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const double ru = (J[d][0] * p0 + J[d][1] * p1 + J[d][2] * p2) / det;
-          row[O_U + k * 3 + d] = sgk * ru;
+          const double ru = (J[d][0] * p0 + J[d][1] * p1 + J[d][2] * p2) * idet;
+          row[P_U + k * 3 + d] = sgk * ru;
           if (SYSTEM) ou[d] += s.U[NW + k] * ru;  // get_function_values: no face sign (:705-708)
         }
-        row[O_D + k] = sgk * __ldg(a.td + k) / det;
+        row[P_D + k] = sgk * __ldg(a.td + k) * idet;
       }
-      (void)idet;
-      s.wq[q] = w;
       if (SYSTEM) {
+        const double w = s.wq[q];
         double T = 0.0;
-        for (int k = 0; k < a.ndt; ++k) T += a.old_temp[a.l2g_t[cell * a.ndt + k]] * __ldg(a.phi_t + q * a.ndt + k);
+        for (int k = 0; k < a.ndt; ++k) T += s.Tn[k] * __ldg(a.phi_t + q * a.ndt + k);
         const double rho = 1.0 - a.prm.beta * (T - a.prm.T_ref);
         double x[3] = {g[nq * 10 + q], g[nq * 11 + q], g[nq * 12 + q]}, grav[3];
         if (a.prm.cuboid) {
@@ -141,72 +230,96 @@ __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs
     }
     __syncwarp();
     if (SYSTEM) {
-      // 78 (w,w) + 72 (w,u) + 21 (u,u) + 6 (u,p) distinct entries
-      for (int e = lane; e < 177; e += 32) {
-        double acc = 0.0;
-        if (e < 78) {
-          int i = 0, r = e;
-          while (r >= NW - i) { r -= NW - i; ++i; }
-          const int j = i + r;
-          for (int q = 0; q < nq; ++q) acc += s.wq[q] * dot3(s.S + q * SV + O_W + i * 3, s.S + q * SV + O_W + j * 3);
-          s.L[i * ND + j] = acc;
-          s.L[j * ND + i] = acc;
-        } else if (e < 150) {
-          const int i = (e - 78) / NU, j = (e - 78) % NU;
-          for (int q = 0; q < nq; ++q) acc += s.wq[q] * dot3(s.S + q * SV + O_C + i * 3, s.S + q * SV + O_U + j * 3);
-          s.L[i * ND + NW + j] = -acc;
-          s.L[(NW + j) * ND + i] = nu * acc;
-        } else if (e < 171) {
-          int i = 0, r = e - 150;
-          while (r >= NU - i) { r -= NU - i; ++i; }
-          const int j = i + r;
-          for (int q = 0; q < nq; ++q) acc += s.wq[q] * dot3(s.S + q * SV + O_U + i * 3, s.S + q * SV + O_U + j * 3);
-          s.L[(NW + i) * ND + NW + j] = acc;
-          s.L[(NW + j) * ND + NW + i] = acc;
-        } else {
-          const int i = e - 171;
-          for (int q = 0; q < nq; ++q) acc += s.wq[q] * s.S[q * SV + O_D + i];
-          s.L[(NW + i) * ND + NW + NU] = -acc;
-          s.L[(NW + NU) * ND + NW + i] = -acc;
-        }
-      }
-      if (lane < ND) {
-        double acc = 0.0;
-        if (lane >= NW && lane < NW + NU) {
-          const int i = lane - NW;
-          for (int q = 0; q < nq; ++q)
-            acc += dot3(s.S + q * SV + O_U + i * 3, s.F + q * 4) + s.S[q * SV + O_D + i] * s.F[q * 4 + 3];
-        }
-        s.l[lane] = acc;
-      }
-    } else {
-      // preconditioner: 78 curl-curl, 72 sign terms, 1 pressure mass
-      for (int e = lane; e < 151; e += 32) {
-        double acc = 0.0;
-        if (e < 78) {
-          int i = 0, r = e;
-          while (r >= NW - i) { r -= NW - i; ++i; }
-          const int j = i + r;
-          for (int q = 0; q < nq; ++q) acc += dot3(s.S + q * SV + O_C + i * 3, s.S + q * SV + O_C + j * 3);
-          s.L[i * ND + j] = nu * acc;
-          s.L[j * ND + i] = nu * acc;
-        } else if (e < 150) {
-          const int i = (e - 78) / NW, j = (e - 78) % NW;  // u_i, w_j
-          for (int q = 0; q < nq; ++q) {
-            const double x = dot3(s.S + q * SV + O_U + i * 3, s.S + q * SV + O_W + j * 3);
-            acc += fabs(x) > 1.0e-9 ? (signbit(x) ? -1.0 : 1.0) : 0.0;
+      // lanes 0-7: (curl w,u) tiles, 8-10: (u,u); lane 11: the 6 (u,p) entries; lanes 12-17: right-hand side
+      if (lane < 11) {
+        const bool cu = lane < 8;
+        int I, Jb;
+        if (cu) {
+          I = lane >> 1;
+          Jb = lane & 1;
+        } else
+          sym_pair(lane - 8, 2, I, Jb);
+        tile((cu ? P_C : P_U) + 9 * I, P_U + 9 * Jb, true, false, acc);
+        const int r0 = (cu ? 0 : NW) + 3 * I, c0 = NW + 3 * Jb;
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+#pragma unroll
+          for (int y = 0; y < 3; ++y) {
+            const double v = acc[x][y];
+            s.L[(r0 + x) * ND + c0 + y] = cu ? -v : v;
+            s.L[(c0 + y) * ND + r0 + x] = cu ? nu * v : v;
           }
-          s.L[(NW + i) * ND + j] = acc;
-          s.L[j * ND + NW + i] = acc;
-        } else {
-          for (int q = 0; q < nq; ++q) acc += s.wq[q];
-          s.L[(NW + NU) * ND + NW + NU] = acc;
+      } else if (lane == 11) {
+        double d[NU] = {0, 0, 0, 0, 0, 0};
+        for (int p = 0; p < nq; ++p)
+#pragma unroll
+          for (int i = 0; i < NU; ++i) d[i] += s.wq[p] * s.S[p * ST + P_D + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          s.L[(NW + i) * ND + NW + NU] = -d[i];
+          s.L[(NW + NU) * ND + NW + i] = -d[i];
         }
+      } else if (lane < 12 + NU) {
+        const int i = lane - 12;
+        double v = 0.0;
+        for (int p = 0; p < nq; ++p)
+          v += dot3(s.S + p * ST + P_U + i * 3, s.F + p * 4) + s.S[p * ST + P_D + i] * s.F[p * 4 + 3];
+        s.l[NW + i] = v;
+      }
+      if (lane >= 20 && lane < 20 + NW) s.l[lane - 20] = 0.0;
+      if (lane == 19) s.l[NW + NU] = 0.0;
+    } else {
+      // preconditioner: lanes 0-9 curl-curl tiles, 10-17 sign tiles (u rows x w columns), lane 18 the pressure mass
+      int I = 0, Jb = 0;
+      const bool cc = lane < 10;
+      if (cc)
+        sym_pair(lane, 4, I, Jb);
+      else {
+        I = (lane - 10) >> 2;
+        Jb = (lane - 10) & 3;
+      }
+      if (lane < 18) {
+        tile((cc ? P_C : P_U) + 9 * I, (cc ? P_C : P_W) + 9 * Jb, false, !cc, acc);
+        const int r0 = (cc ? 0 : NW) + 3 * I, c0 = 3 * Jb;
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+#pragma unroll
+          for (int y = 0; y < 3; ++y) {
+            const double v = cc ? nu * acc[x][y] : acc[x][y];
+            s.L[(r0 + x) * ND + c0 + y] = v;
+            s.L[(c0 + y) * ND + r0 + x] = v;
+          }
+      } else if (lane == 18) {
+        double v = 0.0;
+        for (int p = 0; p < nq; ++p) v += s.wq[p];
+        s.L[(NW + NU) * ND + NW + NU] = v;
       }
     }
     __syncwarp();
-    distribute_local_matrix<true>(cs, ND, ND, s.L, SYSTEM ? s.l : nullptr, s.idx, s.lines, A, SYSTEM ? a.rhs : nullptr,
-                                  lane, 32, false, err);
+    const unsigned short* pp = s.pos;
+    if (pp[0] != 0xfffeu) {
+      for (int t = lane; t < ND * 3; t += 32) {
+        const int i = t / 3, bj = t - 3 * i, bi = i < NW ? 0 : (i < NW + NU ? 1 : 2);
+        const long long* rp = A.rowptr[bi][bj];
+        s.rs[t] = rp ? rp[s.idx[i] - A.start[bi]] : 0;
+      }
+      __syncwarp();
+      for (int e = lane; e < ND * ND; e += 32) {
+        const double v = s.L[e];
+        if (v == 0.0) continue;  // distribute_local_to_global elides exact zeros
+        const int i = e / ND, j = e - i * ND;
+        const int bi = i < NW ? 0 : (i < NW + NU ? 1 : 2), bj = j < NW ? 0 : (j < NW + NU ? 1 : 2);
+        const unsigned o = pp[e];
+        if (o == 0xffffu)
+          atomicAdd(err, 1);  // entry missing from the sparsity pattern
+        else
+          red_add_f64(A.val[bi][bj] + s.rs[i * 3 + bj] + o, v);
+      }
+      if (SYSTEM && lane < ND) red_add_f64(a.rhs + s.idx[lane], s.l[lane]);
+    } else {
+      distribute_local_matrix<true>(cs, ND, ND, s.L, SYSTEM ? s.l : nullptr, s.idx, s.lines, A, SYSTEM ? a.rhs : nullptr,
+                                    lane, 32, false, err);
+    }
     __syncwarp();
   }
 }
@@ -232,28 +345,77 @@ int dcp_launch_feec(dcp_model* m, const dcp_params& p, bool system, const double
   a.old_nse = old_nse;
   a.old_temp = old_temp;
   a.rhs = system ? m->nse_rhs : nullptr;
+  a.pos = system ? m->feec_pos_nse : m->feec_pos_pre;
   a.prm = p;
+  if (!a.pos) {
+    dcp_set_error("FEEC: scatter positions missing (model not fully created)");
+    return DCP_ERR_STATE;
+  }
   if (a.nq > NQMAX) {
     dcp_set_error("FEEC: more than 27 quadrature points per cell is not supported");
     return DCP_ERR_ARG;
   }
   if (m->n_cells == 0) return DCP_OK;
-  const size_t smem = sizeof(FeecScratch) * FWARPS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DCP_CUDA(cudaFuncSetAttribute(feec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DCP_CUDA(cudaFuncSetAttribute(feec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  long long blocks = (m->n_cells + FWARPS - 1) / FWARPS;
-  const long long cap = (long long)ctx->sm_count * 4;
-  if (blocks > cap) blocks = cap;
   const BlockMat& mat = system ? m->nse : m->pre;
+  auto launch = [&](auto kernel, size_t smem) -> int {
+    DCP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * FWARPS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (m->n_cells + FWARPS - 1) / FWARPS;
+    const long long cap = (long long)ctx->sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    kernel<<<(unsigned)blocks, 32 * FWARPS, smem, ctx->stream>>>(a, make_view(m->nse_cs), make_view(mat), ctx->d_err);
+    return DCP_OK;
+  };
   if (system)
-    feec_kernel<true><<<(unsigned)blocks, 32 * FWARPS, smem, ctx->stream>>>(a, make_view(m->nse_cs), make_view(mat), ctx->d_err);
+    DCP_TRY(launch(feec_kernel<true, NQMAX>, sizeof(FeecScratch<NQMAX, SV_SYS>) * FWARPS));
+  else if (a.nq <= 8)
+    DCP_TRY(launch(feec_kernel<false, 8>, sizeof(FeecScratch<8, SV>) * FWARPS));
   else
-    feec_kernel<false><<<(unsigned)blocks, 32 * FWARPS, smem, ctx->stream>>>(a, make_view(m->nse_cs), make_view(mat), ctx->d_err);
+    DCP_TRY(launch(feec_kernel<false, NQMAX>, sizeof(FeecScratch<NQMAX, SV>) * FWARPS));
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;
+}
+
+// Positions of the 19 x 19 local entries inside their CSR rows, for the cells without constrained dofs.
+int dcp_feec_positions_build(dcp_model* m, const dcp_model_desc* d, bool system, uint16_t** out) {
+  *out = nullptr;
+  const int64_t nc = d->n_cells;
+  const dcp_csr_desc(*pat)[DCP_MAX_BLOCKS] = system ? d->nse_pattern : d->pre_pattern;
+  int64_t start[4] = {0, d->nse_block_size[0], d->nse_block_size[0] + d->nse_block_size[1],
+                      d->nse_block_size[0] + d->nse_block_size[1] + d->nse_block_size[2]};
+  std::vector<int32_t> lod((size_t)d->nse_cs.n_dofs, -1);
+  for (int64_t l = 0; l < d->nse_cs.n_lines; ++l) lod[d->nse_cs.line_dof[l]] = (int32_t)l;
+  std::vector<uint16_t> pos((size_t)nc * ND * ND, 0xffff);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nc; ++c) {
+    const int32_t* idx = d->nse_l2g + c * ND;
+    uint16_t* P = &pos[(size_t)c * ND * ND];
+    bool fast = true;
+    for (int i = 0; i < ND && fast; ++i) {
+      const int bi = i < NW ? 0 : (i < NW + NU ? 1 : 2);
+      fast = lod[idx[i]] < 0 && idx[i] >= start[bi] && idx[i] < start[bi + 1];
+    }
+    for (int i = 0; i < ND && fast; ++i) {
+      const int bi = i < NW ? 0 : (i < NW + NU ? 1 : 2);
+      for (int j = 0; j < ND; ++j) {
+        const int bj = j < NW ? 0 : (j < NW + NU ? 1 : 2);
+        const dcp_csr_desc& B = pat[bi][bj];
+        if (!B.rowptr) continue;
+        const int64_t r = idx[i] - start[bi];
+        const int32_t col = (int32_t)(idx[j] - start[bj]);
+        const int32_t* b = B.col + B.rowptr[r];
+        const int32_t* e = B.col + B.rowptr[r + 1];
+        const int32_t* p = std::lower_bound(b, e, col);
+        if (p != e && *p == col && p - b < 0xfffe) P[i * ND + j] = (uint16_t)(p - b);
+        if (p != e && *p == col && p - b >= 0xfffe) fast = false;  // row too long for 16-bit offsets
+      }
+    }
+    if (!fast) P[0] = 0xfffe;
+  }
+  int rc = dcp_upload(m->ctx, out, pos.data(), (int64_t)pos.size());
+  cudaStreamSynchronize(m->ctx->stream);
+  return rc;
 }

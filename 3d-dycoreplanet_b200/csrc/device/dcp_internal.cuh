@@ -155,6 +155,7 @@ struct dcp_model {
   double *feec_w_qn = nullptr, *feec_c_qn = nullptr, *feec_u_qn = nullptr;
   double *feec_w_qp = nullptr, *feec_c_qp = nullptr, *feec_u_qp = nullptr;
   double *feec_u_qt = nullptr, *feec_div = nullptr;
+  uint16_t *feec_pos_nse = nullptr, *feec_pos_pre = nullptr;  // [n_cells][19*19] scatter positions (FEEC)
   // matrices and vectors
   BlockMat nse, pre, tmass, tstiff, tmat;
   double *nse_rhs = nullptr, *temp_rhs = nullptr;
@@ -180,6 +181,7 @@ BlockMat* dcp_select_matrix(dcp_model* m, int which);
 extern "C" int dcp_ilu_destroy(struct dcp_ilu* p);
 
 // ---- kernels' host launchers ---------------------------------------------------------------------
+int dcp_feec_positions_build(dcp_model* m, const dcp_model_desc* d, bool system, uint16_t** out);
 int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit = -1);
 int dcp_launch_gather(dcp_ctx* ctx, int64_t n, const int32_t* idx, const double* src, double* dst, bool scatter);
 int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv);

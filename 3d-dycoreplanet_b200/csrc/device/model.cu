@@ -330,6 +330,8 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->feec_u_qp);
   cudaFree(m->feec_u_qt);
   cudaFree(m->feec_div);
+  cudaFree(m->feec_pos_nse);
+  cudaFree(m->feec_pos_pre);
   free_blockmat(m->nse);
   free_blockmat(m->pre);
   free_blockmat(m->tmass);
@@ -551,6 +553,10 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     m->n_nse_constrained_cells = (int64_t)cells.size();
     M_TRY(dcp_upload(ctx, &m->nse_constrained_cells, cells.data(), (int64_t)cells.size()));
     DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (feec) {
+    M_TRY(dcp_feec_positions_build(m, d, true, &m->feec_pos_nse));
+    M_TRY(dcp_feec_positions_build(m, d, false, &m->feec_pos_pre));
   }
   // position tables for the unconstrained cells (DCP_STRATEGY_POSITIONS; classic family)
   if (!feec) {

@@ -10,6 +10,7 @@ and `BlockSparseMatrix.block(i, j)`.
 There is no CPU fallback: without libdcp.so or without a CUDA device every call raises.
 """
 import ctypes
+import sys
 import os
 
 import numpy as np
@@ -222,6 +223,8 @@ class Context:
             self._h = ctypes.c_void_p()
 
     def __del__(self):
+        if sys.is_finalizing():   # teardown order of native libraries is undefined at exit; the OS reclaims everything
+            return
         try:
             self.close()
         except Exception:
@@ -328,6 +331,8 @@ class PreconditionILU:
         self._h = ctypes.c_void_p()
 
     def __del__(self):
+        if sys.is_finalizing():   # teardown order of native libraries is undefined at exit; the OS reclaims everything
+            return
         try:
             self.close()
         except Exception:
@@ -540,6 +545,8 @@ class BoussinesqModel:
             self._h = ctypes.c_void_p()
 
     def __del__(self):
+        if sys.is_finalizing():   # teardown order of native libraries is undefined at exit; the OS reclaims everything
+            return
         try:
             self.close()
         except Exception:

@@ -6,6 +6,7 @@ device library takes.  Not part of the product path.
 """
 import ctypes
 import os
+import sys
 
 import numpy as np
 
@@ -62,6 +63,8 @@ class Problem:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
