@@ -134,6 +134,9 @@ struct dcp_model {
   int32_t* vel_dof = nullptr;       // [dim][ndu] cell dof of (velocity component, node), classic family
   double* cell_vertices = nullptr;  // [n_cells][2^dim][dim] (optional)
   int64_t n_owned_cells = 0;
+  uint8_t* temp_bc_flag = nullptr;   // [n_cells] 1: the cell holds an inhomogeneously constrained temperature dof
+  int32_t* temp_bc_cells = nullptr;  // those cells
+  int64_t n_temp_bc_cells = 0;
   uint16_t* temp_pos = nullptr;  // [n_cells][nd*nd] scatter positions of the temperature matrices (0xffff row: general)
   int32_t *nse_local_field = nullptr, *nse_local_base = nullptr;
   std::vector<int32_t> h_local_field, h_local_base;

@@ -23,6 +23,7 @@ template int dcp_upload<double>(dcp_ctx*, double**, const double*, int64_t);
 template int dcp_upload<int32_t>(dcp_ctx*, int32_t**, const int32_t*, int64_t);
 template int dcp_upload<int64_t>(dcp_ctx*, int64_t**, const int64_t*, int64_t);
 template int dcp_upload<uint16_t>(dcp_ctx*, uint16_t**, const uint16_t*, int64_t);
+template int dcp_upload<uint8_t>(dcp_ctx*, uint8_t**, const uint8_t*, int64_t);
 
 int dcp_check_device_errors(dcp_ctx* ctx, const char* what) {
   DCP_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -304,6 +305,8 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->nse_l2g);
   cudaFree(m->temp_l2g);
   cudaFree(m->temp_pos);
+  cudaFree(m->temp_bc_flag);
+  cudaFree(m->temp_bc_cells);
   cudaFree(m->vel_dof);
   cudaFree(m->cell_vertices);
   cudaFree(m->nse_local_field);
@@ -537,6 +540,20 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
       }
     }
     M_TRY(dcp_upload(ctx, &m->temp_pos, tp.data(), (int64_t)tp.size()));
+    // cells whose right-hand side needs matrix_for_bc: an inhomogeneously constrained temperature dof
+    std::vector<uint8_t> flag((size_t)std::max<int64_t>(nc, 1), 0);
+    std::vector<int32_t> bc_cells;
+    for (int64_t c = 0; c < nc; ++c) {
+      const int32_t* idx = d->temp_l2g + c * nd;
+      for (int i = 0; i < nd; ++i) {
+        const int32_t li = lod[idx[i]];
+        if (li >= 0 && d->temp_cs.inhom[li] != 0.0) flag[(size_t)c] = 1;
+      }
+      if (flag[(size_t)c]) bc_cells.push_back((int32_t)c);
+    }
+    m->n_temp_bc_cells = (int64_t)bc_cells.size();
+    M_TRY(dcp_upload(ctx, &m->temp_bc_flag, flag.data(), (int64_t)flag.size()));
+    if (!bc_cells.empty()) M_TRY(dcp_upload(ctx, &m->temp_bc_cells, bc_cells.data(), (int64_t)bc_cells.size()));
     DCP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   // cells holding a constrained NSE dof
