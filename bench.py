@@ -27,6 +27,10 @@ import numpy as np  # noqa: E402
 
 
 FP64_DMMA_PEAK_TFLOPS = 37.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (th_mma_kernel<1>, the NSE system
+# pass on a single GPU) from `ncu --set full` captures of this bench command, keyed by refinement:
+# profiles/r01_ncu_full_r5_final.txt, profiles/r01_ncu_full_r6_system_kernel.txt
+NCU_DRAM_BYTES_PER_LAUNCH = {5: 16.150222e9 + 13.920899e9, 6: 165.702325e9 + 127.577328e9}
 
 
 def peaks():
@@ -419,7 +423,11 @@ def main():
                               "frac": 0.60e6 * P.n_cells / (phase_ms["nse_system"] * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
                               "peak_source": "profiles/r01_fp64_peaks.json (mma.sync m8n8k4 f64, measured)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(refine) if (world == 1 and dom == "nse_system") else None,
+                         "traffic_note": "DRAM bytes per launch of the system kernel, ncu --set full capture (profiles/); "
+                                         "algorithmic bytes per launch: %.3e" % ab[dom],
+                         "peak_source": peak_src,
                          "spmv_frac": ab["spmv_nse"] / (phase_ms["spmv_nse"] * 1e-3) / 1e9 / peak},
             "e2e": {"value": total_dofs / (ms_e2e / args.steps * 1e-3), "unit": "DoFs/s",
                     "h2d_bytes_per_step": int(8 * (2 * (n_nse + n_t) + n_nse + n_t)),
