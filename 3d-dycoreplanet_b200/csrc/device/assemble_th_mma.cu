@@ -41,7 +41,8 @@ constexpr int LDB = 148;        // row stride of X (148 mod 16 == 4: conflict-fr
 constexpr int KQ = 28;          // quadrature points padded to a multiple of 4
 constexpr int PSI0 = 128;       // first psi column (node columns 32*alpha + b, b < 32)
 constexpr int PSTR = 1228;       // plan row: NE*NE offsets padded to a multiple of 8 bytes (cp.async granularity)
-constexpr int MSTR = 40;         // mask row: 27 node masks, 8 pressure flags, cell flag, int32 index of the wide table
+constexpr int MSTR = 48;         // mask row: 27 node masks, 8 pressure flags, cell flag, int32 index of the wide table,
+                                 // int32 index of the 9-combination table (no-normal-flux cells of the preconditioner)
 constexpr int IDS = 92;          // dof index buffer stride
 constexpr int MTHREADS = 128;    // 4 warps per CTA, 4 CTAs per SM: several cells in flight per SM hide the per-cell load latency
 
@@ -52,6 +53,7 @@ struct MmaArgs {
   const unsigned char* nmask;       // [n][MSTR]: unconstrained-component mask of the 27 velocity nodes, 8 pressure flags,
                                     // cell flag, then (preconditioner) int32: -1 or index into pos_wide
   const unsigned short* pos_wide;   // [n_wide][3][27][27]
+  const unsigned short* pos9;       // [n_nnf][9][27][27]: preconditioner cells with no-normal-flux lines
   const double* geom;
   const int* l2g;
   const int* l2g_t;
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
     }
     cp_async_commit();
     const int wide = SYSTEM ? -1 : *reinterpret_cast<const int*>(snm + 36);
+    const int nnf = SYSTEM ? -1 : *reinterpret_cast<const int*>(snm + 40);
     if (!SYSTEM && wide >= 0) {
       const unsigned short* p = a.pos_wide + (size_t)wide * (3 * NU * NU);
       for (int i = tid; i < 3 * NU * NU; i += nt) swide[i] = p[i];
@@ -304,6 +307,34 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
               if (!(ca.mask & 1)) red_add_f64(v00 + rb00[na], d00);
               if (!(ca.mask & 2)) red_add_f64(v00 + rb00[NU + na], d11);
               if (!(ca.mask & 4)) red_add_f64(v00 + rb00[2 * NU + na], d22);
+            }
+          } else if (nnf >= 0) {
+            // preconditioner cell with no-normal-flux lines: C^T (dg I) C spreads dg over the component pairs that
+            // involve a master; positions of all nine pairs come from the cell's own table (global memory, few cells)
+            const unsigned short* p9 = a.pos9 + (size_t)nnf * (9 * NU * NU);
+            const double wa[3] = {ca.w0, ca.w1, ca.w2}, wb[3] = {cb.w0, cb.w1, cb.w2};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (!(ca.mask & (1 << c))) {
+                if (na == nb) red_add_f64(v00 + rb00[c * NU + na], fabs(dg));
+                continue;
+              }
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                if (!(cb.mask & (1 << d))) continue;
+                double r = c == d ? 1.0 : 0.0;
+                if (ca.k == d) r += wa[c];
+                if (cb.k == c) r += wb[d];
+                if (ca.k != 3 && ca.k == cb.k) r += wa[c] * wb[d];
+                if (r == 0.0) continue;
+                r *= dg;
+                const unsigned o1 = p9[((c * 3 + d) * NU + na) * NU + nb];
+                if (o1 != 0xffffu) red_add_f64(v00 + rb00[c * NU + na] + o1, r);
+                if (ta != tb) {
+                  const unsigned o2 = p9[((d * 3 + c) * NU + nb) * NU + na];
+                  if (o2 != 0xffffu) red_add_f64(v00 + rb00[d * NU + nb] + o2, r);
+                }
+              }
             }
           } else {
 #pragma unroll
@@ -479,6 +510,7 @@ void dcp_masked_plan_free(MaskedPlan* p) {
   cudaFree(p->nmask);
   cudaFree(p->wide_idx);
   cudaFree(p->pos_wide);
+  cudaFree(p->pos9);
   delete p;
 }
 
@@ -497,7 +529,8 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
   }
   std::vector<int32_t> lod((size_t)d->nse_cs.n_dofs, -1);
   for (int64_t l = 0; l < d->nse_cs.n_lines; ++l) lod[d->nse_cs.line_dof[l]] = (int32_t)l;
-  std::vector<uint8_t> ok((size_t)nc, 0), is_wide((size_t)nc, 0);
+  std::vector<uint8_t> ok((size_t)nc, 0), is_wide((size_t)nc, 0), is_nnf((size_t)nc, 0);
+  std::vector<std::vector<uint16_t>> nnf_rows((size_t)nc);
   std::vector<uint16_t> pos_all((size_t)nc * NE * NE, 0xFFFF);
   std::vector<uint8_t> mask_all((size_t)nc * 36, 0);
   std::vector<std::vector<uint16_t>> wide_rows((size_t)nc);
@@ -529,7 +562,9 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
     // supported constraint lines: homogeneous, masters (if any) are the other components of the same node, at most one
     // such line per node (Dirichlet and no-normal-flux lines of boussinesq_model.tpp:313-329); anything else (periodic,
     // hanging nodes, inhomogeneous) sends the cell to the general kernel
-    bool any_cs = false;
+    bool any_cs = false, any_master = false;
+    int kcomp[NU];
+    for (int a = 0; a < NU; ++a) kcomp[a] = 3;
     for (int a = 0; a < NU && good; ++a) {
       int n_master_lines = 0;
       const int32_t g0 = idx[sys_u[a]];
@@ -541,7 +576,8 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
         const int32_t e0 = d->nse_cs.line_ptr[li], e1 = d->nse_cs.line_ptr[li + 1];
         if (e1 > e0) {
           ++n_master_lines;
-          if (!system) good = false;  // preconditioner: redistributed entries leave the same-component pattern
+          any_master = true;   // preconditioner: redistributed entries leave the same-component pattern (table of 9 below)
+          kcomp[a] = k;
           for (int32_t e = e0; e < e1 && good; ++e) {
             const int32_t md = d->nse_cs.entry_dof[e];
             good = md >= g0 && md < g0 + 3 && md != g0 + k && lod[md] < 0;
@@ -593,6 +629,37 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
           if (good) P[(NU + a) * NE + b] = (uint16_t)off;
         }
       }
+    } else if (any_master) {
+      // preconditioner, no-normal-flux lines: C^T (dg I) C fills the component pairs (c,d) with c == d, d == k_a,
+      // c == k_b, or k_a == k_b; every such entry must exist in the pattern, else the cell goes to the general kernel
+      std::vector<uint16_t> W9(9 * NU * NU, 0xFFFF);
+      for (int a = 0; a < NU && good; ++a)
+        for (int b = 0; b < NU && good; ++b)
+          for (int cc = 0; cc < 3 && good; ++cc) {
+            if (!(mk[a] & (1 << cc))) continue;
+            for (int dd = 0; dd < 3 && good; ++dd) {
+              if (!(mk[b] & (1 << dd))) continue;
+              const int64_t off = A00.find((int64_t)idx[sys_u[a]] + cc, idx[sys_u[b]] + dd);
+              const bool needed = cc == dd || kcomp[a] == dd || kcomp[b] == cc || (kcomp[a] != 3 && kcomp[a] == kcomp[b]);
+              if (off >= 0 && off < 65535)
+                W9[((cc * 3 + dd) * NU + a) * NU + b] = (uint16_t)off;
+              else if (needed)
+                good = false;
+            }
+          }
+      for (int a = 0; a < NP && good; ++a) {
+        if (!mk[NU + a]) continue;
+        for (int b = 0; b < NP && good; ++b) {
+          if (!mk[NU + b]) continue;
+          const int64_t off = A11.find(idx[sys_p[a]] - n_u, (int32_t)(idx[sys_p[b]] - n_u));
+          good = off >= 0 && off < 65535;
+          if (good) P[(NU + a) * NE + NU + b] = (uint16_t)off;
+        }
+      }
+      if (good) {
+        is_nnf[c] = 1;
+        nnf_rows[c].swap(W9);
+      }
     } else {
       // preconditioner: row (a,k) holds column (b,k); the offset is usually the same for the three k
       std::vector<uint16_t> W(3 * NU * NU, 0xFFFF);
@@ -626,8 +693,8 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
     }
     ok[c] = good ? 1 : 0;
   }
-  std::vector<int32_t> cells, other, wide_idx;
-  std::vector<uint16_t> pos, pos_wide;
+  std::vector<int32_t> cells, other, wide_idx, nnf_idx;
+  std::vector<uint16_t> pos, pos_wide, pos9;
   std::vector<uint8_t> nmask;
   for (int64_t c = 0; c < nc; ++c) {
     if (!ok[c]) {
@@ -640,6 +707,12 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
       pos_wide.insert(pos_wide.end(), wide_rows[c].begin(), wide_rows[c].end());
     } else
       wide_idx.push_back(-1);
+    if (is_nnf[c]) {
+      nnf_idx.push_back((int32_t)(pos9.size() / (9 * NU * NU)));
+      pos9.insert(pos9.end(), nnf_rows[c].begin(), nnf_rows[c].end());
+      std::vector<uint16_t>().swap(nnf_rows[c]);
+    } else
+      nnf_idx.push_back(-1);
   }
   pos.resize(cells.size() * (size_t)PSTR, 0xFFFF);
   nmask.resize(cells.size() * (size_t)MSTR, 0);
@@ -648,6 +721,7 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
     std::copy(&pos_all[(size_t)cells[i] * NE * NE], &pos_all[(size_t)cells[i] * NE * NE] + NE * NE, &pos[(size_t)i * PSTR]);
     std::copy(&mask_all[(size_t)cells[i] * 36], &mask_all[(size_t)cells[i] * 36] + 36, &nmask[(size_t)i * MSTR]);
     std::memcpy(&nmask[(size_t)i * MSTR + 36], &wide_idx[i], sizeof(int32_t));
+    std::memcpy(&nmask[(size_t)i * MSTR + 40], &nnf_idx[i], sizeof(int32_t));
   }
   MaskedPlan* P = new MaskedPlan;
   P->n = (int64_t)cells.size();
@@ -660,6 +734,7 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
   if (rc == DCP_OK) rc = upm(ctx, &P->nmask, nmask);
   if (rc == DCP_OK) rc = upm(ctx, &P->wide_idx, wide_idx);
   if (rc == DCP_OK) rc = upm(ctx, &P->pos_wide, pos_wide);
+  if (rc == DCP_OK) rc = upm(ctx, &P->pos9, pos9);
   cudaStreamSynchronize(ctx->stream);
   if (rc != DCP_OK) {
     dcp_masked_plan_free(P);
@@ -678,6 +753,7 @@ int dcp_launch_th_mma(dcp_model* m, const dcp_params& p, bool system, const Mask
   a.pos = plan->pos;
   a.nmask = plan->nmask;
   a.pos_wide = plan->pos_wide;
+  a.pos9 = plan->pos9;
   a.geom = m->geom_qn;
   a.l2g = m->nse_l2g;
   a.l2g_t = m->temp_l2g;

@@ -121,6 +121,7 @@ struct MaskedPlan {
   uint8_t* nmask = nullptr;        // [n][36]
   int32_t* wide_idx = nullptr;     // [n] preconditioner: -1 or row of pos_wide
   uint16_t* pos_wide = nullptr;    // [n_wide][3][27][27]
+  uint16_t* pos9 = nullptr;        // [n_nnf][9][27][27]: preconditioner cells with no-normal-flux lines
 };
 
 struct dcp_model {
