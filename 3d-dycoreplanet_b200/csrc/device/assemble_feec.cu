@@ -47,6 +47,7 @@ struct FeecArgs {
   const double* old_temp;
   double* rhs;
   const unsigned short* pos;  // [n_cells][19*19] position of entry (i,j) inside row i of its block; pos[cell][0] == 0xfffe: general path
+  const int* cell_list;       // warp kernel: the cells to process (nullptr: all)
   dcp_params prm;
 };
 
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs
     }
     J = I + t;
   };
-  for (long long cell = (long long)blockIdx.x * FWARPS + wid; cell < a.n_cells; cell += (long long)gridDim.x * FWARPS) {
+  for (long long it = (long long)blockIdx.x * FWARPS + wid; it < a.n_cells; it += (long long)gridDim.x * FWARPS) {
+    const long long cell = a.cell_list ? a.cell_list[it] : it;
     const double* g = a.geom + cell * a.gstride;
     if (lane < ND) {
       const int gi = a.l2g[cell * ND + lane];
@@ -324,6 +326,241 @@ __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs
   }
 }
 
+
+// ---- system pass, one CTA (4 warps) per cell -------------------------------------------------------------------------
+// The warp-per-cell kernel above is a chain of dependent latencies (ncu: >90 % of the cycles stalled at 11 warps per
+// SM).  Four warps per cell shorten every link of the chain -- the table is built by (point, function group) threads,
+// every 3 x 3 tile by four threads that split the quadrature points -- and 27 kB of scratch per CTA put 32 warps on an SM.
+// Cells with constrained dofs are skipped here and handled by the warp kernel over a cell list.
+constexpr int CT = 128;
+constexpr int SWS = 37;   // row stride of the vorticity table (36 values)
+struct FeecCta {
+  double SW[NQMAX * SWS];
+  double SR[NQMAX * SV_SYS];   // curls (36), velocity values (18), divergences (6)
+  double L[ND * ND];
+  double l[ND];
+  double F[NQMAX * 4];
+  double wq[NQMAX];
+  double ow[NQMAX * 4 * 3];    // partial vorticity at the points, per function group
+  double ou[NQMAX * 2 * 3];    // partial velocity at the points
+  double U[ND];
+  double sg[ND];
+  double Tn[28];
+  long long rs[ND * 3];
+  int idx[ND + 1];
+  unsigned short pos[ND * ND + 3];
+};
+
+__global__ void __launch_bounds__(CT) feec_system_cta_kernel(FeecArgs a, BlockView A, int* err) {
+  extern __shared__ __align__(16) unsigned char raw_smem[];
+  FeecCta& s = *reinterpret_cast<FeecCta*>(raw_smem);
+  const int t = threadIdx.x, lane = t & 31;
+  const int nq = a.nq;
+  const double nu = a.prm.dt * a.prm.inv_re;
+  for (long long cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
+    const unsigned short* pp = a.pos + cell * (long long)(ND * ND);
+    if (pp[0] == 0xfffeu) continue;   // constrained dofs: warp kernel
+    const double* g = a.geom + cell * a.gstride;
+    __syncthreads();                  // the previous cell's scatter is done with the scratch
+    if (t < ND) {
+      const int gi = a.l2g[cell * ND + t];
+      s.idx[t] = gi;
+      s.sg[t] = a.sign[cell * ND + t];
+      s.U[t] = a.old_nse[gi];
+    } else if (t >= 32 && t < 32 + a.ndt)
+      s.Tn[t - 32] = a.old_temp[a.l2g_t[cell * a.ndt + t - 32]];
+    for (int i = t; i < ND * ND; i += CT) {
+      s.pos[i] = pp[i];
+      s.L[i] = 0.0;
+    }
+    __syncthreads();
+    // ---- tables: thread = (point q, group of three functions)
+    if (t < 4 * nq) {
+      const int q = t % nq, grp = t / nq;
+      double J[3][3], K[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          K[i][j] = g[nq * (1 + i * 3 + j) + q];
+          J[i][j] = g[nq * (13 + i * 3 + j) + q];
+        }
+      const double idet = 1.0 / g[nq * 22 + q];
+      if (grp == 0) s.wq[q] = g[q];
+      double ow[3] = {0, 0, 0};
+      for (int kk = 0; kk < 3; ++kk) {
+        const int k = 3 * grp + kk;
+        const double* ph = a.tw + ((size_t)q * NW + k) * 3;
+        const double* ch = a.tc + ((size_t)q * NW + k) * 3;
+        const double p0 = __ldg(ph), p1 = __ldg(ph + 1), p2 = __ldg(ph + 2);
+        const double c0 = __ldg(ch), c1 = __ldg(ch + 1), c2 = __ldg(ch + 2);
+        const double Uk = s.U[k];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double vw = K[0][d] * p0 + K[1][d] * p1 + K[2][d] * p2;
+          s.SW[q * SWS + k * 3 + d] = vw;
+          s.SR[q * SV_SYS + k * 3 + d] = (J[d][0] * c0 + J[d][1] * c1 + J[d][2] * c2) * idet;
+          ow[d] += Uk * vw;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) s.ow[(q * 4 + grp) * 3 + d] = ow[d];
+      if (grp < 2) {  // velocity functions 3 grp .. 3 grp + 2 and their divergences
+        double ou[3] = {0, 0, 0};
+        for (int kk = 0; kk < 3; ++kk) {
+          const int k = 3 * grp + kk;
+          const double* ph = a.tu + ((size_t)q * NU + k) * 3;
+          const double p0 = __ldg(ph), p1 = __ldg(ph + 1), p2 = __ldg(ph + 2);
+          const double sgk = s.sg[NW + k], Uk = s.U[NW + k];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double ru = (J[d][0] * p0 + J[d][1] * p1 + J[d][2] * p2) * idet;
+            s.SR[q * SV_SYS + 36 + k * 3 + d] = sgk * ru;
+            ou[d] += Uk * ru;  // get_function_values: no face sign (:705-708)
+          }
+          s.SR[q * SV_SYS + 54 + k] = sgk * __ldg(a.td + k) * idet;
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) s.ou[(q * 2 + grp) * 3 + d] = ou[d];
+      }
+    }
+    __syncthreads();
+    // ---- warp 0: right-hand-side integrand at the points; warps 1-3: the 21 tiles (four threads each) and the six
+    // (u,p) entries
+    if (t < 32) {
+      if (t < nq) {
+        const int q = t;
+        double ow[3], ou[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          ow[d] = s.ow[(q * 4) * 3 + d] + s.ow[(q * 4 + 1) * 3 + d] + s.ow[(q * 4 + 2) * 3 + d] + s.ow[(q * 4 + 3) * 3 + d];
+          ou[d] = s.ou[(q * 2) * 3 + d] + s.ou[(q * 2 + 1) * 3 + d];
+        }
+        const double w = s.wq[q];
+        double T = 0.0;
+        for (int k = 0; k < a.ndt; ++k) T += s.Tn[k] * __ldg(a.phi_t + q * a.ndt + k);
+        const double rho = 1.0 - a.prm.beta * (T - a.prm.T_ref);
+        double x[3] = {g[nq * 10 + q], g[nq * 11 + q], g[nq * 12 + q]}, grav[3];
+        if (a.prm.cuboid) {
+          grav[0] = grav[1] = 0.0;
+          grav[2] = -a.prm.g_const;
+        } else {
+          const double r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+          const double sc = r > 1.0 ? r : sqrt(r);
+          for (int d = 0; d < 3; ++d) grav[d] = -a.prm.g_const * x[d] / sc;
+        }
+        const double cz = a.prm.cuboid ? a.prm.cor_scale * a.prm.omega : 0.0;
+        const double wxu[3] = {ow[1] * ou[2] - ow[2] * ou[1], ow[2] * ou[0] - ow[0] * ou[2], ow[0] * ou[1] - ow[1] * ou[0]};
+        const double cxu[3] = {-cz * ou[1], cz * ou[0], 0.0};
+        const double dt = a.prm.dt;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          s.F[q * 4 + d] = (ou[d] + dt * rho * (a.prm.g_scale * grav[d]) - dt * wxu[d] - dt * 2.0 * cxu[d]) * w;
+        s.F[q * 4 + 3] = -dt * 0.5 * dot3(ou, ou) * w;
+      }
+    } else {
+      const int u = t - 32;            // 0 .. 95
+      const int tl = u >> 2, split = u & 3;
+      const bool is_tile = tl < 21;
+      // tile kinds: 0-9 (w,w), 10-17 (curl w,u), 18-20 (u,u)
+      int I = 0, Jb = 0, kind = 0;
+      if (tl < 10) {
+        int r = tl;
+        while (r >= 4 - I) { r -= 4 - I; ++I; }
+        Jb = I + r;
+      } else if (tl < 18) {
+        kind = 1;
+        I = (tl - 10) >> 1;
+        Jb = (tl - 10) & 1;
+      } else if (is_tile) {
+        kind = 2;
+        int r = tl - 18;
+        while (r >= 2 - I) { r -= 2 - I; ++I; }
+        Jb = I + r;
+      }
+      double acc[3][3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
+      if (is_tile) {
+        const double* ta = kind == 0 ? s.SW + 9 * I : (kind == 1 ? s.SR + 9 * I : s.SR + 36 + 9 * I);
+        const double* tb = kind == 0 ? s.SW + 9 * Jb : s.SR + 36 + 9 * Jb;
+        const int st = kind == 0 ? SWS : SV_SYS;
+        const int q0 = split * 7, q1 = min(nq, q0 + 7);
+        for (int q = q0; q < q1; ++q) {
+          double va[9], vb[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            va[k] = ta[q * st + k];
+            vb[k] = tb[q * st + k];
+          }
+          const double w = s.wq[q];
+#pragma unroll
+          for (int x = 0; x < 3; ++x)
+#pragma unroll
+            for (int y = 0; y < 3; ++y)
+              acc[x][y] += w * (va[3 * x] * vb[3 * y] + va[3 * x + 1] * vb[3 * y + 1] + va[3 * x + 2] * vb[3 * y + 2]);
+        }
+      }
+      // the four threads of a tile hold partial sums over their points (all lanes of the warp take part)
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) {
+          double v = acc[x][y];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          acc[x][y] = v;
+        }
+      if (is_tile && split == 0) {
+        const int r0 = (kind == 2 ? NW : 0) + 3 * I, c0 = (kind == 0 ? 0 : NW) + 3 * Jb;
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+#pragma unroll
+          for (int y = 0; y < 3; ++y) {
+            const double v = acc[x][y];
+            s.L[(r0 + x) * ND + c0 + y] = kind == 1 ? -v : v;
+            s.L[(c0 + y) * ND + r0 + x] = kind == 1 ? nu * v : v;
+          }
+      }
+      if (!is_tile && u - 84 < NU) {   // the six (u,p) entries
+        const int i = u - 84;
+        double dsum = 0.0;
+        for (int q = 0; q < nq; ++q) dsum += s.wq[q] * s.SR[q * SV_SYS + 54 + i];
+        s.L[(NW + i) * ND + NW + NU] = -dsum;
+        s.L[(NW + NU) * ND + NW + i] = -dsum;
+      }
+    }
+    __syncthreads();
+    // ---- right-hand side (needs F) and the row starts
+    if (t < NU) {
+      double v = 0.0;
+      for (int q = 0; q < nq; ++q)
+        v += dot3(s.SR + q * SV_SYS + 36 + t * 3, s.F + q * 4) + s.SR[q * SV_SYS + 54 + t] * s.F[q * 4 + 3];
+      s.l[NW + t] = v;
+    } else if (t >= 32 && t < 32 + ND * 3) {
+      const int tt = t - 32, i = tt / 3, bj = tt - 3 * i, bi = i < NW ? 0 : (i < NW + NU ? 1 : 2);
+      const long long* rp = A.rowptr[bi][bj];
+      s.rs[tt] = rp ? rp[s.idx[i] - A.start[bi]] : 0;
+    }
+    __syncthreads();
+    for (int e = t; e < ND * ND; e += CT) {
+      const double v = s.L[e];
+      if (v == 0.0) continue;  // distribute_local_to_global elides exact zeros
+      const int i = e / ND, j = e - i * ND;
+      const int bi = i < NW ? 0 : (i < NW + NU ? 1 : 2), bj = j < NW ? 0 : (j < NW + NU ? 1 : 2);
+      const unsigned o = s.pos[e];
+      if (o == 0xffffu)
+        atomicAdd(err, 1);  // entry missing from the sparsity pattern
+      else
+        red_add_f64(A.val[bi][bj] + s.rs[i * 3 + bj] + o, v);
+    }
+    if (t >= NW && t < NW + NU) red_add_f64(a.rhs + s.idx[t], s.l[t]);  // w and p rows of the right-hand side are zero
+    (void)lane;
+  }
+}
+
 }  // namespace
 
 int dcp_launch_feec(dcp_model* m, const dcp_params& p, bool system, const double* old_nse, const double* old_temp) {
@@ -346,6 +583,7 @@ int dcp_launch_feec(dcp_model* m, const dcp_params& p, bool system, const double
   a.old_temp = old_temp;
   a.rhs = system ? m->nse_rhs : nullptr;
   a.pos = system ? m->feec_pos_nse : m->feec_pos_pre;
+  a.cell_list = nullptr;
   a.prm = p;
   if (!a.pos) {
     dcp_set_error("FEEC: scatter positions missing (model not fully created)");
@@ -362,15 +600,33 @@ int dcp_launch_feec(dcp_model* m, const dcp_params& p, bool system, const double
     int per_sm = 1;
     DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * FWARPS, smem));
     if (per_sm < 1) per_sm = 1;
-    long long blocks = (m->n_cells + FWARPS - 1) / FWARPS;
+    long long blocks = (a.n_cells + FWARPS - 1) / FWARPS;
     const long long cap = (long long)ctx->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     kernel<<<(unsigned)blocks, 32 * FWARPS, smem, ctx->stream>>>(a, make_view(m->nse_cs), make_view(mat), ctx->d_err);
     return DCP_OK;
   };
-  if (system)
+  if (system) {
+    // cells without constrained dofs: one CTA per cell; the rest: warp kernel over the list
+    {
+      const size_t smem = sizeof(FeecCta);
+      DCP_CUDA(cudaFuncSetAttribute(feec_system_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;
+      DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, feec_system_cta_kernel, CT, smem));
+      if (per_sm < 1) per_sm = 1;
+      long long blocks = m->n_cells;
+      const long long cap = (long long)ctx->sm_count * per_sm;
+      if (blocks > cap) blocks = cap;
+      a.cell_list = nullptr;
+      feec_system_cta_kernel<<<(unsigned)blocks, CT, smem, ctx->stream>>>(a, make_view(mat), ctx->d_err);
+      ctx->launches++;
+      DCP_CUDA(cudaGetLastError());
+    }
+    if (m->n_feec_general == 0) return DCP_OK;
+    a.cell_list = m->feec_general_cells;
+    a.n_cells = m->n_feec_general;
     DCP_TRY(launch(feec_kernel<true, NQMAX>, sizeof(FeecScratch<NQMAX, SV_SYS>) * FWARPS));
-  else if (a.nq <= 8)
+  } else if (a.nq <= 8)
     DCP_TRY(launch(feec_kernel<false, 8>, sizeof(FeecScratch<8, SV>) * FWARPS));
   else
     DCP_TRY(launch(feec_kernel<false, NQMAX>, sizeof(FeecScratch<NQMAX, SV>) * FWARPS));
@@ -416,6 +672,13 @@ int dcp_feec_positions_build(dcp_model* m, const dcp_model_desc* d, bool system,
     if (!fast) P[0] = 0xfffe;
   }
   int rc = dcp_upload(m->ctx, out, pos.data(), (int64_t)pos.size());
+  if (rc == DCP_OK && system) {
+    std::vector<int32_t> general;
+    for (int64_t c = 0; c < nc; ++c)
+      if (pos[(size_t)c * ND * ND] == 0xfffe) general.push_back((int32_t)c);
+    m->n_feec_general = (int64_t)general.size();
+    if (!general.empty()) rc = dcp_upload(m->ctx, &m->feec_general_cells, general.data(), (int64_t)general.size());
+  }
   cudaStreamSynchronize(m->ctx->stream);
   return rc;
 }

@@ -334,6 +334,7 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->feec_u_qt);
   cudaFree(m->feec_div);
   cudaFree(m->feec_pos_nse);
+  cudaFree(m->feec_general_cells);
   cudaFree(m->feec_pos_pre);
   free_blockmat(m->nse);
   free_blockmat(m->pre);
