@@ -41,7 +41,8 @@ struct FeecArgs {
   const double* sign;
   const int* l2g;
   const int* l2g_t;
-  const double *tw, *tc, *tu, *td;  // reference tables on this rule
+  const double *tw, *tc, *tu, *td;  // reference tables on this rule, [q][function][component]
+  const double *tw_t, *tc_t, *tu_t;  // system rule, point-fastest copies [function][component][q] (CTA kernel)
   const double* phi_t;
   const double* old_nse;
   const double* old_temp;
@@ -390,10 +391,10 @@ __global__ void __launch_bounds__(CT) feec_system_cta_kernel(FeecArgs a, BlockVi
       double ow[3] = {0, 0, 0};
       for (int kk = 0; kk < 3; ++kk) {
         const int k = 3 * grp + kk;
-        const double* ph = a.tw + ((size_t)q * NW + k) * 3;
-        const double* ch = a.tc + ((size_t)q * NW + k) * 3;
-        const double p0 = __ldg(ph), p1 = __ldg(ph + 1), p2 = __ldg(ph + 2);
-        const double c0 = __ldg(ch), c1 = __ldg(ch + 1), c2 = __ldg(ch + 2);
+        const double* ph = a.tw_t + (size_t)(k * 3) * nq + q;
+        const double* ch = a.tc_t + (size_t)(k * 3) * nq + q;
+        const double p0 = __ldg(ph), p1 = __ldg(ph + nq), p2 = __ldg(ph + 2 * nq);
+        const double c0 = __ldg(ch), c1 = __ldg(ch + nq), c2 = __ldg(ch + 2 * nq);
         const double Uk = s.U[k];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -409,8 +410,8 @@ __global__ void __launch_bounds__(CT) feec_system_cta_kernel(FeecArgs a, BlockVi
         double ou[3] = {0, 0, 0};
         for (int kk = 0; kk < 3; ++kk) {
           const int k = 3 * grp + kk;
-          const double* ph = a.tu + ((size_t)q * NU + k) * 3;
-          const double p0 = __ldg(ph), p1 = __ldg(ph + 1), p2 = __ldg(ph + 2);
+          const double* ph = a.tu_t + (size_t)(k * 3) * nq + q;
+          const double p0 = __ldg(ph), p1 = __ldg(ph + nq), p2 = __ldg(ph + 2 * nq);
           const double sgk = s.sg[NW + k], Uk = s.U[NW + k];
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
@@ -578,6 +579,9 @@ int dcp_launch_feec(dcp_model* m, const dcp_params& p, bool system, const double
   a.tc = system ? m->feec_c_qn : m->feec_c_qp;
   a.tu = system ? m->feec_u_qn : m->feec_u_qp;
   a.td = m->feec_div;
+  a.tw_t = m->feec_w_qn_t;
+  a.tc_t = m->feec_c_qn_t;
+  a.tu_t = m->feec_u_qn_t;
   a.phi_t = m->phi_t_qn;
   a.old_nse = old_nse;
   a.old_temp = old_temp;

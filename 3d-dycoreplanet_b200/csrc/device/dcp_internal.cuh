@@ -157,6 +157,7 @@ struct dcp_model {
   int nq_pre = 0;
   double *geom_qp = nullptr, *nse_sign = nullptr;
   double *feec_w_qn = nullptr, *feec_c_qn = nullptr, *feec_u_qn = nullptr;
+  double *feec_w_qn_t = nullptr, *feec_c_qn_t = nullptr, *feec_u_qn_t = nullptr;  // same, stored [function][component][q]
   double *feec_w_qp = nullptr, *feec_c_qp = nullptr, *feec_u_qp = nullptr;
   double *feec_u_qt = nullptr, *feec_div = nullptr;
   int32_t* feec_general_cells = nullptr;  // FEEC cells with constrained dofs (general scatter)

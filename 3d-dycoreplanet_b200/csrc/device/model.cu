@@ -328,6 +328,9 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->feec_w_qn);
   cudaFree(m->feec_c_qn);
   cudaFree(m->feec_u_qn);
+  cudaFree(m->feec_w_qn_t);
+  cudaFree(m->feec_c_qn_t);
+  cudaFree(m->feec_u_qn_t);
   cudaFree(m->feec_w_qp);
   cudaFree(m->feec_c_qp);
   cudaFree(m->feec_u_qp);
@@ -441,6 +444,21 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     M_TRY(dcp_upload(ctx, &m->feec_w_qn, d->feec_phi_w_qn, (int64_t)d->nq_nse * 36));
     M_TRY(dcp_upload(ctx, &m->feec_c_qn, d->feec_curl_w_qn, (int64_t)d->nq_nse * 36));
     M_TRY(dcp_upload(ctx, &m->feec_u_qn, d->feec_phi_u_qn, (int64_t)d->nq_nse * 18));
+    {
+      // point-fastest copies [function][component][q] for the CTA-per-cell system kernel, whose threads of one warp
+      // are consecutive quadrature points: a warp-wide load then touches 2 lines instead of 27
+      auto upload_t = [&](double** dst, const double* src, int nq, int nf) -> int {
+        std::vector<double> t((size_t)nq * nf * 3);
+        for (int q = 0; q < nq; ++q)
+          for (int k = 0; k < nf * 3; ++k) t[(size_t)k * nq + q] = src[(size_t)q * nf * 3 + k];
+        int r = dcp_upload(ctx, dst, t.data(), (int64_t)t.size());
+        cudaStreamSynchronize(ctx->stream);  // `t` dies here
+        return r;
+      };
+      M_TRY(upload_t(&m->feec_w_qn_t, d->feec_phi_w_qn, d->nq_nse, 12));
+      M_TRY(upload_t(&m->feec_c_qn_t, d->feec_curl_w_qn, d->nq_nse, 12));
+      M_TRY(upload_t(&m->feec_u_qn_t, d->feec_phi_u_qn, d->nq_nse, 6));
+    }
     M_TRY(dcp_upload(ctx, &m->feec_w_qp, d->feec_phi_w_qp, (int64_t)d->nq_pre * 36));
     M_TRY(dcp_upload(ctx, &m->feec_c_qp, d->feec_curl_w_qp, (int64_t)d->nq_pre * 36));
     M_TRY(dcp_upload(ctx, &m->feec_u_qp, d->feec_phi_u_qp, (int64_t)d->nq_pre * 18));
