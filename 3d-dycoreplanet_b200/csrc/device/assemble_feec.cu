@@ -29,6 +29,7 @@ namespace {
 using namespace dcpdev;
 
 constexpr int NW = 12, NU = 6, ND = 19;
+constexpr int PROW = 364;  // plan row: 19 * 19 offsets padded to a multiple of 8 bytes (cp.async granularity)
 constexpr int SV = 97;      // preconditioner: values per quadrature point (96) padded to an odd stride
 constexpr int SV_SYS = 61;  // system: the larger of the two table halves (36 + 18 + 6) padded to an odd stride
 constexpr int NQMAX = 27;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs
     }
     if (SYSTEM && lane < a.ndt) s.Tn[lane] = a.old_temp[a.l2g_t[cell * a.ndt + lane]];
     {  // the plan row, staged now so that its latency overlaps the quadrature loop
-      const unsigned short* pp = a.pos + cell * (long long)(ND * ND);
+      const unsigned short* pp = a.pos + cell * (long long)PROW;
       for (int i = lane; i < ND * ND; i += 32) s.pos[i] = pp[i];
     }
     for (int i = lane; i < ND * ND; i += 32) s.L[i] = 0.0;
@@ -336,6 +337,8 @@ __global__ void __launch_bounds__(32 * FWARPS) feec_kernel(FeecArgs a, CsView cs
 constexpr int CT = 128;
 constexpr int SWS = 37;   // row stride of the vorticity table (36 values)
 struct FeecCta {
+  double G[2][NQMAX * 23];     // mapping records of the current and the next cell (cp.async double buffer)
+  double SGN[2][ND + 1];
   double SW[NQMAX * SWS];
   double SR[NQMAX * SV_SYS];   // curls (36), velocity values (18), divergences (6)
   double L[ND * ND];
@@ -345,35 +348,48 @@ struct FeecCta {
   double ow[NQMAX * 4 * 3];    // partial vorticity at the points, per function group
   double ou[NQMAX * 2 * 3];    // partial velocity at the points
   double U[ND];
-  double sg[ND];
   double Tn[28];
   long long rs[ND * 3];
-  int idx[ND + 1];
-  unsigned short pos[ND * ND + 3];
+  unsigned short P[2][PROW];   // plan rows
+  int IDX[2][ND + 1];
 };
 
 __global__ void __launch_bounds__(CT) feec_system_cta_kernel(FeecArgs a, BlockView A, int* err) {
   extern __shared__ __align__(16) unsigned char raw_smem[];
   FeecCta& s = *reinterpret_cast<FeecCta*>(raw_smem);
-  const int t = threadIdx.x, lane = t & 31;
+  const int t = threadIdx.x;
   const int nq = a.nq;
   const double nu = a.prm.dt * a.prm.inv_re;
-  for (long long cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
-    const unsigned short* pp = a.pos + cell * (long long)(ND * ND);
-    if (pp[0] == 0xfffeu) continue;   // constrained dofs: warp kernel
+  // the inputs of the next cell travel while the current one is processed (ncu of the unpipelined version: 29 % of the
+  // stall samples waited for exactly these loads, another 20 % at the barriers behind them)
+  auto issue = [&](int buf, long long cell) {
     const double* g = a.geom + cell * a.gstride;
-    __syncthreads();                  // the previous cell's scatter is done with the scratch
+    for (int i = t; i < a.gstride; i += CT) cp_async8(&s.G[buf][i], g + i);
+    const unsigned short* pp = a.pos + cell * (long long)PROW;
+    for (int i = t; i < PROW / 4; i += CT) cp_async8(&s.P[buf][4 * i], pp + 4 * i);
     if (t < ND) {
-      const int gi = a.l2g[cell * ND + t];
-      s.idx[t] = gi;
-      s.sg[t] = a.sign[cell * ND + t];
-      s.U[t] = a.old_nse[gi];
-    } else if (t >= 32 && t < 32 + a.ndt)
-      s.Tn[t - 32] = a.old_temp[a.l2g_t[cell * a.ndt + t - 32]];
-    for (int i = t; i < ND * ND; i += CT) {
-      s.pos[i] = pp[i];
-      s.L[i] = 0.0;
+      cp_async4(&s.IDX[buf][t], a.l2g + cell * ND + t);
+      cp_async8(&s.SGN[buf][t], a.sign + cell * ND + t);
     }
+  };
+  if ((long long)blockIdx.x < a.n_cells) issue(0, a.cell_list[blockIdx.x]);
+  cp_async_commit();
+  int cur = 0;
+  for (long long it = blockIdx.x; it < a.n_cells; it += gridDim.x, cur ^= 1) {
+    const long long cell = a.cell_list[it];
+    cp_async_wait<0>();
+    __syncthreads();  // this cell's inputs have landed; the previous cell's scatter is done with the scratch
+    if (it + gridDim.x < a.n_cells) issue(cur ^ 1, a.cell_list[it + gridDim.x]);
+    cp_async_commit();
+    const double* g = s.G[cur];
+    const double* sgn = s.SGN[cur];
+    const int* idx = s.IDX[cur];
+    const unsigned short* pos = s.P[cur];
+    if (t < ND)
+      s.U[t] = a.old_nse[idx[t]];
+    else if (t >= 32 && t < 32 + a.ndt)
+      s.Tn[t - 32] = a.old_temp[a.l2g_t[cell * a.ndt + t - 32]];
+    for (int i = t; i < ND * ND; i += CT) s.L[i] = 0.0;
     __syncthreads();
     // ---- tables: thread = (point q, group of three functions)
     if (t < 4 * nq) {
@@ -412,7 +428,7 @@ __global__ void __launch_bounds__(CT) feec_system_cta_kernel(FeecArgs a, BlockVi
           const int k = 3 * grp + kk;
           const double* ph = a.tu_t + (size_t)(k * 3) * nq + q;
           const double p0 = __ldg(ph), p1 = __ldg(ph + nq), p2 = __ldg(ph + 2 * nq);
-          const double sgk = s.sg[NW + k], Uk = s.U[NW + k];
+          const double sgk = sgn[NW + k], Uk = s.U[NW + k];
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const double ru = (J[d][0] * p0 + J[d][1] * p1 + J[d][2] * p2) * idet;
@@ -543,7 +559,7 @@ __global__ void __launch_bounds__(CT) feec_system_cta_kernel(FeecArgs a, BlockVi
     } else if (t >= 32 && t < 32 + ND * 3) {
       const int tt = t - 32, i = tt / 3, bj = tt - 3 * i, bi = i < NW ? 0 : (i < NW + NU ? 1 : 2);
       const long long* rp = A.rowptr[bi][bj];
-      s.rs[tt] = rp ? rp[s.idx[i] - A.start[bi]] : 0;
+      s.rs[tt] = rp ? rp[idx[i] - A.start[bi]] : 0;
     }
     __syncthreads();
     for (int e = t; e < ND * ND; e += CT) {
@@ -551,14 +567,13 @@ __global__ void __launch_bounds__(CT) feec_system_cta_kernel(FeecArgs a, BlockVi
       if (v == 0.0) continue;  // distribute_local_to_global elides exact zeros
       const int i = e / ND, j = e - i * ND;
       const int bi = i < NW ? 0 : (i < NW + NU ? 1 : 2), bj = j < NW ? 0 : (j < NW + NU ? 1 : 2);
-      const unsigned o = s.pos[e];
+      const unsigned o = pos[e];
       if (o == 0xffffu)
         atomicAdd(err, 1);  // entry missing from the sparsity pattern
       else
         red_add_f64(A.val[bi][bj] + s.rs[i * 3 + bj] + o, v);
     }
-    if (t >= NW && t < NW + NU) red_add_f64(a.rhs + s.idx[t], s.l[t]);  // w and p rows of the right-hand side are zero
-    (void)lane;
+    if (t >= NW && t < NW + NU) red_add_f64(a.rhs + idx[t], s.l[t]);  // w and p rows of the right-hand side are zero
   }
 }
 
@@ -618,13 +633,16 @@ int dcp_launch_feec(dcp_model* m, const dcp_params& p, bool system, const double
       int per_sm = 1;
       DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, feec_system_cta_kernel, CT, smem));
       if (per_sm < 1) per_sm = 1;
-      long long blocks = m->n_cells;
+      long long blocks = m->n_feec_fast;
       const long long cap = (long long)ctx->sm_count * per_sm;
       if (blocks > cap) blocks = cap;
-      a.cell_list = nullptr;
-      feec_system_cta_kernel<<<(unsigned)blocks, CT, smem, ctx->stream>>>(a, make_view(mat), ctx->d_err);
-      ctx->launches++;
-      DCP_CUDA(cudaGetLastError());
+      if (blocks > 0) {
+        a.cell_list = m->feec_fast_cells;
+        a.n_cells = m->n_feec_fast;
+        feec_system_cta_kernel<<<(unsigned)blocks, CT, smem, ctx->stream>>>(a, make_view(mat), ctx->d_err);
+        ctx->launches++;
+        DCP_CUDA(cudaGetLastError());
+      }
     }
     if (m->n_feec_general == 0) return DCP_OK;
     a.cell_list = m->feec_general_cells;
@@ -648,11 +666,11 @@ int dcp_feec_positions_build(dcp_model* m, const dcp_model_desc* d, bool system,
                       d->nse_block_size[0] + d->nse_block_size[1] + d->nse_block_size[2]};
   std::vector<int32_t> lod((size_t)d->nse_cs.n_dofs, -1);
   for (int64_t l = 0; l < d->nse_cs.n_lines; ++l) lod[d->nse_cs.line_dof[l]] = (int32_t)l;
-  std::vector<uint16_t> pos((size_t)nc * ND * ND, 0xffff);
+  std::vector<uint16_t> pos((size_t)nc * PROW, 0xffff);
 #pragma omp parallel for schedule(static)
   for (int64_t c = 0; c < nc; ++c) {
     const int32_t* idx = d->nse_l2g + c * ND;
-    uint16_t* P = &pos[(size_t)c * ND * ND];
+    uint16_t* P = &pos[(size_t)c * PROW];
     bool fast = true;
     for (int i = 0; i < ND && fast; ++i) {
       const int bi = i < NW ? 0 : (i < NW + NU ? 1 : 2);
@@ -677,11 +695,12 @@ int dcp_feec_positions_build(dcp_model* m, const dcp_model_desc* d, bool system,
   }
   int rc = dcp_upload(m->ctx, out, pos.data(), (int64_t)pos.size());
   if (rc == DCP_OK && system) {
-    std::vector<int32_t> general;
-    for (int64_t c = 0; c < nc; ++c)
-      if (pos[(size_t)c * ND * ND] == 0xfffe) general.push_back((int32_t)c);
+    std::vector<int32_t> general, fast;
+    for (int64_t c = 0; c < nc; ++c) (pos[(size_t)c * PROW] == 0xfffe ? general : fast).push_back((int32_t)c);
     m->n_feec_general = (int64_t)general.size();
+    m->n_feec_fast = (int64_t)fast.size();
     if (!general.empty()) rc = dcp_upload(m->ctx, &m->feec_general_cells, general.data(), (int64_t)general.size());
+    if (rc == DCP_OK && !fast.empty()) rc = dcp_upload(m->ctx, &m->feec_fast_cells, fast.data(), (int64_t)fast.size());
   }
   cudaStreamSynchronize(m->ctx->stream);
   return rc;

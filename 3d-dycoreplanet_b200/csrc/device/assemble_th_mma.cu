@@ -84,18 +84,6 @@ struct NodeCs {
   double w0, w1, w2;
 };
 
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 // Per-cell inputs (mapping record, dof indices, plan row, masks) are copied with cp.async; the gathers that depend
 // on the dof indices (row starts, old solution values) are cp.async gathers issued before the operand table is built
 // and awaited after it.  A cross-cell double buffer (prefetching cell n+1 while cell n is processed) was measured

@@ -161,7 +161,8 @@ struct dcp_model {
   double *feec_w_qp = nullptr, *feec_c_qp = nullptr, *feec_u_qp = nullptr;
   double *feec_u_qt = nullptr, *feec_div = nullptr;
   int32_t* feec_general_cells = nullptr;  // FEEC cells with constrained dofs (general scatter)
-  int64_t n_feec_general = 0;
+  int32_t* feec_fast_cells = nullptr;     // the others
+  int64_t n_feec_general = 0, n_feec_fast = 0;
   uint16_t *feec_pos_nse = nullptr, *feec_pos_pre = nullptr;  // [n_cells][19*19] scatter positions (FEEC)
   // matrices and vectors
   BlockMat nse, pre, tmass, tstiff, tmat;

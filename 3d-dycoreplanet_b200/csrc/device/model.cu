@@ -338,6 +338,7 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->feec_div);
   cudaFree(m->feec_pos_nse);
   cudaFree(m->feec_general_cells);
+  cudaFree(m->feec_fast_cells);
   cudaFree(m->feec_pos_pre);
   free_blockmat(m->nse);
   free_blockmat(m->pre);
