@@ -276,3 +276,38 @@ def test_device_geometry_matches_host_mapping(ctx, problem_factory, spec, pname)
         assert rel_err_max(model.nse_matrix.block(bi, bj).values(), rv) <= TOL
     assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
     model.close()
+
+
+def test_error_behaviour_of_the_c_abi(ctx, problem_factory):
+    """Every failure is a status code + dcp_last_error(), which the mirrors turn into an exception (the reference's
+    convention: std::runtime_error reaching main.cxx:128-156); no call corrupts the model."""
+    import ctypes
+    from dycore_b200 import device, params
+    from oracle import oracle as orc
+    P = problem_factory(geometry="shell", refine=1)
+    mp = params.NAMED["shell_3d_classic"]
+    u, T = synthetic_fields(P)
+    # inconsistent description: dofs per cell do not match the element
+    d = device.model_desc_from_problem(P)
+    d.nse_n_local = 88
+    with pytest.raises(device.DcpError, match="classic family expects"):
+        device.BoussinesqModel(ctx, d, mp)
+    d = device.model_desc_from_problem(P)
+    d.geom_qn = None
+    with pytest.raises(device.DcpError, match="geom_qn"):
+        device.BoussinesqModel(ctx, d, mp)
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    # call order: the rhs needs the temperature matrices (T = M + dt/n K is built from them, :975-978)
+    with pytest.raises(device.DcpError):
+        model.assemble_temperature_rhs(T, u)
+    # bad selectors
+    rc = device.lib().dcp_vmult(model._h, 99, 0, 0, ctypes.c_void_p(u.ctypes.data), ctypes.c_void_p(u.ctypes.data), device.HOST)
+    assert rc != 0 and b"invalid" in device.lib().dcp_last_error()
+    with pytest.raises(device.DcpError):
+        device.PreconditionILU(model, device.MAT_NSE, 5)
+    assert device.lib().dcp_velocity_extrema(model._h, None, device.HOST, None) != 0
+    # the model still works after the failed calls
+    model.assemble_nse_system(u, T)
+    ref_vals, ref_rhs = orc.assemble_nse_system(P, orc.params_from(mp), u, T)
+    assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
+    model.close()
