@@ -76,6 +76,11 @@ struct BlockMat {
   DevCsr blk[DCP_MAXB][DCP_MAXB];
   double* diag_inv[DCP_MAXB] = {nullptr, nullptr, nullptr};  // Jacobi: 1/diag of the diagonal blocks
   int64_t owned[DCP_MAXB] = {-1, -1, -1};  // rows of each block owned by this rank (-1: all)
+  // multi-GPU overlap: per block row, the owned rows that read ghost columns (flag per row, compact list)
+  uint8_t* ghost_flag[DCP_MAXB] = {nullptr, nullptr, nullptr};
+  int32_t* ghost_list[DCP_MAXB] = {nullptr, nullptr, nullptr};
+  int64_t n_ghost_rows[DCP_MAXB] = {0, 0, 0};
+  bool owns_ghost_rows = true;
 };
 
 // by-value kernel argument describing a block matrix for scatter
@@ -190,7 +195,9 @@ extern "C" int dcp_ilu_destroy(struct dcp_ilu* p);
 
 // ---- kernels' host launchers ---------------------------------------------------------------------
 int dcp_feec_positions_build(dcp_model* m, const dcp_model_desc* d, bool system, uint16_t** out);
-int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit = -1);
+int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit = -1,
+                    const unsigned char* skip = nullptr, const int* list = nullptr, int64_t n_list = 0);
+int dcp_build_ghost_rows(dcp_ctx* ctx, BlockMat& M, int r, const int64_t* owned_cols);
 int dcp_launch_gather(dcp_ctx* ctx, int64_t n, const int32_t* idx, const double* src, double* dst, bool scatter);
 int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv);
 int dcp_launch_jacobi(dcp_ctx* ctx, int64_t n, const double* diag_inv, const double* x, double* y);

@@ -160,6 +160,12 @@ static void free_blockmat(BlockMat& M) {
     for (int j = 0; j < DCP_MAXB; ++j) free_csr(M.blk[i][j]);
     cudaFree(M.diag_inv[i]);
     M.diag_inv[i] = nullptr;
+    if (M.owns_ghost_rows) {
+      cudaFree(M.ghost_flag[i]);
+      cudaFree(M.ghost_list[i]);
+    }
+    M.ghost_flag[i] = nullptr;
+    M.ghost_list[i] = nullptr;
   }
 }
 
@@ -643,6 +649,21 @@ int dcp_model_set_owned(dcp_model* m, const int64_t* nse_owned_per_block, int64_
   }
   if (temp_owned < 0 || temp_owned > m->temp_n_dofs) return DCP_ERR_ARG;
   m->tmass.owned[0] = m->tstiff.owned[0] = m->tmat.owned[0] = temp_owned;
+  // rows that read ghost columns, per block row: dcp_vmult_rows / dcp_block_vmult_rows can then run the other rows
+  // while the ghost exchange is still in flight
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  for (int b = 0; b < m->nse_nb; ++b) {
+    DCP_TRY(dcp_build_ghost_rows(ctx, m->nse, b, nse_owned_per_block));
+    DCP_TRY(dcp_build_ghost_rows(ctx, m->pre, b, nse_owned_per_block));
+  }
+  DCP_TRY(dcp_build_ghost_rows(ctx, m->tmat, 0, &temp_owned));
+  for (BlockMat* M : {&m->tmass, &m->tstiff}) {  // same pattern as tmat
+    M->owns_ghost_rows = false;
+    M->ghost_flag[0] = m->tmat.ghost_flag[0];
+    M->ghost_list[0] = m->tmat.ghost_list[0];
+    M->n_ghost_rows[0] = m->tmat.n_ghost_rows[0];
+  }
   return DCP_OK;
 }
 
@@ -873,6 +894,46 @@ static int vmult_impl(dcp_model* m, int which, int bi, int bj, double* dst, cons
     DCP_TRY(dcp_stage_out_alloc(ctx, 1, dst, A->n_rows, mem, &dy));
   DCP_TRY(dcp_launch_spmv(ctx, *A, dx, dy, add, BM->owned[bi]));
   return dcp_stage_out_finish(ctx, 1, dst, A->n_rows, mem);
+}
+
+// one launch of block (bi,bj) restricted to a row class of block row bi
+static int spmv_rows(dcp_ctx* ctx, BlockMat& M, int bi, int bj, const double* x, double* y, bool add, int rows) {
+  const DevCsr& A = M.blk[bi][bj];
+  if (rows == DCP_ROWS_ALL) return dcp_launch_spmv(ctx, A, x, y, add, M.owned[bi]);
+  if (!M.ghost_flag[bi]) {
+    dcp_set_error("row classes need dcp_model_set_owned first");
+    return DCP_ERR_STATE;
+  }
+  if (rows == DCP_ROWS_INTERIOR) return dcp_launch_spmv(ctx, A, x, y, add, M.owned[bi], M.ghost_flag[bi]);
+  return dcp_launch_spmv(ctx, A, x, y, add, M.owned[bi], nullptr, M.ghost_list[bi], M.n_ghost_rows[bi]);
+}
+
+int dcp_vmult_rows(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int rows) {
+  if (!m || !dst || !src || rows < DCP_ROWS_ALL || rows > DCP_ROWS_GHOSTED) return DCP_ERR_ARG;
+  DevCsr* A;
+  BlockMat* BM;
+  DCP_TRY(get_block(m, which, bi, bj, &A, &BM));
+  DCP_CUDA(cudaSetDevice(m->ctx->device));
+  return spmv_rows(m->ctx, *BM, bi, bj, src, dst, false, rows);
+}
+
+int dcp_block_vmult_rows(dcp_model* m, int which, double* dst, const double* src, int rows) {
+  if (!m || !dst || !src || rows < DCP_ROWS_ALL || rows > DCP_ROWS_GHOSTED) return DCP_ERR_ARG;
+  BlockMat* M = select_matrix(m, which);
+  if (!M) return DCP_ERR_ARG;
+  dcp_ctx* ctx = m->ctx;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  for (int r = 0; r < M->nb; ++r) {
+    bool first = true;
+    for (int c = 0; c < M->nb; ++c) {
+      if (M->blk[r][c].nnz == 0) continue;
+      DCP_TRY(spmv_rows(ctx, *M, r, c, src + M->start[c], dst + M->start[r], !first, rows));
+      first = false;
+    }
+    if (first && rows != DCP_ROWS_GHOSTED)
+      DCP_TRY(dcp_launch_fill(ctx, dst + M->start[r], M->owned[r] >= 0 ? M->owned[r] : M->start[r + 1] - M->start[r], 0.0));
+  }
+  return DCP_OK;
 }
 
 int dcp_vmult(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem) {

@@ -21,15 +21,21 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
 }
 
 // LANES lanes cooperate on one row; 4-way unrolled so each lane keeps 8 independent loads in flight.
+// Row selection for the overlap of the ghost exchange with the product (multi-GPU): `skip` != nullptr leaves out the
+// rows flagged there (rows that read ghost columns); `list` != nullptr processes exactly the listed rows.
 template <int LANES, bool ADD>
 __global__ void __launch_bounds__(256) spmv_csr_kernel(long long n_rows, const long long* __restrict__ rowptr,
                                                        const int* __restrict__ col, const double* __restrict__ val,
-                                                       const double* __restrict__ x, double* __restrict__ y) {
+                                                       const double* __restrict__ x, double* __restrict__ y,
+                                                       const unsigned char* __restrict__ skip, const int* __restrict__ list) {
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long row = gtid / LANES;
+  long long row = gtid / LANES;
   const int lane = threadIdx.x % LANES;
   double sum = 0.0;
-  if (row < n_rows) {
+  bool active = row < n_rows;
+  if (active && list) row = list[row];
+  if (active && skip && skip[row]) active = false;
+  if (active) {
     const long long p0 = rowptr[row], p1 = rowptr[row + 1];
     // 4 x LANES entries per trip, every load predicated: the whole row (mean 200 nnz) is in flight after <= 2 trips
     for (long long p = p0 + lane; p < p1; p += 4 * LANES) {
@@ -50,7 +56,21 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(long long n_rows, const l
   }
 #pragma unroll
   for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (row < n_rows && lane == 0) y[row] = ADD ? y[row] + sum : sum;
+  if (active && lane == 0) y[row] = ADD ? y[row] + sum : sum;
+}
+
+// rows of the owned range whose last (largest) column is a ghost column
+__global__ void flag_ghost_rows_kernel(long long n_rows, const long long* __restrict__ rowptr, const int* __restrict__ col,
+                                       int owned_cols, unsigned char* __restrict__ flag) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const long long a = rowptr[r], b = rowptr[r + 1];
+  if (b > a && col[b - 1] >= owned_cols) flag[r] = 1;
+}
+__global__ void list_flagged_rows_kernel(long long n_rows, const unsigned char* __restrict__ flag, int* __restrict__ list,
+                                         int* __restrict__ count) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows && flag[r]) list[atomicAdd(count, 1)] = (int)r;
 }
 
 __global__ void extract_diag_inv_kernel(long long n_rows, const long long* __restrict__ rowptr,
@@ -90,17 +110,18 @@ __global__ void fill_kernel(double* __restrict__ p, long long n, double v) {
 }
 
 template <int LANES>
-int launch_spmv_t(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, long long n_rows) {
+int launch_spmv_t(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, long long n_rows,
+                  const unsigned char* skip, const int* list) {
   const int threads = 256;
   const long long rows_per_block = threads / LANES;
   const long long blocks = (n_rows + rows_per_block - 1) / rows_per_block;
   if (blocks == 0) return DCP_OK;
   if (add)
     spmv_csr_kernel<LANES, true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-        n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
+        n_rows, (const long long*)A.rowptr, A.col, A.val, x, y, skip, list);
   else
     spmv_csr_kernel<LANES, false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-        n_rows, (const long long*)A.rowptr, A.col, A.val, x, y);
+        n_rows, (const long long*)A.rowptr, A.col, A.val, x, y, skip, list);
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;
@@ -114,19 +135,55 @@ inline unsigned grid_for(dcp_ctx* ctx, long long n, int threads) {
 
 }  // namespace
 
-int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit) {
-  const long long n_rows = row_limit >= 0 && row_limit < A.n_rows ? row_limit : A.n_rows;
+int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, bool add, int64_t row_limit,
+                    const unsigned char* skip, const int* list, int64_t n_list) {
+  long long n_rows = row_limit >= 0 && row_limit < A.n_rows ? row_limit : A.n_rows;
+  if (list) n_rows = n_list;
   if (n_rows == 0) return DCP_OK;
   if (A.rowptr == nullptr || A.nnz == 0) {
-    if (!add) return dcp_launch_fill(ctx, y, n_rows, 0.0);
+    if (!add && !skip && !list) return dcp_launch_fill(ctx, y, n_rows, 0.0);
     return DCP_OK;
   }
   switch (A.lanes) {
-    case 4: return launch_spmv_t<4>(ctx, A, x, y, add, n_rows);
-    case 8: return launch_spmv_t<8>(ctx, A, x, y, add, n_rows);
-    case 16: return launch_spmv_t<16>(ctx, A, x, y, add, n_rows);
-    default: return launch_spmv_t<32>(ctx, A, x, y, add, n_rows);
+    case 4: return launch_spmv_t<4>(ctx, A, x, y, add, n_rows, skip, list);
+    case 8: return launch_spmv_t<8>(ctx, A, x, y, add, n_rows, skip, list);
+    case 16: return launch_spmv_t<16>(ctx, A, x, y, add, n_rows, skip, list);
+    default: return launch_spmv_t<32>(ctx, A, x, y, add, n_rows, skip, list);
   }
+}
+
+// flags + list of the rows of block row r (all its blocks) that read a ghost column
+int dcp_build_ghost_rows(dcp_ctx* ctx, BlockMat& M, int r, const int64_t* owned_cols) {
+  const int64_t n = M.owned[r] >= 0 ? M.owned[r] : M.start[r + 1] - M.start[r];
+  cudaFree(M.ghost_flag[r]);
+  cudaFree(M.ghost_list[r]);
+  M.ghost_flag[r] = nullptr;
+  M.ghost_list[r] = nullptr;
+  M.n_ghost_rows[r] = 0;
+  if (n == 0) return DCP_OK;
+  DCP_CUDA(cudaMalloc((void**)&M.ghost_flag[r], (size_t)n));
+  DCP_CUDA(cudaMemsetAsync(M.ghost_flag[r], 0, (size_t)n, ctx->stream));
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  for (int c = 0; c < M.nb; ++c) {
+    const DevCsr& A = M.blk[r][c];
+    if (A.nnz == 0) continue;
+    flag_ghost_rows_kernel<<<blocks, threads, 0, ctx->stream>>>(n, (const long long*)A.rowptr, A.col, (int)owned_cols[c], M.ghost_flag[r]);
+    ctx->launches++;
+  }
+  int* d_count = nullptr;
+  DCP_CUDA(cudaMalloc((void**)&d_count, sizeof(int)));
+  DCP_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+  DCP_CUDA(cudaMalloc((void**)&M.ghost_list[r], sizeof(int) * (size_t)n));
+  list_flagged_rows_kernel<<<blocks, threads, 0, ctx->stream>>>(n, M.ghost_flag[r], M.ghost_list[r], d_count);
+  ctx->launches++;
+  int h_count = 0;
+  DCP_CUDA(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_count);
+  M.n_ghost_rows[r] = h_count;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
 }
 
 namespace {

@@ -85,7 +85,7 @@ EXPORTS = [
     "dcp_model_destroy", "dcp_model_set_strategy", "dcp_model_set_owned", "dcp_gather_f64", "dcp_scatter_f64", "dcp_assemble_nse_system", "dcp_assemble_nse_preconditioner",
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
-    "dcp_vmult_add", "dcp_block_vmult", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
+    "dcp_vmult_add", "dcp_block_vmult", "dcp_vmult_rows", "dcp_block_vmult_rows", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
     "dcp_vec_scale", "dcp_vec_copy", "dcp_velocity_extrema", "dcp_constraints_distribute",
     "dcp_geometry_create", "dcp_ilu_create", "dcp_ilu_refactor", "dcp_ilu_vmult", "dcp_ilu_levels", "dcp_ilu_destroy",
 ]
@@ -137,6 +137,8 @@ def lib():
         L.dcp_vmult.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_vmult_add.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_block_vmult.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.dcp_vmult_rows.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.dcp_block_vmult_rows.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_jacobi_vmult.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_vec_dot.argtypes = [vp, ctypes.c_int64, vp, vp, c_dp]
         L.dcp_vec_axpy.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp, vp]
@@ -252,6 +254,13 @@ class SparseMatrix:
         assert md == ms
         check(lib().dcp_vmult(self._m._h, self.which, self.bi, self.bj, d, s, md), "vmult")
 
+    def vmult_rows(self, dst, src, rows):
+        """vmult restricted to a row class (ROWS_INTERIOR / ROWS_GHOSTED), device vectors only."""
+        d, md = _vec_arg(dst)
+        s, ms = _vec_arg(src)
+        assert md == ms == DEVICE
+        check(lib().dcp_vmult_rows(self._m._h, self.which, self.bi, self.bj, d, s, rows), "dcp_vmult_rows")
+
     def vmult_add(self, dst, src):
         d, md = _vec_arg(dst)
         s, ms = _vec_arg(src)
@@ -288,6 +297,15 @@ class BlockSparseMatrix:
         s, ms = _vec_arg(src)
         assert md == ms
         check(lib().dcp_block_vmult(self._m._h, self.which, d, s, md), "block vmult")
+
+    def vmult_rows(self, dst, src, rows):
+        d, md = _vec_arg(dst)
+        s, ms = _vec_arg(src)
+        assert md == ms == DEVICE
+        check(lib().dcp_block_vmult_rows(self._m._h, self.which, d, s, rows), "dcp_block_vmult_rows")
+
+
+ROWS_ALL, ROWS_INTERIOR, ROWS_GHOSTED = 0, 1, 2
 
 
 class PreconditionJacobi:

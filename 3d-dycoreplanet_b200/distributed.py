@@ -125,6 +125,41 @@ class DistributedMatrix:
         self.matrix.vmult(dst, src)
 
 
+class OverlappedMatrix:
+    """`vmult` that hides the ghost exchange behind the rows that do not need it (what Epetra does
+    inside Epetra_CrsMatrix::Multiply): the exchange (pack kernel -> NCCL p2p -> unpack kernel) runs on a side
+    stream with a context of its own, the main stream computes the rows that read owned columns only, waits for
+    the exchange and finishes the rows that read ghost columns.  CUDA tensors only."""
+
+    def __init__(self, matrix, halo, device_index, main_stream):
+        from . import device as dv
+        self.dv = dv
+        self.matrix, self.halo, self.main = matrix, halo, main_stream
+        self.side = torch.cuda.Stream(device=device_index)
+        self.side_ctx = dv.Context(device_index)
+        self.side_ctx.set_stream(self.side.cuda_stream)
+        self.ready = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+
+    def vmult(self, dst, src):
+        dv = self.dv
+        if self.halo.world == 1:
+            self.matrix.vmult(dst, src)
+            return
+        self.ready.record(self.main)               # src is final on the main stream from here on
+        # interior rows first: their kernels run while the host is still issuing the exchange
+        self.matrix.vmult_rows(dst, src, dv.ROWS_INTERIOR)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ready)
+            self.halo.exchange(src, self.side_ctx)
+            self.done.record(self.side)
+        self.main.wait_event(self.done)
+        self.matrix.vmult_rows(dst, src, dv.ROWS_GHOSTED)
+
+    def close(self):
+        self.side_ctx.close()
+
+
 def global_dot(a, b, owned_mask_or_slices, group=None):
     """Dot product over owned entries + all-reduce (the Krylov solvers' MPI_Allreduce of one double)."""
     s = torch.zeros(1, dtype=torch.float64, device=a.device)

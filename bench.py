@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--strategy", default="auto", choices=["auto", "search", "positions", "owner"])
     ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the CPU sample (4: ~3 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-halo", action="store_true",
+                    help="N>1: hide the ghost exchange behind the rows without ghost columns (measured: no gain at the "
+                         "bench sizes, the exchange is <10 %% of the product and the second pass costs as much)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -251,6 +254,12 @@ def main():
         torch.cuda.set_stream(stream)
         halo_nse = distributed.HaloPlan(P["nse.dof_key"], P["nse.dof_owner"], rank, world, device="cuda")
         halo_t = distributed.HaloPlan(P["temp.dof_key"], P["temp.dof_owner"], rank, world, device="cuda")
+        if args.overlap_halo:   # ghost exchange hidden behind the rows that do not read ghost columns
+            op_nse = distributed.OverlappedMatrix(model.nse_matrix, halo_nse, local_rank, stream)
+            op_t = distributed.OverlappedMatrix(model.temperature_matrix, halo_t, local_rank, stream)
+        else:                   # exchange, then the product (Epetra_Import + Multiply)
+            op_nse = distributed.DistributedMatrix(model.nse_matrix, halo_nse, ctx)
+            op_t = distributed.DistributedMatrix(model.temperature_matrix, halo_t, ctx)
     t_setup = time.perf_counter() - t_setup
 
     with torch.cuda.stream(stream):
@@ -285,12 +294,14 @@ def main():
             model.assemble_temperature_rhs(d_T, d_u)
             mark(4)
             if halo_nse is not None:
-                halo_nse.exchange(d_x, ctx)     # Epetra_Import of the ghost columns (NCCL p2p over NVLink)
-            model.nse_matrix.vmult(d_y, d_x)
+                op_nse.vmult(d_y, d_x)          # Epetra_Import of the ghost columns (NCCL p2p over NVLink) + product
+            else:
+                model.nse_matrix.vmult(d_y, d_x)
             mark(5)
             if halo_t is not None:
-                halo_t.exchange(d_xt, ctx)
-            model.temperature_matrix.vmult(d_yt, d_xt)
+                op_t.vmult(d_yt, d_xt)
+            else:
+                model.temperature_matrix.vmult(d_yt, d_xt)
             mark(6)
 
     def step_host():
@@ -306,11 +317,11 @@ def main():
             d_x.copy_(h_x, non_blocking=True)
             d_xt.copy_(h_xt, non_blocking=True)
             if halo_nse is not None:
-                halo_nse.exchange(d_x, ctx)
-            model.nse_matrix.vmult(d_y, d_x)
-            if halo_t is not None:
-                halo_t.exchange(d_xt, ctx)
-            model.temperature_matrix.vmult(d_yt, d_xt)
+                op_nse.vmult(d_y, d_x)
+                op_t.vmult(d_yt, d_xt)
+            else:
+                model.nse_matrix.vmult(d_y, d_x)
+                model.temperature_matrix.vmult(d_yt, d_xt)
             h_y.copy_(d_y, non_blocking=True)
             h_yt.copy_(d_yt, non_blocking=True)
         device.check(device.lib().dcp_vector_download(model._h, device.VEC_NSE_RHS, h_rhs.data_ptr()))

@@ -61,6 +61,9 @@ enum {
   DCP_MAT_TEMP_STIFF = 3, /* temperature_stiffness_matrix */
   DCP_MAT_TEMP = 4        /* temperature_matrix = M + dt/n K */
 };
+/* row classes of a row-distributed operator (dcp_vmult_rows): all owned rows, the rows that read owned columns only,
+ * the rows that read at least one ghost column */
+enum { DCP_ROWS_ALL = 0, DCP_ROWS_INTERIOR = 1, DCP_ROWS_GHOSTED = 2 };
 /* which vector of the model */
 enum { DCP_VEC_NSE_RHS = 0, DCP_VEC_TEMP_RHS = 1 };
 /* assembly strategy (dcp_model_set_strategy): all give the same matrix up to summation order */
@@ -259,6 +262,12 @@ int dcp_vmult(dcp_model* m, int which, int bi, int bj, double* dst, const double
 int dcp_vmult_add(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem);
 /* dst = A * src over all blocks; vectors are block-concatenated */
 int dcp_block_vmult(dcp_model* m, int which, double* dst, const double* src, int mem);
+/* The same products restricted to a row class (device pointers only; needs dcp_model_set_owned).  Trilinos overlaps
+ * the Epetra_Import of the ghost entries with the local part of Epetra_CrsMatrix::Multiply; here the caller runs
+ * DCP_ROWS_INTERIOR while its halo exchange is in flight on another stream and DCP_ROWS_GHOSTED after it (a row of a
+ * block row is GHOSTED when any of its blocks has a ghost column in that row, so the two classes partition the rows). */
+int dcp_vmult_rows(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int rows);
+int dcp_block_vmult_rows(dcp_model* m, int which, double* dst, const double* src, int rows);
 /* dst = diag(A(bi,bi))^-1 * src  (Jacobi, one sweep, omega 1).  Diagonals are refreshed by the assemble calls. */
 int dcp_jacobi_vmult(dcp_model* m, int which, int bi, double* dst, const double* src, int mem);
 

@@ -50,6 +50,15 @@ def main():
     distributed.DistributedMatrix(model.nse_matrix, halo, ctx).vmult(d_y, d_x)
     ctx.synchronize()
     y = d_y.cpu().numpy()
+    # the same product with the ghost exchange hidden behind the interior rows: identical result, owned rows
+    d_x2 = torch.from_numpy(xs).cuda()
+    d_y2 = torch.full_like(d_x2, float("nan"))
+    over = distributed.OverlappedMatrix(model.nse_matrix, halo, local, stream)
+    over.vmult(d_y2, d_x2)
+    torch.cuda.synchronize()
+    y2 = d_y2.cpu().numpy()
+    same = bool(np.array_equal(y2[owned], y[owned]))
+    over.close()
     rhs = model.nse_rhs
     gathered = [None] * world
     dist.all_gather_object(gathered, (keys[owned], y[owned], rhs[owned]))
@@ -71,6 +80,11 @@ def main():
         err_r = np.abs(rr - grhs[order][pos]).max() / np.abs(grhs).max()
         ok = len(kk) == len(gk) and err_y <= 1e-12 and err_r <= 1e-12
         print(f"multi_gpu_check world={world} refine={refine}: spmv err {err_y:.2e}, rhs err {err_r:.2e} -> {'OK' if ok else 'FAIL'}")
+    flags = [None] * world
+    dist.all_gather_object(flags, same)
+    if rank == 0:
+        print(f"multi_gpu_check overlapped product identical on all ranks: {all(flags)}")
+        ok = ok and all(flags)
     model.close()
     ctx.close()
     dist.destroy_process_group()
