@@ -311,3 +311,46 @@ def test_error_behaviour_of_the_c_abi(ctx, problem_factory):
     ref_vals, ref_rhs = orc.assemble_nse_system(P, orc.params_from(mp), u, T)
     assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
     model.close()
+
+
+def test_row_classes_partition_the_owned_rows(ctx, problem_factory):
+    """dcp_block_vmult_rows / dcp_vmult_rows: INTERIOR + GHOSTED rows together give exactly the plain product on the
+    owned rows of a rank's subdomain (one rank of a two-rank partition, no exchange needed for this identity)."""
+    import torch
+    from dycore_b200 import device, params
+    P = problem_factory(geometry="shell", refine=2, n_ranks=2, rank=0)
+    mp = params.NAMED["shell_3d_classic"]
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    n_u, n_uo, n_po = P.scalar("nse.n_u"), P.scalar("nse.n_u_owned"), P.scalar("nse.n_p_owned")
+    model.set_owned([n_uo, n_po], P.scalar("temp.n_owned"))
+    u, T = synthetic_fields(P)
+    model.assemble_nse_system(u, T)
+    model.assemble_temperature_matrix()
+    model.assemble_temperature_rhs(T, u)
+    n = model.n_nse
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    x = torch.from_numpy(np.random.default_rng(4).standard_normal(n)).cuda()
+    y = torch.zeros(n, dtype=torch.float64, device="cuda")
+    model.nse_matrix.vmult(y, x)
+    z = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    model.nse_matrix.vmult_rows(z, x, device.ROWS_INTERIOR)
+    n_interior = int((~torch.isnan(z)).sum())
+    model.nse_matrix.vmult_rows(z, x, device.ROWS_GHOSTED)
+    torch.cuda.synchronize()
+    owned = np.concatenate([np.arange(n_uo), n_u + np.arange(n_po)])
+    yh, zh = y.cpu().numpy(), z.cpu().numpy()
+    assert np.array_equal(yh[owned], zh[owned])
+    assert 0 < n_interior < len(owned)            # both classes are populated on a partitioned mesh
+    # single block and the temperature matrix
+    nT = model.n_temp
+    xt = torch.from_numpy(np.random.default_rng(5).standard_normal(nT)).cuda()
+    yt = torch.zeros(nT, dtype=torch.float64, device="cuda")
+    zt = torch.full((nT,), float("nan"), dtype=torch.float64, device="cuda")
+    model.temperature_matrix.vmult(yt, xt)
+    model.temperature_matrix.vmult_rows(zt, xt, device.ROWS_INTERIOR)
+    model.temperature_matrix.vmult_rows(zt, xt, device.ROWS_GHOSTED)
+    torch.cuda.synchronize()
+    no = P.scalar("temp.n_owned")
+    assert np.array_equal(yt.cpu().numpy()[:no], zt.cpu().numpy()[:no])
+    ctx.set_stream(None)
+    model.close()
