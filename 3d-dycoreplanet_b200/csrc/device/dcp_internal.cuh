@@ -75,6 +75,7 @@ struct BlockMat {
   int64_t start[DCP_MAXB + 1] = {0, 0, 0, 0};
   DevCsr blk[DCP_MAXB][DCP_MAXB];
   double* diag_inv[DCP_MAXB] = {nullptr, nullptr, nullptr};  // Jacobi: 1/diag of the diagonal blocks
+  int32_t* diag_off[DCP_MAXB] = {nullptr, nullptr, nullptr};  // offset of the diagonal entry inside its row (cached)
   int64_t owned[DCP_MAXB] = {-1, -1, -1};  // rows of each block owned by this rank (-1: all)
   // multi-GPU overlap: per block row, the owned rows that read ghost columns (flag per row, compact list)
   uint8_t* ghost_flag[DCP_MAXB] = {nullptr, nullptr, nullptr};
@@ -199,7 +200,7 @@ int dcp_launch_spmv(dcp_ctx* ctx, const DevCsr& A, const double* x, double* y, b
                     const unsigned char* skip = nullptr, const int* list = nullptr, int64_t n_list = 0);
 int dcp_build_ghost_rows(dcp_ctx* ctx, BlockMat& M, int r, const int64_t* owned_cols);
 int dcp_launch_gather(dcp_ctx* ctx, int64_t n, const int32_t* idx, const double* src, double* dst, bool scatter);
-int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv);
+int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv, int32_t** diag_off = nullptr);
 int dcp_launch_jacobi(dcp_ctx* ctx, int64_t n, const double* diag_inv, const double* x, double* y);
 int dcp_launch_axpby_values(dcp_ctx* ctx, int64_t n, const double* a, const double* b, double fb, double* out);
 int dcp_launch_fill(dcp_ctx* ctx, double* p, int64_t n, double v);

@@ -113,7 +113,7 @@ static int pick_lanes(int64_t n_rows, int64_t nnz) {
   if (n_rows == 0) return 32;
   double mean = (double)nnz / (double)n_rows;
   if (mean <= 6) return 4;
-  if (mean <= 14) return 8;
+  if (mean <= 16) return 8;
   if (mean <= 40) return 16;
   return 32;
 }
@@ -160,6 +160,8 @@ static void free_blockmat(BlockMat& M) {
     for (int j = 0; j < DCP_MAXB; ++j) free_csr(M.blk[i][j]);
     cudaFree(M.diag_inv[i]);
     M.diag_inv[i] = nullptr;
+    cudaFree(M.diag_off[i]);
+    M.diag_off[i] = nullptr;
     if (M.owns_ghost_rows) {
       cudaFree(M.ghost_flag[i]);
       cudaFree(M.ghost_list[i]);
@@ -181,7 +183,7 @@ static int refresh_jacobi(dcp_ctx* ctx, BlockMat& M) {
     DevCsr& A = M.blk[b][b];
     if (A.nnz == 0) continue;
     if (!M.diag_inv[b]) DCP_CUDA(cudaMalloc((void**)&M.diag_inv[b], sizeof(double) * (size_t)A.n_rows));
-    DCP_TRY(dcp_launch_extract_diag_inv(ctx, A, M.diag_inv[b]));
+    DCP_TRY(dcp_launch_extract_diag_inv(ctx, A, M.diag_inv[b], &M.diag_off[b]));
   }
   return DCP_OK;
 }

@@ -73,9 +73,19 @@ __global__ void list_flagged_rows_kernel(long long n_rows, const unsigned char* 
   if (r < n_rows && flag[r]) list[atomicAdd(count, 1)] = (int)r;
 }
 
+// with a cached offset of the diagonal inside each row (found once per pattern) the refresh is one gather
+__global__ void diag_inv_from_offsets_kernel(long long n_rows, const long long* __restrict__ rowptr, const int* __restrict__ off,
+                                             const double* __restrict__ val, double* __restrict__ dinv) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int o = off[r];
+  const double d = o >= 0 ? val[rowptr[r] + o] : 0.0;
+  dinv[r] = d != 0.0 ? 1.0 / d : 0.0;
+}
+
 __global__ void extract_diag_inv_kernel(long long n_rows, const long long* __restrict__ rowptr,
                                         const int* __restrict__ col, const double* __restrict__ val,
-                                        double* __restrict__ dinv) {
+                                        double* __restrict__ dinv, int* __restrict__ off_out) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   long long lo = rowptr[r], hi = rowptr[r + 1];
@@ -85,8 +95,10 @@ __global__ void extract_diag_inv_kernel(long long n_rows, const long long* __res
     long long mid = (lo + hi) >> 1;
     if (col[mid] < target) lo = mid + 1; else hi = mid;
   }
-  double d = (lo < end && col[lo] == target) ? val[lo] : 0.0;
+  const bool found = lo < end && col[lo] == target;
+  double d = found ? val[lo] : 0.0;
   dinv[r] = d != 0.0 ? 1.0 / d : 0.0;
+  if (off_out) off_out[r] = found ? (int)(lo - rowptr[r]) : -1;
 }
 
 __global__ void jacobi_kernel(long long n, const double* __restrict__ dinv, const double* __restrict__ x,
@@ -209,11 +221,17 @@ int dcp_launch_gather(dcp_ctx* ctx, int64_t n, const int32_t* idx, const double*
   return DCP_OK;
 }
 
-int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv) {
+int dcp_launch_extract_diag_inv(dcp_ctx* ctx, const DevCsr& A, double* diag_inv, int32_t** diag_off) {
   if (A.n_rows == 0) return DCP_OK;
   const int threads = 256;
   unsigned blocks = (unsigned)((A.n_rows + threads - 1) / threads);
-  extract_diag_inv_kernel<<<blocks, threads, 0, ctx->stream>>>(A.n_rows, (const long long*)A.rowptr, A.col, A.val, diag_inv);
+  if (diag_off && *diag_off) {
+    diag_inv_from_offsets_kernel<<<blocks, threads, 0, ctx->stream>>>(A.n_rows, (const long long*)A.rowptr, *diag_off, A.val, diag_inv);
+  } else {
+    if (diag_off) DCP_CUDA(cudaMalloc((void**)diag_off, sizeof(int32_t) * (size_t)A.n_rows));
+    extract_diag_inv_kernel<<<blocks, threads, 0, ctx->stream>>>(A.n_rows, (const long long*)A.rowptr, A.col, A.val, diag_inv,
+                                                                 diag_off ? *diag_off : nullptr);
+  }
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;
