@@ -115,7 +115,7 @@ static int pick_lanes(int64_t n_rows, int64_t nnz) {
   // measured on block(0,1) of the shell (14.5 entries per row): 16 lanes 2.2 TB/s, 8 lanes 3.5 TB/s, 4 lanes 4.4 TB/s
   if (mean <= 16) return 4;
   if (mean <= 32) return 8;
-  if (mean <= 64) return 16;
+  if (mean <= 256) return 16;
   return 32;
 }
 
