@@ -12,6 +12,7 @@ vectors and SpMV sources, D2H of the right-hand sides and SpMV results inside th
   python bench.py --impl reference ...   # the restated CPU path (oracle, OpenMP) on the host cores
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -304,9 +305,23 @@ def main():
                 model.temperature_matrix.vmult(d_yt, d_xt)
             mark(6)
 
+    copy_stream = torch.cuda.Stream()
+    ev_x, ev_rhs, ev_copy_done, ev_spmv = (torch.cuda.Event() for _ in range(4))
+    d_trhs = torch.zeros(n_t, dtype=torch.float64, device="cuda")
+    rhs_ptr, trhs_ptr, nn = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+    device.check(device.lib().dcp_vector_device(model._h, device.VEC_NSE_RHS, ctypes.byref(rhs_ptr), ctypes.byref(nn)))
+    device.check(device.lib().dcp_vector_device(model._h, device.VEC_TEMP_RHS, ctypes.byref(trhs_ptr), ctypes.byref(nn)))
+
     def step_host():
         # the same step for a caller whose vectors live in host memory: H2D of the solution vectors and SpMV
-        # sources, D2H of the right-hand sides and SpMV results, all inside the timed region
+        # sources, D2H of the right-hand sides and SpMV results, all inside the timed region.  The copies that do
+        # not gate the next kernel run on a second stream, as a careful caller would issue them: the SpMV sources go
+        # up while the assembly runs, the right-hand sides come down while the products run.
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_spmv)                 # the previous step's products are done with d_x
+            d_x.copy_(h_x, non_blocking=True)
+            d_xt.copy_(h_xt, non_blocking=True)
+            ev_x.record(copy_stream)
         with torch.cuda.stream(stream):
             d_u.copy_(h_u, non_blocking=True)
             d_T.copy_(h_T, non_blocking=True)
@@ -314,18 +329,26 @@ def main():
             model.assemble_nse_preconditioner()
             model.assemble_temperature_matrix()
             model.assemble_temperature_rhs(d_T, d_u)
-            d_x.copy_(h_x, non_blocking=True)
-            d_xt.copy_(h_xt, non_blocking=True)
+            device.check(device.lib().dcp_vec_copy(ctx._h, n_nse, rhs_ptr, ctypes.c_void_p(d_rhs.data_ptr())))
+            device.check(device.lib().dcp_vec_copy(ctx._h, n_t, trhs_ptr, ctypes.c_void_p(d_trhs.data_ptr())))
+            ev_rhs.record(stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_rhs)
+            h_rhs.copy_(d_rhs, non_blocking=True)
+            h_trhs.copy_(d_trhs, non_blocking=True)
+            ev_copy_done.record(copy_stream)
+        with torch.cuda.stream(stream):
+            stream.wait_event(ev_x)
             if halo_nse is not None:
                 op_nse.vmult(d_y, d_x)
                 op_t.vmult(d_yt, d_xt)
             else:
                 model.nse_matrix.vmult(d_y, d_x)
                 model.temperature_matrix.vmult(d_yt, d_xt)
+            ev_spmv.record(stream)
             h_y.copy_(d_y, non_blocking=True)
             h_yt.copy_(d_yt, non_blocking=True)
-        device.check(device.lib().dcp_vector_download(model._h, device.VEC_NSE_RHS, h_rhs.data_ptr()))
-        device.check(device.lib().dcp_vector_download(model._h, device.VEC_TEMP_RHS, h_trhs.data_ptr()))
+            stream.wait_event(ev_copy_done)                 # the step ends when every result is in host memory
 
     def barrier():
         if world > 1:
