@@ -496,7 +496,6 @@ void dcp_masked_plan_free(MaskedPlan* p) {
   cudaFree(p->other_cells);
   cudaFree(p->pos);
   cudaFree(p->nmask);
-  cudaFree(p->wide_idx);
   cudaFree(p->pos_wide);
   cudaFree(p->pos9);
   delete p;
@@ -720,7 +719,6 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
   if (rc == DCP_OK) rc = upm(ctx, &P->other_cells, other);
   if (rc == DCP_OK) rc = upm(ctx, &P->pos, pos);
   if (rc == DCP_OK) rc = upm(ctx, &P->nmask, nmask);
-  if (rc == DCP_OK) rc = upm(ctx, &P->wide_idx, wide_idx);
   if (rc == DCP_OK) rc = upm(ctx, &P->pos_wide, pos_wide);
   if (rc == DCP_OK) rc = upm(ctx, &P->pos9, pos9);
   cudaStreamSynchronize(ctx->stream);

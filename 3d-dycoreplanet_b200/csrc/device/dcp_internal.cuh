@@ -123,9 +123,8 @@ struct MaskedPlan {
   int64_t n = 0, n_other = 0, n_wide = 0;
   int32_t* cells = nullptr;
   int32_t* other_cells = nullptr;  // cells that failed the layout check: general kernel, full mode
-  uint16_t* pos = nullptr;         // [n][35*35]
-  uint8_t* nmask = nullptr;        // [n][36]
-  int32_t* wide_idx = nullptr;     // [n] preconditioner: -1 or row of pos_wide
+  uint16_t* pos = nullptr;         // [n][1228]: 35*35 offsets padded to 8 bytes
+  uint8_t* nmask = nullptr;        // [n][48]: node masks, pressure flags, cell flag, wide-table index, 9-table index
   uint16_t* pos_wide = nullptr;    // [n_wide][3][27][27]
   uint16_t* pos9 = nullptr;        // [n_nnf][9][27][27]: preconditioner cells with no-normal-flux lines
 };
