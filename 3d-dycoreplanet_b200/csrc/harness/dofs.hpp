@@ -161,8 +161,65 @@ struct DofMap {
 
 // node_owner (optional): owning rank per lattice node; dofs owned by other ranks are numbered after the owned
 // ones inside each block (Trilinos-style local numbering: owned rows first, then ghost columns).
+// Order in which the pre-dofs (numbered by cell / object order, like DoFHandler::distribute_dofs) are visited by the
+// component-wise stable partition: identity, Cuthill-McKee (what the reference applies before component_wise when the
+// Schur-complement solver is selected, boussinesq_model.tpp:198-202; restated from memory: breadth-first from a dof of
+// least coordination, neighbours in order of increasing coordination), or a seeded random permutation (a numbering
+// with no locality at all -- the device path must not care).
+inline std::vector<int32_t> pre_dof_order(const std::string& mode, int64_t n, int64_t n_cells, int n_pre_per_cell,
+                                          const std::vector<int32_t>& cell_pre /* [n_cells][n_pre_per_cell] */) {
+  std::vector<int32_t> order((size_t)n);
+  for (int64_t i = 0; i < n; ++i) order[(size_t)i] = (int32_t)i;
+  if (mode == "none" || mode.empty()) return order;
+  if (mode == "random") {
+    uint64_t st = 0x9E3779B97F4A7C15ull;
+    for (int64_t i = n - 1; i > 0; --i) {
+      st ^= st << 13;
+      st ^= st >> 7;
+      st ^= st << 17;
+      std::swap(order[(size_t)i], order[(size_t)(st % (uint64_t)(i + 1))]);
+    }
+    return order;
+  }
+  if (mode != "cuthill_mckee") throw std::runtime_error("harness: unknown renumber mode " + mode);
+  // dof graph: two dofs are adjacent when a cell holds both
+  std::vector<std::vector<int32_t>> adj((size_t)n);
+  for (int64_t c = 0; c < n_cells; ++c) {
+    const int32_t* d = &cell_pre[(size_t)c * n_pre_per_cell];
+    for (int i = 0; i < n_pre_per_cell; ++i)
+      for (int j = 0; j < n_pre_per_cell; ++j)
+        if (i != j) adj[(size_t)d[i]].push_back(d[j]);
+  }
+  for (auto& a : adj) {
+    std::sort(a.begin(), a.end());
+    a.erase(std::unique(a.begin(), a.end()), a.end());
+  }
+  std::vector<uint8_t> seen((size_t)n, 0);
+  std::vector<int32_t> by_degree(order);
+  std::stable_sort(by_degree.begin(), by_degree.end(), [&](int32_t x, int32_t y) { return adj[(size_t)x].size() < adj[(size_t)y].size(); });
+  size_t out = 0, head = 0, next_seed = 0;
+  while (out < (size_t)n) {
+    while (seen[(size_t)by_degree[next_seed]]) ++next_seed;
+    const int32_t seed = by_degree[next_seed];
+    seen[(size_t)seed] = 1;
+    order[out++] = seed;
+    while (head < out) {
+      const int32_t v = order[head++];
+      std::vector<int32_t> nb;
+      for (int32_t w : adj[(size_t)v])
+        if (!seen[(size_t)w]) nb.push_back(w);
+      std::stable_sort(nb.begin(), nb.end(), [&](int32_t x, int32_t y) { return adj[(size_t)x].size() < adj[(size_t)y].size(); });
+      for (int32_t w : nb) {
+        seen[(size_t)w] = 1;
+        order[out++] = w;
+      }
+    }
+  }
+  return order;
+}
+
 inline DofMap distribute_dofs(const Mesh& mesh, FESystemDesc fe, const std::vector<int32_t>* node_owner = nullptr,
-                              int rank = 0) {
+                              int rank = 0, const std::string& renumber = "none") {
   DofMap dm;
   fe.dim = mesh.dim;
   fe.finalize();
@@ -239,8 +296,23 @@ inline DofMap distribute_dofs(const Mesh& mesh, FESystemDesc fe, const std::vect
   }
   dm.renumber.resize((size_t)next);
   {
+    std::vector<int32_t> order;
+    if (renumber != "none" && !renumber.empty()) {
+      // pre-dofs of every cell (for the dof graph of Cuthill-McKee)
+      std::vector<int32_t> cell_pre((size_t)mesh.n_cells * fe.n_local);
+      std::vector<int64_t> lids(n3);
+      for (int64_t c = 0; c < mesh.n_cells; ++c) {
+        mesh.cell_nodes(c, lids.data());
+        for (int i = 0; i < fe.n_local; ++i) {
+          const int lx = fe.local_lex[i];
+          cell_pre[(size_t)c * fe.n_local + i] = dm.node_first[lids[lx]] + dm.field_rank[fe.local_field[i]][lex_ed[lx]];
+        }
+      }
+      order = pre_dof_order(renumber, next, mesh.n_cells, fe.n_local, cell_pre);
+    }
     std::vector<int64_t> cur(pseudo_start.begin(), pseudo_start.end() - 1);
-    for (int64_t d = 0; d < next; ++d) {
+    for (int64_t k = 0; k < next; ++k) {
+      const int64_t d = order.empty() ? k : order[(size_t)k];
       dm.renumber[d] = (int32_t)cur[pre_block[d]]++;
       dm.dof_key[dm.renumber[d]] = pre_key[d];
       dm.dof_owner[dm.renumber[d]] = pre_owner[d];

@@ -34,6 +34,7 @@ struct Spec {
   int threads = 0;
   int constraints = 1;    // 0: no boundary conditions at all (used by the oracle identity tests)
   int radial_factor = 1;  // shell only: n_r = 2^refine * radial_factor layers (weak-scaling synthetic refinement)
+  std::string renumber = "none";  // none | cuthill_mckee | random: order of the NSE dofs before component_wise
   int n_ranks = 1, rank = 0;  // contiguous partition of the (tree, Morton) cell order, one ghost-cell layer
 };
 
@@ -60,6 +61,7 @@ inline Spec parse_spec(const std::string& s) {
     else if (k == "radial_factor") sp.radial_factor = std::stoi(v);
     else if (k == "constraints") sp.constraints = std::stoi(v);
     else if (k == "n_ranks") sp.n_ranks = std::stoi(v);
+    else if (k == "renumber") sp.renumber = v;
     else if (k == "rank") sp.rank = std::stoi(v);
     else throw std::runtime_error("unknown spec key: " + k);
   }
@@ -516,7 +518,7 @@ inline void build_feec(Problem* P, const Spec& sp) {
   fe.field_degree = {0, 0, 0};
   fe.field_block = {0, 1, 2};
   fe.field_kind = {1, 2, 3};
-  P->nse = distribute_dofs(mesh, fe, nullptr, 0);
+  P->nse = distribute_dofs(mesh, fe, nullptr, 0, sp.renumber);
   FESystemDesc t_fe;
   t_fe.dim = dim;
   t_fe.field_degree = {sp.temperature_degree};
@@ -746,7 +748,8 @@ inline std::unique_ptr<Problem> build_problem(const Spec& sp) {
   nse_fe.field_degree.push_back(sp.velocity_degree - 1);
   nse_fe.field_block.push_back(1);
   const std::vector<int32_t>* owner = sp.n_ranks > 1 ? &P->node_owner : nullptr;
-  P->nse = distribute_dofs(mesh, nse_fe, owner, sp.rank);
+  if (sp.renumber != "none" && sp.n_ranks > 1) throw std::runtime_error("harness: renumber is implemented for a single rank");
+  P->nse = distribute_dofs(mesh, nse_fe, owner, sp.rank, sp.renumber);
   FESystemDesc t_fe;
   t_fe.dim = dim;
   t_fe.field_degree = {sp.temperature_degree};

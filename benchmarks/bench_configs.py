@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CONFIGS = [
-    ("aqua_planet_test_2d.prm", dict(geometry="annulus", dim=2, R0=10.0, R1=30.0, temperature_degree=2, refine=4), "annulus_2d"),
+    ("aqua_planet_test_2d.prm", dict(geometry="annulus", dim=2, R0=10.0, R1=30.0, temperature_degree=2, refine=4, renumber="cuthill_mckee"), "annulus_2d"),
     ("aqua_planet_cube_test_3d.prm", dict(geometry="cube", family="feec", refine=4), "cube_3d"),
     ("aqua_planet_shell_test_3d-classic.prm", dict(geometry="shell", refine=2), "shell_3d_classic"),
     ("aqua_planet_shell_test_3d-feec.prm", dict(geometry="shell", family="feec", refine=3), "shell_3d_feec"),

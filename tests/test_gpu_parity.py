@@ -354,3 +354,33 @@ def test_row_classes_partition_the_owned_rows(ctx, problem_factory):
     assert np.array_equal(yt.cpu().numpy()[:no], zt.cpu().numpy()[:no])
     ctx.set_stream(None)
     model.close()
+
+
+RENUMBERED = [dict(renumber="cuthill_mckee", refine=2, **ANNULUS), dict(renumber="random", refine=2, **ANNULUS),
+              dict(geometry="shell", refine=1, renumber="random"), dict(geometry="shell", refine=1, renumber="cuthill_mckee")]
+
+
+@pytest.mark.parametrize("spec", RENUMBERED, ids=["annulus-cmk", "annulus-random", "shell-random", "shell-cmk"])
+def test_any_dof_numbering_is_assembled_correctly(ctx, problem_factory, spec):
+    """The device path takes the index maps as they come: with Cuthill-McKee (the reference's numbering on its
+    Schur-complement path, boussinesq_model.tpp:198-202) or a random permutation the position-table plans reject the
+    cells whose layout they cannot verify and the general AffineConstraints scatter takes over -- same matrices."""
+    from dycore_b200 import device
+    from oracle import oracle as orc
+    P = problem_factory(**spec)
+    mp = _params(spec)
+    u, T = synthetic_fields(P)
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)      # default strategy: POSITIONS
+    oprm = orc.params_from(mp)
+    model.assemble_nse_system(u, T)
+    ref_vals, ref_rhs = orc.assemble_nse_system(P, oprm, u, T)
+    for (bi, bj), rv in split_blocks(P, "nse", ref_vals).items():
+        assert rel_err_max(model.nse_matrix.block(bi, bj).values(), rv) <= TOL, f"nse block {bi}{bj}"
+    assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
+    model.assemble_nse_preconditioner()
+    for (bi, bj), rv in split_blocks(P, "pre", orc.assemble_nse_preconditioner(P, oprm)).items():
+        assert rel_err_max(model.nse_preconditioner_matrix.block(bi, bj).values(), rv) <= TOL, f"pre block {bi}{bj}"
+    model.assemble_temperature_matrix()
+    model.assemble_temperature_rhs(T, u)
+    assert rel_err_max(model.temperature_rhs, orc.assemble_temperature_rhs(P, oprm, T, u)) <= TOL
+    model.close()

@@ -57,3 +57,32 @@ def test_mapping_data_positive_and_volume_converges(problem_factory):
         assert (g[:, 0, :] > 0).all()
         errs.append(abs(g[:, 0, :].sum() - exact) / exact)
     assert errs[2] < errs[1] < 0.05
+
+
+@pytest.mark.parametrize("mode", ["cuthill_mckee", "random"])
+def test_renumbering_permutes_the_system(problem_factory, mode):
+    """`renumber` (the reference applies DoFRenumbering::Cuthill_McKee before component_wise on the Schur path,
+    boussinesq_model.tpp:198-202) only permutes the dofs inside their blocks: the oracle's right-hand side and
+    matrix-vector product agree entry by entry when matched through the numbering-independent dof keys."""
+    import numpy as np
+    from dycore_b200 import params
+    from oracle import oracle as orc
+    spec = dict(geometry="annulus", dim=2, R0=10.0, R1=30.0, temperature_degree=2, refine=2)
+    P0, P1 = problem_factory(**spec), problem_factory(renumber=mode, **spec)
+    k0, k1 = P0["nse.dof_key"], P1["nse.dof_key"]
+    assert sorted(k0) == sorted(k1) and not np.array_equal(k0, k1)
+    assert P0.scalar("nse.n_u") == P1.scalar("nse.n_u")
+    prm = orc.params_from(params.NAMED["annulus_2d"])
+
+    def field(keys, s):
+        return np.ascontiguousarray(np.sin(0.37 * s * (keys % 1013)) + 0.2 * np.cos(0.11 * (keys % 7919)))
+    T0 = np.ascontiguousarray(2.0 + 0.1 * np.sin(0.5 * (P0["temp.dof_key"] % 101)))
+    out = []
+    for P, k in ((P0, k0), (P1, k1)):
+        vals, rhs = orc.assemble_nse_system(P, prm, field(k, 1.0) * 0.1, T0)
+        rp, col, _, _ = P.csr("nse.full")
+        y = orc.spmv(rp, col, vals, field(k, 2.0))
+        order = np.argsort(k)
+        out.append((rhs[order], y[order]))
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-13 * np.abs(out[0][0]).max()
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-12 * np.abs(out[0][1]).max()

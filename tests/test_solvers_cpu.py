@@ -80,7 +80,8 @@ def test_stokes_solve_chains_reduce_the_residual(problem_factory, which):
         step = K.cpu_time_step
     else:
         mp = params.NAMED["annulus_2d"]
-        P = problem_factory(geometry="annulus", dim=2, R0=10.0, R1=30.0, temperature_degree=2, refine=2)
+        P = problem_factory(geometry="annulus", dim=2, R0=10.0, R1=30.0, temperature_degree=2, refine=2,
+                            renumber="cuthill_mckee")
         step = K.cpu_schur_step
     n, n_u = P.scalar("nse.n_dofs"), P.scalar("nse.n_u")
     u0 = np.zeros(n)
