@@ -31,6 +31,10 @@ struct ScalarArgs {
   const unsigned short* tpos;  // [n_cells][nd*nd] positions inside the row, tpos[cell][0] == 0xffff: general scatter
   const double* phi;   // [nq][nd]
   const double* dphi;  // [nq][nd][dim]
+  // point-fastest copies for the loads with lane = quadrature point (2 cache lines per warp-wide load instead of 27)
+  const double* phiT;    // [nd][nq]
+  const double* dphiT;   // [nd][dim][nq]
+  const double* phi_uT;  // classic velocity base element on the temperature rule, [ndu][nq]
   dcp_params prm;
   // rhs only
   const int* l2g_nse;
@@ -76,11 +80,10 @@ __device__ __forceinline__ void map_point(const ScalarArgs& a, const double* g, 
 #pragma unroll
     for (int d = 0; d < DIM; ++d) K[e][d] = g[a.nq * (1 + e * DIM + d) + q];
   for (int k = 0; k < a.nd; ++k) {
-    const double* dr = a.dphi + ((size_t)q * a.nd + k) * DIM;
     double r[DIM];
 #pragma unroll
-    for (int e = 0; e < DIM; ++e) r[e] = __ldg(dr + e);
-    row[k * 4] = __ldg(a.phi + (size_t)q * a.nd + k);
+    for (int e = 0; e < DIM; ++e) r[e] = __ldg(a.dphiT + (size_t)(k * DIM + e) * a.nq + q);
+    row[k * 4] = __ldg(a.phiT + (size_t)k * a.nq + q);
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       double v = 0.0;
@@ -280,9 +283,8 @@ __global__ void __launch_bounds__(128) temperature_rhs_kernel(ScalarArgs a, CsVi
                              g[a.nq * (15 + d * 3) + q] * p2) / det);
           }
         } else {
-          const double* pu = a.phi_u + (size_t)q * a.ndu;
           for (int n = 0; n < a.ndu; ++n) {
-            const double ph = __ldg(pu + n);
+            const double ph = __ldg(a.phi_uT + (size_t)n * a.nq + q);
 #pragma unroll
             for (int d = 0; d < DIM; ++d) u[d] += U[d * a.ndu + n] * ph;
           }
@@ -368,12 +370,11 @@ __global__ void __launch_bounds__(128, 8) temperature_rhs_plain_kernel(ScalarArg
           for (int d = 0; d < DIM; ++d) K[e][d] = g[a.nq * (1 + e * DIM + d) + q];
         double oldT = 0.0, gT[3] = {0.0, 0.0, 0.0}, u[3] = {0.0, 0.0, 0.0};
         for (int k = 0; k < nd; ++k) {
-          const double* dr = a.dphi + ((size_t)q * nd + k) * DIM;
           const double Tk = T[k];
-          oldT += Tk * __ldg(a.phi + (size_t)q * nd + k);
+          oldT += Tk * __ldg(a.phiT + (size_t)k * a.nq + q);
           double r[DIM];
 #pragma unroll
-          for (int e = 0; e < DIM; ++e) r[e] = __ldg(dr + e);
+          for (int e = 0; e < DIM; ++e) r[e] = __ldg(a.dphiT + (size_t)(k * DIM + e) * a.nq + q);
 #pragma unroll
           for (int d = 0; d < DIM; ++d) {
             double v = 0.0;
@@ -393,9 +394,8 @@ __global__ void __launch_bounds__(128, 8) temperature_rhs_plain_kernel(ScalarArg
                              g[a.nq * (15 + d * 3) + q] * p2) / det);
           }
         } else {
-          const double* pu = a.phi_u + (size_t)q * a.ndu;
           for (int n = 0; n < a.ndu; ++n) {
-            const double ph = __ldg(pu + n);
+            const double ph = __ldg(a.phi_uT + (size_t)n * a.nq + q);
 #pragma unroll
             for (int d = 0; d < DIM; ++d) u[d] += U[d * a.ndu + n] * ph;
           }
@@ -454,6 +454,9 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
   a.tpos = m->temp_pos;
   a.phi = m->phi_t_qt;
   a.dphi = m->dphi_t_qt;
+  a.phiT = m->phi_t_qt_T;
+  a.dphiT = m->dphi_t_qt_T;
+  a.phi_uT = m->phi_u_qt_T;
   a.prm = p;
   if (m->n_cells == 0) return DCP_OK;
   const ScalarLaunch s = scalar_launch(ctx, m->n_cells, a.nd, 0);
@@ -483,6 +486,9 @@ int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* 
   a.l2g = m->temp_l2g;
   a.phi = m->phi_t_qt;
   a.dphi = m->dphi_t_qt;
+  a.phiT = m->phi_t_qt_T;
+  a.dphiT = m->dphi_t_qt_T;
+  a.phi_uT = m->phi_u_qt_T;
   a.prm = p;
   a.l2g_nse = m->nse_l2g;
   a.nd_nse = m->nse_n_local;

@@ -154,6 +154,7 @@ struct dcp_model {
   int nq_nse = 0, nq_temp = 0, ndu = 0, ndp = 0, ndt = 0;
   double *phi_u_qn = nullptr, *dphi_u_qn = nullptr, *phi_p_qn = nullptr, *phi_t_qn = nullptr;
   double *phi_u_qt = nullptr, *phi_t_qt = nullptr, *dphi_t_qt = nullptr;
+  double *phi_u_qt_T = nullptr, *phi_t_qt_T = nullptr, *dphi_t_qt_T = nullptr;  // point-fastest copies [function(,dim)][q]
   // mapping data
   double *geom_qn = nullptr, *geom_qt = nullptr;
   bool geom_shared = false;

@@ -330,6 +330,9 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->phi_u_qt);
   cudaFree(m->phi_t_qt);
   cudaFree(m->dphi_t_qt);
+  cudaFree(m->phi_u_qt_T);
+  cudaFree(m->phi_t_qt_T);
+  cudaFree(m->dphi_t_qt_T);
   cudaFree(m->geom_qn);
   if (!m->geom_shared) cudaFree(m->geom_qt);
   cudaFree(m->geom_qp);
@@ -482,6 +485,20 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
   M_TRY(dcp_upload(ctx, &m->phi_t_qn, d->phi_t_qn, (int64_t)d->nq_nse * d->ndt));
   M_TRY(dcp_upload(ctx, &m->phi_t_qt, d->phi_t_qt, (int64_t)d->nq_temp * d->ndt));
   M_TRY(dcp_upload(ctx, &m->dphi_t_qt, d->dphi_t_qt, (int64_t)d->nq_temp * d->ndt * dim));
+  {
+    // point-fastest copies of the temperature-rule tables: the temperature kernels read them with lane = point
+    auto upload_T = [&](double** dst, const double* src, int nq, int inner) -> int {
+      std::vector<double> t((size_t)nq * inner);
+      for (int q = 0; q < nq; ++q)
+        for (int k = 0; k < inner; ++k) t[(size_t)k * nq + q] = src[(size_t)q * inner + k];
+      int r = dcp_upload(ctx, dst, t.data(), (int64_t)t.size());
+      cudaStreamSynchronize(ctx->stream);  // `t` dies here
+      return r;
+    };
+    M_TRY(upload_T(&m->phi_t_qt_T, d->phi_t_qt, d->nq_temp, d->ndt));
+    M_TRY(upload_T(&m->dphi_t_qt_T, d->dphi_t_qt, d->nq_temp, d->ndt * dim));
+    if (!feec) M_TRY(upload_T(&m->phi_u_qt_T, d->phi_u_qt, d->nq_temp, d->ndu));
+  }
   if (d->geom_on_device)
     m->geom_qn = const_cast<double*>(d->geom_qn);
   else
