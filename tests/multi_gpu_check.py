@@ -59,6 +59,22 @@ def main():
     y2 = d_y2.cpu().numpy()
     same = bool(np.array_equal(y2[owned], y[owned]))
     over.close()
+    # temperature: matrices, right-hand side (advected with the nse vector) and a halo product of temperature_matrix
+    tkeys, towners = P["temp.dof_key"], P["temp.dof_owner"]
+    n_to = P.scalar("temp.n_owned")
+    halo_t = distributed.HaloPlan(tkeys, towners, rank, world, device="cuda")
+    model.assemble_temperature_matrix()
+    model.assemble_temperature_rhs(d_T, d_u)
+    xt = field(tkeys, 5.0)
+    xt[towners != rank] = 0.0
+    d_xt = torch.from_numpy(xt).cuda()
+    d_yt = torch.zeros_like(d_xt)
+    distributed.DistributedMatrix(model.temperature_matrix, halo_t, ctx).vmult(d_yt, d_xt)
+    ctx.synchronize()
+    yt = d_yt.cpu().numpy()
+    trhs = model.temperature_rhs
+    tgathered = [None] * world
+    dist.all_gather_object(tgathered, (tkeys[:n_to], yt[:n_to], trhs[:n_to]))
     rhs = model.nse_rhs
     gathered = [None] * world
     dist.all_gather_object(gathered, (keys[owned], y[owned], rhs[owned]))
@@ -79,6 +95,24 @@ def main():
         err_y = np.abs(yy - yg[order][pos]).max() / np.abs(yg).max()
         err_r = np.abs(rr - grhs[order][pos]).max() / np.abs(grhs).max()
         ok = len(kk) == len(gk) and err_y <= 1e-12 and err_r <= 1e-12
+        # temperature reference on the unpartitioned mesh
+        gtk = G["temp.dof_key"]
+        uT = np.ascontiguousarray(field(gk, 1.0) * 0.1)
+        TT = np.ascontiguousarray(2.0 + 0.2 * field(gtk, 2.0))
+        rm, rk = orc.assemble_temperature_matrix(G, prm)
+        tm = orc.temperature_matrix_combine(rm, rk, mp_.time_step / mp_.NSE_solver_interval)
+        gtr = orc.assemble_temperature_rhs(G, prm, TT, uT)
+        trp, tcol, _, _ = G.csr("temp.pat")
+        ytg = orc.spmv(trp, tcol, tm, field(gtk, 5.0))
+        torder = np.argsort(gtk)
+        tk = np.concatenate([g[0] for g in tgathered])
+        ty = np.concatenate([g[1] for g in tgathered])
+        tr = np.concatenate([g[2] for g in tgathered])
+        tpos = np.searchsorted(gtk[torder], tk)
+        err_ty = np.abs(ty - ytg[torder][tpos]).max() / np.abs(ytg).max()
+        err_tr = np.abs(tr - gtr[torder][tpos]).max() / np.abs(gtr).max()
+        ok = ok and len(tk) == len(gtk) and err_ty <= 1e-12 and err_tr <= 1e-12
+        print(f"multi_gpu_check temperature: spmv err {err_ty:.2e}, rhs err {err_tr:.2e}")
         print(f"multi_gpu_check world={world} refine={refine}: spmv err {err_y:.2e}, rhs err {err_r:.2e} -> {'OK' if ok else 'FAIL'}")
     flags = [None] * world
     dist.all_gather_object(flags, same)
