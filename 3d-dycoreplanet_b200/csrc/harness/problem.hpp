@@ -512,18 +512,19 @@ inline void build_feec(Problem* P, const Spec& sp) {
   const Mesh& mesh = *P->mesh;
   const int dim = 3;
   const bool cuboid = sp.geometry == "cube";
-  if (sp.n_ranks > 1) throw std::runtime_error("harness: FEEC family is not partitioned yet");
+  const std::vector<int32_t>* owner = sp.n_ranks > 1 ? &P->node_owner : nullptr;
+  if (sp.renumber != "none" && sp.n_ranks > 1) throw std::runtime_error("harness: renumber is implemented for a single rank");
   FESystemDesc fe;
   fe.dim = dim;
   fe.field_degree = {0, 0, 0};
   fe.field_block = {0, 1, 2};
   fe.field_kind = {1, 2, 3};
-  P->nse = distribute_dofs(mesh, fe, nullptr, 0, sp.renumber);
+  P->nse = distribute_dofs(mesh, fe, owner, sp.rank, sp.renumber);
   FESystemDesc t_fe;
   t_fe.dim = dim;
   t_fe.field_degree = {sp.temperature_degree};
   t_fe.field_block = {0};
-  P->temp = distribute_dofs(mesh, t_fe, nullptr, 0);
+  P->temp = distribute_dofs(mesh, t_fe, owner, sp.rank);
   P->nse_block_start = {0, P->nse.block_size[0], P->nse.block_size[0] + P->nse.block_size[1],
                         P->nse.block_size[0] + P->nse.block_size[1] + P->nse.block_size[2]};
   const int mdeg = 1;  // FEValues without a mapping argument (boussineq_model_assembly_FEEC.tpp:24,67,160); T: MappingQ(1)
@@ -557,18 +558,30 @@ inline void build_feec(Problem* P, const Spec& sp) {
     const int nl = P->nse.fe.n_local;
     P->nse_sign.assign((size_t)mesh.n_cells * nl, 1.0);
     auto offs = hierarchical_offsets(dim);
-    std::vector<int8_t> first_side((size_t)mesh.n_nodes, -1);
+    // "First" is decided on the whole mesh in global cell order, so that every rank of a partition (whose local
+    // cell order is owned cells, then ghosts) sees the same sign on a shared face.
+    const Mesh& whole = P->base_mesh ? *P->base_mesh : mesh;
+    std::vector<int8_t> first_side((size_t)whole.n_nodes, -1);
+    std::vector<int64_t> first_cell((size_t)whole.n_nodes, -1);
     int64_t ids[27];
+    for (int64_t c = 0; c < whole.n_cells; ++c) {
+      whole.cell_nodes(c, ids);
+      for (int f = 0; f < 6; ++f) {
+        if (whole.face_boundary_id(c, f) >= 0) continue;
+        int64_t node = ids[lex_index(dim, offs[20 + f])];
+        if (first_side[node] < 0) {
+          first_side[node] = (int8_t)(f % 2);
+          first_cell[node] = c;
+        }
+      }
+    }
     for (int64_t c = 0; c < mesh.n_cells; ++c) {
+      const int64_t gc = P->base_mesh ? P->cell_global[(size_t)c] : c;
       mesh.cell_nodes(c, ids);
       for (int f = 0; f < 6; ++f) {
         if (mesh.face_boundary_id(c, f) >= 0) continue;
         int64_t node = ids[lex_index(dim, offs[20 + f])];
-        int side = f % 2;
-        if (first_side[node] < 0)
-          first_side[node] = (int8_t)side;
-        else if (first_side[node] == side)
-          P->nse_sign[(size_t)c * nl + 12 + f] = -1.0;
+        if (first_cell[node] != gc && first_side[node] == f % 2) P->nse_sign[(size_t)c * nl + 12 + f] = -1.0;
       }
     }
   }
@@ -609,9 +622,12 @@ inline void build_feec(Problem* P, const Spec& sp) {
   S["dim"] = dim;
   S["feec"] = 1;
   S["n_cells"] = mesh.n_cells;
-  S["n_owned_cells"] = mesh.n_cells;
-  S["n_ranks"] = 1;
-  S["rank"] = 0;
+  S["n_owned_cells"] = P->n_owned_cells;
+  S["n_ranks"] = sp.n_ranks;
+  S["rank"] = sp.rank;
+  S["nse.n_w_owned"] = P->nse.owned_size[0];
+  S["nse.n_u_owned"] = P->nse.owned_size[1];
+  S["nse.n_p_owned"] = P->nse.owned_size[2];
   S["nse.n_dofs"] = P->nse.n_dofs;
   S["nse.n_w"] = P->nse.block_size[0];
   S["nse.n_u"] = P->nse.block_size[1];
@@ -619,7 +635,7 @@ inline void build_feec(Problem* P, const Spec& sp) {
   S["nse.n_local"] = P->nse.fe.n_local;
   S["temp.n_dofs"] = P->temp.n_dofs;
   S["temp.n_local"] = P->temp.fe.n_local;
-  S["temp.n_owned"] = P->temp.n_dofs;
+  S["temp.n_owned"] = P->temp.owned_size[0];
   S["q_nse.nq"] = P->q_nse.nq;
   S["q_pre.nq"] = P->q_pre.nq;
   S["q_temp.nq"] = P->q_temp.nq;
@@ -635,6 +651,9 @@ inline void build_feec(Problem* P, const Spec& sp) {
   P->reg("nse.dof_comp", P->nse_dof_comp, I8);
   P->reg("nse.dof_key", P->nse.dof_key, I64);
   P->reg("temp.dof_key", P->temp.dof_key, I64);
+  P->reg("nse.dof_owner", P->nse.dof_owner, I32);
+  P->reg("temp.dof_owner", P->temp.dof_owner, I32);
+  P->reg("cell_global", P->cell_global, I64);
   P->reg_cs("nse.cs", P->nse_cs);
   P->reg_cs("temp.cs", P->temp_cs);
   P->reg("q_nse.w", P->q_nse.w, F64);

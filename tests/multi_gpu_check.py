@@ -26,11 +26,21 @@ def main():
     from dycore_b200 import device, distributed, harness, params
     from oracle import oracle as orc
     refine = int(os.environ.get("DCP_CHECK_REFINE", "2"))
-    mp_ = params.NAMED["shell_3d_classic"]
-    P = harness.Problem(geometry="shell", refine=refine, n_ranks=world, rank=rank)
+    family = os.environ.get("DCP_CHECK_FAMILY", "classic")
+    feec = family == "feec"
+    mp_ = params.NAMED["shell_3d_feec" if feec else "shell_3d_classic"]
+    assemble_ref = orc.feec_assemble_nse_system if feec else orc.assemble_nse_system
+    assemble_tm = orc.feec_assemble_temperature_matrix if feec else orc.assemble_temperature_matrix
+    assemble_tr = orc.feec_assemble_temperature_rhs if feec else orc.assemble_temperature_rhs
+    P = harness.Problem(geometry="shell", refine=refine, n_ranks=world, rank=rank, family=family)
     keys, owners = P["nse.dof_key"], P["nse.dof_owner"]
-    n_u, n_uo, n_po = P.scalar("nse.n_u"), P.scalar("nse.n_u_owned"), P.scalar("nse.n_p_owned")
-    owned = np.concatenate([np.arange(n_uo), n_u + np.arange(n_po)])
+    blocks = ("n_w", "n_u", "n_p") if feec else ("n_u", "n_p")
+    start, owned, owned_counts = 0, [], []
+    for b in blocks:
+        owned_counts.append(P.scalar("nse." + b + "_owned"))
+        owned.append(start + np.arange(owned_counts[-1]))
+        start += P.scalar("nse." + b)
+    owned = np.concatenate(owned)
     u = np.ascontiguousarray(field(keys, 1.0) * 0.1)
     T = np.ascontiguousarray(2.0 + 0.2 * field(P["temp.dof_key"], 2.0))
     ctx = device.Context(local)
@@ -38,7 +48,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     torch.cuda.set_stream(stream)
     model = device.BoussinesqModel.from_problem(ctx, P, mp_)
-    model.set_owned([n_uo, n_po], P.scalar("temp.n_owned"))
+    model.set_owned(owned_counts, P.scalar("temp.n_owned"))
     halo = distributed.HaloPlan(keys, owners, rank, world, device="cuda")
     d_u, d_T = torch.from_numpy(u).cuda(), torch.from_numpy(T).cuda()
     model.assemble_nse_system(d_u, d_T)
@@ -80,11 +90,11 @@ def main():
     dist.all_gather_object(gathered, (keys[owned], y[owned], rhs[owned]))
     ok = True
     if rank == 0:
-        G = harness.Problem(geometry="shell", refine=refine)
+        G = harness.Problem(geometry="shell", refine=refine, family=family)
         gk = G["nse.dof_key"]
         prm = orc.params_from(mp_)
-        gv, grhs = orc.assemble_nse_system(G, prm, np.ascontiguousarray(field(gk, 1.0) * 0.1),
-                                           np.ascontiguousarray(2.0 + 0.2 * field(G["temp.dof_key"], 2.0)))
+        gv, grhs = assemble_ref(G, prm, np.ascontiguousarray(field(gk, 1.0) * 0.1),
+                                np.ascontiguousarray(2.0 + 0.2 * field(G["temp.dof_key"], 2.0)))
         grp, gcol, _, _ = G.csr("nse.full")
         yg = orc.spmv(grp, gcol, gv, field(gk, 3.0))
         order = np.argsort(gk)
@@ -99,9 +109,9 @@ def main():
         gtk = G["temp.dof_key"]
         uT = np.ascontiguousarray(field(gk, 1.0) * 0.1)
         TT = np.ascontiguousarray(2.0 + 0.2 * field(gtk, 2.0))
-        rm, rk = orc.assemble_temperature_matrix(G, prm)
+        rm, rk = assemble_tm(G, prm)
         tm = orc.temperature_matrix_combine(rm, rk, mp_.time_step / mp_.NSE_solver_interval)
-        gtr = orc.assemble_temperature_rhs(G, prm, TT, uT)
+        gtr = assemble_tr(G, prm, TT, uT)
         trp, tcol, _, _ = G.csr("temp.pat")
         ytg = orc.spmv(trp, tcol, tm, field(gtk, 5.0))
         torder = np.argsort(gtk)
@@ -113,7 +123,7 @@ def main():
         err_tr = np.abs(tr - gtr[torder][tpos]).max() / np.abs(gtr).max()
         ok = ok and len(tk) == len(gtk) and err_ty <= 1e-12 and err_tr <= 1e-12
         print(f"multi_gpu_check temperature: spmv err {err_ty:.2e}, rhs err {err_tr:.2e}")
-        print(f"multi_gpu_check world={world} refine={refine}: spmv err {err_y:.2e}, rhs err {err_r:.2e} -> {'OK' if ok else 'FAIL'}")
+        print(f"multi_gpu_check {family} world={world} refine={refine}: spmv err {err_y:.2e}, rhs err {err_r:.2e} -> {'OK' if ok else 'FAIL'}")
     flags = [None] * world
     dist.all_gather_object(flags, same)
     if rank == 0:

@@ -17,7 +17,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, refine, out):
+def _worker(rank, world, port, refine, out, family="classic"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -27,13 +27,20 @@ def _worker(rank, world, port, refine, out):
         import dycore_b200  # noqa: F401
         from dycore_b200 import distributed, harness, params
         from oracle import oracle as orc
-        mp_ = params.NAMED["shell_3d_classic"]
+        feec = family == "feec"
+        mp_ = params.NAMED["shell_3d_feec" if feec else "shell_3d_classic"]
         prm = orc.params_from(mp_)
-        P = harness.Problem(geometry="shell", refine=refine, n_ranks=world, rank=rank)
+        assemble = orc.feec_assemble_nse_system if feec else orc.assemble_nse_system
+        P = harness.Problem(geometry="shell", refine=refine, n_ranks=world, rank=rank, family=family)
         n = P.scalar("nse.n_dofs")
         keys, owners = P["nse.dof_key"], P["nse.dof_owner"]
-        n_u, n_uo, n_po = P.scalar("nse.n_u"), P.scalar("nse.n_u_owned"), P.scalar("nse.n_p_owned")
-        owned = np.concatenate([np.arange(n_uo), n_u + np.arange(n_po)])
+        # owned dofs come first inside every block (Trilinos-style local numbering)
+        blocks = ("n_w", "n_u", "n_p") if feec else ("n_u", "n_p")
+        start, owned = 0, []
+        for b in blocks:
+            owned.append(start + np.arange(P.scalar("nse." + b + "_owned")))
+            start += P.scalar("nse." + b)
+        owned = np.concatenate(owned)
         assert (owners[owned] == rank).all() and (np.delete(owners, owned) != rank).all()
 
         # fields defined through the global key so that every rank sees the same function
@@ -42,7 +49,7 @@ def _worker(rank, world, port, refine, out):
         u = field(keys, 1.0) * 0.1
         tkeys = P["temp.dof_key"]
         T = 2.0 + 0.2 * field(tkeys, 2.0)
-        vals, rhs = orc.assemble_nse_system(P, prm, np.ascontiguousarray(u), np.ascontiguousarray(T))
+        vals, rhs = assemble(P, prm, np.ascontiguousarray(u), np.ascontiguousarray(T))
         rp, col, _, _ = P.csr("nse.full")
 
         halo = distributed.HaloPlan(keys, owners, rank, world)
@@ -56,11 +63,11 @@ def _worker(rank, world, port, refine, out):
         gathered = [None] * world
         dist.all_gather_object(gathered, (keys[owned], y[owned], rhs[owned]))
         if rank == 0:
-            G = harness.Problem(geometry="shell", refine=refine)
+            G = harness.Problem(geometry="shell", refine=refine, family=family)
             gk = G["nse.dof_key"]
             ug = field(gk, 1.0) * 0.1
             Tg = 2.0 + 0.2 * field(G["temp.dof_key"], 2.0)
-            gv, grhs = orc.assemble_nse_system(G, prm, np.ascontiguousarray(ug), np.ascontiguousarray(Tg))
+            gv, grhs = assemble(G, prm, np.ascontiguousarray(ug), np.ascontiguousarray(Tg))
             grp, gcol, _, _ = G.csr("nse.full")
             yg = orc.spmv(grp, gcol, gv, field(gk, 3.0))
             order = np.argsort(gk)
@@ -77,12 +84,12 @@ def _worker(rank, world, port, refine, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("refine", [1, 2])
-def test_two_ranks_reproduce_single_rank_operator(refine):
+@pytest.mark.parametrize("refine,family", [(1, "classic"), (2, "classic"), (2, "feec")])
+def test_two_ranks_reproduce_single_rank_operator(refine, family):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + refine
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, refine, out)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + refine + (7 if family == "feec" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, refine, out, family)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
