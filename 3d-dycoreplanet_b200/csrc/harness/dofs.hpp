@@ -423,9 +423,23 @@ inline Csr make_sparsity_pattern(const DofMap& dm, const Constraints& cs, const 
     const int t = omp_get_thread_num();
     std::vector<int32_t> tmp;
     std::vector<int32_t>& mine = arena[t];
+    int64_t prev = -1;  // row whose columns `tmp` holds
 #pragma omp for schedule(dynamic, 4096)
     for (int64_t g = 0; g < dm.n_dofs; ++g) {
-      row_cols(g, tmp);
+      // consecutive unconstrained rows that live on the same cells and couple to the same fields (the velocity
+      // components of one node in the system pattern) have the same columns: build them once
+      bool same = prev == g - 1 && prev >= 0 && cs.line_of_dof[g] < 0 && cs.line_of_dof[prev] < 0 &&
+                  ra.ptr[g + 1] - ra.ptr[g] == ra.ptr[prev + 1] - ra.ptr[prev];
+      for (int64_t k = 0, n = ra.ptr[g + 1] - ra.ptr[g]; same && k < n; ++k) {
+        const int64_t p = ra.ptr[g] + k, q = ra.ptr[prev] + k;
+        same = ra.cell[p] == ra.cell[q];
+        if (same) {
+          const int fa = dm.fe.local_field[ra.loc[p]], fb = dm.fe.local_field[ra.loc[q]];
+          for (int f = 0; f < nf && same; ++f) same = coupling[fa * nf + f] == coupling[fb * nf + f];
+        }
+      }
+      if (!same) row_cols(g, tmp);
+      prev = g;
       A.rowptr[g + 1] = (int64_t)tmp.size();
       row_off[g] = (int64_t)mine.size();
       row_thr[g] = (uint8_t)t;
