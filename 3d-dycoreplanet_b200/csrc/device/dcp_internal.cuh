@@ -118,6 +118,17 @@ struct FastPlan {
   int ne = 0;
 };
 
+// (chunk, node) items of the write-once gather pass (assemble_th_stage.cu)
+struct GatherPlan {
+  int64_t chunk = 0, n_chunks = 0, n_cells = 0;
+  int32_t *v_g0 = nullptr, *p_g0 = nullptr;            // per item: first dof of the velocity node / pressure row
+  uint32_t *v_incptr = nullptr, *p_incptr = nullptr;   // per item: range in *_inc
+  uint32_t *v_inc = nullptr, *p_inc = nullptr;         // (cell index inside the chunk << 5) | local node
+  uint8_t *v_flag = nullptr, *p_flag = nullptr;        // bit 0: first chunk that touches the node (store, else accumulate)
+  std::vector<int64_t> v_chunk_ptr, p_chunk_ptr;       // host: item range of every chunk
+  double* staging = nullptr;                           // [chunk][7892]
+};
+
 // masked position tables for the DMMA path (assemble_th_mma.cu): every node-blocked cell, constrained or not
 struct MaskedPlan {
   int64_t n = 0, n_other = 0, n_wide = 0;
@@ -127,6 +138,7 @@ struct MaskedPlan {
   uint8_t* nmask = nullptr;        // [n][48]: node masks, pressure flags, cell flag, wide-table index, 9-table index
   uint16_t* pos_wide = nullptr;    // [n_wide][3][27][27]
   uint16_t* pos9 = nullptr;        // [n_nnf][9][27][27]: preconditioner cells with no-normal-flux lines
+  GatherPlan* gather = nullptr;    // write-once path (system matrix, n_other == 0)
 };
 
 struct dcp_model {
@@ -223,6 +235,9 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
 void dcp_masked_plan_free(MaskedPlan* p);
 int dcp_launch_th_mma(dcp_model* m, const dcp_params& p, bool system, const MaskedPlan* plan, const double* old_nse,
                       const double* old_temp);
+int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vector<int32_t>& cells, GatherPlan** out);
+void dcp_gather_plan_free(GatherPlan* p);
+int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* plan, const double* old_nse, const double* old_temp);
 int dcp_owner_plan_build(dcp_model* m, bool system, const dcp_model_desc* desc);
 void dcp_owner_plan_free(OwnerPlan* p);
 int dcp_launch_th_owner(dcp_model* m, const dcp_params& p, bool system);

@@ -626,6 +626,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     if (dim == 3) {
       M_TRY(dcp_masked_plan_build(m, d, true, &m->masked_nse));
       M_TRY(dcp_masked_plan_build(m, d, false, &m->masked_pre));
+      if (m->masked_nse->gather) m->strategy = DCP_STRATEGY_STAGED;
     } else {
       M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
       M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
@@ -649,7 +650,11 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
 }
 
 int dcp_model_set_strategy(dcp_model* m, int strategy) {
-  if (!m || strategy < DCP_STRATEGY_SEARCH || strategy > DCP_STRATEGY_OWNER) return DCP_ERR_ARG;
+  if (!m || strategy < DCP_STRATEGY_SEARCH || strategy > DCP_STRATEGY_STAGED) return DCP_ERR_ARG;
+  if (strategy == DCP_STRATEGY_STAGED && !(m->masked_nse && m->masked_nse->gather)) {
+    dcp_set_error("DCP_STRATEGY_STAGED is not available for this model (classic 3-D family, every cell in the position plan, rows within the gather capacity)");
+    return DCP_ERR_STATE;
+  }
   if (strategy == DCP_STRATEGY_OWNER && (!m->owner_nse || !m->owner_pre)) {
     dcp_set_error("DCP_STRATEGY_OWNER is not available for this model (needs dcp_model_desc.build_owner_plan, classic 3-D family, node-blocked numbering)");
     return DCP_ERR_STATE;
@@ -657,6 +662,8 @@ int dcp_model_set_strategy(dcp_model* m, int strategy) {
   m->strategy = strategy;
   return DCP_OK;
 }
+
+int dcp_model_get_strategy(const dcp_model* m) { return m ? m->strategy : -1; }
 
 int dcp_model_set_owned(dcp_model* m, const int64_t* nse_owned_per_block, int64_t temp_owned) {
   if (!m || !nse_owned_per_block) return DCP_ERR_ARG;
@@ -716,6 +723,9 @@ int dcp_assemble_nse_system(dcp_model* m, const dcp_params* p, const double* old
     DCP_TRY(dcp_launch_th_owner(m, *p, true));
     DCP_TRY(dcp_launch_th_rhs(m, *p, d_nse, d_temp));
     DCP_TRY(dcp_launch_th_cells(m, *p, true, d_nse, d_temp, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
+  } else if (m->strategy == DCP_STRATEGY_STAGED) {
+    // write-once: no zero-fill, no reductions into the matrix (assemble_th_stage.cu)
+    DCP_TRY(dcp_launch_th_staged(m, *p, m->masked_nse, d_nse, d_temp));
   } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
     DCP_TRY(zero_blockmat(ctx, m->nse));
     if (m->dim == 3) {
@@ -749,7 +759,7 @@ int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_th_owner(m, *p, false));
     DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
-  } else if (m->strategy == DCP_STRATEGY_POSITIONS) {
+  } else if (m->strategy == DCP_STRATEGY_POSITIONS || m->strategy == DCP_STRATEGY_STAGED) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     if (m->dim == 3) {
       DCP_TRY(dcp_launch_th_mma(m, *p, false, m->masked_pre, nullptr, nullptr));

@@ -43,6 +43,9 @@ __global__ void sadd_kernel(long long n, double s, double a, const double* __res
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = s * y[i] + a * x[i];
 }
+__global__ void shift_kernel(long long n, double a, double* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a;
+}
 __global__ void scale_kernel(long long n, double a, double* __restrict__ y) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] *= a;
@@ -96,6 +99,23 @@ int dcp_vec_scale(dcp_ctx* ctx, int64_t n, double a, double* y_dev) {
   if (!ctx || n < 0) return DCP_ERR_ARG;
   if (n == 0) return DCP_OK;
   scale_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, a, y_dev);
+  ctx->launches++;
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
+}
+
+int dcp_vec_fill(dcp_ctx* ctx, int64_t n, double value, double* y_dev) {
+  if (!ctx || n < 0 || (n > 0 && !y_dev)) return DCP_ERR_ARG;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return DCP_OK;
+  return dcp_launch_fill(ctx, y_dev, n, value);
+}
+
+int dcp_vec_shift(dcp_ctx* ctx, int64_t n, double a, double* y_dev) {
+  if (!ctx || n < 0 || (n > 0 && !y_dev)) return DCP_ERR_ARG;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return DCP_OK;
+  shift_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, a, y_dev);
   ctx->launches++;
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;

@@ -22,7 +22,7 @@ _LIB = None
 HOST, DEVICE = 0, 1
 MAT_NSE, MAT_NSE_PRECOND, MAT_TEMP_MASS, MAT_TEMP_STIFF, MAT_TEMP = 0, 1, 2, 3, 4
 VEC_NSE_RHS, VEC_TEMP_RHS = 0, 1
-STRATEGY_SEARCH, STRATEGY_POSITIONS, STRATEGY_OWNER = 0, 1, 2
+STRATEGY_SEARCH, STRATEGY_POSITIONS, STRATEGY_OWNER, STRATEGY_STAGED = 0, 1, 2, 3
 MAXB = 3
 
 c_dp = ctypes.POINTER(ctypes.c_double)
@@ -82,11 +82,11 @@ class MappingDesc(ctypes.Structure):
 EXPORTS = [
     "dcp_ctx_create", "dcp_ctx_destroy", "dcp_ctx_set_stream", "dcp_ctx_synchronize", "dcp_last_error",
     "dcp_ctx_launch_count", "dcp_malloc", "dcp_free", "dcp_memcpy_h2d", "dcp_memcpy_d2h", "dcp_model_create",
-    "dcp_model_destroy", "dcp_model_set_strategy", "dcp_model_set_owned", "dcp_gather_f64", "dcp_scatter_f64", "dcp_assemble_nse_system", "dcp_assemble_nse_preconditioner",
+    "dcp_model_destroy", "dcp_model_set_strategy", "dcp_model_get_strategy", "dcp_model_set_owned", "dcp_gather_f64", "dcp_scatter_f64", "dcp_assemble_nse_system", "dcp_assemble_nse_preconditioner",
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
     "dcp_vmult_add", "dcp_block_vmult", "dcp_vmult_rows", "dcp_block_vmult_rows", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
-    "dcp_vec_scale", "dcp_vec_copy", "dcp_velocity_extrema", "dcp_constraints_distribute",
+    "dcp_vec_scale", "dcp_vec_copy", "dcp_vec_fill", "dcp_vec_shift", "dcp_velocity_extrema", "dcp_constraints_distribute",
     "dcp_geometry_create", "dcp_ilu_create", "dcp_ilu_refactor", "dcp_ilu_vmult", "dcp_ilu_levels", "dcp_ilu_destroy",
 ]
 
@@ -121,6 +121,7 @@ def lib():
         L.dcp_model_create.argtypes = [vp, ctypes.POINTER(ModelDesc), ctypes.POINTER(vp)]
         L.dcp_model_destroy.argtypes = [vp]
         L.dcp_model_set_strategy.argtypes = [vp, ctypes.c_int]
+        L.dcp_model_get_strategy.argtypes = [vp]
         L.dcp_model_set_owned.argtypes = [vp, c_lp, ctypes.c_int64]
         L.dcp_gather_f64.argtypes = [vp, ctypes.c_int64, vp, vp, vp]
         L.dcp_scatter_f64.argtypes = [vp, ctypes.c_int64, vp, vp, vp]
@@ -145,6 +146,8 @@ def lib():
         L.dcp_vec_sadd.argtypes = [vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, vp, vp]
         L.dcp_vec_scale.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
         L.dcp_vec_copy.argtypes = [vp, ctypes.c_int64, vp, vp]
+        L.dcp_vec_fill.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
+        L.dcp_vec_shift.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
         L.dcp_geometry_create.argtypes = [vp, ctypes.POINTER(MappingDesc), ctypes.POINTER(vp)]
         L.dcp_ilu_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
         L.dcp_ilu_refactor.argtypes = [vp]
@@ -492,6 +495,10 @@ class BoussinesqModel:
 
     def set_strategy(self, s):
         check(lib().dcp_model_set_strategy(self._h, s), "dcp_model_set_strategy")
+
+    @property
+    def strategy(self):
+        return int(lib().dcp_model_get_strategy(self._h))
 
     def set_owned(self, nse_owned_per_block, temp_owned):
         arr = (ctypes.c_int64 * MAXB)(*(list(nse_owned_per_block) + [0] * (MAXB - len(nse_owned_per_block))))

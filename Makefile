@@ -16,9 +16,16 @@ lib/libdcp_harness.so: $(wildcard $(PKG)/csrc/harness/*.hpp) $(PKG)/csrc/harness
 oracle:
 	$(MAKE) -C oracle
 
-lib/libdcp.so: $(CU_SRCS) $(CU_HDRS)
-	mkdir -p lib build
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRCS) -lcudart > build/ptxas.log 2>&1 || (cat build/ptxas.log; false)
+CU_OBJS := $(patsubst $(PKG)/csrc/device/%.cu,build/obj/%.o,$(CU_SRCS))
+
+build/obj/%.o: $(PKG)/csrc/device/%.cu $(CU_HDRS)
+	mkdir -p build/obj build/ptxas
+	$(NVCC) $(NVFLAGS) -c -o $@ $< > build/ptxas/$*.log 2>&1 || (cat build/ptxas/$*.log; false)
+
+lib/libdcp.so: $(CU_OBJS)
+	mkdir -p lib
+	$(NVCC) -shared -Xcompiler -fopenmp -o $@ $(CU_OBJS) -lcudart -lgomp
+	cat build/ptxas/*.log > build/ptxas.log
 
 # C++ host mirror (include/dcp.hpp) checked against the oracle; the oracle is linked as the checker only
 tests/cpp/host_mirror_test: tests/cpp/host_mirror_test.cpp include/dcp.hpp include/dcp.h include/dcp_harness.h lib/libdcp.so lib/libdcp_harness.so oracle

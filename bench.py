@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N>1: strong = the same shell cut into N chunks; weak = N x the radial layers")
     ap.add_argument("--temperature-degree", type=int, default=1)
-    ap.add_argument("--strategy", default="auto", choices=["auto", "search", "positions", "owner"])
+    ap.add_argument("--strategy", default="auto", choices=["auto", "search", "positions", "owner", "staged"])
     ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the CPU sample (4: ~3 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap-halo", action="store_true",
@@ -244,10 +244,12 @@ def main():
     ctx = device.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    strategy = "positions" if args.strategy == "auto" else args.strategy
-    model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == "owner"), device_geometry=True)
-    model.set_strategy({"search": device.STRATEGY_SEARCH, "positions": device.STRATEGY_POSITIONS,
-                        "owner": device.STRATEGY_OWNER}[strategy])
+    names = {"search": device.STRATEGY_SEARCH, "positions": device.STRATEGY_POSITIONS, "owner": device.STRATEGY_OWNER,
+             "staged": device.STRATEGY_STAGED}
+    model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(args.strategy == "owner"), device_geometry=True)
+    if args.strategy != "auto":
+        model.set_strategy(names[args.strategy])
+    strategy = {v: k for k, v in names.items()}[model.strategy]   # auto: the library's default (staged when the model qualifies)
     halo_nse = halo_t = None
     if world > 1:
         from dycore_b200 import distributed

@@ -71,10 +71,15 @@ enum {
   DCP_STRATEGY_SEARCH = 0,    /* every cell: general AffineConstraints scatter, column positions by binary search */
   DCP_STRATEGY_POSITIONS = 1, /* unconstrained cells scatter from registers through a precomputed position table
                                  (no search, no local matrix in shared memory); constrained cells use SEARCH */
-  DCP_STRATEGY_OWNER = 2      /* row-owner tiles: a CTA owns a contiguous row range, accumulates in shared memory and
+  DCP_STRATEGY_OWNER = 2,     /* row-owner tiles: a CTA owns a contiguous row range, accumulates in shared memory and
                                  writes every CSR value of an unconstrained row exactly once (no atomics);
                                  contributions of constrained dofs are added afterwards by SEARCH on the constrained
                                  cells */
+  DCP_STRATEGY_STAGED = 3     /* write-once (classic 3-D family, every cell in the position plan): the cell blocks go
+                                 through a cell-major staging buffer, a row-owner gather pass writes every CSR value
+                                 once -- no atomics on the matrix, no zero-fill.  Default when the model qualifies;
+                                 matrices without a staged path (e.g. the preconditioner until it has one) use
+                                 POSITIONS */
 };
 
 typedef struct dcp_ctx dcp_ctx;
@@ -226,6 +231,8 @@ int dcp_geometry_create(dcp_ctx* ctx, const dcp_mapping_desc* desc, double** geo
 int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* desc, dcp_model** out);
 int dcp_model_destroy(dcp_model* m);
 int dcp_model_set_strategy(dcp_model* m, int strategy);
+/* the strategy in use (DCP_STRATEGY_STAGED by default when the model qualifies, else DCP_STRATEGY_POSITIONS); < 0: bad handle */
+int dcp_model_get_strategy(const dcp_model* m);
 /* Multi-GPU (one process per GPU, cells partitioned along the p4est curve as the reference does over MPI,
  * include/core/boussinesq_model.tpp:241-252, 491-494): the rank's local numbering puts the dofs it owns first
  * inside every block, ghost dofs after them.  After this call the operators (vmult, vmult_add, block_vmult,
@@ -309,6 +316,10 @@ int dcp_vec_axpy(dcp_ctx* ctx, int64_t n, double a, const double* x_dev, double*
 int dcp_vec_sadd(dcp_ctx* ctx, int64_t n, double s, double a, const double* x_dev, double* y_dev);
 int dcp_vec_scale(dcp_ctx* ctx, int64_t n, double a, double* y_dev);
 int dcp_vec_copy(dcp_ctx* ctx, int64_t n, const double* x_dev, double* y_dev);
+/* y = value (deal.II `dst = 0`: an assignment, so NaN / Inf in an uninitialised destination do not survive) */
+int dcp_vec_fill(dcp_ctx* ctx, int64_t n, double value, double* y_dev);
+/* y += a in every entry (Vector::add(a): the zero-mean correction of the FEEC pressure, nested_schur_complement.hpp:180-182) */
+int dcp_vec_shift(dcp_ctx* ctx, int64_t n, double a, double* y_dev);
 
 #ifdef __cplusplus
 }

@@ -237,6 +237,7 @@ class BoussinesqModel {
   int64_t n_nse_dofs() const { return n_nse_; }
   int64_t n_temperature_dofs() const { return n_temp_; }
   void set_strategy(int strategy) { check(dcp_model_set_strategy(h_, strategy), "dcp_model_set_strategy"); }
+  int strategy() const { return dcp_model_get_strategy(h_); }
   void set_owned(const std::array<int64_t, DCP_MAX_BLOCKS>& nse_owned_per_block, int64_t temp_owned) {
     check(dcp_model_set_owned(h_, nse_owned_per_block.data(), temp_owned), "dcp_model_set_owned");
   }

@@ -5,9 +5,10 @@ matrix, RHS and SpMV within 1e-12 relative in FP64 (norm-relative comparator, SU
 import numpy as np
 import pytest
 
-from util import rel_err_max, split_blocks, synthetic_fields
+from util import rel_err_max, rel_err_rows, split_blocks, synthetic_fields
 
 TOL = 1e-12
+ROW_TOL = 1e-11   # per-row-scaled comparator: every row against its own largest entry (rows of small cells count like the others)
 
 pytestmark = pytest.mark.gpu
 
@@ -23,7 +24,8 @@ def ctx():
 
 ANNULUS = dict(geometry="annulus", dim=2, R0=10.0, R1=30.0, temperature_degree=2)   # data/aqua_planet_test_2d.prm
 CASES = [dict(geometry="shell", refine=1), dict(geometry="shell", refine=2), dict(geometry="cube", refine=2),
-         dict(geometry="shell", refine=1, temperature_degree=2), dict(refine=2, **ANNULUS), dict(refine=4, **ANNULUS)]
+         dict(geometry="shell", refine=1, temperature_degree=2), dict(refine=2, **ANNULUS), dict(refine=4, **ANNULUS),
+         dict(geometry="shell", refine=3), dict(geometry="cube", refine=3)]
 
 
 def _params(spec):
@@ -32,17 +34,25 @@ def _params(spec):
 
 
 @pytest.mark.parametrize("spec", CASES, ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
-@pytest.mark.parametrize("strategy", [0, 1, 2], ids=["search", "positions", "owner"])
-def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy):
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4], ids=["search", "positions", "owner", "staged", "staged-chunk37"])
+def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy, monkeypatch):
     from dycore_b200 import device
     from oracle import oracle as orc
+    if spec["refine"] == 3 and spec["geometry"] != "annulus" and strategy in (0, 2):
+        pytest.skip("refine 3: the default and the staged strategies only (run time)")
     P = problem_factory(**spec)
     mp = _params(spec)
     if strategy == 2 and P.dim == 2:
         pytest.skip("row-owner tiles are built for the 3-D family only")
+    if strategy >= 3 and spec["geometry"] != "shell":
+        pytest.skip("write-once staging: classic 3-D family with every cell in the position plan (the shell)")
     u, T = synthetic_fields(P)
+    if strategy == 4:   # many small chunks: nodes are visited by several chunks (store first, accumulate later)
+        monkeypatch.setenv("DCP_GATHER_CHUNK", "37")
     model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == 2))
-    model.set_strategy(strategy)
+    if spec["geometry"] == "shell":
+        assert model.strategy == device.STRATEGY_STAGED, "the shell qualifies for the write-once path by default"
+    model.set_strategy(min(strategy, 3))
     oprm = orc.params_from(mp)
 
     # NSE system
@@ -52,6 +62,7 @@ def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy):
     for (bi, bj), rv in ref_blocks.items():
         gv = model.nse_matrix.block(bi, bj).values()
         assert rel_err_max(gv, rv) <= TOL, f"nse block {bi}{bj}"
+        assert rel_err_rows(gv, rv, P[f"nse.b{bi}{bj}.rowptr"]) <= ROW_TOL, f"nse block {bi}{bj} (row-scaled)"
     assert rel_err_max(model.nse_rhs, ref_rhs) <= TOL
 
     # NSE preconditioner
@@ -60,6 +71,7 @@ def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy):
     for (bi, bj), rv in ref_blocks.items():
         gv = model.nse_preconditioner_matrix.block(bi, bj).values()
         assert rel_err_max(gv, rv) <= TOL, f"pre block {bi}{bj}"
+        assert rel_err_rows(gv, rv, P[f"pre.b{bi}{bj}.rowptr"]) <= ROW_TOL, f"pre block {bi}{bj} (row-scaled)"
 
     # every time step re-assembles (quirk Q16): a second pass must not accumulate onto the first
     model.assemble_nse_system(u, T)

@@ -27,6 +27,22 @@ def rel_err_max(a, b):
     return float(np.abs(a - b).max() / (denom if denom > 0 else 1.0))
 
 
+def rel_err_rows(a, b, rowptr):
+    """max over rows of max|a_row - b_row| / max|b_row|: every row is judged against its own scale, so a row whose
+    entries are 1e-6 of the block maximum cannot hide a 1e-6 relative error."""
+    if a.size == 0:
+        return 0.0
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    nz = np.flatnonzero(np.diff(rowptr) > 0)
+    starts = rowptr[nz]
+    scale = np.maximum.reduceat(np.abs(b), starts)
+    err = np.maximum.reduceat(np.abs(a - b), starts)
+    ok = scale > 0
+    worst = float((err[ok] / scale[ok]).max()) if ok.any() else 0.0
+    assert not (err[~ok] > 0).any(), "non-zero entries in a row the oracle leaves empty"
+    return worst
+
+
 def synthetic_fields(P, seed=20261018, amplitude=0.1):
     """Seeded smooth state: low-order polynomials of the support point + uniform perturbation,
     so that advection / buoyancy terms are exercised.  Returns (nse_vector, temperature_vector)."""
