@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_mma_kernel(MmaArgs a, BlockVie
       for (int i = tid; i < a.ndt; i += nt) cp_async4(sidt2 + i, a.l2g_t + cell * a.ndt + i);
   };
 
-  for (long long w = blockIdx.x; w < a.n_fast; w += gridDim.x) {
+  for (long long wi = blockIdx.x; wi < a.n_fast; wi += gridDim.x) {
+    const long long w = a.wlist ? a.wlist[wi] : wi;
     __syncthreads();  // every warp is done with the previous cell
     issue_raw(w, a.cells[w]);
     cp_async_commit();
@@ -665,6 +666,8 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
     std::memcpy(&nmask[(size_t)i * MSTR + 40], &nnf_idx[i], sizeof(int32_t));
   }
   MaskedPlan* P = new MaskedPlan;
+  P->h_cells = cells;
+  P->h_nnf_idx = nnf_idx;
   P->n = (int64_t)cells.size();
   P->n_other = (int64_t)other.size();
   P->n_wide = (int64_t)(pos_wide.size() / (3 * NU * NU));
@@ -676,7 +679,11 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
   if (rc == DCP_OK) rc = upm(ctx, &P->pos_wide, pos_wide);
   if (rc == DCP_OK) rc = upm(ctx, &P->pos9, pos9);
   cudaStreamSynchronize(ctx->stream);
-  if (rc == DCP_OK && system && other.empty() && !std::getenv("DCP_NO_GATHER_PLAN")) rc = dcp_gather_plan_build(m, d, cells, &P->gather);
+  if (rc == DCP_OK && system && other.empty() && !std::getenv("DCP_NO_GATHER_PLAN")) {
+    std::vector<uint8_t> has_cs(cells.size());
+    for (size_t i = 0; i < cells.size(); ++i) has_cs[i] = mask_all[(size_t)cells[i] * 36 + 35];
+    rc = dcp_gather_plan_build(m, d, cells, has_cs, &P->gather);
+  }
   if (rc != DCP_OK) {
     dcp_masked_plan_free(P);
     return rc;
@@ -686,10 +693,11 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
 }
 
 int dcp_launch_th_mma(dcp_model* m, const dcp_params& p, bool system, const MaskedPlan* plan, const double* old_nse,
-                      const double* old_temp) {
+                      const double* old_temp, const int32_t* wlist, int64_t n_list) {
   dcp_ctx* ctx = m->ctx;
   MmaArgs a;
-  a.n_fast = plan->n;
+  a.n_fast = wlist ? n_list : plan->n;
+  a.wlist = wlist;
   a.cells = plan->cells;
   a.pos = plan->pos;
   a.nmask = plan->nmask;

@@ -29,54 +29,78 @@ namespace {
 using namespace dcpdev;
 using namespace thmma;
 
-constexpr int VROW = 268;                   // staged velocity-node row: [9][27] + pad + [3][8]
-constexpr int VPRS = 244;                   // start of the pressure columns inside a velocity-node row
-constexpr int PROW = 82;                    // staged pressure-node row: [3][27] + pad
-constexpr int REC = NU * VROW + NP * PROW;  // doubles per cell record
-constexpr int TBUF = 8 * 74;                // per-warp transposition buffer (direct: stride 72, transposed: stride 74)
+constexpr int BW = 28;                      // column nodes per staged row segment (27 + pad: 32-byte sectors stay aligned)
+constexpr int VROW = 9 * BW + 3 * NP;       // staged velocity-node row: [r = 3c+d][28] then [c][8 pressure nodes]  (276)
+constexpr int VPRS = 9 * BW;                // start of the pressure columns inside a velocity-node row
+constexpr int PROW = 3 * BW;                // staged pressure-node row: [c][28]
+constexpr int OFF_DG = NU * VROW + NP * PROW;   // fused preconditioner: m + nu k of every node pair, [27][28]
+constexpr int OFF_PP = OFF_DG + NU * BW;        // pressure mass block [8][8]
+constexpr int REC = OFF_PP + NP * NP;           // doubles per cell record (8 944)
 constexpr int LROW = 384;                   // longest block(0,0) / block(1,0) row the gather accumulators hold
 constexpr int ASTR = 387;                   // accumulator row stride (387 mod 16 == 3: the three components of one column land in different banks)
 constexpr int L01 = 32;                     // longest block(0,1) row
 constexpr int GACC = 3 * ASTR + 3 * L01 + 7;  // per-warp accumulators (+3 diagonal slots of constrained components), 1264
 constexpr int GWARPS = 8;
 static_assert(GACC % 2 == 0, "accumulator alignment");
-static_assert((REC * 8) % 16 == 0, "record alignment");
+static_assert((REC * 8) % 32 == 0 && (VROW * 8) % 32 == 0 && (PROW * 8) % 32 == 0 && (BW * 8) % 32 == 0, "sector alignment of the staged segments");
 
 // ---- stage: contraction + constraint epilogue, coalesced write of the cell record ---------------------------------
-__global__ void __launch_bounds__(MTHREADS, 3)
-th_stage_kernel(MmaArgs a, CsView cs, double* __restrict__ stage, long long w_begin, long long w_end, long long ring) {
+// The DMMA accumulator layout does the transposition: lane (frow = lane / 4, fk = lane % 4) holds the 3x3 blocks of
+// (row node 8 ta + frow, column nodes 8 tb + 2 fk + {0,1}).  Direct orientation: for every r = 3c+d the warp writes
+// 8 rows x 64 contiguous bytes with one 16-byte store per lane; transposed orientation (row node b, column node a,
+// entry [d][c]): for every (r, jj) 4 rows x 64 contiguous bytes with one 8-byte store per lane.  All segments start
+// on 32-byte sector boundaries (BW = 28).
+__constant__ unsigned char c_task_ta[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
+__constant__ unsigned char c_task_tb[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
+
+__global__ void __launch_bounds__(MTHREADS, 4)
+th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, double* __restrict__ stage, long long w_begin, long long w_end,
+                int slot_begin, int ring) {
   extern __shared__ __align__(16) double smem[];
   double* X = smem;                     // KQ * LDB
   double* wq = X + KQ * LDB;            // KQ (+4)
-  double* sgeo2 = wq + 32;              // GS
-  double* swt = sgeo2 + GS + 1;         // 3*NU
+  double* sgeo2 = wq + 32;              // 2 x (GS + 1): mapping record of this cell and of the CTA's next one
+  double* swt = sgeo2 + 2 * (GS + 1);   // 3*NU
   double* sF = swt + 3 * NU + 1;        // NQ*3
-  double* sU = sF + NQ * 3;             // ND
-  double* sT = sU + ND + 1;             // 32
+  double* sUc = sF + NQ * 3;            // 3*BW: old velocity, component-major, entry 27 of every row stays zero
+  double* sT = sUc + 3 * BW;            // 32
   double* sTn = sT + 32;                // 28
   double* sGU = sTn + 28;               // NQ*12
-  double* tbuf_all = sGU + NQ * 12 + 1; // 4 * TBUF   (offset 5166: 16-byte aligned)
-  unsigned char* snm2 = (unsigned char*)(tbuf_all + 4 * TBUF);  // MSTR
-  int* sidx2 = (int*)(snm2 + MSTR);                            // IDS
-  int* sidt2 = sidx2 + IDS;                                    // 28
-  int* sys_u = sidt2 + 28;                                     // 3*NU
+  unsigned char* snm2 = (unsigned char*)(sGU + NQ * 12);       // 2 x MSTR
+  int* sidx2 = (int*)(snm2 + 2 * MSTR);                        // 2 x IDS
+  int* sidt2 = sidx2 + 2 * IDS;                                // 2 x 28
+  int* sys_u = sidt2 + 2 * 28;                                 // 3*NU
   int* sys_p = sys_u + 3 * NU;                                 // NP
   unsigned char* skc = (unsigned char*)(sys_p + NP);           // 28
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  double* tb = tbuf_all + warp * TBUF;
 
   for (int i = tid; i < ND; i += nt) {
     const int f = a.local_field[i], bs = a.local_base[i];
     if (f < 3) sys_u[f * NU + bs] = i; else sys_p[bs] = i;
   }
   for (int i = tid; i < KQ * LDB; i += nt) X[i] = 0.0;
+  for (int i = tid; i < 3 * BW; i += nt) sUc[i] = 0.0;
   if (tid < 4) wq[NQ + tid] = 0.0;
+  __syncthreads();
+  // cell-independent operand columns: reference values of the Q2 functions (alpha = 3) and of the Q1 functions
+  for (int i = tid; i < NQ * NU; i += nt) X[(i / NU) * LDB + 96 + (i % NU)] = __ldg(a.phi_u + i);
+  for (int i = tid; i < NQ * NP; i += nt) X[(i / NP) * LDB + PSI0 + (i % NP)] = __ldg(a.phi_p + i);
   const double nu = a.prm.dt * a.prm.inv_re;
   const bool do_rhs = a.rhs != nullptr;
   const double* sgeo = sgeo2;
   const unsigned char* snm = snm2;
   const int* sidx = sidx2;
   const int* sidt = sidt2;
+  // mapping record, masks and dof indices of a cell, copied asynchronously into buffer `b`
+  auto issue_raw = [&](long long w, int b) {
+    const long long cell = a.cells[w];
+    const double* g = a.geom + cell * GS;
+    for (int i = tid; i < GS; i += nt) cp_async8(sgeo2 + b * (GS + 1) + i, g + i);
+    if (tid < MSTR / 8) cp_async8(snm2 + b * MSTR + 8 * tid, a.nmask + w * MSTR + 8 * tid);
+    for (int i = tid; i < ND; i += nt) cp_async4(sidx2 + b * IDS + i, a.l2g + cell * ND + i);
+    if (do_rhs)
+      for (int i = tid; i < a.ndt; i += nt) cp_async4(sidt2 + b * 28 + i, a.l2g_t + cell * a.ndt + i);
+  };
   auto node_cs = [&](int n) {
     NodeCs c;
     c.mask = snm[n];
@@ -86,33 +110,38 @@ th_stage_kernel(MmaArgs a, CsView cs, double* __restrict__ stage, long long w_be
     c.w2 = swt[3 * n + 2];
     return c;
   };
+  const int frow = lane >> 2, fk = lane & 3;
 
-  for (long long w = w_begin + blockIdx.x; w < w_end; w += gridDim.x) {
-    const long long cell = a.cells[w];
-    double* S = stage + (size_t)(w % ring) * REC;
-    __syncthreads();
-    {
-      const double* g = a.geom + cell * GS;
-      for (int i = tid; i < GS; i += nt) cp_async8(sgeo2 + i, g + i);
-      if (tid < MSTR / 8) cp_async8(snm2 + 8 * tid, a.nmask + w * MSTR + 8 * tid);
-      for (int i = tid; i < ND; i += nt) cp_async4(sidx2 + i, a.l2g + cell * ND + i);
-      if (do_rhs)
-        for (int i = tid; i < a.ndt; i += nt) cp_async4(sidt2 + i, a.l2g_t + cell * a.ndt + i);
-    }
-    cp_async_commit();
+  int buf = 0;
+  if (w_begin + blockIdx.x < w_end) issue_raw(w_begin + blockIdx.x, 0);
+  cp_async_commit();
+  for (long long w = w_begin + blockIdx.x; w < w_end; w += gridDim.x, buf ^= 1) {
+    int slot = slot_begin + (int)(w - w_begin);
+    if (slot >= ring) slot -= ring;
+    double* S = stage + (size_t)slot * REC;
+    sgeo = sgeo2 + buf * (GS + 1);
+    snm = snm2 + buf * MSTR;
+    sidx = sidx2 + buf * IDS;
+    sidt = sidt2 + buf * 28;
     cp_async_wait<0>();
-    __syncthreads();
+    __syncthreads();   // this cell's raw inputs have landed; every warp is done with the previous cell
     if (do_rhs) {
-      for (int i = tid; i < ND; i += nt) cp_async8(sU + i, a.old_nse + sidx[i]);
+      for (int i = tid; i < 3 * NU; i += nt) {
+        const int c = i / NU, n = i - c * NU;
+        cp_async8(sUc + c * BW + n, a.old_nse + sidx[sys_u[i]]);
+      }
       for (int i = tid; i < a.ndt; i += nt) cp_async8(sTn + i, a.old_temp + sidt[i]);
     }
     cp_async_commit();
+    if (w + gridDim.x < w_end) issue_raw(w + gridDim.x, buf ^ 1);   // the CTA's next cell, while this one is computed
+    cp_async_commit();
     const int cflag = snm[35];
-    if (tid < NU) {
+    if (tid >= 96 && tid - 96 < NU) {   // warp 3 (the table build below keeps warps 0..3 busy with tid < 108 only partly)
+      const int n = tid - 96;
       int kc = 3;
       double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-      if (cflag && snm[tid] != 7) {
-        const int g0 = sidx[sys_u[tid]];
+      if (cflag && snm[n] != 7) {
+        const int g0 = sidx[sys_u[n]];
         for (int c = 0; c < 3; ++c) {
           const int li = cs.line_of_dof[g0 + c];
           if (li >= 0 && cs.line_ptr[li + 1] > cs.line_ptr[li]) {
@@ -125,39 +154,58 @@ th_stage_kernel(MmaArgs a, CsView cs, double* __restrict__ stage, long long w_be
           }
         }
       }
-      skc[tid] = (unsigned char)kc;
-      swt[tid * 3] = w0;
-      swt[tid * 3 + 1] = w1;
-      swt[tid * 3 + 2] = w2;
+      skc[n] = (unsigned char)kc;
+      swt[n * 3] = w0;
+      swt[n * 3 + 1] = w1;
+      swt[n * 3 + 2] = w2;
     }
     if (tid < NQ) wq[tid] = sgeo[tid];
-    for (int i = tid; i < NQ * NU; i += nt) {
-      const int q = i / NU, b = i - q * NU;
-      const double r0 = __ldg(a.dphi_u + i * 3), r1 = __ldg(a.dphi_u + i * 3 + 1), r2 = __ldg(a.dphi_u + i * 3 + 2);
-      double* x = X + q * LDB + b;
+    // operand table, physical gradients: thread = (quadrature point, group of 7 nodes); the 9 entries of d xi / d x stay
+    // in registers, the stores of one warp instruction fall into 16 different bank pairs ((4 q + 7 group) mod 16)
+    if (tid < 4 * NQ) {
+      const int q = tid >> 2, bg = tid & 3;
+      double kinv[3][3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
-        x[32 * d] = sgeo[NQ * (1 + d) + q] * r0 + sgeo[NQ * (4 + d) + q] * r1 + sgeo[NQ * (7 + d) + q] * r2;
-      x[96] = __ldg(a.phi_u + i);
+      for (int e = 0; e < 3; ++e)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) kinv[e][d] = sgeo[NQ * (1 + 3 * e + d) + q];
+      double* x = X + q * LDB + bg * 7;
+      const int nb = bg == 3 ? 6 : 7;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        if (j >= nb) break;
+        const double r0 = __ldg(dphi_lane + (j * 3) * (4 * NQ) + tid), r1 = __ldg(dphi_lane + (j * 3 + 1) * (4 * NQ) + tid),
+                     r2 = __ldg(dphi_lane + (j * 3 + 2) * (4 * NQ) + tid);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[32 * d + j] = kinv[0][d] * r0 + kinv[1][d] * r1 + kinv[2][d] * r2;
+      }
     }
-    for (int i = tid; i < NQ * NP; i += nt) X[(i / NP) * LDB + PSI0 + (i % NP)] = __ldg(a.phi_p + i);
-    cp_async_wait<0>();
+    cp_async_wait<1>();   // the gathered old solution (the next cell's raw inputs may still be in flight)
     __syncthreads();
 
     // ---- tasks: 10 node x node blocks (ta <= tb), 4 node x psi blocks; weights 10 : 3, so the four warps take
     // {0,1,2}, {3,4,5}, {6,7,10,11}, {8,9,12,13}
-    const int frow = lane >> 2, fk = lane & 3;
     for (int s = 0; s < 4; ++s) {
       int t;
       if (warp < 2) {
-        if (s == 3) break;
+        if (s == 3) {
+          if (warp == 1) {   // pressure mass block of the preconditioner, psi x psi (:455-462)
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KQ / 4; ++ks) {
+              const int q = 4 * ks + fk;
+              const double pv = X[q * LDB + PSI0 + frow];
+              dmma(c0, c1, wq[q] * pv, pv);
+            }
+            __stcg(reinterpret_cast<double2*>(S + OFF_PP + frow * NP + 2 * fk), make_double2(c0, c1));
+          }
+          break;
+        }
         t = 3 * warp + s;
       } else
         t = s < 2 ? (warp == 2 ? 6 : 8) + s : (warp == 2 ? 10 : 12) + (s - 2);
       if (t < 10) {
-        int ta = 0, r = t;
-        while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
-        const int tb_ = ta + r;
+        const int ta = c_task_ta[t], tb_ = c_task_tb[t];
         double acc[4][4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -181,74 +229,69 @@ th_stage_kernel(MmaArgs a, CsView cs, double* __restrict__ stage, long long w_be
               if ((i < 3 && k < 3) || (i == 3 && k == 3)) dmma(acc[i][k][0], acc[i][k][1], af[i], bf[k]);   // the value x gradient cross terms are not needed
         }
         const int na = 8 * ta + frow;
-        double Fj[2][9];
+        double Fj[2][9], dgj[2];
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int nb = 8 * tb_ + 2 * fk + jj;
-#pragma unroll
-          for (int r9 = 0; r9 < 9; ++r9) Fj[jj][r9] = 0.0;
-          if (na >= NU || nb >= NU) continue;
-          const NodeCs ca = node_cs(na), cb = node_cs(nb);
           const double dg = acc[3][3][jj] + nu * (acc[0][0][jj] + acc[1][1][jj] + acc[2][2][jj]);
-          double F[3][3];
+          dgj[jj] = dg;   // m_ab + nu k_ab: the velocity block of the preconditioner (:455-462)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int d = 0; d < 3; ++d) F[c][d] = nu * acc[d][c][jj] + (c == d ? dg : 0.0);
-          const double d00 = fabs(F[0][0]), d11 = fabs(F[1][1]), d22 = fabs(F[2][2]);
-          if (ca.k != 3 || cb.k != 3) {
-            const double wa[3] = {ca.w0, ca.w1, ca.w2}, wb[3] = {cb.w0, cb.w1, cb.w2};
-            double Fa[3], Fb[3], Fab;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) Fa[d] = ca.k == 0 ? F[0][d] : (ca.k == 1 ? F[1][d] : (ca.k == 2 ? F[2][d] : 0.0));
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Fb[c] = cb.k == 0 ? F[c][0] : (cb.k == 1 ? F[c][1] : (cb.k == 2 ? F[c][2] : 0.0));
-            Fab = cb.k == 0 ? Fa[0] : (cb.k == 1 ? Fa[1] : (cb.k == 2 ? Fa[2] : 0.0));
+            for (int d = 0; d < 3; ++d) Fj[jj][c * 3 + d] = nu * acc[d][c][jj] + (c == d ? dg : 0.0);
+          if (cflag && na < NU && nb < NU) {   // constraint lines in this cell: C^T F C and the diagonals of constrained dofs
+            const NodeCs ca = node_cs(na), cb = node_cs(nb);
+            double F[3][3];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
-              for (int d = 0; d < 3; ++d) F[c][d] += wa[c] * Fa[d] + wb[d] * Fb[c] + wa[c] * wb[d] * Fab;
+              for (int d = 0; d < 3; ++d) F[c][d] = Fj[jj][c * 3 + d];
+            const double d00 = fabs(F[0][0]), d11 = fabs(F[1][1]), d22 = fabs(F[2][2]);
+            if (ca.k != 3 || cb.k != 3) {
+              const double wa[3] = {ca.w0, ca.w1, ca.w2}, wb[3] = {cb.w0, cb.w1, cb.w2};
+              double Fa[3], Fb[3], Fab;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) Fa[d] = ca.k == 0 ? F[0][d] : (ca.k == 1 ? F[1][d] : (ca.k == 2 ? F[2][d] : 0.0));
+#pragma unroll
+              for (int c = 0; c < 3; ++c) Fb[c] = cb.k == 0 ? F[c][0] : (cb.k == 1 ? F[c][1] : (cb.k == 2 ? F[c][2] : 0.0));
+              Fab = cb.k == 0 ? Fa[0] : (cb.k == 1 ? Fa[1] : (cb.k == 2 ? Fa[2] : 0.0));
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) F[c][d] += wa[c] * Fa[d] + wb[d] * Fb[c] + wa[c] * wb[d] * Fab;
+            }
+            if (na == nb) {  // constrained dofs keep |L_ii| on their own diagonal: staged in the (unused) slot [c][c]
+              if (!(ca.mask & 1)) F[0][0] = d00;
+              if (!(ca.mask & 2)) F[1][1] = d11;
+              if (!(ca.mask & 4)) F[2][2] = d22;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int d = 0; d < 3; ++d) Fj[jj][c * 3 + d] = F[c][d];
           }
-          if (na == nb) {  // constrained dofs keep |L_ii| on their own diagonal: staged in the (unused) slot [c][c]
-            if (!(ca.mask & 1)) F[0][0] = d00;
-            if (!(ca.mask & 2)) F[1][1] = d11;
-            if (!(ca.mask & 4)) F[2][2] = d22;
-          }
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) Fj[jj][c * 3 + d] = F[c][d];
         }
-        // direct orientation: rows 8ta.., columns 8tb..; buffer [a][r][b], conflict-free 16-byte stores
+        // direct orientation: row 8ta + frow, columns 8tb + 2fk + {0,1} (padding nodes contribute exact zeros)
+        if (na < NU && 8 * tb_ + 2 * fk < BW) {
+          double* row = S + na * VROW + 8 * tb_ + 2 * fk;
 #pragma unroll
-        for (int r9 = 0; r9 < 9; ++r9)
-          *reinterpret_cast<double2*>(tb + (frow * 9 + r9) * 8 + 2 * fk) = make_double2(Fj[0][r9], Fj[1][r9]);
-        __syncwarp();
-#pragma unroll 6
-        for (int k = 0; k < 18; ++k) {
-          const int seg = 4 * k + (lane >> 3), e = lane & 7;
-          const int al = seg / 9, r9 = seg - 9 * al;
-          const int na2 = 8 * ta + al, nb2 = 8 * tb_ + e;
-          if (na2 < NU && nb2 < NU) __stcg(S + na2 * VROW + r9 * NU + nb2, tb[seg * 8 + e]);
+          for (int r9 = 0; r9 < 9; ++r9) __stcg(reinterpret_cast<double2*>(row + r9 * BW), make_double2(Fj[0][r9], Fj[1][r9]));
+          __stcg(reinterpret_cast<double2*>(S + OFF_DG + na * BW + 8 * tb_ + 2 * fk), make_double2(dgj[0], dgj[1]));
         }
-        __syncwarp();
         if (ta != tb_) {
-          // transposed orientation: row node b, column node a, entry [d][c] = F[c][d]; buffer [b] stride 74, [r][a]
+          // transposed orientation: row node b, column node a, entry [d][c] = F[c][d]
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
+          for (int jj = 0; jj < 2; ++jj) {
+            const int nb = 8 * tb_ + 2 * fk + jj;
+            if (nb < NU) {   // column 8ta + frow <= 23 is always a real node here (ta < tb)
+              double* row = S + nb * VROW + 8 * ta + frow;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+              for (int c = 0; c < 3; ++c)
 #pragma unroll
-              for (int d = 0; d < 3; ++d) tb[(2 * fk + jj) * 74 + (d * 3 + c) * 8 + frow] = Fj[jj][c * 3 + d];
-          __syncwarp();
-#pragma unroll 6
-          for (int k = 0; k < 18; ++k) {
-            const int seg = 4 * k + (lane >> 3), e = lane & 7;
-            const int bl = seg / 9, r9 = seg - 9 * bl;
-            const int nb2 = 8 * tb_ + bl, na2 = 8 * ta + e;
-            if (na2 < NU && nb2 < NU) __stcg(S + nb2 * VROW + r9 * NU + na2, tb[bl * 74 + r9 * 8 + e]);
+                for (int d = 0; d < 3; ++d) __stcg(row + (d * 3 + c) * BW, Fj[jj][c * 3 + d]);
+              __stcg(S + OFF_DG + nb * BW + 8 * ta + frow, dgj[jj]);
+            }
           }
-          __syncwarp();
         }
       } else {
         // velocity-pressure coupling: rows (a, c) of row block ta against the 8 psi columns   (:633-635)
@@ -264,43 +307,65 @@ th_stage_kernel(MmaArgs a, CsView cs, double* __restrict__ stage, long long w_be
         }
         const int na = 8 * ta + frow;
         if (na < NU) {
-          const NodeCs ca = node_cs(na);
           double sv[2][3];
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             sv[jj][0] = -acc[0][jj];
             sv[jj][1] = -acc[1][jj];
             sv[jj][2] = -acc[2][jj];
+          }
+          if (cflag) {
+            const NodeCs ca = node_cs(na);
             if (ca.k != 3) {
-              const double sk = ca.k == 0 ? sv[jj][0] : (ca.k == 1 ? sv[jj][1] : sv[jj][2]);
-              sv[jj][0] += ca.w0 * sk;
-              sv[jj][1] += ca.w1 * sk;
-              sv[jj][2] += ca.w2 * sk;
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const double sk = ca.k == 0 ? sv[jj][0] : (ca.k == 1 ? sv[jj][1] : sv[jj][2]);
+                sv[jj][0] += ca.w0 * sk;
+                sv[jj][1] += ca.w1 * sk;
+                sv[jj][2] += ca.w2 * sk;
+              }
             }
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             // velocity-node row: [c][p]; pressure-node rows: [c][a]
-            *reinterpret_cast<double2*>(S + na * VROW + VPRS + c * 8 + 2 * fk) = make_double2(sv[0][c], sv[1][c]);
-            __stcg(S + NU * VROW + (2 * fk) * PROW + c * NU + na, sv[0][c]);
-            __stcg(S + NU * VROW + (2 * fk + 1) * PROW + c * NU + na, sv[1][c]);
+            __stcg(reinterpret_cast<double2*>(S + na * VROW + VPRS + c * 8 + 2 * fk), make_double2(sv[0][c], sv[1][c]));
+            __stcg(S + NU * VROW + (2 * fk) * PROW + c * BW + na, sv[0][c]);
+            __stcg(S + NU * VROW + (2 * fk + 1) * PROW + c * BW + na, sv[1][c]);
           }
         }
       }
     }
     if (do_rhs) {
-      for (int q = tid; q < NQ; q += nt) {
-        double tq = 0.0;
-        for (int k = 0; k < a.ndt; ++k) tq += sTn[k] * __ldg(a.phi_t + q * a.ndt + k);
-        sT[q] = tq;
+      // old velocity and its gradient at the quadrature points on the tensor cores, too: for alpha = warp,
+      // G[q][c] = sum_n X[q][32 alpha + n] u_c[n]  (4 row tiles of quadrature points x 7 k-steps over the nodes)
+      {
+        const int e = warp;
+        double g4[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+        for (int ks = 0; ks < 7; ++ks) {
+          const double bfr = frow < 3 ? sUc[frow * BW + 4 * ks + fk] : 0.0;
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int q = 8 * t4 + frow;
+            const double afr = q < KQ ? X[q * LDB + 32 * e + 4 * ks + fk] : 0.0;
+            dmma(g4[t4][0], g4[t4][1], afr, bfr);
+          }
+        }
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          const int q = 8 * t4 + frow;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int c = 2 * fk + jj;
+            if (q < NQ && c < 3) sGU[q * 12 + c * 4 + e] = g4[t4][jj];
+          }
+        }
       }
-      __syncthreads();
-      for (int i = tid; i < NQ * 12; i += nt) {
-        const int q = i / 12, r = i - q * 12, c = r >> 2, e = r & 3;
-        const double* x = X + q * LDB + 32 * e;
-        double sacc = 0.0;
-        for (int n = 0; n < NU; ++n) sacc += sU[sys_u[c * NU + n]] * x[n];
-        sGU[i] = sacc;
+      if (warp == 2 && lane < NQ) {
+        double tq = 0.0;
+        for (int k = 0; k < a.ndt; ++k) tq += sTn[k] * __ldg(a.phi_t + lane * a.ndt + k);
+        sT[lane] = tq;
       }
       __syncthreads();
       for (int q = tid; q < NQ; q += nt) {
@@ -349,11 +414,19 @@ th_stage_kernel(MmaArgs a, CsView cs, double* __restrict__ stage, long long w_be
   }
 }
 
-constexpr size_t stage_smem_bytes() {
-  return sizeof(double) * (KQ * LDB + 32 + GS + 1 + 3 * NU + 1 + NQ * 3 + ND + 1 + 32 + 28 + NQ * 12 + 1 + 4 * TBUF) + MSTR +
-         sizeof(int) * (IDS + 28 + 3 * NU + NP) + 28 + 36;
+// reference gradients in the order the table build reads them: [node of the group j][e][thread = 4 q + group]
+__global__ void dphi_lane_kernel(const double* __restrict__ dphi_u, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 7 * 3 * 4 * NQ) return;
+  const int t = i % (4 * NQ), je = i / (4 * NQ), e = je % 3, j = je / 3;
+  const int q = t >> 2, b = (t & 3) * 7 + j;
+  out[i] = b < NU ? dphi_u[(size_t)(q * NU + b) * 3 + e] : 0.0;
 }
-static_assert((KQ * LDB + 32 + GS + 1 + 3 * NU + 1 + NQ * 3 + ND + 1 + 32 + 28 + NQ * 12 + 1) % 2 == 0, "tbuf alignment");
+
+constexpr size_t stage_smem_bytes() {
+  return sizeof(double) * (KQ * LDB + 32 + 2 * (GS + 1) + 3 * NU + 1 + NQ * 3 + 3 * BW + 32 + 28 + NQ * 12) + 2 * MSTR +
+         sizeof(int) * (2 * IDS + 2 * 28 + 3 * NU + NP) + 28 + 36;
+}
 
 // ---- gather: one warp per (chunk, node) -------------------------------------------------------------------------
 struct GatherArgs {
@@ -367,10 +440,185 @@ struct GatherArgs {
   const unsigned* p_inc;
   long long v_begin, v_end, p_begin, p_end;  // item ranges of this chunk
   long long w_base;                          // first plan cell of the chunk
-  long long ring;
+  int slot_base, ring;                       // its staging slot; slots wrap at `ring`
   const unsigned short* pos;
   const unsigned char* nmask;
   const double* stage;
+};
+
+constexpr unsigned INC_CS = 0x80000000u;     // incidence word: the cell holds constrained velocity dofs
+
+// what one incidence (cell of the chunk, local node) contributes to a velocity node: loaded one incidence ahead
+struct VInc {
+  double v[9];   // lane = column node b: staged [r][b]
+  double vp;     // lanes < 24: staged [c][p]
+  int ob, mb, op, a, maskA;
+};
+
+__device__ __forceinline__ void load_vinc(VInc& I, const GatherArgs& g, unsigned e, int lane) {
+  const int a = e & 31;
+  const unsigned wl = (e & ~INC_CS) >> 5;
+  const size_t w = (size_t)g.w_base + wl;
+  int slot = g.slot_base + (int)wl;
+  if (slot >= g.ring) slot -= g.ring;
+  const unsigned short* prow = g.pos + w * PSTR + a * NE;
+  const double* S = g.stage + (size_t)slot * REC + a * VROW;
+  I.a = a;
+  I.ob = lane < NU ? prow[lane] : 0;
+  I.op = lane < NP ? prow[NU + lane] : 0;
+  if (e & INC_CS) {
+    const unsigned char* mrow = g.nmask + w * MSTR;
+    I.mb = lane < NU ? mrow[lane] : 0;
+    I.maskA = mrow[a];
+  } else {
+    I.mb = 7;
+    I.maskA = 7;
+  }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) I.v[r] = lane < NU ? __ldcg(S + r * BW + lane) : 0.0;
+  I.vp = lane < 24 ? __ldcg(S + VPRS + lane) : 0.0;
+}
+
+// add one incidence into the warp's accumulators (the nine targets of a lane are distinct: load all, then store all)
+__device__ __forceinline__ void add_vinc(const VInc& I, double* acc, double* acc01, double* accd, int lane) {
+  if (I.maskA == 7 && __all_sync(0xffffffffu, lane >= NU || I.mb == 7)) {
+    if (lane < NU) {
+      double tv[9];
+#pragma unroll
+      for (int r = 0; r < 9; ++r) tv[r] = acc[(r / 3) * ASTR + I.ob + (r % 3)];
+#pragma unroll
+      for (int r = 0; r < 9; ++r) acc[(r / 3) * ASTR + I.ob + (r % 3)] = tv[r] + I.v[r];
+    }
+    const int o = __shfl_sync(0xffffffffu, I.op, lane & 7);
+    if (lane < 24) acc01[(lane >> 3) * L01 + o] += I.vp;
+  } else {
+    const int maskA = I.maskA;
+    if (lane < NU) {
+      int idx[9];
+      double tv[9];
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const int c = r / 3, d = r - 3 * c;
+        const bool on = ((maskA >> c) & 1) && ((I.mb >> d) & 1);
+        idx[r] = on ? c * ASTR + I.ob + __popc(I.mb & ((1 << d) - 1)) : -1;
+      }
+#pragma unroll
+      for (int r = 0; r < 9; ++r) tv[r] = idx[r] >= 0 ? acc[idx[r]] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 9; ++r)
+        if (idx[r] >= 0) acc[idx[r]] = tv[r] + I.v[r];
+      if (lane == I.a && maskA != 7) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (!((maskA >> c) & 1)) accd[c] += I.v[4 * c];
+      }
+    }
+    const int c = lane >> 3;
+    const int o = __shfl_sync(0xffffffffu, I.op, lane & 7);
+    if (lane < 24 && ((maskA >> c) & 1)) acc01[c * L01 + o] += I.vp;
+  }
+  __syncwarp();
+}
+
+// write `len` accumulated entries to the row at `out` (store, or add to what earlier chunks left there) and leave the
+// accumulators zero for the next item
+__device__ __forceinline__ void flush_row(double* __restrict__ out, double* acc, int len, bool first, int lane) {
+  if (first) {
+#pragma unroll 4
+    for (int k = lane; k < len; k += 32) {
+      out[k] = acc[k];
+      acc[k] = 0.0;
+    }
+  } else {
+    for (int k0 = lane; k0 < len; k0 += 128) {
+      double old[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) old[u] = k0 + 32 * u < len ? __ldcg(out + k0 + 32 * u) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        if (k < len) {
+          out[k] = old[u] + acc[k];
+          acc[k] = 0.0;
+        }
+      }
+    }
+  }
+}
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int WB = 32;   // items per block: a warp takes blocks round-robin, so expensive items (rows that earlier chunks
+                         // already touched are read-modify-written) spread over all warps
+
+// Walk the items [begin, end) block-cyclically.  Per block: the 32 item headers are read at once (lane t <-> item t);
+// the incidence words of the block are read 32 at a time, one batch ahead; the loads of incidence i + 1 (`load`) and
+// the row starts of item t + 1 (`rows`) are in flight while incidence i / item t are processed (`add`, `flush`).
+// `aux` maps an incidence word to a second index that is fetched together with the words.
+template <class Inc, class AuxF, class RowF, class LoadF, class AddF, class FlushF>
+__device__ __forceinline__ void walk_items(const int* __restrict__ g0s, const unsigned char* __restrict__ flags, const unsigned* __restrict__ incptr,
+                                           const unsigned* __restrict__ incs, long long begin, long long end, long long gw, long long nw, int lane,
+                                           AuxF aux, RowF rows, LoadF load, AddF add, FlushF flush) {
+  for (long long j_lo = begin + gw * WB; j_lo < end; j_lo += nw * WB) {
+    const int n_it = (int)((j_lo + WB < end ? j_lo + WB : end) - j_lo);
+    int h_g0 = 0, h_first = 0;
+    unsigned h_iend = 0;
+    if (lane < n_it) {
+      h_g0 = g0s[j_lo + lane];
+      h_first = flags[j_lo + lane] & 1;
+      h_iend = incptr[j_lo + lane + 1];
+    }
+    const unsigned i_lo = incptr[j_lo], i_hi = __shfl_sync(FULLM, h_iend, n_it - 1);
+    unsigned ec = 0, en = 0, ib = i_lo;
+    int ac = -1, an = -1;
+    if (ib + lane < i_hi) { ec = incs[ib + lane]; ac = aux(ec); }
+    if (ib + 32 + lane < i_hi) { en = incs[ib + 32 + lane]; an = aux(en); }
+    auto rotate = [&]() {
+      ib += 32;
+      ec = en; ac = an;
+      en = 0; an = -1;
+      if (ib + 32 + lane < i_hi) { en = incs[ib + 32 + lane]; an = aux(en); }
+    };
+    auto word = [&](unsigned i) {
+      const unsigned k = i - ib;
+      return k < 32 ? __shfl_sync(FULLM, ec, (int)k) : __shfl_sync(FULLM, en, (int)(k - 32));
+    };
+    auto auxw = [&](unsigned i) {
+      const unsigned k = i - ib;
+      return k < 32 ? __shfl_sync(FULLM, ac, (int)k) : __shfl_sync(FULLM, an, (int)(k - 32));
+    };
+    long long rnext = rows(__shfl_sync(FULLM, h_g0, 0));
+    Inc bufA, bufB;
+    unsigned i = i_lo;
+    load(bufA, word(i), auxw(i));
+    for (int t = 0; t < n_it; ++t) {
+      const unsigned it_end = __shfl_sync(FULLM, h_iend, t);
+      const bool first = __shfl_sync(FULLM, h_first, t) != 0;
+      const long long rcur = rnext;
+      if (t + 1 < n_it) rnext = rows(__shfl_sync(FULLM, h_g0, t + 1));
+      // incidences of the item, two per trip: one buffer is consumed while the other one's loads are in flight
+      while (i < it_end) {
+        if (i - ib >= 32) rotate();
+        if (i + 1 < i_hi) load(bufB, word(i + 1), auxw(i + 1));
+        add(bufA);
+        ++i;
+        if (i < it_end) {
+          if (i - ib >= 32) rotate();
+          if (i + 1 < i_hi) load(bufA, word(i + 1), auxw(i + 1));
+          add(bufB);
+          ++i;
+        } else {
+          bufA = bufB;   // the prefetched incidence belongs to the next item
+          break;
+        }
+      }
+      flush(rcur, first);
+    }
+  }
+}
+
+struct PInc {
+  double v[3];
+  int ob, mb;
 };
 
 __global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g, BlockView A) {
@@ -386,121 +634,216 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g,
   double* v00 = A.val[0][0];
   double* v01 = A.val[0][1];
   double* v10 = A.val[1][0];
+  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;   // invariant: all accumulators are zero between items
+  __syncwarp();
+  auto no_aux = [](unsigned) { return 0; };
 
   // velocity nodes: rows (g0 + c) of block(0,0) and block(0,1)
-  for (long long j = g.v_begin + gw; j < g.v_end; j += nw) {
-    const int g0 = g.v_g0[j];
-    const unsigned i0 = g.v_incptr[j], i1 = g.v_incptr[j + 1];
-    const bool first = g.v_flag[j] & 1;
-    long long ra = 0, rb = 0;
-    if (lane < 4) {
-      ra = rp00[g0 + lane];
-      rb = rp01[g0 + lane];
-    }
-    long long rs[3], rs01[3];
-    int len[3], len01[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      rs[c] = __shfl_sync(0xffffffffu, ra, c);
-      len[c] = (int)(__shfl_sync(0xffffffffu, ra, c + 1) - rs[c]);
-      rs01[c] = __shfl_sync(0xffffffffu, rb, c);
-      len01[c] = (int)(__shfl_sync(0xffffffffu, rb, c + 1) - rs01[c]);
-    }
-    for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;
-    __syncwarp();
+  {
     int maskA = 7;
-    for (unsigned i = i0; i < i1; ++i) {
-      const unsigned e = g.v_inc[i];
-      const int a = e & 31;
-      const long long w = g.w_base + (e >> 5);
-      const unsigned short* prow = g.pos + w * PSTR + a * NE;
-      const unsigned char* mrow = g.nmask + w * MSTR;
-      const int ob = lane < NU ? prow[lane] : 0;
-      const int op = lane < NP ? prow[NU + lane] : 0;
-      const int mb = lane < NU ? mrow[lane] : 0;
-      maskA = mrow[a];
-      const double* S = g.stage + (size_t)(w % g.ring) * REC + a * VROW;
-      if (lane < NU) {
-        double v[9];
+    auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : (lane < 8 ? rp01[g0 + lane - 4] : 0ll); };
+    auto load = [&](VInc& I, unsigned e, int) { load_vinc(I, g, e, lane); };
+    auto add = [&](const VInc& I) {
+      maskA = I.maskA;
+      add_vinc(I, acc, acc01, accd, lane);
+    };
+    auto flush = [&](long long rcur, bool first) {
 #pragma unroll
-        for (int r = 0; r < 9; ++r) v[r] = __ldcg(S + r * NU + lane);
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
-          const int c = r / 3, d = r - 3 * c;
-          if (((maskA >> c) & 1) && ((mb >> d) & 1)) acc[c * ASTR + ob + __popc(mb & ((1 << d) - 1))] += v[r];
-        }
-        if (lane == a && maskA != 7) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            if (!((maskA >> c) & 1)) accd[c] += v[4 * c];
+      for (int c = 0; c < 3; ++c) {
+        const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
+        const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
+        if ((maskA >> c) & 1) {
+          flush_row(v00 + rs, acc + c * ASTR, len, first, lane);
+          flush_row(v01 + rs01, acc01 + c * L01, len01, first, lane);
+        } else if (lane == 0) {
+          // constrained dof: the row holds its diagonal only
+          double* out = v00 + rs;
+          if (first) {
+            out[0] = accd[c];
+            for (int k = 1; k < len; ++k) out[k] = 0.0;
+            for (int k = 0; k < len01; ++k) v01[rs01 + k] = 0.0;
+          } else
+            out[0] = __ldcg(out) + accd[c];
+          accd[c] = 0.0;
         }
       }
-      {
-        const int c = lane >> 3, pb = lane & 7;
-        const int o = __shfl_sync(0xffffffffu, op, pb);
-        if (lane < 24 && ((maskA >> c) & 1)) acc01[c * L01 + o] += __ldcg(S + VPRS + lane);
-      }
+      maskA = 7;
       __syncwarp();
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if ((maskA >> c) & 1) {
-        double* out = v00 + rs[c];
-        for (int k = lane; k < len[c]; k += 32) {
-          const double v = acc[c * ASTR + k];
-          if (first) out[k] = v; else if (v != 0.0) out[k] = __ldcg(out + k) + v;
-        }
-        double* out1 = v01 + rs01[c];
-        for (int k = lane; k < len01[c]; k += 32) {
-          const double v = acc01[c * L01 + k];
-          if (first) out1[k] = v; else if (v != 0.0) out1[k] = __ldcg(out1 + k) + v;
-        }
-      } else if (lane == 0) {
-        // constrained dof: the row holds its diagonal only
-        double* out = v00 + rs[c];
-        if (first) {
-          out[0] = accd[c];
-          for (int k = 1; k < len[c]; ++k) out[k] = 0.0;
-          for (int k = 0; k < len01[c]; ++k) v01[rs01[c] + k] = 0.0;
-        } else
-          out[0] = __ldcg(out) + accd[c];
-      }
-    }
-    __syncwarp();
+    };
+    walk_items<VInc>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, no_aux, rows, load, add, flush);
   }
 
   // pressure nodes: row of block(1,0)
-  for (long long j = g.p_begin + gw; j < g.p_end; j += nw) {
-    const int pr = g.p_g0[j];
-    const unsigned i0 = g.p_incptr[j], i1 = g.p_incptr[j + 1];
-    const bool first = g.p_flag[j] & 1;
-    const long long rs = rp10[pr];
-    const int len = (int)(rp10[pr + 1] - rs);
-    for (int k = lane; k < ASTR; k += 32) acc[k] = 0.0;
-    __syncwarp();
-    for (unsigned i = i0; i < i1; ++i) {
-      const unsigned e = g.p_inc[i];
-      const int pa = e & 31;
-      const long long w = g.w_base + (e >> 5);
-      const unsigned short* prow = g.pos + w * PSTR + (NU + pa) * NE;
+  {
+    auto rows = [&](int pr) { return lane < 2 ? rp10[pr + lane] : 0ll; };
+    auto load = [&](PInc& I, unsigned e, int) {
+      const int pn = e & 31;
+      const unsigned wl = (e & ~INC_CS) >> 5;
+      const size_t w = (size_t)g.w_base + wl;
+      int slot = g.slot_base + (int)wl;
+      if (slot >= g.ring) slot -= g.ring;
+      I.ob = 0;
+      I.mb = 0;
+      I.v[0] = I.v[1] = I.v[2] = 0.0;
       if (lane < NU) {
-        const int ob = prow[lane];
-        const int mb = g.nmask[w * MSTR + lane];
-        const double* S = g.stage + (size_t)(w % g.ring) * REC + NU * VROW + pa * PROW;
+        I.ob = g.pos[w * PSTR + (NU + pn) * NE + lane];
+        I.mb = (e & INC_CS) ? g.nmask[w * MSTR + lane] : 7;
+        const double* S = g.stage + (size_t)slot * REC + NU * VROW + pn * PROW;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const double v = __ldcg(S + c * NU + lane);
-          if ((mb >> c) & 1) acc[ob + __popc(mb & ((1 << c) - 1))] += v;
+        for (int c = 0; c < 3; ++c) I.v[c] = __ldcg(S + c * BW + lane);
+      }
+    };
+    auto add = [&](const PInc& I) {
+      if (lane < NU) {
+        int idx[3];
+        double tv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) idx[c] = ((I.mb >> c) & 1) ? I.ob + __popc(I.mb & ((1 << c) - 1)) : -1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tv[c] = idx[c] >= 0 ? acc[idx[c]] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (idx[c] >= 0) acc[idx[c]] = tv[c] + I.v[c];
+      }
+      __syncwarp();
+    };
+    auto flush = [&](long long rcur, bool first) {
+      const long long rs = __shfl_sync(FULLM, rcur, 0);
+      const int len = (int)(__shfl_sync(FULLM, rcur, 1) - rs);
+      flush_row(v10 + rs, acc, len, first, lane);
+      __syncwarp();
+    };
+    walk_items<PInc>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, no_aux, rows, load, add, flush);
+  }
+}
+
+// ---- fused preconditioner: second gather over the same (chunk, node) items ---------------------------------------
+// nse_preconditioner_matrix (include/core/boussinesq_model.tpp:421-476): velocity rows hold m + nu k on the same
+// component only, pressure rows the pressure mass matrix.  Positions and masks come from the preconditioner's own plan
+// (pre_w: its index of a system-plan cell).  Cells with no-normal-flux lines -- their C^T (dg I) C spreads over other
+// component pairs -- and cells outside that plan are skipped here and added afterwards by the reduction kernels; the
+// first chunk that touches a node stores its whole rows, so those later additions start from a defined state.
+struct PreArgs {
+  const int* pre_w;
+  const unsigned short* pos;
+  const unsigned char* nmask;
+  const unsigned short* pos_wide;
+};
+
+struct PVInc {
+  double v;
+  int o0, o1, o2, mb, maskA, a, skip;
+};
+struct PPInc {
+  double v;
+  int o, skip;
+};
+
+__global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArgs g, PreArgs pa, BlockView A) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* acc = smem + warp * GACC;
+  double* accd = acc + 3 * ASTR + 3 * L01;
+  const long long gw = (long long)blockIdx.x * GWARPS + warp, nw = (long long)gridDim.x * GWARPS;
+  const long long* rp00 = A.rowptr[0][0];
+  const long long* rp11 = A.rowptr[1][1];
+  double* v00 = A.val[0][0];
+  double* v11 = A.val[1][1];
+  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;
+  __syncwarp();
+  auto aux = [&](unsigned e) { return pa.pre_w[(size_t)g.w_base + ((e & ~INC_CS) >> 5)]; };
+  auto slot_of = [&](unsigned e) {
+    int slot = g.slot_base + (int)((e & ~INC_CS) >> 5);
+    return slot >= g.ring ? slot - g.ring : slot;
+  };
+  // velocity nodes
+  {
+    int maskA_item = 7;
+    auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : 0ll; };
+    auto load = [&](PVInc& I, unsigned e, int wp) {
+      I.skip = wp < 0;
+      I.a = e & 31;
+      I.v = 0.0;
+      I.o0 = I.o1 = I.o2 = 0xffff;
+      I.mb = I.maskA = 7;
+      if (wp < 0) return;
+      const unsigned char* nm = pa.nmask + (size_t)wp * MSTR;
+      const int cflag = nm[35], wide = *reinterpret_cast<const int*>(nm + 36);
+      if (lane < NU) {
+        I.v = __ldcg(g.stage + (size_t)slot_of(e) * REC + OFF_DG + I.a * BW + lane);
+        if (wide >= 0) {
+          const unsigned short* b = pa.pos_wide + (size_t)wide * (3 * NU * NU) + I.a * NU + lane;
+          I.o0 = b[0];
+          I.o1 = b[NU * NU];
+          I.o2 = b[2 * NU * NU];
+        } else
+          I.o0 = I.o1 = I.o2 = pa.pos[(size_t)wp * PSTR + I.a * NE + lane];
+        if (cflag) I.mb = nm[lane];
+      }
+      if (cflag) I.maskA = nm[I.a];
+    };
+    auto add = [&](const PVInc& I) {
+      if (!I.skip) {
+        maskA_item = I.maskA;
+        if (lane < NU) {
+          const int mm = I.maskA & I.mb;
+          if ((mm & 1) && I.o0 != 0xffff) acc[I.o0] += I.v;
+          if ((mm & 2) && I.o1 != 0xffff) acc[ASTR + I.o1] += I.v;
+          if ((mm & 4) && I.o2 != 0xffff) acc[2 * ASTR + I.o2] += I.v;
+          if (lane == I.a && I.maskA != 7) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (!((I.maskA >> c) & 1)) accd[c] += fabs(I.v);
+          }
         }
       }
       __syncwarp();
-    }
-    double* out = v10 + rs;
-    for (int k = lane; k < len; k += 32) {
-      const double v = acc[k];
-      if (first) out[k] = v; else if (v != 0.0) out[k] = __ldcg(out + k) + v;
-    }
-    __syncwarp();
+    };
+    auto flush = [&](long long rcur, bool first) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const long long rs = __shfl_sync(FULLM, rcur, c);
+        const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs);
+        if ((maskA_item >> c) & 1)
+          flush_row(v00 + rs, acc + c * ASTR, len, first, lane);
+        else if (lane == 0) {
+          double* out = v00 + rs;
+          if (first) {
+            out[0] = accd[c];
+            for (int k = 1; k < len; ++k) out[k] = 0.0;
+          } else
+            out[0] = __ldcg(out) + accd[c];
+          accd[c] = 0.0;
+        }
+      }
+      maskA_item = 7;
+      __syncwarp();
+    };
+    walk_items<PVInc>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, aux, rows, load, add, flush);
+  }
+  // pressure nodes: rows of block(1,1)
+  {
+    auto rows = [&](int pr) { return lane < 2 ? rp11[pr + lane] : 0ll; };
+    auto load = [&](PPInc& I, unsigned e, int wp) {
+      I.skip = wp < 0;
+      I.v = 0.0;
+      I.o = 0xffff;
+      if (wp < 0 || lane >= NP) return;
+      const int pn = e & 31;
+      I.v = __ldcg(g.stage + (size_t)slot_of(e) * REC + OFF_PP + pn * NP + lane);
+      I.o = pa.pos[(size_t)wp * PSTR + (NU + pn) * NE + NU + lane];
+    };
+    auto add = [&](const PPInc& I) {
+      if (!I.skip && lane < NP && I.o != 0xffff) acc[I.o] += I.v;
+      __syncwarp();
+    };
+    auto flush = [&](long long rcur, bool first) {
+      const long long rs = __shfl_sync(FULLM, rcur, 0);
+      const int len = (int)(__shfl_sync(FULLM, rcur, 1) - rs);
+      flush_row(v11 + rs, acc, len, first, lane);
+      __syncwarp();
+    };
+    walk_items<PPInc>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, aux, rows, load, add, flush);
   }
 }
 
@@ -529,13 +872,17 @@ void dcp_gather_plan_free(GatherPlan* p) {
   cudaFree(p->p_flag);
   cudaFree(p->p_inc);
   cudaFree(p->staging);
+  cudaFree(p->dphi_lane);
+  cudaFree(p->pre_w);
+  cudaFree(p->pre_rest);
   delete p;
 }
 
 // Items (chunk, node) with their incidences (cell of the chunk, local node) for the gather pass.  `cells` is the plan
 // order of the masked plan.  Returns DCP_OK with *out == nullptr when the model does not qualify (row longer than the
 // accumulators): the caller keeps the reduction path.
-int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vector<int32_t>& cells, GatherPlan** out) {
+int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vector<int32_t>& cells,
+                          const std::vector<uint8_t>& cell_has_constraints, GatherPlan** out) {
   *out = nullptr;
   const int64_t n = (int64_t)cells.size(), n_u = d->nse_block_size[0], n_p = d->nse_block_size[1];
   if (n == 0) return DCP_OK;
@@ -577,6 +924,7 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     std::vector<uint8_t> flag;
   };
   std::vector<ChunkItems> V((size_t)n_chunks), P((size_t)n_chunks);
+  bool too_many = false;   // the gather walks at most 8 incidences per item (hexahedral meshes without extraordinary edges)
 #pragma omp parallel
   {
     std::vector<uint64_t> keys;
@@ -591,7 +939,7 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
           const int32_t* idx = d->nse_l2g + (int64_t)cells[w] * ND;
           for (int a = 0; a < nl; ++a) {
             const uint64_t g0 = pass == 0 ? (uint64_t)idx[sys_u[a]] : (uint64_t)(idx[sys_p[a]] - n_u);
-            keys.push_back((g0 << 32) | ((uint64_t)(w - w0) << 5) | (uint64_t)a);
+            keys.push_back((g0 << 32) | (cell_has_constraints[w] ? (uint64_t)INC_CS : 0) | ((uint64_t)(w - w0) << 5) | (uint64_t)a);
           }
         }
         std::sort(keys.begin(), keys.end());
@@ -606,12 +954,14 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
           }
           I.g0.push_back((int32_t)g0);
           I.cnt.push_back((uint32_t)(e - k));
+          if (e - k > 8) too_many = true;
           I.flag.push_back(fst[g0] == (int32_t)ch ? 1 : 0);
           k = e;
         }
       }
     }
   }
+  if (too_many) return DCP_OK;
   GatherPlan* G = new GatherPlan;
   G->chunk = chunk;
   G->n_chunks = n_chunks;
@@ -658,6 +1008,16 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     if (rc == DCP_OK) rc = upg(ctx, pass == 0 ? &G->v_flag : &G->p_flag, flag);
     cudaStreamSynchronize(ctx->stream);
   }
+  if (rc == DCP_OK) {
+    if (cudaMalloc((void**)&G->dphi_lane, sizeof(double) * 7 * 3 * 4 * NQ) != cudaSuccess) {
+      cudaGetLastError();
+      dcp_set_error("gather plan: table allocation failed");
+      rc = DCP_ERR_CUDA;
+    } else {
+      dphi_lane_kernel<<<(7 * 3 * 4 * NQ + 255) / 256, 256, 0, ctx->stream>>>(m->dphi_u_qn, G->dphi_lane);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = DCP_ERR_CUDA;
+    }
+  }
   if (rc == DCP_OK && cudaMalloc((void**)&G->staging, sizeof(double) * (size_t)REC * (size_t)chunk) != cudaSuccess) {
     cudaGetLastError();
     dcp_set_error("gather plan: staging allocation failed");
@@ -668,6 +1028,36 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     return rc;
   }
   *out = G;
+  return DCP_OK;
+}
+
+// Fused preconditioner: map the system plan's cells to the preconditioner plan.  Not attached (the preconditioner keeps
+// its own pass) when a row of that matrix is longer than the accumulators.
+int dcp_gather_plan_attach_pre(dcp_model* m, const dcp_model_desc* d, GatherPlan* G, const MaskedPlan* nse_plan, const MaskedPlan* pre_plan) {
+  if (!G || !nse_plan || !pre_plan || std::getenv("DCP_NO_FUSED_PRECONDITIONER")) return DCP_OK;
+  const dcp_csr_desc(*pat)[DCP_MAX_BLOCKS] = d->pre_pattern;
+  for (const dcp_csr_desc* P : {&pat[0][0], &pat[1][1]}) {
+    int64_t mx = 0;
+#pragma omp parallel for reduction(max : mx)
+    for (int64_t r = 0; r < P->n_rows; ++r) mx = std::max(mx, P->rowptr[r + 1] - P->rowptr[r]);
+    if (mx > LROW) return DCP_OK;
+  }
+  std::vector<int32_t> of_cell((size_t)d->n_cells, -1);
+  for (size_t i = 0; i < pre_plan->h_cells.size(); ++i) of_cell[pre_plan->h_cells[i]] = (int32_t)i;
+  std::vector<int32_t> pre_w(nse_plan->h_cells.size(), -1), rest;
+  for (size_t w = 0; w < nse_plan->h_cells.size(); ++w) {
+    const int32_t wp = of_cell[nse_plan->h_cells[w]];
+    if (wp >= 0 && pre_plan->h_nnf_idx[wp] < 0) pre_w[w] = wp;
+  }
+  for (size_t i = 0; i < pre_plan->h_cells.size(); ++i)
+    if (pre_plan->h_nnf_idx[i] >= 0) rest.push_back((int32_t)i);
+  dcp_ctx* ctx = m->ctx;
+  int rc = upg(ctx, &G->pre_w, pre_w);
+  if (rc == DCP_OK) rc = upg(ctx, &G->pre_rest, rest);
+  if (rc != DCP_OK) return rc;
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  G->n_pre_rest = (int64_t)rest.size();
+  G->has_pre = true;
   return DCP_OK;
 }
 
@@ -714,25 +1104,50 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   g.p_incptr = G->p_incptr;
   g.p_flag = G->p_flag;
   g.p_inc = G->p_inc;
-  g.ring = G->chunk;
+  g.ring = (int)G->chunk;
   g.pos = plan->pos;
   g.nmask = plan->nmask;
   g.stage = G->staging;
   const BlockView A = make_view(m->nse);
   const CsView cs = make_view(m->nse_cs);
+  const bool fuse_pre = G->has_pre && m->masked_pre;
+  PreArgs pa{};
+  BlockView Apre = make_view(m->pre);
+  if (fuse_pre) {
+    pa.pre_w = G->pre_w;
+    pa.pos = m->masked_pre->pos;
+    pa.nmask = m->masked_pre->nmask;
+    pa.pos_wide = m->masked_pre->pos_wide;
+    DCP_CUDA(cudaFuncSetAttribute(th_pre_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  }
   for (int64_t ch = 0; ch < G->n_chunks; ++ch) {
     const long long w0 = ch * G->chunk, w1 = std::min<long long>(plan->n, w0 + G->chunk);
     long long grid = std::min<long long>((long long)ctx->sm_count * per_sm_s, w1 - w0);
-    th_stage_kernel<<<(unsigned)grid, MTHREADS, smem_s, ctx->stream>>>(a, cs, G->staging, w0, w1, G->chunk);
+    th_stage_kernel<<<(unsigned)grid, MTHREADS, smem_s, ctx->stream>>>(a, cs, G->dphi_lane, G->staging, w0, w1, 0, (int)G->chunk);
     g.v_begin = G->v_chunk_ptr[ch];
     g.v_end = G->v_chunk_ptr[ch + 1];
     g.p_begin = G->p_chunk_ptr[ch];
     g.p_end = G->p_chunk_ptr[ch + 1];
     g.w_base = w0;
+    g.slot_base = 0;
     const long long items = (g.v_end - g.v_begin) + (g.p_end - g.p_begin);
     grid = std::min<long long>((long long)ctx->sm_count * per_sm_g, (items + GWARPS - 1) / GWARPS);
     if (grid > 0) th_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, ctx->stream>>>(g, A);
     ctx->launches += 2;
+    if (fuse_pre && grid > 0) {
+      th_pre_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, ctx->stream>>>(g, pa, Apre);
+      ctx->launches++;
+    }
+  }
+  if (fuse_pre) {
+    // the cells the second gather skipped: no-normal-flux cells through the reduction kernel, cells outside the
+    // preconditioner's plan through the general kernel -- both add to rows the gather has already stored
+    if (G->n_pre_rest > 0) DCP_TRY(dcp_launch_th_mma(m, p, false, m->masked_pre, nullptr, nullptr, G->pre_rest, G->n_pre_rest));
+    if (m->masked_pre->n_other > 0)
+      DCP_TRY(dcp_launch_th_cells(m, p, false, nullptr, nullptr, m->masked_pre->other_cells, m->masked_pre->n_other, false));
+    m->pre_fused_valid = true;
+    m->pre_fused_dt = p.dt;
+    m->pre_fused_inv_re = p.inv_re;
   }
   DCP_CUDA(cudaGetLastError());
   return DCP_OK;

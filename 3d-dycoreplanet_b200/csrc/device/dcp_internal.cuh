@@ -126,7 +126,15 @@ struct GatherPlan {
   uint32_t *v_inc = nullptr, *p_inc = nullptr;         // (cell index inside the chunk << 5) | local node
   uint8_t *v_flag = nullptr, *p_flag = nullptr;        // bit 0: first chunk that touches the node (store, else accumulate)
   std::vector<int64_t> v_chunk_ptr, p_chunk_ptr;       // host: item range of every chunk
-  double* staging = nullptr;                           // [chunk][7892]
+  double* staging = nullptr;                           // [chunk][8124]
+  double* dphi_lane = nullptr;                         // reference gradients in table-build order [7][3][108]
+  // fused preconditioner (the system pass also stages m + nu k and the pressure mass block; a second gather writes
+  // nse_preconditioner_matrix): index of every system-plan cell in the preconditioner plan (-1: the cell is assembled by
+  // the reduction kernels afterwards), and those cells as a list of preconditioner-plan indices
+  int32_t* pre_w = nullptr;
+  int32_t* pre_rest = nullptr;
+  int64_t n_pre_rest = 0;
+  bool has_pre = false;
 };
 
 // masked position tables for the DMMA path (assemble_th_mma.cu): every node-blocked cell, constrained or not
@@ -139,6 +147,7 @@ struct MaskedPlan {
   uint16_t* pos_wide = nullptr;    // [n_wide][3][27][27]
   uint16_t* pos9 = nullptr;        // [n_nnf][9][27][27]: preconditioner cells with no-normal-flux lines
   GatherPlan* gather = nullptr;    // write-once path (system matrix, n_other == 0)
+  std::vector<int32_t> h_cells, h_nnf_idx;   // host copies: plan order, 9-table index per plan cell
 };
 
 struct dcp_model {
@@ -186,6 +195,8 @@ struct dcp_model {
   BlockMat nse, pre, tmass, tstiff, tmat;
   double *nse_rhs = nullptr, *temp_rhs = nullptr;
   bool temp_matrices_ready = false;
+  bool pre_fused_valid = false;     // nse_preconditioner_matrix was written by the last staged system pass ...
+  double pre_fused_dt = 0.0, pre_fused_inv_re = 0.0;   // ... for these parameters
   OwnerPlan* owner_nse = nullptr;
   OwnerPlan* owner_pre = nullptr;
   FastPlan* fast_nse = nullptr;
@@ -234,8 +245,10 @@ int dcp_launch_th_fast(dcp_model* m, const dcp_params& p, bool system, const Fas
 int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, MaskedPlan** out);
 void dcp_masked_plan_free(MaskedPlan* p);
 int dcp_launch_th_mma(dcp_model* m, const dcp_params& p, bool system, const MaskedPlan* plan, const double* old_nse,
-                      const double* old_temp);
-int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vector<int32_t>& cells, GatherPlan** out);
+                      const double* old_temp, const int32_t* wlist = nullptr, int64_t n_list = 0);
+int dcp_gather_plan_attach_pre(dcp_model* m, const dcp_model_desc* d, GatherPlan* G, const MaskedPlan* nse_plan, const MaskedPlan* pre_plan);
+int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vector<int32_t>& cells,
+                          const std::vector<uint8_t>& cell_has_constraints, GatherPlan** out);
 void dcp_gather_plan_free(GatherPlan* p);
 int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* plan, const double* old_nse, const double* old_temp);
 int dcp_owner_plan_build(dcp_model* m, bool system, const dcp_model_desc* desc);

@@ -626,7 +626,10 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     if (dim == 3) {
       M_TRY(dcp_masked_plan_build(m, d, true, &m->masked_nse));
       M_TRY(dcp_masked_plan_build(m, d, false, &m->masked_pre));
-      if (m->masked_nse->gather) m->strategy = DCP_STRATEGY_STAGED;
+      if (m->masked_nse->gather) {
+        m->strategy = DCP_STRATEGY_STAGED;
+        M_TRY(dcp_gather_plan_attach_pre(m, d, m->masked_nse->gather, m->masked_nse, m->masked_pre));
+      }
     } else {
       M_TRY(dcp_fast_plan_build(m, d, true, &m->fast_nse));
       M_TRY(dcp_fast_plan_build(m, d, false, &m->fast_pre));
@@ -660,6 +663,7 @@ int dcp_model_set_strategy(dcp_model* m, int strategy) {
     return DCP_ERR_STATE;
   }
   m->strategy = strategy;
+  m->pre_fused_valid = false;
   return DCP_OK;
 }
 
@@ -759,6 +763,10 @@ int dcp_assemble_nse_preconditioner(dcp_model* m, const dcp_params* p) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     DCP_TRY(dcp_launch_th_owner(m, *p, false));
     DCP_TRY(dcp_launch_th_cells(m, *p, false, nullptr, nullptr, m->nse_constrained_cells, m->n_nse_constrained_cells, true));
+  } else if (m->strategy == DCP_STRATEGY_STAGED && m->pre_fused_valid && m->pre_fused_dt == p->dt && m->pre_fused_inv_re == p->inv_re) {
+    // nse_preconditioner_matrix was written by the staged system pass for the same parameters: the reference calls
+    // the two assemblers back to back (boussinesq_model.tpp:1869-1880), the velocity block m + nu k is a by-product
+    // of the system's contraction.  Only the Jacobi set-up is left.
   } else if (m->strategy == DCP_STRATEGY_POSITIONS || m->strategy == DCP_STRATEGY_STAGED) {
     DCP_TRY(zero_blockmat(ctx, m->pre));
     if (m->dim == 3) {
@@ -882,6 +890,7 @@ int dcp_matrix_upload(dcp_model* m, int which, int bi, int bj, const double* hos
   DCP_TRY(dcp_memcpy_h2d(m->ctx, A->val, host_values, (int64_t)sizeof(double) * A->nnz));
   if (bi == bj) DCP_TRY(refresh_jacobi(m->ctx, *M));
   if (which == DCP_MAT_TEMP_MASS || which == DCP_MAT_TEMP_STIFF) m->temp_matrices_ready = true;
+  if (which == DCP_MAT_NSE_PRECOND) m->pre_fused_valid = false;   // the caller's values replace the fused pass's
   return DCP_OK;
 }
 
@@ -906,6 +915,13 @@ int dcp_vector_download(dcp_model* m, int which, double* host) {
   return dcp_memcpy_d2h(m->ctx, host, d, (int64_t)sizeof(double) * n);
 }
 
+// After dcp_model_set_owned only the owned rows are computed; a host destination would receive the staging buffer's
+// stale tail for the other rows.  Row-distributed products take device vectors (the ghost exchange lives there, too).
+static int partitioned_host_error() {
+  dcp_set_error("row-distributed model (dcp_model_set_owned): operator products take DCP_DEVICE vectors only");
+  return DCP_ERR_STATE;
+}
+
 static int vmult_impl(dcp_model* m, int which, int bi, int bj, double* dst, const double* src, int mem, bool add) {
   if (!m || !dst || !src) return DCP_ERR_ARG;
   DevCsr* A;
@@ -913,6 +929,7 @@ static int vmult_impl(dcp_model* m, int which, int bi, int bj, double* dst, cons
   DCP_TRY(get_block(m, which, bi, bj, &A, &BM));
   dcp_ctx* ctx = m->ctx;
   DCP_CUDA(cudaSetDevice(ctx->device));
+  if (mem == DCP_HOST && BM->owned[bi] >= 0) return partitioned_host_error();
   const double* dx;
   double* dy;
   DCP_TRY(dcp_stage_in(ctx, 0, src, A->n_cols, mem, &dx));
@@ -980,6 +997,7 @@ int dcp_block_vmult(dcp_model* m, int which, double* dst, const double* src, int
   dcp_ctx* ctx = m->ctx;
   DCP_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = M->start[M->nb];
+  if (mem == DCP_HOST && M->owned[0] >= 0) return partitioned_host_error();
   const double* dx;
   double* dy;
   DCP_TRY(dcp_stage_in(ctx, 0, src, n, mem, &dx));
@@ -1008,6 +1026,7 @@ int dcp_jacobi_vmult(dcp_model* m, int which, int bi, double* dst, const double*
   }
   dcp_ctx* ctx = m->ctx;
   const int64_t n = M->start[bi + 1] - M->start[bi];
+  if (mem == DCP_HOST && M->owned[bi] >= 0) return partitioned_host_error();
   const double* dx;
   double* dy;
   DCP_TRY(dcp_stage_in(ctx, 0, src, n, mem, &dx));

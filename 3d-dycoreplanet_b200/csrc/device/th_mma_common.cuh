@@ -19,6 +19,7 @@ constexpr int MTHREADS = 128;    // 4 warps per CTA, 4 CTAs per SM: several cell
 
 struct MmaArgs {
   long long n_fast;
+  const int* wlist;                 // optional: plan indices to process (n_fast of them) instead of 0 .. n_fast-1
   const int* cells;
   const unsigned short* pos;
   const unsigned char* nmask;       // [n][MSTR]: unconstrained-component mask of the 27 velocity nodes, 8 pressure flags,

@@ -86,7 +86,9 @@ EXPORTS = [
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
     "dcp_vmult_add", "dcp_block_vmult", "dcp_vmult_rows", "dcp_block_vmult_rows", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
-    "dcp_vec_scale", "dcp_vec_copy", "dcp_vec_fill", "dcp_vec_shift", "dcp_velocity_extrema", "dcp_constraints_distribute",
+    "dcp_vec_scale", "dcp_vec_copy", "dcp_vec_fill", "dcp_vec_shift", "dcp_comm_unique_id", "dcp_comm_create", "dcp_comm_adopt", "dcp_comm_info",
+    "dcp_comm_destroy", "dcp_halo_create", "dcp_halo_destroy", "dcp_halo_exchange", "dcp_halo_block_vmult",
+    "dcp_vec_dot_allreduce", "dcp_allreduce_max", "dcp_velocity_extrema", "dcp_constraints_distribute",
     "dcp_geometry_create", "dcp_ilu_create", "dcp_ilu_refactor", "dcp_ilu_vmult", "dcp_ilu_levels", "dcp_ilu_destroy",
 ]
 
@@ -148,6 +150,17 @@ def lib():
         L.dcp_vec_copy.argtypes = [vp, ctypes.c_int64, vp, vp]
         L.dcp_vec_fill.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
         L.dcp_vec_shift.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
+        L.dcp_comm_unique_id.argtypes = [vp]
+        L.dcp_comm_create.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        L.dcp_comm_adopt.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        L.dcp_comm_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        L.dcp_comm_destroy.argtypes = [vp]
+        L.dcp_halo_create.argtypes = [vp, ctypes.c_int64, vp, c_lp, vp, c_lp, ctypes.POINTER(vp)]
+        L.dcp_halo_destroy.argtypes = [vp]
+        L.dcp_halo_exchange.argtypes = [vp, vp]
+        L.dcp_halo_block_vmult.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int]
+        L.dcp_vec_dot_allreduce.argtypes = [vp, ctypes.c_int, c_lp, c_lp, vp, vp, ctypes.POINTER(ctypes.c_double)]
+        L.dcp_allreduce_max.argtypes = [vp, ctypes.c_int, c_dp]
         L.dcp_geometry_create.argtypes = [vp, ctypes.POINTER(MappingDesc), ctypes.POINTER(vp)]
         L.dcp_ilu_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
         L.dcp_ilu_refactor.argtypes = [vp]

@@ -10,7 +10,10 @@ The reference shards this path over MPI ranks along the p4est curve (`LocallyOwn
     kernel, moved with grouped point-to-point sends (torch.distributed, NCCL over NVLink on GPUs, gloo in the
     CPU tests) and unpacked with the scatter kernel into the ghost slots of the source vector.
 
-torch is used for device memory, streams and the process group only.
+torch is used for device memory, streams and the process group only.  On GPUs the data plane is the library's own
+(`Communicator`, `DeviceHalo`: dcp_comm_* / dcp_halo_* / dcp_vec_dot_allreduce in include/dcp.h, NCCL inside libdcp);
+torch.distributed only carries the 128-byte NCCL id and the index lists at set-up.  `HaloPlan.exchange` (torch p2p) is
+what the CPU (gloo) tests run.
 """
 import ctypes
 
@@ -114,6 +117,84 @@ class HaloPlan:
             x[self.t_recv_idx.long()] = self.recv_buf[:nr]
 
 
+class Communicator:
+    """The library's NCCL communicator (dcp_comm_create): rank 0 draws the id, the process group broadcasts it."""
+
+    def __init__(self, ctx, rank, world, group=None):
+        from . import device as dv
+        self.dv, self.ctx, self.rank, self.world = dv, ctx, rank, world
+        ident = [None]
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            dv.check(dv.lib().dcp_comm_unique_id(buf), "dcp_comm_unique_id")
+            ident = [bytes(buf.raw)]
+        if world > 1:
+            dist.broadcast_object_list(ident, src=0, group=group)
+        self._h = ctypes.c_void_p()
+        dv.check(dv.lib().dcp_comm_create(ctx._h, ctypes.c_char_p(ident[0]), rank, world, ctypes.byref(self._h)), "dcp_comm_create")
+        self._res = ctypes.c_double()
+
+    def dot(self, x, y, owned_ranges):
+        """Inner product over the owned entries (list of (begin, end)), all-reduced: the solvers' MPI_Allreduce."""
+        n = len(owned_ranges)
+        rb = (ctypes.c_int64 * n)(*[int(b) for b, _ in owned_ranges])
+        re = (ctypes.c_int64 * n)(*[int(e) for _, e in owned_ranges])
+        self.dv.check(self.dv.lib().dcp_vec_dot_allreduce(self._h, n, rb, re, ctypes.c_void_p(x.data_ptr()),
+                                                          ctypes.c_void_p(y.data_ptr()), ctypes.byref(self._res)),
+                      "dcp_vec_dot_allreduce")
+        return self._res.value
+
+    def max(self, values):
+        arr = (ctypes.c_double * len(values))(*[float(v) for v in values])
+        self.dv.check(self.dv.lib().dcp_allreduce_max(self._h, len(values), arr), "dcp_allreduce_max")
+        return list(arr)
+
+    def close(self):
+        if self._h:
+            self.dv.lib().dcp_comm_destroy(self._h)
+            self._h = None
+
+
+class DeviceHalo:
+    """Ghost exchange and row-distributed products inside libdcp (dcp_halo_create from a HaloPlan's index lists)."""
+
+    def __init__(self, plan, comm):
+        from . import device as dv
+        self.dv, self.plan, self.comm = dv, plan, comm
+        si = np.ascontiguousarray(plan.send_idx, dtype=np.int32)
+        ri = np.ascontiguousarray(plan.recv_idx, dtype=np.int32)
+        sc = np.ascontiguousarray(plan.send_counts, dtype=np.int64)
+        rc = np.ascontiguousarray(plan.recv_counts, dtype=np.int64)
+        self._h = ctypes.c_void_p()
+        dv.check(dv.lib().dcp_halo_create(comm._h, plan.n_local, si.ctypes.data_as(ctypes.c_void_p),
+                                          sc.ctypes.data_as(dv.c_lp), ri.ctypes.data_as(ctypes.c_void_p),
+                                          rc.ctypes.data_as(dv.c_lp), ctypes.byref(self._h)), "dcp_halo_create")
+
+    def exchange(self, x):
+        self.dv.check(self.dv.lib().dcp_halo_exchange(self._h, ctypes.c_void_p(x.data_ptr())), "dcp_halo_exchange")
+
+    def vmult(self, model, which, dst, src, overlap=False):
+        """dst(owned rows) = A src of the row-distributed matrix `which`, ghost refresh of src included."""
+        self.dv.check(self.dv.lib().dcp_halo_block_vmult(model._h, which, self._h, ctypes.c_void_p(dst.data_ptr()),
+                                                         ctypes.c_void_p(src.data_ptr()), 1 if overlap else 0),
+                      "dcp_halo_block_vmult")
+
+    def close(self):
+        if self._h:
+            self.dv.lib().dcp_halo_destroy(self._h)
+            self._h = None
+
+
+class HaloMatrix:
+    """Operator concept (vmult) of a row-distributed matrix through the library's halo product."""
+
+    def __init__(self, model, which, halo, overlap=False):
+        self.model, self.which, self.halo, self.overlap = model, which, halo, overlap
+
+    def vmult(self, dst, src):
+        self.halo.vmult(self.model, self.which, dst, src, self.overlap)
+
+
 class DistributedMatrix:
     """`vmult` of a row-distributed matrix: halo exchange of the source, then the owned rows on the device."""
 
@@ -168,3 +249,40 @@ def global_dot(a, b, owned_mask_or_slices, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(s, group=group)
     return s
+
+
+class DistributedDeviceBackend:
+    """Vector backend of solvers.py for row-distributed device vectors (local layout: owned entries first inside each
+    block, ghost slots after them).  Element-wise operations act on the whole local vector (ghost slots hold stale
+    values that no owned result depends on); inner products run over the owned entries and are all-reduced inside
+    libdcp (dcp_vec_dot_allreduce) -- the MPI_Allreduce of the reference's l2_norm / operator*
+    (boussinesq_model.tpp:1165, 1427; inverse_matrix.hpp:99).
+
+    owned_by_length: {local vector length: [(begin, end), ...]} -- which entries of a vector of that length are
+    owned (the full block vector and every block sub-vector a solver chain takes dots of)."""
+
+    def __init__(self, ctx, comm, owned_by_length):
+        from . import solvers
+        self._b = solvers.DeviceBackend(ctx)
+        self.comm, self.owned = comm, dict(owned_by_length)
+
+    def dot(self, x, y):
+        return self.comm.dot(x, y, self.owned[x.numel()])
+
+    def __getattr__(self, name):          # zeros, copy, assign, axpy, sadd, scale, zero, add_scalar, to_numpy, from_numpy
+        return getattr(self._b, name)
+
+
+class HaloBlock:
+    """block(i,j).vmult of a row-distributed block matrix: ghost refresh of the source block, then the owned rows."""
+
+    def __init__(self, matrix_block, halo_of_source_block):
+        self.block, self.halo = matrix_block, halo_of_source_block
+
+    def vmult(self, dst, src):
+        self.halo.exchange(src)
+        self.block.vmult(dst, src)
+
+    def vmult_add(self, dst, src):
+        self.halo.exchange(src)
+        self.block.vmult_add(dst, src)

@@ -24,7 +24,7 @@ build/obj/%.o: $(PKG)/csrc/device/%.cu $(CU_HDRS)
 
 lib/libdcp.so: $(CU_OBJS)
 	mkdir -p lib
-	$(NVCC) -shared -Xcompiler -fopenmp -o $@ $(CU_OBJS) -lcudart -lgomp
+	$(NVCC) -shared -Xcompiler -fopenmp -o $@ $(CU_OBJS) -lcudart -lgomp -ldl
 	cat build/ptxas/*.log > build/ptxas.log
 
 # C++ host mirror (include/dcp.hpp) checked against the oracle; the oracle is linked as the checker only

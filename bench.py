@@ -28,10 +28,25 @@ import numpy as np  # noqa: E402
 
 
 FP64_DMMA_PEAK_TFLOPS = 37.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (th_mma_kernel<1>, the NSE system
-# pass on a single GPU) from `ncu --set full` captures of this bench command, keyed by refinement:
-# profiles/r01_ncu_full_r5_final.txt, profiles/r01_ncu_full_r6_system_kernel.txt
-NCU_DRAM_BYTES_PER_LAUNCH = {5: 16.150222e9 + 13.920899e9, 6: 165.702325e9 + 127.577328e9}
+
+
+def ncu_traffic(strategy, refine):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the NSE system pass (all its launches of one step, single GPU)
+    from the `ncu --set full` capture recorded in profiles/traffic.json (written from the .ncu-rep by
+    profiles/extract_traffic.py together with the commit it was taken at); None when no capture matches."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = d.get(f"{strategy}:r{refine}")
+        return (float(e["dram_bytes_per_step"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def key_field(keys, seed):
+    """Deterministic field as a function of the global dof identity: every partition of the same mesh sees the same
+    values, so the checksums of a run at N ranks can be compared with the run at 1 rank."""
+    k = np.asarray(keys, dtype=np.int64)
+    return np.ascontiguousarray(np.sin(0.37 * (k % 1000003) + seed) + 0.1 * np.cos(0.011 * (k % 7919)))
 
 
 def peaks():
@@ -173,18 +188,24 @@ def main():
                          "when the box has the host and device memory for it, else 5")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N>1: strong = the same shell cut into N chunks; weak = N x the radial layers")
-    ap.add_argument("--temperature-degree", type=int, default=1)
+    ap.add_argument("--temperature-degree", type=int, default=0,
+                    help="0 = 1 on one GPU (41.2 M DoFs at refine 6, the largest that fits 180 GB) and 2 on several "
+                         "(52.3 M DoFs at refine 6: the >= 50 M-DoF point of the 6-tree shell)")
     ap.add_argument("--strategy", default="auto", choices=["auto", "search", "positions", "owner", "staged"])
     ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the CPU sample (4: ~3 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap-halo", action="store_true",
-                    help="N>1: hide the ghost exchange behind the rows without ghost columns (measured: no gain at the "
-                         "bench sizes, the exchange is <10 %% of the product and the second pass costs as much)")
+                    help="N>1: hide the ghost exchange behind the rows without ghost columns (dcp_halo_block_vmult with "
+                         "overlap = 1)")
+    ap.add_argument("--torch-halo", action="store_true",
+                    help="N>1: exchange through torch.distributed p2p (round-1 path) instead of the library's NCCL halo")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.temperature_degree == 0:
+        args.temperature_degree = 2 if (world > 1 and args.scaling == "strong" and args.refine in (0, 6)) else 1
 
     import dycore_b200  # noqa: F401
     from dycore_b200 import params
@@ -236,7 +257,9 @@ def main():
         if args.scaling == "weak":
             spec.update(radial_factor=world)
     P = harness.Problem(**spec)
-    u, T = synthetic_fields(P)
+    # state and SpMV sources as functions of the global dof identity (the same numbers on every partition)
+    u = 0.1 * key_field(P["nse.dof_key"], 1.0)
+    T = 2.0 + 0.2 * key_field(P["temp.dof_key"], 2.0)
     n_nse, n_t = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
     n_u = P.scalar("nse.n_u")
     owned = [P.scalar("nse.n_u_owned"), P.scalar("nse.n_p_owned")]
@@ -250,35 +273,43 @@ def main():
     if args.strategy != "auto":
         model.set_strategy(names[args.strategy])
     strategy = {v: k for k, v in names.items()}[model.strategy]   # auto: the library's default (staged when the model qualifies)
-    halo_nse = halo_t = None
+    halo_nse = halo_t = comm = None
     if world > 1:
         from dycore_b200 import distributed
         model.set_owned(owned, P.scalar("temp.n_owned"))
         torch.cuda.set_stream(stream)
         halo_nse = distributed.HaloPlan(P["nse.dof_key"], P["nse.dof_owner"], rank, world, device="cuda")
         halo_t = distributed.HaloPlan(P["temp.dof_key"], P["temp.dof_owner"], rank, world, device="cuda")
-        if args.overlap_halo:   # ghost exchange hidden behind the rows that do not read ghost columns
-            op_nse = distributed.OverlappedMatrix(model.nse_matrix, halo_nse, local_rank, stream)
-            op_t = distributed.OverlappedMatrix(model.temperature_matrix, halo_t, local_rank, stream)
-        else:                   # exchange, then the product (Epetra_Import + Multiply)
-            op_nse = distributed.DistributedMatrix(model.nse_matrix, halo_nse, ctx)
-            op_t = distributed.DistributedMatrix(model.temperature_matrix, halo_t, ctx)
+        comm = distributed.Communicator(ctx, rank, world)
+        if args.torch_halo:     # round-1 path: pack kernel, torch.distributed p2p, unpack kernel
+            if args.overlap_halo:
+                op_nse = distributed.OverlappedMatrix(model.nse_matrix, halo_nse, local_rank, stream)
+                op_t = distributed.OverlappedMatrix(model.temperature_matrix, halo_t, local_rank, stream)
+            else:
+                op_nse = distributed.DistributedMatrix(model.nse_matrix, halo_nse, ctx)
+                op_t = distributed.DistributedMatrix(model.temperature_matrix, halo_t, ctx)
+        else:                   # the library's data plane: Epetra_Import + Multiply as one C-ABI call
+            dh_nse, dh_t = distributed.DeviceHalo(halo_nse, comm), distributed.DeviceHalo(halo_t, comm)
+            op_nse = distributed.HaloMatrix(model, device.MAT_NSE, dh_nse, overlap=args.overlap_halo)
+            op_t = distributed.HaloMatrix(model, device.MAT_TEMP, dh_t, overlap=args.overlap_halo)
     t_setup = time.perf_counter() - t_setup
 
     with torch.cuda.stream(stream):
         d_u = torch.from_numpy(u).cuda()
         d_T = torch.from_numpy(T).cuda()
-        rng = np.random.default_rng(1)
-        d_x = torch.from_numpy(rng.standard_normal(n_nse)).cuda()
+        x_np, xt_np = key_field(P["nse.dof_key"], 3.0), key_field(P["temp.dof_key"], 5.0)
+        if world > 1:          # ghost slots start empty: the halo exchange has to fill them
+            x_np[P["nse.dof_owner"] != rank] = 0.0
+            xt_np[P["temp.dof_owner"] != rank] = 0.0
+        d_x = torch.from_numpy(x_np).cuda()
         d_y = torch.zeros(n_nse, dtype=torch.float64, device="cuda")
-        d_xt = torch.from_numpy(rng.standard_normal(n_t)).cuda()
+        d_xt = torch.from_numpy(xt_np).cuda()
         d_yt = torch.zeros(n_t, dtype=torch.float64, device="cuda")
     # pinned host buffers for the e2e leg
     h_u, h_T = torch.from_numpy(u).pin_memory(), torch.from_numpy(T).pin_memory()
     h_x, h_y = d_x.cpu().pin_memory(), torch.zeros(n_nse, dtype=torch.float64).pin_memory()
     h_xt, h_yt = d_xt.cpu().pin_memory(), torch.zeros(n_t, dtype=torch.float64).pin_memory()
     h_rhs, h_trhs = torch.zeros(n_nse, dtype=torch.float64).pin_memory(), torch.zeros(n_t, dtype=torch.float64).pin_memory()
-    d_rhs = torch.zeros(n_nse, dtype=torch.float64, device="cuda")
 
     phases = ["nse_system", "nse_preconditioner", "temperature_matrix", "temperature_rhs", "spmv_nse", "spmv_temperature"]
 
@@ -307,50 +338,33 @@ def main():
                 model.temperature_matrix.vmult(d_yt, d_xt)
             mark(6)
 
-    copy_stream = torch.cuda.Stream()
-    ev_x, ev_rhs, ev_copy_done, ev_spmv = (torch.cuda.Event() for _ in range(4))
-    d_trhs = torch.zeros(n_t, dtype=torch.float64, device="cuda")
-    rhs_ptr, trhs_ptr, nn = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
-    device.check(device.lib().dcp_vector_device(model._h, device.VEC_NSE_RHS, ctypes.byref(rhs_ptr), ctypes.byref(nn)))
-    device.check(device.lib().dcp_vector_device(model._h, device.VEC_TEMP_RHS, ctypes.byref(trhs_ptr), ctypes.byref(nn)))
+    def hp(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    L = device.lib()
 
     def step_host():
-        # the same step for a caller whose vectors live in host memory: H2D of the solution vectors and SpMV
-        # sources, D2H of the right-hand sides and SpMV results, all inside the timed region.  The copies that do
-        # not gate the next kernel run on a second stream, as a careful caller would issue them: the SpMV sources go
-        # up while the assembly runs, the right-hand sides come down while the products run.
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_spmv)                 # the previous step's products are done with d_x
-            d_x.copy_(h_x, non_blocking=True)
-            d_xt.copy_(h_xt, non_blocking=True)
-            ev_x.record(copy_stream)
-        with torch.cuda.stream(stream):
-            d_u.copy_(h_u, non_blocking=True)
-            d_T.copy_(h_T, non_blocking=True)
-            model.assemble_nse_system(d_u, d_T)
-            model.assemble_nse_preconditioner()
-            model.assemble_temperature_matrix()
-            model.assemble_temperature_rhs(d_T, d_u)
-            device.check(device.lib().dcp_vec_copy(ctx._h, n_nse, rhs_ptr, ctypes.c_void_p(d_rhs.data_ptr())))
-            device.check(device.lib().dcp_vec_copy(ctx._h, n_t, trhs_ptr, ctypes.c_void_p(d_trhs.data_ptr())))
-            ev_rhs.record(stream)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_rhs)
-            h_rhs.copy_(d_rhs, non_blocking=True)
-            h_trhs.copy_(d_trhs, non_blocking=True)
-            ev_copy_done.record(copy_stream)
-        with torch.cuda.stream(stream):
-            stream.wait_event(ev_x)
-            if halo_nse is not None:
-                op_nse.vmult(d_y, d_x)
-                op_t.vmult(d_yt, d_xt)
-            else:
-                model.nse_matrix.vmult(d_y, d_x)
-                model.temperature_matrix.vmult(d_yt, d_xt)
-            ev_spmv.record(stream)
-            h_y.copy_(d_y, non_blocking=True)
-            h_yt.copy_(d_yt, non_blocking=True)
-            stream.wait_event(ev_copy_done)                 # the step ends when every result is in host memory
+        # the same step for a caller whose vectors live in HOST memory, through the C ABI's DCP_HOST path: the assemblers
+        # and (single rank) the products take host pointers, the library stages them in and out (H2D of the solution
+        # vectors and SpMV sources, D2H of the right-hand sides and SpMV results inside the call).  Row-distributed
+        # products take device vectors (the ghost exchange lives there), so with several ranks the sources go up and the
+        # results come down through dcp_memcpy_h2d / dcp_memcpy_d2h around dcp_halo_block_vmult.
+        model.assemble_nse_system(h_u, h_T)
+        model.assemble_nse_preconditioner()
+        model.assemble_temperature_matrix()
+        model.assemble_temperature_rhs(h_T, h_u)
+        device.check(L.dcp_vector_download(model._h, device.VEC_NSE_RHS, hp(h_rhs)), "dcp_vector_download")
+        device.check(L.dcp_vector_download(model._h, device.VEC_TEMP_RHS, hp(h_trhs)), "dcp_vector_download")
+        if halo_nse is not None:
+            device.check(L.dcp_memcpy_h2d(ctx._h, hp(d_x), hp(h_x), 8 * n_nse))
+            device.check(L.dcp_memcpy_h2d(ctx._h, hp(d_xt), hp(h_xt), 8 * n_t))
+            op_nse.vmult(d_y, d_x)
+            op_t.vmult(d_yt, d_xt)
+            device.check(L.dcp_memcpy_d2h(ctx._h, hp(h_y), hp(d_y), 8 * n_nse))
+            device.check(L.dcp_memcpy_d2h(ctx._h, hp(h_yt), hp(d_yt), 8 * n_t))
+        else:
+            model.nse_matrix.vmult(h_y, h_x)
+            model.temperature_matrix.vmult(h_yt, h_xt)
 
     def barrier():
         if world > 1:
@@ -388,6 +402,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     phase_ms = {p: float(np.mean([evs[s][i].elapsed_time(evs[s][i + 1]) for s in range(args.steps)]))
                 for i, p in enumerate(phases)}
+    if rank == 0:
+        print("[bench] device-resident: %.3f ms/step %s" % (ms / args.steps, json.dumps(phase_ms)), file=sys.stderr, flush=True)
     for _ in range(2):
         step_host()
     ms_e2e, _ = timed(step_host, args.steps, False)
@@ -418,6 +434,22 @@ def main():
                                  "l2_resident": bool(nbytes < 126e6)}
         assert n_p == model.nse_matrix.block(1, 0).m()
 
+    # correctness signal carried by every line: l2 norms over the owned entries of A x, the NSE right-hand side, the
+    # temperature right-hand side and T x_T for inputs that are functions of the global dof identity -- the same
+    # numbers (to summation order) for every number of ranks
+    def owned_norm(t, ranges):
+        if comm is not None:
+            return float(np.sqrt(comm.dot(t, t, ranges)))
+        return float(np.sqrt(sum(float(torch.dot(t[b:e], t[b:e])) for b, e in ranges)))
+    with torch.cuda.stream(stream):
+        step_device()
+        nse_ranges = [(0, owned[0]), (n_u, n_u + owned[1])]
+        t_ranges = [(0, P.scalar("temp.n_owned"))]
+        d_rhs = torch.from_numpy(model.nse_rhs).cuda()
+        d_trhs = torch.from_numpy(model.temperature_rhs).cuda()
+        checksum = {"norm_A_x": owned_norm(d_y, nse_ranges), "norm_nse_rhs": owned_norm(d_rhs, nse_ranges),
+                    "norm_temperature_rhs": owned_norm(d_trhs, t_ranges), "norm_T_x": owned_norm(d_yt, t_ranges)}
+
     total_dofs = n_dofs
     if world > 1:
         t = torch.tensor([n_dofs], dtype=torch.float64, device="cuda")
@@ -429,6 +461,7 @@ def main():
         ms_step = ms / args.steps
         dom = max(("nse_system", "nse_preconditioner"), key=lambda k: phase_ms[k])
         ach = ab[dom] / (phase_ms[dom] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(strategy, refine) if (world == 1 and dom == "nse_system") else (None, None)
         asm_ms = sum(phase_ms[p] for p in phases[:4])
         spmv_ms = phase_ms["spmv_nse"] + phase_ms["spmv_temperature"]
         line = {
@@ -460,15 +493,17 @@ def main():
                               "peak_source": "profiles/r01_fp64_peaks.json (mma.sync m8n8k4 f64, measured)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(refine) if (world == 1 and dom == "nse_system") else None,
-                         "traffic_note": "DRAM bytes per launch of the system kernel, ncu --set full capture (profiles/); "
-                                         "algorithmic bytes per launch: %.3e" % ab[dom],
+                         "traffic": traffic,
+                         "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the NSE system pass (all its launches "
+                                          "of one step), " + (traffic_src or "no ncu capture for this strategy / refinement")
+                                          + "; algorithmic bytes of the pass: %.3e" % ab[dom]),
                          "peak_source": peak_src,
                          "spmv_frac": ab["spmv_nse"] / (phase_ms["spmv_nse"] * 1e-3) / 1e9 / peak},
             "e2e": {"value": total_dofs / (ms_e2e / args.steps * 1e-3), "unit": "DoFs/s",
-                    "h2d_bytes_per_step": int(8 * (2 * (n_nse + n_t) + n_nse + n_t)),
+                    "h2d_bytes_per_step": int(8 * (2 * (n_nse + n_t))),
                     "d2h_bytes_per_step": int(8 * (2 * (n_nse + n_t)))},
             "gpu_launches": int(launches), "clocks": clocks,
+            "parity_checksum": checksum,
         }
         if not args.no_cpu_baseline and world == 1:
             base, _, _ = cpu_leg(args.cpu_refine, args.temperature_degree, 3, 1, mp)

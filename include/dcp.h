@@ -321,6 +321,46 @@ int dcp_vec_fill(dcp_ctx* ctx, int64_t n, double value, double* y_dev);
 /* y += a in every entry (Vector::add(a): the zero-mean correction of the FEEC pressure, nested_schur_complement.hpp:180-182) */
 int dcp_vec_shift(dcp_ctx* ctx, int64_t n, double a, double* y_dev);
 
+/* ---- multi-GPU data plane (one process per GPU, NCCL over NVLink; csrc/device/halo.cu) --------------------------
+ * Replaces what Trilinos / deal.II hide behind MPI in the reference: the Epetra_Import of off-rank source entries
+ * inside every LA::SparseMatrix::vmult (include/linear_algebra/schur_complement.hpp:143-150,
+ * block_schur_preconditioner.hpp:55), the ghost refresh `nse_solution = distributed_nse_solution`
+ * (include/core/boussinesq_model.tpp:1241, 1444), the MPI_Allreduce of l2_norm / operator* (:1165, 1427) and
+ * Utilities::MPI::max (:1050, 1094, 1467).  NCCL is bound at run time (libnccl.so.2); single-GPU use never needs it.
+ *
+ * dcp_comm_unique_id: rank 0 fills 128 bytes (ncclUniqueId) and broadcasts them by whatever means the host has
+ * (MPI_Bcast in a deal.II build); every rank then calls dcp_comm_create.  dcp_comm_adopt wraps an ncclComm_t the host
+ * already owns (not destroyed with the handle). */
+#define DCP_UNIQUE_ID_BYTES 128
+typedef struct dcp_comm dcp_comm;
+typedef struct dcp_halo dcp_halo;
+int dcp_comm_unique_id(void* id_out);
+int dcp_comm_create(dcp_ctx* ctx, const void* id, int rank, int n_ranks, dcp_comm** out);
+int dcp_comm_adopt(dcp_ctx* ctx, void* nccl_comm, int rank, int n_ranks, dcp_comm** out);
+int dcp_comm_info(const dcp_comm* c, int* rank, int* n_ranks);
+int dcp_comm_destroy(dcp_comm* c);
+/* Ghost plan of one local vector layout (n_local entries, owned entries first inside each block, ghosts after them):
+ * send_idx = local indices of the owned entries other ranks read, grouped by destination rank (send_counts[n_ranks]);
+ * recv_idx = local ghost slots grouped by owning rank (recv_counts[n_ranks]), in the order the owner sends them.
+ * All arrays are host arrays and are copied. */
+int dcp_halo_create(dcp_comm* c, int64_t n_local, const int32_t* send_idx, const int64_t* send_counts,
+                    const int32_t* recv_idx, const int64_t* recv_counts, dcp_halo** out);
+int dcp_halo_destroy(dcp_halo* h);
+/* refresh the ghost entries of the device vector x in place (pack kernel -> grouped ncclSend/ncclRecv -> unpack
+ * kernel on the context's stream; no host synchronisation) */
+int dcp_halo_exchange(dcp_halo* h, double* x_dev);
+/* dst(owned rows) = A * src for the row-distributed matrix `which` (all blocks; a single-block matrix is its own block
+ * matrix): ghost refresh of src, then the products.  overlap != 0: the exchange runs on the communicator's stream while
+ * the rows that read owned columns only are computed; the rows with ghost columns follow (needs dcp_model_set_owned).
+ * Device pointers; src's ghost slots are overwritten. */
+int dcp_halo_block_vmult(dcp_model* m, int which, dcp_halo* h, double* dst_dev, double* src_dev, int overlap);
+/* sum over the given index ranges (the owned entries of each block) of x[i] * y[i], all-reduced over the ranks: the
+ * Krylov solvers' inner product.  At most 16 ranges.  The scalar is returned to the host. */
+int dcp_vec_dot_allreduce(dcp_comm* c, int n_ranges, const int64_t* range_begin, const int64_t* range_end,
+                          const double* x_dev, const double* y_dev, double* result_host);
+/* Utilities::MPI::max over the ranks of up to 8 host scalars, in place */
+int dcp_allreduce_max(dcp_comm* c, int n, double* values_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,3 +151,89 @@ def gpu_schur_step(ctx, P, mp, u0, T0):
     ilu.close()
     model.close()
     return out
+
+
+# ---- FEEC block-preconditioned path (data/aqua_planet_shell_test_3d-feec.prm) --------------------------------------
+def feec_mean_weights(P, n_gauss):
+    """|K| / sum |K| in pressure-dof order: the weights of VectorTools::compute_mean_value for the DG0 pressure."""
+    from dycore_b200 import solvers as S
+    nw, nu, n = P.scalar("nse.n_w"), P.scalar("nse.n_u"), P.scalar("nse.n_dofs")
+    vol = S.feec_cell_volumes(P["cell_vertices"], n_gauss)
+    l2g = P["nse.l2g"].reshape(P.scalar("n_cells"), -1)
+    pdof = l2g[:, -1].astype(np.int64) - (nw + nu)          # FE_DGQ(0): the last cell dof
+    assert pdof.min() >= 0 and pdof.max() < n - nw - nu
+    w = np.zeros(n - nw - nu)
+    np.add.at(w, pdof, vol)
+    return w / vol.sum()
+
+
+def cpu_feec_step(P, mp, u0, T0):
+    """assemble_nse_system + solve_NSE_block_preconditioned of ExteriorCalculus::BoussinesqModel
+    (boussineq_model_FEEC.tpp:2255-2299, 1268-1477) on the CPU: oracle assembly + numpy Krylov vectors."""
+    from dycore_b200 import solvers as S
+    from oracle import oracle as orc
+    prm = orc.params_from(mp)
+    B = S.NumpyBackend()
+    n = P.scalar("nse.n_dofs")
+    nw, nu = P.scalar("nse.n_w"), P.scalar("nse.n_u")
+    sizes = (nw, nu, n - nw - nu)
+    vals, rhs = orc.feec_assemble_nse_system(P, prm, u0, T0)
+    rp, col, _, _ = P.csr("nse.full")
+    A = sp.csr_matrix((vals, col, rp), shape=(n, n))
+    off = [0, nw, nw + nu, n]
+
+    class Mat:
+        def __init__(self, M):
+            self.M = M
+
+        def vmult(self, dst, src, B=None):
+            dst[...] = self.M @ src
+
+        def vmult_add(self, dst, src, B=None):
+            dst += self.M @ src
+
+    def jac(M):
+        d = M.diagonal()
+        return S.Wrap(lambda dst, src, d=d: dst.__setitem__(slice(None), src / d))
+    blocks = {}
+    for i in range(3):
+        for j in range(3):
+            Mij = A[off[i]:off[i + 1], off[j]:off[j + 1]].tocsr()
+            if P.scalar(f"nse.b{i}{j}.nnz") > 0:
+                blocks[(i, j)] = Mat(Mij)
+    x, its, inner = S.solve_nse_block_preconditioned_feec(
+        B, Mat(A), blocks, jac(A[:nw, :nw]), jac(A[nw:nw + nu, nw:nw + nu]), rhs, u0, sizes, mp.time_step,
+        S.MeanValue(feec_mean_weights(P, 1), B), S.MeanValue(feec_mean_weights(P, 2), B))
+    x = S.distribute(B, cs_lines(P, "nse.cs"), x)
+    x[nw + nu:] /= mp.time_step
+    return dict(nse=x, gmres=its, inner=inner)
+
+
+def gpu_feec_step(ctx, P, mp, u0, T0):
+    """The same with assembly, SpMVs, Jacobi sweeps and Krylov vectors on the device."""
+    import ctypes
+    import torch
+    from dycore_b200 import device
+    from dycore_b200 import solvers as S
+    B = S.DeviceBackend(ctx)
+    n = P.scalar("nse.n_dofs")
+    nw, nu = P.scalar("nse.n_w"), P.scalar("nse.n_u")
+    sizes = (nw, nu, n - nw - nu)
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    d_u, d_T = torch.from_numpy(u0).cuda(), torch.from_numpy(T0).cuda()
+    torch.cuda.synchronize()
+    model.assemble_nse_system(d_u, d_T)
+    ptr, nn = ctypes.c_void_p(), ctypes.c_int64()
+    device.check(device.lib().dcp_vector_device(model._h, device.VEC_NSE_RHS, ctypes.byref(ptr), ctypes.byref(nn)))
+    rhs = torch.empty(n, dtype=torch.float64, device="cuda")
+    device.check(device.lib().dcp_vec_copy(ctx._h, n, ptr, ctypes.c_void_p(rhs.data_ptr())))
+    blocks = {(i, j): S.Wrap(model.nse_matrix.block(i, j)) for i in range(3) for j in range(3)
+              if P.scalar(f"nse.b{i}{j}.nnz") > 0}
+    x, its, inner = S.solve_nse_block_preconditioned_feec(
+        B, S.Wrap(model.nse_matrix), blocks, S.Wrap(device.PreconditionJacobi(model, device.MAT_NSE, 0)),
+        S.Wrap(device.PreconditionJacobi(model, device.MAT_NSE, 1)), rhs, d_u, sizes, mp.time_step,
+        S.MeanValue(feec_mean_weights(P, 1), B), S.MeanValue(feec_mean_weights(P, 2), B))
+    xh = S.distribute(B, cs_lines(P, "nse.cs"), B.to_numpy(x))
+    xh[nw + nu:] /= mp.time_step
+    model.close()
+    return dict(nse=xh, gmres=its, inner=inner)

@@ -61,3 +61,29 @@ def test_schur_complement_step_of_the_2d_config(problem_factory, refine):
     for name, g, r in (("velocity", got["nse"][:n_u], ref["nse"][:n_u]), ("pressure", got["nse"][n_u:], ref["nse"][n_u:])):
         err = np.abs(g - r).max() / max(np.abs(r).max(), 1e-300)
         assert err <= 2e-4, (name, err)
+
+
+@pytest.mark.parametrize("refine", [2, 3])
+def test_feec_block_preconditioned_step(problem_factory, refine):
+    """data/aqua_planet_shell_test_3d-feec.prm (refine 3 is the named configuration): assemble_nse_system +
+    solve_NSE_block_preconditioned of the FEEC model (boussineq_model_FEEC.tpp:1268-1477) -- GMRES(100) with
+    BlockSchurPreconditionerFEEC, i.e. Jacobi(Mw), GMRES on the shifted Schur complement, GMRES on B Jac(Mu) B^T with
+    the zero-mean correction -- with every operator and vector on the device, against the CPU mirror."""
+    from dycore_b200 import device, params
+    mp = params.NAMED["shell_3d_feec"]
+    P = problem_factory(geometry="shell", refine=refine, family="feec")
+    n = P.scalar("nse.n_dofs")
+    nw, nu = P.scalar("nse.n_w"), P.scalar("nse.n_u")
+    u0, T0 = np.zeros(n), K.initial_temperature(P, mp)
+    ref = K.cpu_feec_step(P, mp, u0, T0)
+    ctx = device.Context(0)
+    got = K.gpu_feec_step(ctx, P, mp, u0, T0)
+    ctx.close()
+    assert abs(got["gmres"] - ref["gmres"]) <= 1, (got["gmres"], ref["gmres"])
+    for key in ("shifted", "nested"):
+        a, b = got["inner"][key], ref["inner"][key]
+        assert abs(len(a) - len(b)) <= 1
+        assert all(abs(x - y) <= 1 for x, y in zip(a, b)), (key, a, b)
+    for name, sl in (("vorticity", slice(0, nw)), ("velocity", slice(nw, nw + nu)), ("pressure", slice(nw + nu, n))):
+        err = np.abs(got["nse"][sl] - ref["nse"][sl]).max() / np.abs(ref["nse"][sl]).max()
+        assert err <= 1e-8, (name, err)
