@@ -13,6 +13,9 @@
 // (phi, d_x phi, d_y phi, d_z phi) in a shared-memory row S[lane][.] of odd stride (conflict-free for the
 // writer "lane = point" and for the readers "lane = matrix entry").  Lanes then own the symmetric local
 // matrix entries.  8..27 dofs per cell: these kernels are HBM/latency bound, not FLOP bound.
+#include <algorithm>
+#include <cstdlib>
+
 #include "scatter.cuh"
 
 namespace {
@@ -109,7 +112,8 @@ __global__ void __launch_bounds__(128) temperature_matrix_kernel(ScalarArgs a, C
   int* idx = reinterpret_cast<int*>(base + L.o_idx);
   int* lines = idx + MAX_ND + 1;
   const int nd = a.nd, nsym = nd * (nd + 1) / 2;
-  for (long long cell = (long long)blockIdx.x * nwarps + wid; cell < a.n_cells; cell += (long long)gridDim.x * nwarps) {
+  for (long long ci = (long long)blockIdx.x * nwarps + wid; ci < a.n_cells; ci += (long long)gridDim.x * nwarps) {
+    const long long cell = a.cell_list ? a.cell_list[ci] : ci;
     const double* g = a.geom + cell * a.gstride;
     if (lane < nd) idx[lane] = a.l2g[cell * nd + lane];
     const unsigned short* tp = a.tpos + cell * (long long)(nd * nd);
@@ -436,6 +440,112 @@ ScalarLaunch scalar_launch(dcp_ctx* ctx, long long n_cells, int nd, int nd_nse) 
   return s;
 }
 
+
+// ---- Q2 temperature in 3-D: mass and stiffness matrices on the FP64 tensor cores ---------------------------------
+// 27 dofs and 64 quadrature points per cell (QGauss(temperature_degree + 2), boussinesq_model.tpp:834): the symmetric
+// DFMA loop above spends 378 entries x 64 points x 8 shared-memory loads per cell.  Here, like the Stokes kernel,
+//   X[q][32 alpha + b] = (d_0 phi_b, d_1 phi_b, d_2 phi_b, phi_b)(x_q)            (27 nodes padded to 32)
+//   M_ab = sum_q w_q X[q][96 + a] X[q][96 + b],   K_ab = (1/Pe) sum_q w_q sum_e X[q][32 e + a] X[q][32 e + b]
+// with mma.sync.m8n8k4.f64: one CTA (4 warps) per cell, the points in two halves of 32 (33 kB operand table), the 10
+// node-block pairs (ta <= tb) spread over the warps with both accumulators kept across the halves; lane-local scatter
+// through the position row (cells with constrained dofs take the general kernel).
+constexpr int TQ_LDB = 132;   // 132 mod 16 == 4: conflict-free fragment loads
+constexpr int TQ_HALF = 32;
+
+__global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArgs a, BlockView Mass, BlockView Stiff) {
+  extern __shared__ __align__(16) double smem_d[];
+  double* X = smem_d;                      // [32][TQ_LDB]
+  double* wq = X + TQ_HALF * TQ_LDB;       // [32]
+  int* idx = reinterpret_cast<int*>(wq + TQ_HALF);   // [28]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frow = lane >> 2, fk = lane & 3;
+  constexpr int ND2 = 27;
+  for (int i = tid; i < TQ_HALF * TQ_LDB; i += 128) X[i] = 0.0;   // padding nodes 27..31 stay zero
+  const long long* rp = Mass.rowptr[0][0];
+  double* vm = Mass.val[0][0];
+  double* vk = Stiff.val[0][0];
+  for (long long ci = blockIdx.x; ci < a.n_cells; ci += gridDim.x) {
+    const long long cell = a.cell_list ? a.cell_list[ci] : ci;
+    const double* g = a.geom + cell * a.gstride;
+    const unsigned short* tp = a.tpos + cell * (long long)(ND2 * ND2);
+    __syncthreads();   // every warp is done with the previous cell
+    if (tid < ND2) idx[tid] = a.l2g[cell * ND2 + tid];
+    // tasks of this warp: t = warp, warp + 4, warp + 8 (< 10)
+    double am[3][2], ak[3][2];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) am[s][0] = am[s][1] = ak[s][0] = ak[s][1] = 0.0;
+    for (int half = 0; half < 2; ++half) {
+      if (half) __syncthreads();
+      // operand table of 32 points: thread = (point, group of 7 nodes)
+      {
+        const int ql = tid >> 2, bg = tid & 3, q = half * TQ_HALF + ql;
+        double kinv[3][3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) kinv[e][d] = g[a.nq * (1 + 3 * e + d) + q];
+        if (bg == 0) wq[ql] = g[q];
+        double* x = X + ql * TQ_LDB + bg * 7;
+        const int nb = bg == 3 ? 6 : 7;
+        for (int j = 0; j < nb; ++j) {
+          const int b = bg * 7 + j;
+          const double* rr = a.dphi + ((size_t)q * ND2 + b) * 3;
+          const double r0 = __ldg(rr), r1 = __ldg(rr + 1), r2 = __ldg(rr + 2);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) x[32 * d + j] = kinv[0][d] * r0 + kinv[1][d] * r1 + kinv[2][d] * r2;
+          x[96 + j] = __ldg(a.phi + (size_t)q * ND2 + b);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int t = warp + 4 * s;
+        if (t < 10) {
+          int ta = 0, r = t;
+          while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
+          const int tb = ta + r;
+#pragma unroll
+          for (int ks = 0; ks < TQ_HALF / 4; ++ks) {
+            const int ql = 4 * ks + fk;
+            const double* xr = X + ql * TQ_LDB;
+            const double wv = wq[ql];
+#pragma unroll
+            for (int al = 0; al < 4; ++al) {
+              const double af = wv * xr[32 * al + 8 * ta + frow], bf = xr[32 * al + 8 * tb + frow];
+              if (al < 3) dmma_m8n8k4(ak[s][0], ak[s][1], af, bf); else dmma_m8n8k4(am[s][0], am[s][1], af, bf);
+            }
+          }
+        }
+      }
+    }
+    // scatter: lane holds (na, nb = 8 tb + 2 fk + jj); the transposed pair comes from the same registers
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int t = warp + 4 * s;
+      if (t < 10) {
+        int ta = 0, r = t;
+        while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
+        const int tb = ta + r;
+        const int na = 8 * ta + frow;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int nb = 8 * tb + 2 * fk + jj;
+          if (na >= ND2 || nb >= ND2) continue;
+          const double mv = am[s][jj], kv = ak[s][jj] * a.prm.inv_pe;
+          const long long at = rp[idx[na]] + tp[na * ND2 + nb];
+          red_add_f64(vm + at, mv);
+          red_add_f64(vk + at, kv);
+          if (ta != tb) {
+            const long long at2 = rp[idx[nb]] + tp[nb * ND2 + na];
+            red_add_f64(vm + at2, mv);
+            red_add_f64(vk + at2, kv);
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
@@ -459,6 +569,31 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
   a.phi_uT = m->phi_u_qt_T;
   a.prm = p;
   if (m->n_cells == 0) return DCP_OK;
+  if (m->dim == 3 && a.nd == 27 && a.nq == 64 && !std::getenv("DCP_NO_Q2_DMMA")) {
+    // Q2 temperature: tensor-core kernel on the cells with a position row, general kernel on the others
+    if (m->n_temp_fast > 0) {
+      ScalarArgs f = a;
+      f.cell_list = m->temp_fast_cells;
+      f.n_cells = m->n_temp_fast;
+      const size_t smem = sizeof(double) * (TQ_HALF * TQ_LDB + TQ_HALF) + sizeof(int) * 28;
+      DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const long long grid = std::min<long long>((long long)ctx->sm_count * 4, f.n_cells);
+      temperature_matrix_q2_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(f, make_view(m->tmass), make_view(m->tstiff));
+      ctx->launches++;
+    }
+    if (m->n_temp_general > 0) {
+      ScalarArgs gn = a;
+      gn.cell_list = m->temp_general_cells;
+      gn.n_cells = m->n_temp_general;
+      const ScalarLaunch sg = scalar_launch(ctx, gn.n_cells, a.nd, 0);
+      DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg.smem));
+      temperature_matrix_kernel<3><<<sg.grid, 32 * sg.warps, sg.smem, ctx->stream>>>(
+          gn, make_view(m->temp_cs), make_view(m->tmass), make_view(m->tstiff), ctx->d_err);
+      ctx->launches++;
+    }
+    DCP_CUDA(cudaGetLastError());
+    return DCP_OK;
+  }
   const ScalarLaunch s = scalar_launch(ctx, m->n_cells, a.nd, 0);
   if (m->dim == 3) {
     DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));

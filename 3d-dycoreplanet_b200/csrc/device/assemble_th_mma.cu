@@ -668,6 +668,9 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
   MaskedPlan* P = new MaskedPlan;
   P->h_cells = cells;
   P->h_nnf_idx = nnf_idx;
+  P->h_wide_idx = wide_idx;
+  P->h_cflag.resize(cells.size());
+  for (size_t i = 0; i < cells.size(); ++i) P->h_cflag[i] = mask_all[(size_t)cells[i] * 36 + 35];
   P->n = (int64_t)cells.size();
   P->n_other = (int64_t)other.size();
   P->n_wide = (int64_t)(pos_wide.size() / (3 * NU * NU));

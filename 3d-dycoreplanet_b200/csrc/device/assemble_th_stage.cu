@@ -40,7 +40,11 @@ constexpr int LROW = 384;                   // longest block(0,0) / block(1,0) r
 constexpr int ASTR = 387;                   // accumulator row stride (387 mod 16 == 3: the three components of one column land in different banks)
 constexpr int L01 = 32;                     // longest block(0,1) row
 constexpr int GACC = 3 * ASTR + 3 * L01 + 7;  // per-warp accumulators (+3 diagonal slots of constrained components), 1264
-constexpr int GWARPS = 8;
+constexpr int GWARPS = 8;                  // warps per CTA of the preconditioner's gather
+constexpr int GSW = 6;                     // warps per CTA of the system gather (each with a ring of staged rows)
+constexpr int GD = 3;                      // depth of that ring: staged rows in flight per warp
+constexpr int GSWARP = GACC + GD * VROW + 4;   // doubles per warp: accumulators, ring, mbarriers
+static_assert(GSWARP % 2 == 0 && GACC % 2 == 0 && VROW % 2 == 0, "16-byte alignment of the ring slots");
 static_assert(GACC % 2 == 0, "accumulator alignment");
 static_assert((REC * 8) % 32 == 0 && (VROW * 8) % 32 == 0 && (PROW * 8) % 32 == 0 && (BW * 8) % 32 == 0, "sector alignment of the staged segments");
 
@@ -53,9 +57,11 @@ static_assert((REC * 8) % 32 == 0 && (VROW * 8) % 32 == 0 && (PROW * 8) % 32 == 
 __constant__ unsigned char c_task_ta[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
 __constant__ unsigned char c_task_tb[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
 
-__global__ void __launch_bounds__(MTHREADS, 4)
-th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, double* __restrict__ stage, long long w_begin, long long w_end,
-                int slot_begin, int ring) {
+// `sched` names the cells of this CTA (cell(k, w, slot): its k-th plan cell and staging slot) and, in the persistent
+// kernel, waits for the slot to be free (wait_slot) and publishes the finished record (signal).
+template <class Sched>
+__device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, const double* __restrict__ dphi_lane, double* __restrict__ stage,
+                                            const Sched sched) {
   extern __shared__ __align__(16) double smem[];
   double* X = smem;                     // KQ * LDB
   double* wq = X + KQ * LDB;            // KQ (+4)
@@ -112,12 +118,14 @@ th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, doub
   };
   const int frow = lane >> 2, fk = lane & 3;
 
-  int buf = 0;
-  if (w_begin + blockIdx.x < w_end) issue_raw(w_begin + blockIdx.x, 0);
+  int buf = 0, k = 0;
+  long long w = 0, w_next = 0;
+  int slot = 0, slot_next = 0;
+  bool have = sched.cell(0, w, slot), have_next = false;
+  if (have) issue_raw(w, 0);
   cp_async_commit();
-  for (long long w = w_begin + blockIdx.x; w < w_end; w += gridDim.x, buf ^= 1) {
-    int slot = slot_begin + (int)(w - w_begin);
-    if (slot >= ring) slot -= ring;
+  for (; have; ++k, buf ^= 1, w = w_next, slot = slot_next, have = have_next) {
+    have_next = sched.cell(k + 1, w_next, slot_next);
     double* S = stage + (size_t)slot * REC;
     sgeo = sgeo2 + buf * (GS + 1);
     snm = snm2 + buf * MSTR;
@@ -125,6 +133,7 @@ th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, doub
     sidt = sidt2 + buf * 28;
     cp_async_wait<0>();
     __syncthreads();   // this cell's raw inputs have landed; every warp is done with the previous cell
+    if (Sched::FUSED && k > 0 && tid == 0) sched.signal(k - 1);   // ... and has fenced its stores of that cell
     if (do_rhs) {
       for (int i = tid; i < 3 * NU; i += nt) {
         const int c = i / NU, n = i - c * NU;
@@ -133,7 +142,7 @@ th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, doub
       for (int i = tid; i < a.ndt; i += nt) cp_async8(sTn + i, a.old_temp + sidt[i]);
     }
     cp_async_commit();
-    if (w + gridDim.x < w_end) issue_raw(w + gridDim.x, buf ^ 1);   // the CTA's next cell, while this one is computed
+    if (have_next) issue_raw(w_next, buf ^ 1);   // the CTA's next cell, while this one is computed
     cp_async_commit();
     const int cflag = snm[35];
     if (tid >= 96 && tid - 96 < NU) {   // warp 3 (the table build below keeps warps 0..3 busy with tid < 108 only partly)
@@ -180,6 +189,7 @@ th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, doub
         for (int d = 0; d < 3; ++d) x[32 * d + j] = kinv[0][d] * r0 + kinv[1][d] * r1 + kinv[2][d] * r2;
       }
     }
+    if (Sched::FUSED && tid == 0) sched.wait_slot(k);   // the gather pass is done with the record this cell overwrites
     cp_async_wait<1>();   // the gathered old solution (the next cell's raw inputs may still be in flight)
     __syncthreads();
 
@@ -411,7 +421,34 @@ th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, doub
         }
       }
     }
+    if (Sched::FUSED) __threadfence();   // staged record visible device-wide before the barrier that precedes signal()
   }
+  if (Sched::FUSED) {
+    __syncthreads();
+    if (tid == 0 && k > 0) sched.signal(k - 1);
+  }
+}
+
+// one launch per chunk: the CTAs stride over the chunk's cells
+struct LaunchSched {
+  static constexpr bool FUSED = false;
+  long long w_begin, w_end;
+  int slot_begin, ring;
+  __device__ __forceinline__ bool cell(int k, long long& w, int& slot) const {
+    w = w_begin + blockIdx.x + (long long)k * gridDim.x;
+    if (w >= w_end) return false;
+    slot = slot_begin + (int)(w - w_begin);
+    if (slot >= ring) slot -= ring;
+    return true;
+  }
+  __device__ __forceinline__ void wait_slot(int) const {}
+  __device__ __forceinline__ void signal(int) const {}
+};
+
+__global__ void __launch_bounds__(MTHREADS, 4)
+th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, double* __restrict__ stage, long long w_begin, long long w_end,
+                int slot_begin, int ring) {
+  stage_cells(a, cs, dphi_lane, stage, LaunchSched{w_begin, w_end, slot_begin, ring});
 }
 
 // reference gradients in the order the table build reads them: [node of the group j][e][thread = 4 q + group]
@@ -554,12 +591,12 @@ constexpr int WB = 32;   // items per block: a warp takes blocks round-robin, so
 // the incidence words of the block are read 32 at a time, one batch ahead; the loads of incidence i + 1 (`load`) and
 // the row starts of item t + 1 (`rows`) are in flight while incidence i / item t are processed (`add`, `flush`).
 // `aux` maps an incidence word to a second index that is fetched together with the words.
-template <class Inc, class AuxF, class RowF, class LoadF, class AddF, class FlushF>
+template <class Inc, int WBT, class AuxF, class RowF, class LoadF, class AddF, class FlushF>
 __device__ __forceinline__ void walk_items(const int* __restrict__ g0s, const unsigned char* __restrict__ flags, const unsigned* __restrict__ incptr,
                                            const unsigned* __restrict__ incs, long long begin, long long end, long long gw, long long nw, int lane,
                                            AuxF aux, RowF rows, LoadF load, AddF add, FlushF flush) {
-  for (long long j_lo = begin + gw * WB; j_lo < end; j_lo += nw * WB) {
-    const int n_it = (int)((j_lo + WB < end ? j_lo + WB : end) - j_lo);
+  for (long long j_lo = begin + gw * WBT; j_lo < end; j_lo += nw * WBT) {
+    const int n_it = (int)((j_lo + WBT < end ? j_lo + WBT : end) - j_lo);
     int h_g0 = 0, h_first = 0;
     unsigned h_iend = 0;
     if (lane < n_it) {
@@ -569,7 +606,7 @@ __device__ __forceinline__ void walk_items(const int* __restrict__ g0s, const un
     }
     const unsigned i_lo = incptr[j_lo], i_hi = __shfl_sync(FULLM, h_iend, n_it - 1);
     unsigned ec = 0, en = 0, ib = i_lo;
-    int ac = -1, an = -1;
+    long long ac = -1, an = -1;
     if (ib + lane < i_hi) { ec = incs[ib + lane]; ac = aux(ec); }
     if (ib + 32 + lane < i_hi) { en = incs[ib + 32 + lane]; an = aux(en); }
     auto rotate = [&]() {
@@ -616,33 +653,181 @@ __device__ __forceinline__ void walk_items(const int* __restrict__ g0s, const un
   }
 }
 
+// ---- TMA bulk copies into a per-warp ring ---------------------------------------------------------------------------
+// A staged velocity-node row is one regular 2 208-byte tile: one elected lane fetches it with cp.async.bulk (SASS UBLKCP),
+// completion is counted on an mbarrier of the slot.  GD rows are in flight per warp while one is added -- the gather is
+// bound by the latency of these loads, not by their bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load_row(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's previous readers (generic proxy) come first
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// velocity items of one chunk through the ring (same item / incidence walk as walk_items)
+template <int WBT>
+__device__ __forceinline__ void gather_system_velocity_bulk(const GatherArgs& g, const BlockView& A, double* acc, double* ring,
+                                                            unsigned long long* bars, long long gw, long long nw, int lane) {
+  double* acc01 = acc + 3 * ASTR;
+  double* accd = acc01 + 3 * L01;
+  const long long* rp00 = A.rowptr[0][0];
+  const long long* rp01 = A.rowptr[0][1];
+  double* v00 = A.val[0][0];
+  double* v01 = A.val[0][1];
+  unsigned phases = 0;   // parity of every slot's next completion
+  for (long long j_lo = g.v_begin + gw * WBT; j_lo < g.v_end; j_lo += nw * WBT) {
+    const int n_it = (int)((j_lo + WBT < g.v_end ? j_lo + WBT : g.v_end) - j_lo);
+    int h_g0 = 0, h_first = 0;
+    unsigned h_iend = 0;
+    if (lane < n_it) {
+      h_g0 = g.v_g0[j_lo + lane];
+      h_first = g.v_flag[j_lo + lane] & 1;
+      h_iend = g.v_incptr[j_lo + lane + 1];
+    }
+    const unsigned i_lo = g.v_incptr[j_lo], i_hi = __shfl_sync(FULLM, h_iend, n_it - 1);
+    unsigned ec = 0, en = 0, ib = i_lo;
+    if (ib + lane < i_hi) ec = g.v_inc[ib + lane];
+    if (ib + 32 + lane < i_hi) en = g.v_inc[ib + 32 + lane];
+    auto word = [&](unsigned i) {
+      const unsigned k = i - ib;
+      return k < 32 ? __shfl_sync(FULLM, ec, (int)k) : __shfl_sync(FULLM, en, (int)(k - 32));
+    };
+    auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : (lane < 8 ? rp01[g0 + lane - 4] : 0ll); };
+    // per-slot metadata (registers; the slot index is a compile-time constant everywhere below)
+    int m_ob[GD], m_mb[GD], m_op[GD], m_a[GD], m_maskA[GD];
+    auto issue = [&](unsigned i, int u, int& ob, int& mb, int& op, int& aa, int& maskA) {
+      const unsigned e = word(i);
+      const int a = e & 31;
+      const unsigned wl = (e & ~INC_CS) >> 5;
+      const size_t w = (size_t)g.w_base + wl;
+      int slot = g.slot_base + (int)wl;
+      if (slot >= g.ring) slot -= g.ring;
+      if (lane == 0) bulk_load_row(ring + u * VROW, g.stage + (size_t)slot * REC + a * VROW, VROW * 8, bars + u);
+      const unsigned short* prow = g.pos + w * PSTR + a * NE;
+      aa = a;
+      ob = lane < NU ? prow[lane] : 0;
+      op = lane < NP ? prow[NU + lane] : 0;
+      if (e & INC_CS) {
+        const unsigned char* mrow = g.nmask + w * MSTR;
+        mb = lane < NU ? mrow[lane] : 0;
+        maskA = mrow[a];
+      } else {
+        mb = 7;
+        maskA = 7;
+      }
+    };
+    long long rnext = rows(__shfl_sync(FULLM, h_g0, 0));
+#pragma unroll
+    for (int u = 0; u < GD; ++u)
+      if (i_lo + u < i_hi) issue(i_lo + u, u, m_ob[u], m_mb[u], m_op[u], m_a[u], m_maskA[u]);
+    unsigned i = i_lo;
+    int t = 0, maskA_item = 7;
+    unsigned it_end = __shfl_sync(FULLM, h_iend, 0);
+    bool first = __shfl_sync(FULLM, h_first, 0) != 0;
+    long long rcur = rnext;
+    if (n_it > 1) rnext = rows(__shfl_sync(FULLM, h_g0, 1));
+    while (i < i_hi) {
+#pragma unroll
+      for (int u = 0; u < GD; ++u) {
+        if (i < i_hi) {
+          mbar_wait(bars + u, (phases >> u) & 1u);
+          phases ^= 1u << u;
+          VInc I;
+          const double* S = ring + u * VROW;
+#pragma unroll
+          for (int r = 0; r < 9; ++r) I.v[r] = lane < NU ? S[r * BW + lane] : 0.0;
+          I.vp = lane < 24 ? S[VPRS + lane] : 0.0;
+          I.ob = m_ob[u];
+          I.mb = m_mb[u];
+          I.op = m_op[u];
+          I.a = m_a[u];
+          I.maskA = m_maskA[u];
+          maskA_item = I.maskA;
+          add_vinc(I, acc, acc01, accd, lane);   // ends with __syncwarp: every lane has read the slot
+          if (i - ib >= 32) {   // keep the word window ahead of the prefetch distance
+            ib += 32;
+            ec = en;
+            en = 0;
+            if (ib + 32 + lane < i_hi) en = g.v_inc[ib + 32 + lane];
+          }
+          if (i + GD < i_hi) issue(i + GD, u, m_ob[u], m_mb[u], m_op[u], m_a[u], m_maskA[u]);
+          ++i;
+          if (i == it_end) {   // the item is complete: write its rows, move to the next item
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
+              const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
+              if ((maskA_item >> c) & 1) {
+                flush_row(v00 + rs, acc + c * ASTR, len, first, lane);
+                flush_row(v01 + rs01, acc01 + c * L01, len01, first, lane);
+              } else if (lane == 0) {
+                double* out = v00 + rs;   // constrained dof: the row holds its diagonal only
+                if (first) {
+                  out[0] = accd[c];
+                  for (int k = 1; k < len; ++k) out[k] = 0.0;
+                  for (int k = 0; k < len01; ++k) v01[rs01 + k] = 0.0;
+                } else
+                  out[0] = __ldcg(out) + accd[c];
+                accd[c] = 0.0;
+              }
+            }
+            __syncwarp();
+            maskA_item = 7;
+            ++t;
+            if (t < n_it) {
+              it_end = __shfl_sync(FULLM, h_iend, t);
+              first = __shfl_sync(FULLM, h_first, t) != 0;
+              rcur = rnext;
+              if (t + 1 < n_it) rnext = rows(__shfl_sync(FULLM, h_g0, t + 1));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 struct PInc {
   double v[3];
   int ob, mb;
 };
 
-__global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g, BlockView A) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = smem + warp * GACC;         // [3][ASTR]
+// the items of one chunk, system matrix: `acc` = this warp's zeroed accumulators [3][ASTR] + [3][L01] + diagonals
+template <int WBT, bool VELOCITY = true>
+__device__ __forceinline__ void gather_system(const GatherArgs& g, const BlockView& A, double* acc, long long gw, long long nw, int lane) {
   double* acc01 = acc + 3 * ASTR;           // [3][L01]
   double* accd = acc01 + 3 * L01;           // [3] constrained diagonals
-  const long long gw = (long long)blockIdx.x * GWARPS + warp, nw = (long long)gridDim.x * GWARPS;
   const long long* rp00 = A.rowptr[0][0];
   const long long* rp01 = A.rowptr[0][1];
   const long long* rp10 = A.rowptr[1][0];
   double* v00 = A.val[0][0];
   double* v01 = A.val[0][1];
   double* v10 = A.val[1][0];
-  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;   // invariant: all accumulators are zero between items
-  __syncwarp();
-  auto no_aux = [](unsigned) { return 0; };
+  auto no_aux = [](unsigned) { return 0ll; };
 
   // velocity nodes: rows (g0 + c) of block(0,0) and block(0,1)
-  {
+  if (VELOCITY) {
     int maskA = 7;
     auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : (lane < 8 ? rp01[g0 + lane - 4] : 0ll); };
-    auto load = [&](VInc& I, unsigned e, int) { load_vinc(I, g, e, lane); };
+    auto load = [&](VInc& I, unsigned e, long long) { load_vinc(I, g, e, lane); };
     auto add = [&](const VInc& I) {
       maskA = I.maskA;
       add_vinc(I, acc, acc01, accd, lane);
@@ -670,13 +855,13 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g,
       maskA = 7;
       __syncwarp();
     };
-    walk_items<VInc>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, no_aux, rows, load, add, flush);
+    walk_items<VInc, WBT>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, no_aux, rows, load, add, flush);
   }
 
   // pressure nodes: row of block(1,0)
   {
     auto rows = [&](int pr) { return lane < 2 ? rp10[pr + lane] : 0ll; };
-    auto load = [&](PInc& I, unsigned e, int) {
+    auto load = [&](PInc& I, unsigned e, long long) {
       const int pn = e & 31;
       const unsigned wl = (e & ~INC_CS) >> 5;
       const size_t w = (size_t)g.w_base + wl;
@@ -713,8 +898,25 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g,
       flush_row(v10 + rs, acc, len, first, lane);
       __syncwarp();
     };
-    walk_items<PInc>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, no_aux, rows, load, add, flush);
+    walk_items<PInc, WBT>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, no_aux, rows, load, add, flush);
   }
+}
+
+__global__ void __launch_bounds__(GSW * 32, 2) th_gather_kernel(GatherArgs g, BlockView A) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* acc = smem + warp * GSWARP;
+  double* ring = acc + GACC;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + GD * VROW);
+  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;   // invariant: all accumulators are zero between items
+  if (lane == 0) {
+    for (int u = 0; u < GD; ++u) mbar_init(bars + u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const long long gw = (long long)blockIdx.x * GSW + warp, nw = (long long)gridDim.x * GSW;
+  gather_system_velocity_bulk<WB>(g, A, acc, ring, bars, gw, nw, lane);
+  gather_system<WB, false>(g, A, acc, gw, nw, lane);
 }
 
 // ---- fused preconditioner: second gather over the same (chunk, node) items ---------------------------------------
@@ -724,7 +926,8 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g,
 // component pairs -- and cells outside that plan are skipped here and added afterwards by the reduction kernels; the
 // first chunk that touches a node stores its whole rows, so those later additions start from a defined state.
 struct PreArgs {
-  const int* pre_w;
+  const long long* pre_w;           // per system-plan cell: low word = index in the preconditioner plan (-1: skipped here),
+                                    // high word = (index of its wide table + 1) << 1 | cell has constrained dofs
   const unsigned short* pos;
   const unsigned char* nmask;
   const unsigned short* pos_wide;
@@ -739,18 +942,13 @@ struct PPInc {
   int o, skip;
 };
 
-__global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArgs g, PreArgs pa, BlockView A) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = smem + warp * GACC;
+template <int WBT>
+__device__ __forceinline__ void gather_pre(const GatherArgs& g, const PreArgs& pa, const BlockView& A, double* acc, long long gw, long long nw, int lane) {
   double* accd = acc + 3 * ASTR + 3 * L01;
-  const long long gw = (long long)blockIdx.x * GWARPS + warp, nw = (long long)gridDim.x * GWARPS;
   const long long* rp00 = A.rowptr[0][0];
   const long long* rp11 = A.rowptr[1][1];
   double* v00 = A.val[0][0];
   double* v11 = A.val[1][1];
-  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;
-  __syncwarp();
   auto aux = [&](unsigned e) { return pa.pre_w[(size_t)g.w_base + ((e & ~INC_CS) >> 5)]; };
   auto slot_of = [&](unsigned e) {
     int slot = g.slot_base + (int)((e & ~INC_CS) >> 5);
@@ -760,7 +958,8 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArg
   {
     int maskA_item = 7;
     auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : 0ll; };
-    auto load = [&](PVInc& I, unsigned e, int wp) {
+    auto load = [&](PVInc& I, unsigned e, long long ax) {
+      const int wp = (int)(ax & 0xffffffffll), hi = (int)(ax >> 32);
       I.skip = wp < 0;
       I.a = e & 31;
       I.v = 0.0;
@@ -768,7 +967,7 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArg
       I.mb = I.maskA = 7;
       if (wp < 0) return;
       const unsigned char* nm = pa.nmask + (size_t)wp * MSTR;
-      const int cflag = nm[35], wide = *reinterpret_cast<const int*>(nm + 36);
+      const int cflag = hi & 1, wide = (hi >> 1) - 1;
       if (lane < NU) {
         I.v = __ldcg(g.stage + (size_t)slot_of(e) * REC + OFF_DG + I.a * BW + lane);
         if (wide >= 0) {
@@ -819,12 +1018,13 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArg
       maskA_item = 7;
       __syncwarp();
     };
-    walk_items<PVInc>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, aux, rows, load, add, flush);
+    walk_items<PVInc, WBT>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, aux, rows, load, add, flush);
   }
   // pressure nodes: rows of block(1,1)
   {
     auto rows = [&](int pr) { return lane < 2 ? rp11[pr + lane] : 0ll; };
-    auto load = [&](PPInc& I, unsigned e, int wp) {
+    auto load = [&](PPInc& I, unsigned e, long long ax) {
+      const int wp = (int)(ax & 0xffffffffll);
       I.skip = wp < 0;
       I.v = 0.0;
       I.o = 0xffff;
@@ -843,7 +1043,130 @@ __global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArg
       flush_row(v11 + rs, acc, len, first, lane);
       __syncwarp();
     };
-    walk_items<PPInc>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, aux, rows, load, add, flush);
+    walk_items<PPInc, WBT>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, aux, rows, load, add, flush);
+  }
+}
+
+__global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArgs g, PreArgs pa, BlockView A) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* acc = smem + warp * GACC;
+  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;
+  __syncwarp();
+  gather_pre<WB>(g, pa, A, acc, (long long)blockIdx.x * GWARPS + warp, (long long)gridDim.x * GWARPS, lane);
+}
+
+// ---- persistent kernel: staging ring in L2 ------------------------------------------------------------------------
+// One cooperative launch for the whole pass.  The first n_stage CTAs stage cells (chunk k = the k-th cell of every
+// stage CTA), the other CTAs gather: chunk by chunk, as soon as all its records are staged.  The ring holds `ring_chunks`
+// chunks (a few tens of MB: it lives in L2, the records never travel to HBM and back); a stage CTA overwrites a slot
+// once every gather warp has finished the chunk that used it.  Gather warps finish chunk c before any of them starts
+// c + 1, so the rows a node shares between chunks are read-modify-written in chunk order without atomics.
+// Dependencies: stage(k) <- gathered(k - ring_chunks) <- staged(k - ring_chunks): no cycle; the launch is cooperative, so
+// all CTAs are resident.  Every wait gives up after about a second and raises the abort flag (d_err[1]) instead of
+// hanging the device.
+struct FusedSync {
+  unsigned* staged;    // [n_chunks] records published
+  unsigned* gdone;     // [n_chunks] gather warps finished
+  int* err;            // d_err: [1] = abort
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned* p, unsigned target, int* err) {
+  for (unsigned it = 0; it < (1u << 23); ++it) {
+    if (ld_acquire_u32(p) >= target) return;
+    if ((it & 1023) == 1023 && *reinterpret_cast<volatile int*>(err + 1) != 0) return;
+    __nanosleep(100);
+  }
+  atomicExch(err + 1, 1);   // give up: the results are invalid, the host reports it (dcp_check_device_errors)
+}
+
+struct FusedSched {
+  static constexpr bool FUSED = true;
+  long long n_cells;
+  int n_stage, ring_chunks, n_gather_warps, rank;
+  FusedSync sy;
+  __device__ __forceinline__ bool cell(int k, long long& w, int& slot) const {
+    w = (long long)k * n_stage + rank;
+    if (w >= n_cells) return false;
+    slot = (k % ring_chunks) * n_stage + rank;
+    return true;
+  }
+  __device__ __forceinline__ void wait_slot(int k) const {
+    if (k >= ring_chunks) spin_until(sy.gdone + (k - ring_chunks), (unsigned)n_gather_warps, sy.err);
+  }
+  __device__ __forceinline__ void signal(int k) const {
+    __threadfence();
+    atomicAdd(sy.staged + k, 1u);
+  }
+};
+
+struct FusedArgs {
+  MmaArgs a;
+  CsView cs;
+  const double* dphi_lane;
+  double* stage;
+  GatherArgs g;            // item arrays, plan, staging (per-chunk fields are set in the kernel)
+  PreArgs pa;
+  const long long* v_chunk_ptr;
+  const long long* p_chunk_ptr;
+  long long n_cells, n_chunks;
+  int n_stage, n_gather_ctas, ring_chunks, fuse_pre;
+  FusedSync sy;
+};
+
+constexpr size_t fused_smem_bytes() {
+  return stage_smem_bytes() > sizeof(double) * GACC * (MTHREADS / 32) ? stage_smem_bytes() : sizeof(double) * GACC * (MTHREADS / 32);
+}
+
+constexpr int WBF = 2;   // items per block in the persistent kernel (a chunk has about 8 items per gather warp)
+
+__global__ void __launch_bounds__(MTHREADS, 4) th_fused_kernel(const __grid_constant__ FusedArgs f, const __grid_constant__ BlockView A,
+                                                               const __grid_constant__ BlockView Apre) {
+  if ((int)blockIdx.x < f.n_stage) {
+    FusedSched sc;
+    sc.n_cells = f.n_cells;
+    sc.n_stage = f.n_stage;
+    sc.ring_chunks = f.ring_chunks;
+    sc.n_gather_warps = f.n_gather_ctas * (MTHREADS / 32);
+    sc.rank = (int)blockIdx.x;
+    sc.sy = f.sy;
+    stage_cells(f.a, f.cs, f.dphi_lane, f.stage, sc);
+    return;
+  }
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* acc = smem + warp * GACC;
+  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;
+  __syncwarp();
+  const long long gw = (long long)((int)blockIdx.x - f.n_stage) * (MTHREADS / 32) + warp, nw = (long long)f.n_gather_ctas * (MTHREADS / 32);
+  GatherArgs g = f.g;
+  g.ring = f.ring_chunks * f.n_stage;
+  for (long long c = 0; c < f.n_chunks; ++c) {
+    const long long w0 = c * f.n_stage;
+    const unsigned cells = (unsigned)(f.n_cells - w0 < f.n_stage ? f.n_cells - w0 : f.n_stage);
+    if (lane == 0) {
+      if (c > 0) spin_until(f.sy.gdone + (c - 1), (unsigned)nw, f.sy.err);   // rows shared with the previous chunk are final
+      spin_until(f.sy.staged + c, cells, f.sy.err);
+    }
+    __syncwarp();
+    g.v_begin = f.v_chunk_ptr[c];
+    g.v_end = f.v_chunk_ptr[c + 1];
+    g.p_begin = f.p_chunk_ptr[c];
+    g.p_end = f.p_chunk_ptr[c + 1];
+    g.w_base = w0;
+    g.slot_base = (int)(c % f.ring_chunks) * f.n_stage;
+    gather_system<WBF>(g, A, acc, gw, nw, lane);
+    if (f.fuse_pre) gather_pre<WBF>(g, f.pa, Apre, acc, gw, nw, lane);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(f.sy.gdone + c, 1u);
+    }
   }
 }
 
@@ -875,6 +1198,9 @@ void dcp_gather_plan_free(GatherPlan* p) {
   cudaFree(p->dphi_lane);
   cudaFree(p->pre_w);
   cudaFree(p->pre_rest);
+  cudaFree(p->d_v_chunk_ptr);
+  cudaFree(p->d_p_chunk_ptr);
+  cudaFree(p->sync);
   delete p;
 }
 
@@ -894,9 +1220,44 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     return mx;
   };
   if (max_len(pat[0][0]) > LROW || max_len(pat[1][0]) > LROW || max_len(pat[0][1]) > L01) return DCP_OK;
+  // Default: one stage + gather launch pair per chunk of DCP_GATHER_CHUNK cells (65 536), staging in HBM.
+  // DCP_STAGED_MODE=persistent: one cooperative launch, chunk = one cell per staging CTA, the ring of `ring_chunks`
+  // chunks stays in L2.  Measured 7x slower than the launch pairs at refine 5 and 6 (the gather needs two thirds of the
+  // SMs at equal occupancy, and blocks of two items expose every load latency); kept as an experiment.
   int64_t chunk = 65536;
-  if (const char* e = std::getenv("DCP_GATHER_CHUNK")) chunk = std::max<int64_t>(1, std::atoll(e));
+  bool fused = false;
+  if (const char* e = std::getenv("DCP_STAGED_MODE")) fused = std::string(e) == "persistent";
+  int n_stage = 0, n_gather_ctas = 0, ring_chunks = 2;
+  if (const char* e = std::getenv("DCP_GATHER_CHUNK")) {
+    chunk = std::max<int64_t>(1, std::atoll(e));
+    fused = false;
+  }
+  if (fused) {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->ctx->device);
+    const size_t smem_f = fused_smem_bytes();
+    const cudaError_t e1 = cudaFuncSetAttribute(th_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+    const cudaError_t e2 = e1 == cudaSuccess ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, th_fused_kernel, MTHREADS, smem_f) : e1;
+    if (!coop || e2 != cudaSuccess || per_sm < 2) {
+      if (std::getenv("DCP_VERBOSE"))
+        std::fprintf(stderr, "[dcp] persistent assembly kernel not used: cooperative launch %d, %s, %d CTAs per SM, %zu B shared memory\n", coop,
+                     cudaGetErrorString(e2), per_sm, smem_f);
+      cudaGetLastError();
+      fused = false;
+    } else {
+      const int total = per_sm * m->ctx->sm_count;
+      double frac = 0.25;   // share of the CTAs that gather
+      if (const char* e = std::getenv("DCP_FUSED_GATHER_FRACTION")) frac = std::min(0.75, std::max(0.05, std::atof(e)));
+      if (const char* e = std::getenv("DCP_FUSED_RING_CHUNKS")) ring_chunks = std::min(8, std::max(2, std::atoi(e)));
+      n_gather_ctas = std::max(1, (int)(total * frac + 0.5));
+      n_stage = total - n_gather_ctas;
+      chunk = n_stage;
+    }
+  }
   chunk = std::min<int64_t>(chunk, n);
+  if (fused && chunk < n_stage) {   // fewer cells than staging CTAs: one chunk
+    n_stage = (int)chunk;
+  }
   if (chunk >= (int64_t(1) << 26)) return DCP_OK;
   const int64_t n_chunks = (n + chunk - 1) / chunk;
   std::vector<int> sys_u(3 * NU), sys_p(NP);
@@ -966,6 +1327,14 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
   G->chunk = chunk;
   G->n_chunks = n_chunks;
   G->n_cells = n;
+  G->fused = fused;
+  G->n_stage = n_stage;
+  G->n_gather_ctas = n_gather_ctas;
+  G->ring_chunks = ring_chunks;
+  if (std::getenv("DCP_VERBOSE"))
+    std::fprintf(stderr, "[dcp] staged assembly: %s, %lld cells in %lld chunks of %lld, %d staging + %d gathering CTAs, ring of %d chunks\n",
+                 fused ? "persistent kernel" : "one launch pair per chunk", (long long)n, (long long)n_chunks, (long long)chunk, n_stage,
+                 n_gather_ctas, ring_chunks);
   dcp_ctx* ctx = m->ctx;
   int rc = DCP_OK;
   for (int pass = 0; pass < 2 && rc == DCP_OK; ++pass) {
@@ -1018,7 +1387,14 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
       if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = DCP_ERR_CUDA;
     }
   }
-  if (rc == DCP_OK && cudaMalloc((void**)&G->staging, sizeof(double) * (size_t)REC * (size_t)chunk) != cudaSuccess) {
+  if (rc == DCP_OK && fused) {
+    rc = upg(ctx, reinterpret_cast<int64_t**>(&G->d_v_chunk_ptr), G->v_chunk_ptr);
+    if (rc == DCP_OK) rc = upg(ctx, reinterpret_cast<int64_t**>(&G->d_p_chunk_ptr), G->p_chunk_ptr);
+    if (rc == DCP_OK && cudaMalloc((void**)&G->sync, sizeof(unsigned) * 2 * (size_t)n_chunks) != cudaSuccess) rc = DCP_ERR_CUDA;
+    cudaStreamSynchronize(ctx->stream);
+  }
+  const size_t staging_cells = fused ? (size_t)ring_chunks * (size_t)n_stage : (size_t)chunk;
+  if (rc == DCP_OK && cudaMalloc((void**)&G->staging, sizeof(double) * (size_t)REC * staging_cells) != cudaSuccess) {
     cudaGetLastError();
     dcp_set_error("gather plan: staging allocation failed");
     rc = DCP_ERR_CUDA;
@@ -1044,10 +1420,14 @@ int dcp_gather_plan_attach_pre(dcp_model* m, const dcp_model_desc* d, GatherPlan
   }
   std::vector<int32_t> of_cell((size_t)d->n_cells, -1);
   for (size_t i = 0; i < pre_plan->h_cells.size(); ++i) of_cell[pre_plan->h_cells[i]] = (int32_t)i;
-  std::vector<int32_t> pre_w(nse_plan->h_cells.size(), -1), rest;
+  std::vector<long long> pre_w(nse_plan->h_cells.size(), -1ll);
+  std::vector<int32_t> rest;
   for (size_t w = 0; w < nse_plan->h_cells.size(); ++w) {
     const int32_t wp = of_cell[nse_plan->h_cells[w]];
-    if (wp >= 0 && pre_plan->h_nnf_idx[wp] < 0) pre_w[w] = wp;
+    if (wp >= 0 && pre_plan->h_nnf_idx[wp] < 0) {
+      const long long hi = ((long long)(pre_plan->h_wide_idx[wp] + 1) << 1) | (pre_plan->h_cflag[wp] ? 1 : 0);
+      pre_w[w] = (hi << 32) | (unsigned)wp;
+    }
   }
   for (size_t i = 0; i < pre_plan->h_cells.size(); ++i)
     if (pre_plan->h_nnf_idx[i] >= 0) rest.push_back((int32_t)i);
@@ -1087,14 +1467,16 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   a.rhs = m->nse_rhs;
   a.n_u = m->nse.start[1];
   a.prm = p;
-  const size_t smem_s = stage_smem_bytes(), smem_g = sizeof(double) * GACC * GWARPS;
+  const size_t smem_s = stage_smem_bytes(), smem_g = sizeof(double) * GACC * GWARPS, smem_gs = sizeof(double) * GSWARP * GSW;
   DCP_CUDA(cudaFuncSetAttribute(th_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-  DCP_CUDA(cudaFuncSetAttribute(th_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  int per_sm_s = 1, per_sm_g = 1;
+  DCP_CUDA(cudaFuncSetAttribute(th_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gs));
+  int per_sm_s = 1, per_sm_g = 1, per_sm_p = 1;
   DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, th_stage_kernel, MTHREADS, smem_s));
-  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_kernel, GWARPS * 32, smem_g));
+  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_kernel, GSW * 32, smem_gs));
+  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, th_pre_gather_kernel, GWARPS * 32, smem_g));
   per_sm_s = std::max(per_sm_s, 1);
   per_sm_g = std::max(per_sm_g, 1);
+  per_sm_p = std::max(per_sm_p, 1);
   GatherArgs g;
   g.v_g0 = G->v_g0;
   g.v_incptr = G->v_incptr;
@@ -1111,6 +1493,52 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   const BlockView A = make_view(m->nse);
   const CsView cs = make_view(m->nse_cs);
   const bool fuse_pre = G->has_pre && m->masked_pre;
+  if (G->fused) {
+    FusedArgs f{};
+    f.a = a;
+    f.cs = cs;
+    f.dphi_lane = G->dphi_lane;
+    f.stage = G->staging;
+    f.g = g;
+    f.g.w_base = 0;
+    f.g.slot_base = 0;
+    f.g.v_begin = f.g.v_end = f.g.p_begin = f.g.p_end = 0;
+    if (fuse_pre) {
+      f.pa.pre_w = G->pre_w;
+      f.pa.pos = m->masked_pre->pos;
+      f.pa.nmask = m->masked_pre->nmask;
+      f.pa.pos_wide = m->masked_pre->pos_wide;
+    }
+    f.v_chunk_ptr = G->d_v_chunk_ptr;
+    f.p_chunk_ptr = G->d_p_chunk_ptr;
+    f.n_cells = plan->n;
+    f.n_chunks = G->n_chunks;
+    f.n_stage = G->n_stage;
+    f.n_gather_ctas = G->n_gather_ctas;
+    f.ring_chunks = G->ring_chunks;
+    f.fuse_pre = fuse_pre ? 1 : 0;
+    f.sy.staged = G->sync;
+    f.sy.gdone = G->sync + G->n_chunks;
+    f.sy.err = ctx->d_err;
+    BlockView Av = A, Apv = make_view(m->pre);
+    DCP_CUDA(cudaMemsetAsync(G->sync, 0, sizeof(unsigned) * 2 * (size_t)G->n_chunks, ctx->stream));
+    const size_t smem_f = fused_smem_bytes();
+    DCP_CUDA(cudaFuncSetAttribute(th_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+    void* params[] = {(void*)&f, (void*)&Av, (void*)&Apv};
+    DCP_CUDA(cudaLaunchCooperativeKernel((const void*)th_fused_kernel, dim3((unsigned)(G->n_stage + G->n_gather_ctas)), dim3(MTHREADS), params,
+                                         smem_f, ctx->stream));
+    ctx->launches++;
+    if (fuse_pre) {
+      if (G->n_pre_rest > 0) DCP_TRY(dcp_launch_th_mma(m, p, false, m->masked_pre, nullptr, nullptr, G->pre_rest, G->n_pre_rest));
+      if (m->masked_pre->n_other > 0)
+        DCP_TRY(dcp_launch_th_cells(m, p, false, nullptr, nullptr, m->masked_pre->other_cells, m->masked_pre->n_other, false));
+      m->pre_fused_valid = true;
+      m->pre_fused_dt = p.dt;
+      m->pre_fused_inv_re = p.inv_re;
+    }
+    DCP_CUDA(cudaGetLastError());
+    return DCP_OK;
+  }
   PreArgs pa{};
   BlockView Apre = make_view(m->pre);
   if (fuse_pre) {
@@ -1131,9 +1559,11 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
     g.w_base = w0;
     g.slot_base = 0;
     const long long items = (g.v_end - g.v_begin) + (g.p_end - g.p_begin);
-    grid = std::min<long long>((long long)ctx->sm_count * per_sm_g, (items + GWARPS - 1) / GWARPS);
-    if (grid > 0) th_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, ctx->stream>>>(g, A);
+    const long long blocks = (items + WB - 1) / WB;   // a warp takes blocks of WB items
+    grid = std::min<long long>((long long)ctx->sm_count * per_sm_g, (blocks + GSW - 1) / GSW);
+    if (grid > 0) th_gather_kernel<<<(unsigned)grid, GSW * 32, smem_gs, ctx->stream>>>(g, A);
     ctx->launches += 2;
+    grid = std::min<long long>((long long)ctx->sm_count * per_sm_p, (blocks + GWARPS - 1) / GWARPS);
     if (fuse_pre && grid > 0) {
       th_pre_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, ctx->stream>>>(g, pa, Apre);
       ctx->launches++;

@@ -131,10 +131,15 @@ struct GatherPlan {
   // fused preconditioner (the system pass also stages m + nu k and the pressure mass block; a second gather writes
   // nse_preconditioner_matrix): index of every system-plan cell in the preconditioner plan (-1: the cell is assembled by
   // the reduction kernels afterwards), and those cells as a list of preconditioner-plan indices
-  int32_t* pre_w = nullptr;
+  long long* pre_w = nullptr;
   int32_t* pre_rest = nullptr;
   int64_t n_pre_rest = 0;
   bool has_pre = false;
+  // persistent kernel (staging ring in L2): chunk == n_stage cells, one per staging CTA
+  bool fused = false;
+  int n_stage = 0, n_gather_ctas = 0, ring_chunks = 0;
+  long long *d_v_chunk_ptr = nullptr, *d_p_chunk_ptr = nullptr;
+  unsigned* sync = nullptr;                            // [2][n_chunks]: records staged, gather warps done
 };
 
 // masked position tables for the DMMA path (assemble_th_mma.cu): every node-blocked cell, constrained or not
@@ -147,7 +152,8 @@ struct MaskedPlan {
   uint16_t* pos_wide = nullptr;    // [n_wide][3][27][27]
   uint16_t* pos9 = nullptr;        // [n_nnf][9][27][27]: preconditioner cells with no-normal-flux lines
   GatherPlan* gather = nullptr;    // write-once path (system matrix, n_other == 0)
-  std::vector<int32_t> h_cells, h_nnf_idx;   // host copies: plan order, 9-table index per plan cell
+  std::vector<int32_t> h_cells, h_nnf_idx, h_wide_idx;   // host copies: plan order, 9-table / wide-table index per plan cell
+  std::vector<uint8_t> h_cflag;                          // the plan cell holds constrained velocity dofs
 };
 
 struct dcp_model {
@@ -165,6 +171,8 @@ struct dcp_model {
   int32_t* temp_bc_cells = nullptr;  // those cells
   int64_t n_temp_bc_cells = 0;
   uint16_t* temp_pos = nullptr;  // [n_cells][nd*nd] scatter positions of the temperature matrices (0xffff row: general)
+  int32_t *temp_fast_cells = nullptr, *temp_general_cells = nullptr;   // cells with / without a position row
+  int64_t n_temp_fast = 0, n_temp_general = 0;
   int32_t *nse_local_field = nullptr, *nse_local_base = nullptr;
   std::vector<int32_t> h_local_field, h_local_base;
   DevCs nse_cs, temp_cs;

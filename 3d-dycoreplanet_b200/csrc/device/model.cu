@@ -34,6 +34,12 @@ int dcp_check_device_errors(dcp_ctx* ctx, const char* what) {
     dcp_set_error(std::string(what) + ": " + std::to_string(n) + " scatter targets are not in the sparsity pattern");
     return DCP_ERR_PATTERN;
   }
+  if (ctx->h_err[1] != 0) {
+    cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
+    dcp_set_error(std::string(what) + ": the persistent assembly kernel gave up waiting for a staging-ring dependency; the matrices of that "
+                  "pass are invalid (DCP_STAGED_MODE=persistent is an experiment; unset it to use the per-chunk launches)");
+    return DCP_ERR_STATE;
+  }
   return DCP_OK;
 }
 
@@ -314,6 +320,8 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->nse_l2g);
   cudaFree(m->temp_l2g);
   cudaFree(m->temp_pos);
+  cudaFree(m->temp_fast_cells);
+  cudaFree(m->temp_general_cells);
   cudaFree(m->temp_bc_flag);
   cudaFree(m->temp_bc_cells);
   cudaFree(m->vel_dof);
@@ -586,6 +594,16 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
       }
     }
     M_TRY(dcp_upload(ctx, &m->temp_pos, tp.data(), (int64_t)tp.size()));
+    // the two classes as lists (Q2 temperature in 3-D: tensor-core kernel on the first, general kernel on the second)
+    {
+      std::vector<int32_t> fast, general;
+      for (int64_t c = 0; c < nc; ++c) (tp[(size_t)c * nd * nd] != 0xffff ? fast : general).push_back((int32_t)c);
+      m->n_temp_fast = (int64_t)fast.size();
+      m->n_temp_general = (int64_t)general.size();
+      if (!fast.empty()) M_TRY(dcp_upload(ctx, &m->temp_fast_cells, fast.data(), (int64_t)fast.size()));
+      if (!general.empty()) M_TRY(dcp_upload(ctx, &m->temp_general_cells, general.data(), (int64_t)general.size()));
+      DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     // cells whose right-hand side needs matrix_for_bc: an inhomogeneously constrained temperature dof
     std::vector<uint8_t> flag((size_t)std::max<int64_t>(nc, 1), 0);
     std::vector<int32_t> bc_cells;

@@ -7,7 +7,7 @@ NVFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xco
 CU_SRCS := $(wildcard $(PKG)/csrc/device/*.cu)
 CU_HDRS := $(wildcard $(PKG)/csrc/device/*.cuh) $(wildcard $(PKG)/csrc/device/*.h) include/dcp.h
 
-all: lib/libdcp_harness.so oracle lib/libdcp.so tests/cpp/host_mirror_test
+all: lib/libdcp_harness.so oracle lib/libdcp.so tests/cpp/host_mirror_test tests/cpp/halo_test
 
 lib/libdcp_harness.so: $(wildcard $(PKG)/csrc/harness/*.hpp) $(PKG)/csrc/harness/harness_api.cpp include/dcp_harness.h
 	mkdir -p lib
@@ -32,6 +32,10 @@ tests/cpp/host_mirror_test: tests/cpp/host_mirror_test.cpp include/dcp.hpp inclu
 	$(CXX) -std=c++17 -O2 -Wall -Wextra -I include -o $@ tests/cpp/host_mirror_test.cpp -L lib -ldcp -ldcp_harness -L oracle/_build -loracle \
 	  -Wl,-rpath,'$$ORIGIN/../../lib' -Wl,-rpath,'$$ORIGIN/../../oracle/_build'
 
+# two ranks through the multi-GPU part of the ABI (needs two GPUs to run)
+tests/cpp/halo_test: tests/cpp/halo_test.cpp include/dcp.h lib/libdcp.so
+	$(CXX) -std=c++17 -O2 -Wall -Wextra -I include -o $@ tests/cpp/halo_test.cpp -L lib -ldcp -Wl,-rpath,'$$ORIGIN/../../lib'
+
 clean:
-	rm -rf lib build oracle/_build tests/cpp/host_mirror_test
+	rm -rf lib build oracle/_build tests/cpp/host_mirror_test tests/cpp/halo_test
 .PHONY: all oracle clean

@@ -96,17 +96,21 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def algorithmic_bytes(P, T_deg_rule_shared=True):
-    """Per-kernel algorithmic bytes (DESIGN.md 'roofline accounting')."""
+def algorithmic_bytes(P, T_deg_rule_shared=True, nb=2):
+    """Per-kernel algorithmic bytes (DESIGN.md 'roofline accounting').  nb = 3: FEEC family (the mapping
+    record carries J, J^-1, det J and x_q: 23 doubles per point; the preconditioner runs on its own 8-point rule)."""
     nc, nq, dim = P.n_cells, P.scalar("q_nse.nq"), P.dim
     nqt = P.scalar("q_temp.nq")
     nd, ndt = P.scalar("nse.n_local"), P.scalar("temp.n_local")
     n_nse, n_t = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
     geom_n = nc * nq * (1 + dim * dim + dim) * 8
     geom_n_noxq = nc * nq * (1 + dim * dim) * 8
+    if nb == 3:
+        geom_n = nc * nq * 23 * 8
+        geom_n_noxq = nc * 8 * 23 * 8
     geom_t = nc * nqt * (1 + dim * dim) * 8
-    nnz_nse = sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(2) for j in range(2))
-    nnz_pre = sum(P.scalar(f"pre.b{i}{j}.nnz") for i in range(2) for j in range(2))
+    nnz_nse = sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(nb) for j in range(nb))
+    nnz_pre = sum(P.scalar(f"pre.b{i}{j}.nnz") for i in range(nb) for j in range(nb))
     nnz_t = P.scalar("temp.pat.nnz")
     out = {
         "nse_system": geom_n + nc * nd * 4 + nc * ndt * 4 + n_nse * 8 + n_t * 8 + nnz_nse * 8 + n_nse * 8,
@@ -115,26 +119,37 @@ def algorithmic_bytes(P, T_deg_rule_shared=True):
         "temperature_rhs": geom_t + nc * ndt * 4 + nc * nd * 4 + n_nse * 8 + n_t * 8 + 3 * nnz_t * 8 + n_t * 8,
     }
     spmv = 0
-    for i in range(2):
-        for j in range(2):
+    for i in range(nb):
+        first = True
+        for j in range(nb):
             z = P.scalar(f"nse.b{i}{j}.nnz")
             if z:
                 spmv += z * 12 + P.scalar(f"nse.b{i}{j}.n_rows") * 16 + P.scalar(f"nse.b{i}{j}.n_cols") * 8
-    spmv += P.scalar("nse.b00.n_rows") * 8  # block(0,1) is applied as vmult_add on the velocity rows
+                if not first:
+                    spmv += P.scalar(f"nse.b{i}{j}.n_rows") * 8   # further blocks of a block row are applied as vmult_add
+                first = False
     out["spmv_nse"] = spmv
     out["spmv_temperature"] = nnz_t * 12 + n_t * 16 + n_t * 8
     return out
 
 
-def cpu_leg(refine, temperature_degree, steps, warmup, mp):
+def cpu_leg(refine, temperature_degree, steps, warmup, mp, family="classic"):
     """The restated CPU path (oracle, OpenMP over cells with atomic adds) on the host cores."""
     import dycore_b200  # noqa: F401
     from dycore_b200 import harness
     from oracle import oracle as orc
-    from util import synthetic_fields
-    P = harness.Problem(geometry="shell", refine=refine, temperature_degree=temperature_degree,
-                        threads=os.cpu_count() or 1)
-    u, T = synthetic_fields(P)
+    feec = family == "feec"
+    if feec:
+        P = harness.Problem(geometry="shell", refine=refine, family="feec", threads=os.cpu_count() or 1)
+    else:
+        P = harness.Problem(geometry="shell", refine=refine, temperature_degree=temperature_degree,
+                            threads=os.cpu_count() or 1)
+    u = 0.1 * key_field(P["nse.dof_key"], 1.0)
+    T = 2.0 + 0.2 * key_field(P["temp.dof_key"], 2.0)
+    asm_sys = orc.feec_assemble_nse_system if feec else orc.assemble_nse_system
+    asm_pre = orc.feec_assemble_nse_preconditioner if feec else orc.assemble_nse_preconditioner
+    asm_tm = orc.feec_assemble_temperature_matrix if feec else orc.assemble_temperature_matrix
+    asm_tr = orc.feec_assemble_temperature_rhs if feec else orc.assemble_temperature_rhs
     prm = orc.params_from(mp)
     n_dofs = P.scalar("nse.n_dofs") + P.scalar("temp.n_dofs")
     rp, col, _, _ = P.csr("nse.full")
@@ -144,11 +159,11 @@ def cpu_leg(refine, temperature_degree, steps, warmup, mp):
     times, t_spmv = [], []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        vals, _ = orc.assemble_nse_system(P, prm, u, T, use_omp=True)
-        orc.assemble_nse_preconditioner(P, prm, use_omp=True)
-        m, k = orc.assemble_temperature_matrix(P, prm, use_omp=True)
+        vals, _ = asm_sys(P, prm, u, T, use_omp=True)
+        asm_pre(P, prm, use_omp=True)
+        m, k = asm_tm(P, prm, use_omp=True)
         tm = orc.temperature_matrix_combine(m, k, mp.time_step / mp.NSE_solver_interval)
-        orc.assemble_temperature_rhs(P, prm, T, u, use_omp=True)
+        asm_tr(P, prm, T, u, use_omp=True)
         t1 = time.perf_counter()
         orc.spmv(rp, col, vals, x, use_omp=True)
         orc.spmv(rpt, colt, tm, xt, use_omp=True)
@@ -156,10 +171,10 @@ def cpu_leg(refine, temperature_degree, steps, warmup, mp):
         if it >= warmup:
             times.append(t2 - t0)
             t_spmv.append(t2 - t1)
-    ab = algorithmic_bytes(P)
+    ab = algorithmic_bytes(P, nb=3 if feec else 2)
     dt = float(np.mean(times))
     return {"value": n_dofs / dt, "unit": "DoFs/s", "cores": orc.max_threads(), "kind": "port",
-            "sample": f"hypershell classic refine={refine} ({P.n_cells} cells, {n_dofs} DoFs), {steps} step(s) "
+            "sample": f"hypershell {family} refine={refine} ({P.n_cells} cells, {n_dofs} DoFs), {steps} step(s) "
                       f"after {warmup} warm-up; restated CPU path (oracle), OpenMP, not the deal.II/Trilinos MPI binary",
             "ms_per_step": dt * 1e3,
             "spmv_gbs": (ab["spmv_nse"] + ab["spmv_temperature"]) / float(np.mean(t_spmv)) / 1e9}, n_dofs, dt
@@ -191,6 +206,9 @@ def main():
     ap.add_argument("--temperature-degree", type=int, default=0,
                     help="0 = 1 on one GPU (41.2 M DoFs at refine 6, the largest that fits 180 GB) and 2 on several "
                          "(52.3 M DoFs at refine 6: the >= 50 M-DoF point of the 6-tree shell)")
+    ap.add_argument("--family", default="classic", choices=["classic", "feec"],
+                    help="classic = Taylor-Hood Q2/Q1 (the headline metric); feec = the FEEC element family of "
+                         "aqua_planet_shell_test_3d-feec.prm on the same shell (Nedelec/Raviart-Thomas/DG0, 19 dofs per cell)")
     ap.add_argument("--strategy", default="auto", choices=["auto", "search", "positions", "owner", "staged"])
     ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the CPU sample (4: ~3 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,11 +234,14 @@ def main():
             return
         warm = min(args.warmup, 1)
         steps = min(args.steps, 3)
-        base, n_dofs, dt = cpu_leg(args.cpu_refine, args.temperature_degree, steps, warm, mp)
+        if args.family == "feec":
+            mp = params.NAMED["shell_3d_feec"]
+        base, n_dofs, dt = cpu_leg(args.cpu_refine, max(args.temperature_degree, 1), steps, warm, mp, args.family)
         line = {"impl": "reference", "metric": "dofs_assembled_per_s", "value": base["value"], "unit": "DoFs/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "hypershell classic (Taylor-Hood Q2/Q1 + Q1 temperature): full Boussinesq "
+                "config": {"workload": ("hypershell FEEC (Nedelec/Raviart-Thomas/DG0 + Q1 temperature)" if args.family == "feec" else
+                                        "hypershell classic (Taylor-Hood Q2/Q1 + Q1 temperature)") + ": full Boussinesq "
                                        "assembly pass + nse_matrix/temperature_matrix SpMV",
                            "note": "bounded sample: " + base["sample"]},
                 "cpu_baseline": base,
@@ -250,8 +271,14 @@ def main():
         shared = world == 1 or args.scaling == "strong"
         refine = 6 if (shared and host_gb >= 150 and dev_gb * world >= 170) else 5
     t_setup = time.perf_counter()
+    feec = args.family == "feec"
+    nb = 3 if feec else 2
+    if feec:
+        mp = params.NAMED["shell_3d_feec"]
     spec = dict(geometry="shell", refine=refine, temperature_degree=args.temperature_degree, geometry_data=0,
                 threads=max(1, (os.cpu_count() or 1) // world))  # torchrun pins OMP_NUM_THREADS=1
+    if feec:
+        spec.update(family="feec", temperature_degree=1)
     if world > 1:
         spec.update(n_ranks=world, rank=rank)
         if args.scaling == "weak":
@@ -261,9 +288,11 @@ def main():
     u = 0.1 * key_field(P["nse.dof_key"], 1.0)
     T = 2.0 + 0.2 * key_field(P["temp.dof_key"], 2.0)
     n_nse, n_t = P.scalar("nse.n_dofs"), P.scalar("temp.n_dofs")
-    n_u = P.scalar("nse.n_u")
-    owned = [P.scalar("nse.n_u_owned"), P.scalar("nse.n_p_owned")]
-    n_dofs = owned[0] + owned[1] + P.scalar("temp.n_owned")
+    block_names = ("n_w", "n_u", "n_p") if feec else ("n_u", "n_p")
+    block_sizes = [P.scalar("nse." + b) for b in block_names]
+    owned = [P.scalar("nse." + b + "_owned") for b in block_names]
+    n_u = block_sizes[0]   # first block (classic: velocity)
+    n_dofs = sum(owned) + P.scalar("temp.n_owned")
     ctx = device.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
@@ -412,7 +441,7 @@ def main():
     # (M2) the operators the Krylov solves apply one by one: block(0,0), block(0,1), block(1,0) of nse_matrix and
     # temperature_matrix, each timed alone (single rank only: block products need no extra exchange pattern here)
     spmv_blocks = {}
-    if world == 1:
+    if world == 1 and not feec:
         n_p = n_nse - n_u
         views = {"b00": (d_y[:n_u], d_x[:n_u]), "b01": (d_y[:n_u], d_x[n_u:]), "b10": (d_y[n_u:], d_x[:n_u])}
         reps = 5
@@ -443,7 +472,10 @@ def main():
         return float(np.sqrt(sum(float(torch.dot(t[b:e], t[b:e])) for b, e in ranges)))
     with torch.cuda.stream(stream):
         step_device()
-        nse_ranges = [(0, owned[0]), (n_u, n_u + owned[1])]
+        nse_ranges, off = [], 0
+        for bsz, own in zip(block_sizes, owned):
+            nse_ranges.append((off, off + own))
+            off += bsz
         t_ranges = [(0, P.scalar("temp.n_owned"))]
         d_rhs = torch.from_numpy(model.nse_rhs).cuda()
         d_trhs = torch.from_numpy(model.temperature_rhs).cuda()
@@ -456,9 +488,15 @@ def main():
         dist.all_reduce(t)
         total_dofs = int(t.item())
     if rank == 0:
-        ab = algorithmic_bytes(P)
+        ab = algorithmic_bytes(P, nb=nb)
         peak, peak_src = peaks()
         ms_step = ms / args.steps
+        # staged strategy: the system pass also writes the preconditioner matrix (its second gather), the preconditioner
+        # call only refreshes the Jacobi diagonals -- the roofline of the fused pass counts both matrices' bytes
+        fused = strategy == "staged" and phase_ms["nse_preconditioner"] < 0.05 * phase_ms["nse_system"]
+        if fused:
+            ab["nse_system"] += ab["nse_preconditioner"]
+            ab["nse_preconditioner"] = sum(P.scalar(f"pre.b{i}{i}.nnz") * 8 + P.scalar(f"pre.b{i}{i}.n_rows") * 12 for i in range(nb))
         dom = max(("nse_system", "nse_preconditioner"), key=lambda k: phase_ms[k])
         ach = ab[dom] / (phase_ms[dom] * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic(strategy, refine) if (world == 1 and dom == "nse_system") else (None, None)
@@ -468,12 +506,14 @@ def main():
             "metric": "dofs_assembled_per_s", "value": total_dofs / (ms_step * 1e-3), "unit": "DoFs/s",
             "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"hypershell classic refine={refine} (Taylor-Hood Q2/Q1 + Q{args.temperature_degree} "
-                                   f"temperature): full Boussinesq assembly pass + nse_matrix/temperature_matrix SpMV",
+            "config": {"workload": (f"hypershell FEEC refine={refine} (Nedelec/Raviart-Thomas/DG0 + Q1 temperature, "
+                                    "aqua_planet_shell_test_3d-feec.prm)" if feec else
+                                    f"hypershell classic refine={refine} (Taylor-Hood Q2/Q1 + Q{args.temperature_degree} temperature)")
+                                   + ": full Boussinesq assembly pass + nse_matrix/temperature_matrix SpMV",
                        "cells_per_gpu": P.scalar("n_owned_cells"), "dofs_per_gpu": n_dofs, "total_dofs": total_dofs,
                        "ghost_cells_rank0": P.n_cells - P.scalar("n_owned_cells"),
-                       "nnz_nse": sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(2) for j in range(2)),
-                       "strategy": strategy, "l2": "inputs larger than L2" if ab["nse_system"] > 4 * 126e6 else "inputs fit L2",
+                       "nnz_nse": sum(P.scalar(f"nse.b{i}{j}.nnz") for i in range(nb) for j in range(nb)),
+                       "strategy": strategy, "fused_preconditioner": bool(fused), "l2": "inputs larger than L2" if ab["nse_system"] > 4 * 126e6 else "inputs fit L2",
                        "partition": ((f"shell with {world}x radial layers" if args.scaling == "weak" else "the same shell")
                                      + f" cut into {world} contiguous (tree, Morton) chunks, one ghost-cell layer, "
                                      "ghost-dof halo over NCCL p2p") if world > 1 else "single GPU",
@@ -487,11 +527,12 @@ def main():
             "spmv_blocks": spmv_blocks,
             # FP64 roofline of the local-matrix contraction (0.60 MFLOP/cell, unsymmetrised structure-
             # exploiting count) against the DMMA peak measured by benchmarks/fp64_peaks.cu on this pool
-            "fp64_roofline": {"kernel": "nse_system", "flop_per_cell": 0.60e6, "peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+            "fp64_roofline": None if feec else
+                             {"kernel": "nse_system", "flop_per_cell": 0.60e6, "peak_tflops": FP64_DMMA_PEAK_TFLOPS,
                               "achieved_tflops": 0.60e6 * P.n_cells / (phase_ms["nse_system"] * 1e-3) / 1e12,
                               "frac": 0.60e6 * P.n_cells / (phase_ms["nse_system"] * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
                               "peak_source": "profiles/r01_fp64_peaks.json (mma.sync m8n8k4 f64, measured)"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom + (" (+ nse_preconditioner, fused pass)" if fused and dom == "nse_system" else ""), "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak,
                          "traffic": traffic,
                          "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the NSE system pass (all its launches "
@@ -506,7 +547,7 @@ def main():
             "parity_checksum": checksum,
         }
         if not args.no_cpu_baseline and world == 1:
-            base, _, _ = cpu_leg(args.cpu_refine, args.temperature_degree, 3, 1, mp)
+            base, _, _ = cpu_leg(args.cpu_refine, args.temperature_degree, 3, 1, mp, args.family)
             line["cpu_baseline"] = base
         emit(line)
     model.close()

@@ -19,3 +19,15 @@ def test_two_gpus_partitioned_assembly_and_halo_spmv(family):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, DCP_CHECK_FAMILY=family))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "-> OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_two_ranks_through_the_c_abi():
+    """tests/cpp/halo_test.cpp: communicator, ghost exchange, all-reduced dot and max through include/dcp.h only."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = os.path.join(ROOT, "tests", "cpp", "halo_test")
+    assert os.path.exists(exe), "tests/cpp/halo_test is not built (make)"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "halo_test: OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
