@@ -486,10 +486,14 @@ struct GatherArgs {
 constexpr unsigned INC_CS = 0x80000000u;     // incidence word: the cell holds constrained velocity dofs
 
 // what one incidence (cell of the chunk, local node) contributes to a velocity node: loaded one incidence ahead
+// (positions and masks keep their 16- / 8-bit types until they are used: a widening right after the load would make the
+// prefetch wait for it)
 struct VInc {
   double v[9];   // lane = column node b: staged [r][b]
   double vp;     // lanes < 24: staged [c][p]
-  int ob, mb, op, a, maskA;
+  unsigned short ob, op;
+  unsigned char mb, maskA;
+  int a;
 };
 
 __device__ __forceinline__ void load_vinc(VInc& I, const GatherArgs& g, unsigned e, int lane) {
@@ -501,15 +505,17 @@ __device__ __forceinline__ void load_vinc(VInc& I, const GatherArgs& g, unsigned
   const unsigned short* prow = g.pos + w * PSTR + a * NE;
   const double* S = g.stage + (size_t)slot * REC + a * VROW;
   I.a = a;
-  I.ob = lane < NU ? prow[lane] : 0;
-  I.op = lane < NP ? prow[NU + lane] : 0;
+  I.ob = 0;
+  I.op = 0;
+  if (lane < NU) I.ob = prow[lane];
+  if (lane < NP) I.op = prow[NU + lane];
+  I.mb = 7;
+  I.maskA = 7;
   if (e & INC_CS) {
     const unsigned char* mrow = g.nmask + w * MSTR;
-    I.mb = lane < NU ? mrow[lane] : 0;
+    I.mb = 0;
+    if (lane < NU) I.mb = mrow[lane];
     I.maskA = mrow[a];
-  } else {
-    I.mb = 7;
-    I.maskA = 7;
   }
 #pragma unroll
   for (int r = 0; r < 9; ++r) I.v[r] = lane < NU ? __ldcg(S + r * BW + lane) : 0.0;
@@ -518,15 +524,16 @@ __device__ __forceinline__ void load_vinc(VInc& I, const GatherArgs& g, unsigned
 
 // add one incidence into the warp's accumulators (the nine targets of a lane are distinct: load all, then store all)
 __device__ __forceinline__ void add_vinc(const VInc& I, double* acc, double* acc01, double* accd, int lane) {
-  if (I.maskA == 7 && __all_sync(0xffffffffu, lane >= NU || I.mb == 7)) {
+  const int ob = I.ob, mb = I.mb;
+  if (I.maskA == 7 && __all_sync(0xffffffffu, lane >= NU || mb == 7)) {
     if (lane < NU) {
       double tv[9];
 #pragma unroll
-      for (int r = 0; r < 9; ++r) tv[r] = acc[(r / 3) * ASTR + I.ob + (r % 3)];
+      for (int r = 0; r < 9; ++r) tv[r] = acc[(r / 3) * ASTR + ob + (r % 3)];
 #pragma unroll
-      for (int r = 0; r < 9; ++r) acc[(r / 3) * ASTR + I.ob + (r % 3)] = tv[r] + I.v[r];
+      for (int r = 0; r < 9; ++r) acc[(r / 3) * ASTR + ob + (r % 3)] = tv[r] + I.v[r];
     }
-    const int o = __shfl_sync(0xffffffffu, I.op, lane & 7);
+    const int o = __shfl_sync(0xffffffffu, (int)I.op, lane & 7);
     if (lane < 24) acc01[(lane >> 3) * L01 + o] += I.vp;
   } else {
     const int maskA = I.maskA;
@@ -536,8 +543,8 @@ __device__ __forceinline__ void add_vinc(const VInc& I, double* acc, double* acc
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int c = r / 3, d = r - 3 * c;
-        const bool on = ((maskA >> c) & 1) && ((I.mb >> d) & 1);
-        idx[r] = on ? c * ASTR + I.ob + __popc(I.mb & ((1 << d) - 1)) : -1;
+        const bool on = ((maskA >> c) & 1) && ((mb >> d) & 1);
+        idx[r] = on ? c * ASTR + ob + __popc(mb & ((1 << d) - 1)) : -1;
       }
 #pragma unroll
       for (int r = 0; r < 9; ++r) tv[r] = idx[r] >= 0 ? acc[idx[r]] : 0.0;
@@ -551,7 +558,7 @@ __device__ __forceinline__ void add_vinc(const VInc& I, double* acc, double* acc
       }
     }
     const int c = lane >> 3;
-    const int o = __shfl_sync(0xffffffffu, I.op, lane & 7);
+    const int o = __shfl_sync(0xffffffffu, (int)I.op, lane & 7);
     if (lane < 24 && ((maskA >> c) & 1)) acc01[c * L01 + o] += I.vp;
   }
   __syncwarp();
@@ -653,6 +660,10 @@ __device__ __forceinline__ void walk_items(const int* __restrict__ g0s, const un
   }
 }
 
+// (A register ring with 3-4 incidences in flight per warp was measured slower than the two-buffer walk above: 1.5 ms
+// against 1.16 ms per 65 536 cells for the preconditioner's gather -- these passes are bound by the DRAM efficiency of
+// their 2 kB-granular accesses, not by the depth of the prefetch.)
+
 // ---- TMA bulk copies into a per-warp ring ---------------------------------------------------------------------------
 // A staged velocity-node row is one regular 2 208-byte tile: one elected lane fetches it with cp.async.bulk (SASS UBLKCP),
 // completion is counted on an mbarrier of the slot.  GD rows are in flight per warp while one is added -- the gather is
@@ -712,8 +723,10 @@ __device__ __forceinline__ void gather_system_velocity_bulk(const GatherArgs& g,
     };
     auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : (lane < 8 ? rp01[g0 + lane - 4] : 0ll); };
     // per-slot metadata (registers; the slot index is a compile-time constant everywhere below)
-    int m_ob[GD], m_mb[GD], m_op[GD], m_a[GD], m_maskA[GD];
-    auto issue = [&](unsigned i, int u, int& ob, int& mb, int& op, int& aa, int& maskA) {
+    unsigned short m_ob[GD], m_op[GD];
+    unsigned char m_mb[GD], m_maskA[GD];
+    int m_a[GD];
+    auto issue = [&](unsigned i, int u, unsigned short& ob, unsigned char& mb, unsigned short& op, int& aa, unsigned char& maskA) {
       const unsigned e = word(i);
       const int a = e & 31;
       const unsigned wl = (e & ~INC_CS) >> 5;
@@ -723,15 +736,17 @@ __device__ __forceinline__ void gather_system_velocity_bulk(const GatherArgs& g,
       if (lane == 0) bulk_load_row(ring + u * VROW, g.stage + (size_t)slot * REC + a * VROW, VROW * 8, bars + u);
       const unsigned short* prow = g.pos + w * PSTR + a * NE;
       aa = a;
-      ob = lane < NU ? prow[lane] : 0;
-      op = lane < NP ? prow[NU + lane] : 0;
+      ob = 0;
+      op = 0;
+      if (lane < NU) ob = prow[lane];
+      if (lane < NP) op = prow[NU + lane];
+      mb = 7;
+      maskA = 7;
       if (e & INC_CS) {
         const unsigned char* mrow = g.nmask + w * MSTR;
-        mb = lane < NU ? mrow[lane] : 0;
+        mb = 0;
+        if (lane < NU) mb = mrow[lane];
         maskA = mrow[a];
-      } else {
-        mb = 7;
-        maskA = 7;
       }
     };
     long long rnext = rows(__shfl_sync(FULLM, h_g0, 0));
@@ -807,7 +822,8 @@ __device__ __forceinline__ void gather_system_velocity_bulk(const GatherArgs& g,
 
 struct PInc {
   double v[3];
-  int ob, mb;
+  unsigned short ob;
+  unsigned char mb;
 };
 
 // the items of one chunk, system matrix: `acc` = this warp's zeroed accumulators [3][ASTR] + [3][L01] + diagonals
@@ -872,7 +888,8 @@ __device__ __forceinline__ void gather_system(const GatherArgs& g, const BlockVi
       I.v[0] = I.v[1] = I.v[2] = 0.0;
       if (lane < NU) {
         I.ob = g.pos[w * PSTR + (NU + pn) * NE + lane];
-        I.mb = (e & INC_CS) ? g.nmask[w * MSTR + lane] : 7;
+        I.mb = 7;
+        if (e & INC_CS) I.mb = g.nmask[w * MSTR + lane];
         const double* S = g.stage + (size_t)slot * REC + NU * VROW + pn * PROW;
 #pragma unroll
         for (int c = 0; c < 3; ++c) I.v[c] = __ldcg(S + c * BW + lane);
@@ -883,7 +900,7 @@ __device__ __forceinline__ void gather_system(const GatherArgs& g, const BlockVi
         int idx[3];
         double tv[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) idx[c] = ((I.mb >> c) & 1) ? I.ob + __popc(I.mb & ((1 << c) - 1)) : -1;
+        for (int c = 0; c < 3; ++c) idx[c] = ((I.mb >> c) & 1) ? (int)I.ob + __popc((int)I.mb & ((1 << c) - 1)) : -1;
 #pragma unroll
         for (int c = 0; c < 3; ++c) tv[c] = idx[c] >= 0 ? acc[idx[c]] : 0.0;
 #pragma unroll
@@ -902,7 +919,19 @@ __device__ __forceinline__ void gather_system(const GatherArgs& g, const BlockVi
   }
 }
 
-__global__ void __launch_bounds__(GSW * 32, 2) th_gather_kernel(GatherArgs g, BlockView A) {
+__global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g, BlockView A) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* acc = smem + warp * GACC;
+  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;   // invariant: all accumulators are zero between items
+  __syncwarp();
+  gather_system<WB>(g, A, acc, (long long)blockIdx.x * GWARPS + warp, (long long)gridDim.x * GWARPS, lane);
+}
+
+// The same pass with the staged rows fetched by TMA bulk copies into a ring of GD rows per warp (DCP_GATHER_BULK=1).
+// Measured slower than the register pipeline above (2.7 ms against 1.9 ms per 65 536 cells: the ring costs a quarter of
+// the resident warps and the pass is bound by DRAM efficiency, not by the depth of the prefetch); kept selectable.
+__global__ void __launch_bounds__(GSW * 32, 2) th_gather_bulk_kernel(GatherArgs g, BlockView A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* acc = smem + warp * GSWARP;
@@ -935,11 +964,14 @@ struct PreArgs {
 
 struct PVInc {
   double v;
-  int o0, o1, o2, mb, maskA, a, skip;
+  unsigned short o0, o1, o2;
+  unsigned char mb, maskA;
+  int a, skip;
 };
 struct PPInc {
   double v;
-  int o, skip;
+  unsigned short o;
+  int skip;
 };
 
 template <int WBT>
@@ -975,8 +1007,12 @@ __device__ __forceinline__ void gather_pre(const GatherArgs& g, const PreArgs& p
           I.o0 = b[0];
           I.o1 = b[NU * NU];
           I.o2 = b[2 * NU * NU];
-        } else
-          I.o0 = I.o1 = I.o2 = pa.pos[(size_t)wp * PSTR + I.a * NE + lane];
+        } else {
+          const unsigned short o = pa.pos[(size_t)wp * PSTR + I.a * NE + lane];
+          I.o0 = o;
+          I.o1 = o;
+          I.o2 = o;
+        }
         if (cflag) I.mb = nm[lane];
       }
       if (cflag) I.maskA = nm[I.a];
@@ -1469,10 +1505,15 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   a.prm = p;
   const size_t smem_s = stage_smem_bytes(), smem_g = sizeof(double) * GACC * GWARPS, smem_gs = sizeof(double) * GSWARP * GSW;
   DCP_CUDA(cudaFuncSetAttribute(th_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-  DCP_CUDA(cudaFuncSetAttribute(th_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gs));
+  const bool bulk = std::getenv("DCP_GATHER_BULK") != nullptr;
+  DCP_CUDA(cudaFuncSetAttribute(th_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  DCP_CUDA(cudaFuncSetAttribute(th_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gs));
   int per_sm_s = 1, per_sm_g = 1, per_sm_p = 1;
   DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, th_stage_kernel, MTHREADS, smem_s));
-  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_kernel, GSW * 32, smem_gs));
+  if (bulk)
+    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_bulk_kernel, GSW * 32, smem_gs));
+  else
+    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_kernel, GWARPS * 32, smem_g));
   DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, th_pre_gather_kernel, GWARPS * 32, smem_g));
   per_sm_s = std::max(per_sm_s, 1);
   per_sm_g = std::max(per_sm_g, 1);
@@ -1560,8 +1601,14 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
     g.slot_base = 0;
     const long long items = (g.v_end - g.v_begin) + (g.p_end - g.p_begin);
     const long long blocks = (items + WB - 1) / WB;   // a warp takes blocks of WB items
-    grid = std::min<long long>((long long)ctx->sm_count * per_sm_g, (blocks + GSW - 1) / GSW);
-    if (grid > 0) th_gather_kernel<<<(unsigned)grid, GSW * 32, smem_gs, ctx->stream>>>(g, A);
+    const int gwarps = bulk ? GSW : GWARPS;
+    grid = std::min<long long>((long long)ctx->sm_count * per_sm_g, (blocks + gwarps - 1) / gwarps);
+    if (grid > 0) {
+      if (bulk)
+        th_gather_bulk_kernel<<<(unsigned)grid, GSW * 32, smem_gs, ctx->stream>>>(g, A);
+      else
+        th_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, ctx->stream>>>(g, A);
+    }
     ctx->launches += 2;
     grid = std::min<long long>((long long)ctx->sm_count * per_sm_p, (blocks + GWARPS - 1) / GWARPS);
     if (fuse_pre && grid > 0) {

@@ -34,7 +34,8 @@ def _params(spec):
 
 
 @pytest.mark.parametrize("spec", CASES, ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
-@pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4, 5], ids=["search", "positions", "owner", "staged", "staged-chunk37", "staged-persistent"])
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4, 5, 6],
+                         ids=["search", "positions", "owner", "staged", "staged-chunk37", "staged-persistent", "staged-bulk"])
 def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy, monkeypatch):
     from dycore_b200 import device
     from oracle import oracle as orc
@@ -51,6 +52,8 @@ def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy, m
         monkeypatch.setenv("DCP_GATHER_CHUNK", "37")
     if strategy == 5:   # the cooperative kernel with the staging ring (an experiment)
         monkeypatch.setenv("DCP_STAGED_MODE", "persistent")
+    if strategy == 6:   # staged rows fetched with TMA bulk copies into a per-warp ring (slower, kept selectable)
+        monkeypatch.setenv("DCP_GATHER_BULK", "1")
     model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == 2))
     if spec["geometry"] == "shell":
         assert model.strategy == device.STRATEGY_STAGED, "the shell qualifies for the write-once path by default"
