@@ -1234,6 +1234,11 @@ void dcp_gather_plan_free(GatherPlan* p) {
   cudaFree(p->dphi_lane);
   cudaFree(p->pre_w);
   cudaFree(p->pre_rest);
+  if (p->stream2) cudaStreamDestroy(p->stream2);
+  for (int i = 0; i < 2; ++i) {
+    if (p->ev_staged[i]) cudaEventDestroy(p->ev_staged[i]);
+    if (p->ev_gathered[i]) cudaEventDestroy(p->ev_gathered[i]);
+  }
   cudaFree(p->d_v_chunk_ptr);
   cudaFree(p->d_p_chunk_ptr);
   cudaFree(p->sync);
@@ -1429,7 +1434,26 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     if (rc == DCP_OK && cudaMalloc((void**)&G->sync, sizeof(unsigned) * 2 * (size_t)n_chunks) != cudaSuccess) rc = DCP_ERR_CUDA;
     cudaStreamSynchronize(ctx->stream);
   }
-  const size_t staging_cells = fused ? (size_t)ring_chunks * (size_t)n_stage : (size_t)chunk;
+  // DCP_STAGED_OVERLAP=1: two streams (see dcp_launch_th_staged).  Measured slower at refine 5 for every split of the SMs
+  // (19.2 ms with 2 + 1 CTAs per SM, 15.1 ms with full grids on both streams, against 14.1 ms on one stream): both sides
+  // are occupancy-starved already, halving their resident warps costs more than the overlap returns.
+  bool overlap = false;
+  if (const char* e = std::getenv("DCP_STAGED_OVERLAP")) overlap = !fused && n_chunks > 1 && std::atoi(e) != 0;
+  if (overlap) {
+    if (const char* e = std::getenv("DCP_OVERLAP_STAGE_CTAS")) G->overlap_stage_ctas = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("DCP_OVERLAP_GATHER_CTAS")) G->overlap_gather_ctas = std::max(1, std::atoi(e));
+    bool ok = cudaStreamCreateWithFlags(&G->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&G->ev_staged[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&G->ev_gathered[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      if (G->stream2) cudaStreamDestroy(G->stream2);
+      G->stream2 = nullptr;
+      overlap = false;
+    }
+  }
+  const size_t staging_cells = fused ? (size_t)ring_chunks * (size_t)n_stage : (size_t)chunk * (overlap ? 2 : 1);
   if (rc == DCP_OK && cudaMalloc((void**)&G->staging, sizeof(double) * (size_t)REC * staging_cells) != cudaSuccess) {
     cudaGetLastError();
     dcp_set_error("gather plan: staging allocation failed");
@@ -1589,10 +1613,27 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
     pa.pos_wide = m->masked_pre->pos_wide;
     DCP_CUDA(cudaFuncSetAttribute(th_pre_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   }
+  // Two streams: the stage pass of chunk c + 1 (tensor / LSU bound, writes) runs next to the gather passes of chunk c
+  // (DRAM bound, reads and writes).  Both kernels stride over their work with a fixed grid, so the grids set the split
+  // of the SMs: 2 staging CTAs + 1 gathering CTA per SM fit together (registers, shared memory).  The staging buffer has
+  // two halves; events order reuse.  Opt-in (DCP_STAGED_OVERLAP=1): measured slower than one stream with full grids.
+  const bool overlap = G->stream2 != nullptr && G->n_chunks > 1;
+  cudaStream_t s_stage = ctx->stream, s_gather = overlap ? G->stream2 : ctx->stream;
+  const int stage_per_sm = overlap ? std::min(per_sm_s, G->overlap_stage_ctas) : per_sm_s;
+  const int gather_per_sm = overlap ? std::min(per_sm_g, G->overlap_gather_ctas) : per_sm_g;
+  const int pre_per_sm = overlap ? std::min(per_sm_p, G->overlap_gather_ctas) : per_sm_p;
   for (int64_t ch = 0; ch < G->n_chunks; ++ch) {
+    const int half = overlap ? (int)(ch & 1) : 0;
     const long long w0 = ch * G->chunk, w1 = std::min<long long>(plan->n, w0 + G->chunk);
-    long long grid = std::min<long long>((long long)ctx->sm_count * per_sm_s, w1 - w0);
-    th_stage_kernel<<<(unsigned)grid, MTHREADS, smem_s, ctx->stream>>>(a, cs, G->dphi_lane, G->staging, w0, w1, 0, (int)G->chunk);
+    long long grid = std::min<long long>((long long)ctx->sm_count * stage_per_sm, w1 - w0);
+    if (overlap && ch >= 2) DCP_CUDA(cudaStreamWaitEvent(s_stage, G->ev_gathered[half], 0));   // the half is free again
+    double* half_base = G->staging + (size_t)half * (size_t)G->chunk * REC;
+    th_stage_kernel<<<(unsigned)grid, MTHREADS, smem_s, s_stage>>>(a, cs, G->dphi_lane, half_base, w0, w1, 0, (int)G->chunk);
+    if (overlap) {
+      DCP_CUDA(cudaEventRecord(G->ev_staged[half], s_stage));
+      DCP_CUDA(cudaStreamWaitEvent(s_gather, G->ev_staged[half], 0));
+    }
+    g.stage = half_base;
     g.v_begin = G->v_chunk_ptr[ch];
     g.v_end = G->v_chunk_ptr[ch + 1];
     g.p_begin = G->p_chunk_ptr[ch];
@@ -1602,19 +1643,24 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
     const long long items = (g.v_end - g.v_begin) + (g.p_end - g.p_begin);
     const long long blocks = (items + WB - 1) / WB;   // a warp takes blocks of WB items
     const int gwarps = bulk ? GSW : GWARPS;
-    grid = std::min<long long>((long long)ctx->sm_count * per_sm_g, (blocks + gwarps - 1) / gwarps);
+    grid = std::min<long long>((long long)ctx->sm_count * gather_per_sm, (blocks + gwarps - 1) / gwarps);
     if (grid > 0) {
       if (bulk)
-        th_gather_bulk_kernel<<<(unsigned)grid, GSW * 32, smem_gs, ctx->stream>>>(g, A);
+        th_gather_bulk_kernel<<<(unsigned)grid, GSW * 32, smem_gs, s_gather>>>(g, A);
       else
-        th_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, ctx->stream>>>(g, A);
+        th_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, s_gather>>>(g, A);
     }
     ctx->launches += 2;
-    grid = std::min<long long>((long long)ctx->sm_count * per_sm_p, (blocks + GWARPS - 1) / GWARPS);
+    grid = std::min<long long>((long long)ctx->sm_count * pre_per_sm, (blocks + GWARPS - 1) / GWARPS);
     if (fuse_pre && grid > 0) {
-      th_pre_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, ctx->stream>>>(g, pa, Apre);
+      th_pre_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, s_gather>>>(g, pa, Apre);
       ctx->launches++;
     }
+    if (overlap) DCP_CUDA(cudaEventRecord(G->ev_gathered[half], s_gather));
+  }
+  if (overlap) {   // the context's stream continues after the last gathers
+    DCP_CUDA(cudaStreamWaitEvent(s_stage, G->ev_gathered[0], 0));
+    DCP_CUDA(cudaStreamWaitEvent(s_stage, G->ev_gathered[1], 0));
   }
   if (fuse_pre) {
     // the cells the second gather skipped: no-normal-flux cells through the reduction kernel, cells outside the

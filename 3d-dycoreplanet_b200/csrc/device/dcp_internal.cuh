@@ -135,6 +135,10 @@ struct GatherPlan {
   int32_t* pre_rest = nullptr;
   int64_t n_pre_rest = 0;
   bool has_pre = false;
+  // two-stream overlap of the stage pass of chunk c + 1 with the gather passes of chunk c (staging has two halves)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_gathered[2] = {nullptr, nullptr};
+  int overlap_stage_ctas = 2, overlap_gather_ctas = 1;   // CTAs per SM of each side while both run
   // persistent kernel (staging ring in L2): chunk == n_stage cells, one per staging CTA
   bool fused = false;
   int n_stage = 0, n_gather_ctas = 0, ring_chunks = 0;
