@@ -48,6 +48,7 @@ struct ScalarArgs {
   const double* old_temp;
   const double* nse_solution;
   double* rhs;
+  const double* q2_tab;            // Q2 matrix kernel: reference gradients and values in table-build order
   const int* cell_list;            // rhs, full kernel: the cells to process (nullptr: all)
   const unsigned char* bc_flag;    // rhs, plain kernel: cells to skip (they hold inhomogeneously constrained dofs)
 };
@@ -441,6 +442,16 @@ ScalarLaunch scalar_launch(dcp_ctx* ctx, long long n_cells, int nd, int nd_nse) 
 }
 
 
+// reference table of the Q2 kernel in the order its table build reads it: [half][node of the group j][e: 3 gradients,
+// value][thread = 4 * point + group]
+__global__ void q2_tab_kernel(const double* __restrict__ phi, const double* __restrict__ dphi, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * 7 * 4 * 128) return;
+  const int t = i & 127, e = (i >> 7) & 3, j = (i >> 9) % 7, half = i / (7 * 4 * 128);
+  const int q = half * 32 + (t >> 2), b = (t & 3) * 7 + j;
+  out[i] = b < 27 ? (e < 3 ? dphi[((size_t)q * 27 + b) * 3 + e] : phi[(size_t)q * 27 + b]) : 0.0;
+}
+
 // ---- Q2 temperature in 3-D: mass and stiffness matrices on the FP64 tensor cores ---------------------------------
 // 27 dofs and 64 quadrature points per cell (QGauss(temperature_degree + 2), boussinesq_model.tpp:834): the symmetric
 // DFMA loop above spends 378 entries x 64 points x 8 shared-memory loads per cell.  Here, like the Stokes kernel,
@@ -487,13 +498,14 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
         if (bg == 0) wq[ql] = g[q];
         double* x = X + ql * TQ_LDB + bg * 7;
         const int nb = bg == 3 ? 6 : 7;
-        for (int j = 0; j < nb; ++j) {
-          const int b = bg * 7 + j;
-          const double* rr = a.dphi + ((size_t)q * ND2 + b) * 3;
-          const double r0 = __ldg(rr), r1 = __ldg(rr + 1), r2 = __ldg(rr + 2);
+        const double* tb = a.q2_tab + (size_t)half * (7 * 4 * 128) + tid;   // [half][j][e][thread]: coalesced
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          if (j >= nb) break;
+          const double r0 = __ldg(tb + (j * 4) * 128), r1 = __ldg(tb + (j * 4 + 1) * 128), r2 = __ldg(tb + (j * 4 + 2) * 128);
 #pragma unroll
           for (int d = 0; d < 3; ++d) x[32 * d + j] = kinv[0][d] * r0 + kinv[1][d] * r1 + kinv[2][d] * r2;
-          x[96 + j] = __ldg(a.phi + (size_t)q * ND2 + b);
+          x[96 + j] = __ldg(tb + (j * 4 + 3) * 128);
         }
       }
       __syncthreads();
@@ -572,6 +584,11 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
   if (m->dim == 3 && a.nd == 27 && a.nq == 64 && !std::getenv("DCP_NO_Q2_DMMA")) {
     // Q2 temperature: tensor-core kernel on the cells with a position row, general kernel on the others
     if (m->n_temp_fast > 0) {
+      if (!m->temp_q2_tab) {
+        DCP_CUDA(cudaMalloc((void**)&m->temp_q2_tab, sizeof(double) * 2 * 7 * 4 * 128));
+        q2_tab_kernel<<<(2 * 7 * 4 * 128 + 255) / 256, 256, 0, ctx->stream>>>(m->phi_t_qt, m->dphi_t_qt, m->temp_q2_tab);
+      }
+      a.q2_tab = m->temp_q2_tab;
       ScalarArgs f = a;
       f.cell_list = m->temp_fast_cells;
       f.n_cells = m->n_temp_fast;

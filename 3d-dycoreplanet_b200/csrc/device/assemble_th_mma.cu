@@ -476,6 +476,7 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
   std::vector<uint16_t> pos_all((size_t)nc * NE * NE, 0xFFFF);
   std::vector<uint8_t> mask_all((size_t)nc * 36, 0);
   std::vector<std::vector<uint16_t>> wide_rows((size_t)nc);
+  std::vector<uint16_t> cell_max_off((size_t)nc, 0);   // preconditioner, cells without no-normal-flux lines: largest row offset
 #pragma omp parallel for schedule(dynamic, 256)
   for (int64_t c = 0; c < nc; ++c) {
     const int32_t* idx = d->nse_l2g + c * ND;
@@ -615,6 +616,7 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
             good = off >= 0 && off < 65535;
             if (!good) break;
             W[(k * NU + a) * NU + b] = (uint16_t)off;
+            if (off > cell_max_off[c]) cell_max_off[c] = (uint16_t)off;
             if (common < 0) common = off; else if (common != off) uniform = false;
           }
           if (good && common >= 0) P[a * NE + b] = (uint16_t)common;
@@ -669,6 +671,9 @@ int dcp_masked_plan_build(dcp_model* m, const dcp_model_desc* d, bool system, Ma
   P->h_cells = cells;
   P->h_nnf_idx = nnf_idx;
   P->h_wide_idx = wide_idx;
+  P->max_off_plain = 0;
+  for (size_t i = 0; i < cells.size(); ++i)
+    if (nnf_idx[i] < 0) P->max_off_plain = std::max<int>(P->max_off_plain, cell_max_off[cells[i]]);
   P->h_cflag.resize(cells.size());
   for (size_t i = 0; i < cells.size(); ++i) P->h_cflag[i] = mask_all[(size_t)cells[i] * 36 + 35];
   P->n = (int64_t)cells.size();

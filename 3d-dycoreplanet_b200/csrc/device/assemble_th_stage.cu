@@ -974,9 +974,23 @@ struct PPInc {
   int skip;
 };
 
+// Accumulators of the preconditioner's gather: [3][PSTRIDE] + 3 diagonals.  The gathered contributions land on the
+// same component only (at most 125 entries per row; checked when the plan is attached); rows of nodes with
+// no-normal-flux lines are longer, but all their cells are skipped here, so the tail beyond PSTRIDE is stored as zeros.
+constexpr int PSTRIDE = 131;                   // 131 mod 16 == 3
+constexpr int PACC = 3 * PSTRIDE + 7;          // 400 doubles per warp
+
 template <int WBT>
+__device__ __forceinline__ void flush_row_capped(double* __restrict__ out, double* acc, int len, int cap, bool first, int lane) {
+  const int n = len < cap ? len : cap;
+  flush_row(out, acc, n, first, lane);
+  if (first)
+    for (int k = cap + lane; k < len; k += 32) out[k] = 0.0;
+}
+
+template <int WBT, int PS = PSTRIDE>
 __device__ __forceinline__ void gather_pre(const GatherArgs& g, const PreArgs& pa, const BlockView& A, double* acc, long long gw, long long nw, int lane) {
-  double* accd = acc + 3 * ASTR + 3 * L01;
+  double* accd = acc + 3 * PS;
   const long long* rp00 = A.rowptr[0][0];
   const long long* rp11 = A.rowptr[1][1];
   double* v00 = A.val[0][0];
@@ -1023,8 +1037,8 @@ __device__ __forceinline__ void gather_pre(const GatherArgs& g, const PreArgs& p
         if (lane < NU) {
           const int mm = I.maskA & I.mb;
           if ((mm & 1) && I.o0 != 0xffff) acc[I.o0] += I.v;
-          if ((mm & 2) && I.o1 != 0xffff) acc[ASTR + I.o1] += I.v;
-          if ((mm & 4) && I.o2 != 0xffff) acc[2 * ASTR + I.o2] += I.v;
+          if ((mm & 2) && I.o1 != 0xffff) acc[PS + I.o1] += I.v;
+          if ((mm & 4) && I.o2 != 0xffff) acc[2 * PS + I.o2] += I.v;
           if (lane == I.a && I.maskA != 7) {
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -1040,7 +1054,7 @@ __device__ __forceinline__ void gather_pre(const GatherArgs& g, const PreArgs& p
         const long long rs = __shfl_sync(FULLM, rcur, c);
         const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs);
         if ((maskA_item >> c) & 1)
-          flush_row(v00 + rs, acc + c * ASTR, len, first, lane);
+          flush_row_capped<WBT>(v00 + rs, acc + c * PS, len, PS, first, lane);
         else if (lane == 0) {
           double* out = v00 + rs;
           if (first) {
@@ -1076,18 +1090,18 @@ __device__ __forceinline__ void gather_pre(const GatherArgs& g, const PreArgs& p
     auto flush = [&](long long rcur, bool first) {
       const long long rs = __shfl_sync(FULLM, rcur, 0);
       const int len = (int)(__shfl_sync(FULLM, rcur, 1) - rs);
-      flush_row(v11 + rs, acc, len, first, lane);
+      flush_row_capped<WBT>(v11 + rs, acc, len, PS, first, lane);
       __syncwarp();
     };
     walk_items<PPInc, WBT>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, aux, rows, load, add, flush);
   }
 }
 
-__global__ void __launch_bounds__(GWARPS * 32, 2) th_pre_gather_kernel(GatherArgs g, PreArgs pa, BlockView A) {
+__global__ void __launch_bounds__(GWARPS * 32, 3) th_pre_gather_kernel(GatherArgs g, PreArgs pa, BlockView A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = smem + warp * GACC;
-  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;
+  double* acc = smem + warp * PACC;
+  for (int k = lane; k < PACC; k += 32) acc[k] = 0.0;
   __syncwarp();
   gather_pre<WB>(g, pa, A, acc, (long long)blockIdx.x * GWARPS + warp, (long long)gridDim.x * GWARPS, lane);
 }
@@ -1197,7 +1211,7 @@ __global__ void __launch_bounds__(MTHREADS, 4) th_fused_kernel(const __grid_cons
     g.w_base = w0;
     g.slot_base = (int)(c % f.ring_chunks) * f.n_stage;
     gather_system<WBF>(g, A, acc, gw, nw, lane);
-    if (f.fuse_pre) gather_pre<WBF>(g, f.pa, Apre, acc, gw, nw, lane);
+    if (f.fuse_pre) gather_pre<WBF, ASTR>(g, f.pa, Apre, acc, gw, nw, lane);
     __syncwarp();
     if (lane == 0) {
       __threadfence();
@@ -1478,6 +1492,14 @@ int dcp_gather_plan_attach_pre(dcp_model* m, const dcp_model_desc* d, GatherPlan
     for (int64_t r = 0; r < P->n_rows; ++r) mx = std::max(mx, P->rowptr[r + 1] - P->rowptr[r]);
     if (mx > LROW) return DCP_OK;
   }
+  if (pre_plan->max_off_plain >= PSTRIDE) return DCP_OK;   // a gathered entry would not fit the compact accumulators
+  {
+    int64_t mx = 0;   // pressure mass rows go through the same accumulators
+    const dcp_csr_desc& P11 = pat[1][1];
+#pragma omp parallel for reduction(max : mx)
+    for (int64_t r = 0; r < P11.n_rows; ++r) mx = std::max(mx, P11.rowptr[r + 1] - P11.rowptr[r]);
+    if (mx > PSTRIDE) return DCP_OK;
+  }
   std::vector<int32_t> of_cell((size_t)d->n_cells, -1);
   for (size_t i = 0; i < pre_plan->h_cells.size(); ++i) of_cell[pre_plan->h_cells[i]] = (int32_t)i;
   std::vector<long long> pre_w(nse_plan->h_cells.size(), -1ll);
@@ -1527,7 +1549,8 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   a.rhs = m->nse_rhs;
   a.n_u = m->nse.start[1];
   a.prm = p;
-  const size_t smem_s = stage_smem_bytes(), smem_g = sizeof(double) * GACC * GWARPS, smem_gs = sizeof(double) * GSWARP * GSW;
+  const size_t smem_s = stage_smem_bytes(), smem_g = sizeof(double) * GACC * GWARPS, smem_gs = sizeof(double) * GSWARP * GSW,
+               smem_p = sizeof(double) * PACC * GWARPS;
   DCP_CUDA(cudaFuncSetAttribute(th_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
   const bool bulk = std::getenv("DCP_GATHER_BULK") != nullptr;
   DCP_CUDA(cudaFuncSetAttribute(th_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
@@ -1538,7 +1561,7 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
     DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_bulk_kernel, GSW * 32, smem_gs));
   else
     DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_kernel, GWARPS * 32, smem_g));
-  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, th_pre_gather_kernel, GWARPS * 32, smem_g));
+  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, th_pre_gather_kernel, GWARPS * 32, smem_p));
   per_sm_s = std::max(per_sm_s, 1);
   per_sm_g = std::max(per_sm_g, 1);
   per_sm_p = std::max(per_sm_p, 1);
@@ -1611,7 +1634,7 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
     pa.pos = m->masked_pre->pos;
     pa.nmask = m->masked_pre->nmask;
     pa.pos_wide = m->masked_pre->pos_wide;
-    DCP_CUDA(cudaFuncSetAttribute(th_pre_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    DCP_CUDA(cudaFuncSetAttribute(th_pre_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
   }
   // Two streams: the stage pass of chunk c + 1 (tensor / LSU bound, writes) runs next to the gather passes of chunk c
   // (DRAM bound, reads and writes).  Both kernels stride over their work with a fixed grid, so the grids set the split
@@ -1653,7 +1676,7 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
     ctx->launches += 2;
     grid = std::min<long long>((long long)ctx->sm_count * pre_per_sm, (blocks + GWARPS - 1) / GWARPS);
     if (fuse_pre && grid > 0) {
-      th_pre_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, s_gather>>>(g, pa, Apre);
+      th_pre_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_p, s_gather>>>(g, pa, Apre);
       ctx->launches++;
     }
     if (overlap) DCP_CUDA(cudaEventRecord(G->ev_gathered[half], s_gather));

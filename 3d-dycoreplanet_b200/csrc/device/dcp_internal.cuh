@@ -158,6 +158,7 @@ struct MaskedPlan {
   GatherPlan* gather = nullptr;    // write-once path (system matrix, n_other == 0)
   std::vector<int32_t> h_cells, h_nnf_idx, h_wide_idx;   // host copies: plan order, 9-table / wide-table index per plan cell
   std::vector<uint8_t> h_cflag;                          // the plan cell holds constrained velocity dofs
+  int max_off_plain = 0;   // preconditioner plan: largest velocity-row offset used by cells without no-normal-flux lines
 };
 
 struct dcp_model {
@@ -175,6 +176,7 @@ struct dcp_model {
   int32_t* temp_bc_cells = nullptr;  // those cells
   int64_t n_temp_bc_cells = 0;
   uint16_t* temp_pos = nullptr;  // [n_cells][nd*nd] scatter positions of the temperature matrices (0xffff row: general)
+  double* temp_q2_tab = nullptr;   // Q2 temperature matrix kernel: reference table in table-build order
   int32_t *temp_fast_cells = nullptr, *temp_general_cells = nullptr;   // cells with / without a position row
   int64_t n_temp_fast = 0, n_temp_general = 0;
   int32_t *nse_local_field = nullptr, *nse_local_base = nullptr;

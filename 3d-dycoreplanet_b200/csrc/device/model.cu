@@ -320,6 +320,7 @@ int dcp_model_destroy(dcp_model* m) {
   cudaFree(m->nse_l2g);
   cudaFree(m->temp_l2g);
   cudaFree(m->temp_pos);
+  cudaFree(m->temp_q2_tab);
   cudaFree(m->temp_fast_cells);
   cudaFree(m->temp_general_cells);
   cudaFree(m->temp_bc_flag);
