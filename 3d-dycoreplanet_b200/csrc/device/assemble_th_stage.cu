@@ -1,17 +1,23 @@
-// Classic 3-D Taylor-Hood NSE system: write-once assembly (DCP_STRATEGY_POSITIONS when every cell is a plan cell).
+// Classic 3-D Taylor-Hood NSE system and its preconditioner: write-once assembly (DCP_STRATEGY_STAGED).
 //
 // Same integrals and the same tensor-core contraction as assemble_th_mma.cu (reference:
-// include/core/boussinesq_model.tpp:550-687), but the scatter of copy_local_to_global_nse_system (:677-687) is split
-// in two so that no CSR value is ever reduced with red.global.add.f64 and the matrix needs no zero-fill:
+// include/core/boussinesq_model.tpp:550-687 and :421-476), but the scatter of copy_local_to_global_nse_system
+// (:677-687) is split in two so that no CSR value is ever reduced with red.global.add.f64 and the matrices need no
+// zero-fill:
 //
-//   1. th_stage_kernel: per cell, the constraint-resolved 3x3 blocks L[(a,.),(b,.)] and the velocity-pressure
-//      coupling leave the DMMA registers through a per-warp shared-memory transposition and are written, coalesced,
-//      to a cell-major staging record (7 892 doubles: 27 velocity-node rows [r = 3c+d][b] + [c][p], 8 pressure-node
-//      rows [c][b]).  The symmetric half is computed, both orientations are staged.
-//   2. th_gather_kernel: one warp per (chunk, node).  It sums the staged rows of the node's cells inside the chunk in
-//      shared-memory accumulators at the plan's row positions and writes the node's CSR rows once (first chunk that
-//      touches the node: plain store of the whole row; later chunks: read-modify-write of the touched entries; the
-//      chunks are stream-ordered, rows are owned by one warp, so no atomics are needed).
+//   1. th_stage_kernel: per cell, the constraint-resolved 3x3 blocks L[(a,.),(b,.)], the velocity-pressure coupling and
+//      (for the preconditioner) m + nu k and the pressure mass block leave the DMMA registers as 64-byte row segments.
+//      The staging buffer is NODE-MAJOR: the row a cell contributes to a node is written to the slot of that
+//      (node, cell) incidence, and the slots of one node are consecutive.  Velocity-node row (304 doubles):
+//      [m + nu k: 28][component c: [d][28 column nodes] + 8 pressure columns] x 3; pressure-node row (92 doubles):
+//      [c][28] + 8 pressure-mass columns.
+//   2. th_gather_kernel: one warp per (chunk, node) item.  Everything the item needs lies in one contiguous piece of the
+//      staging buffer; the warp streams it with TMA bulk copies (cp.async.bulk + mbarrier) through a ring of RD slots
+//      in shared memory, one component row at a time (three sweeps over the item's incidences), adds the segments at
+//      the plan's row positions into shared-memory accumulators and writes every CSR row of nse_matrix and of
+//      nse_preconditioner_matrix once (first chunk that touches the node: plain store of the whole row, which doubles
+//      as the zero-fill; later chunks: read-modify-write; chunks are stream-ordered and a row belongs to one warp, so
+//      no atomics are needed).
 //
 // The cells are processed in chunks of the plan order; a chunk's staging is consumed before the next chunk overwrites
 // it.  Right-hand side: as in assemble_th_mma.cu (reductions into nse_rhs, 81 per cell).
@@ -30,38 +36,36 @@ using namespace dcpdev;
 using namespace thmma;
 
 constexpr int BW = 28;                      // column nodes per staged row segment (27 + pad: 32-byte sectors stay aligned)
-constexpr int VROW = 9 * BW + 3 * NP;       // staged velocity-node row: [r = 3c+d][28] then [c][8 pressure nodes]  (276)
-constexpr int VPRS = 9 * BW;                // start of the pressure columns inside a velocity-node row
-constexpr int PROW = 3 * BW;                // staged pressure-node row: [c][28]
-constexpr int OFF_DG = NU * VROW + NP * PROW;   // fused preconditioner: m + nu k of every node pair, [27][28]
-constexpr int OFF_PP = OFF_DG + NU * BW;        // pressure mass block [8][8]
-constexpr int REC = OFF_PP + NP * NP;           // doubles per cell record (8 944)
+constexpr int CSEG = 3 * BW + NP;           // one component of a velocity-node row: [d][28] then 8 pressure columns (92)
+constexpr int VROW = BW + 3 * CSEG;         // staged velocity-node row: [m + nu k][c = 0][c = 1][c = 2]  (304)
+constexpr int PROW = 3 * BW + NP;           // staged pressure-node row: [c][28] then the pressure mass columns (92)
+constexpr int REC = NU * VROW + NP * PROW;  // staged doubles per cell (8 944)
+constexpr int SLOTS = 36;                   // slot table row: 27 velocity-node slots, 8 pressure-node slots, pad
 constexpr int LROW = 384;                   // longest block(0,0) / block(1,0) row the gather accumulators hold
-constexpr int ASTR = 387;                   // accumulator row stride (387 mod 16 == 3: the three components of one column land in different banks)
+constexpr int ACC0 = 388;                   // accumulator of one block(0,0) / block(1,0) row
 constexpr int L01 = 32;                     // longest block(0,1) row
-constexpr int GACC = 3 * ASTR + 3 * L01 + 7;  // per-warp accumulators (+3 diagonal slots of constrained components), 1264
-constexpr int GWARPS = 8;                  // warps per CTA of the preconditioner's gather
-constexpr int GSW = 6;                     // warps per CTA of the system gather (each with a ring of staged rows)
-constexpr int GD = 3;                      // depth of that ring: staged rows in flight per warp
-constexpr int GSWARP = GACC + GD * VROW + 4;   // doubles per warp: accumulators, ring, mbarriers
-static_assert(GSWARP % 2 == 0 && GACC % 2 == 0 && VROW % 2 == 0, "16-byte alignment of the ring slots");
-static_assert(GACC % 2 == 0, "accumulator alignment");
-static_assert((REC * 8) % 32 == 0 && (VROW * 8) % 32 == 0 && (PROW * 8) % 32 == 0 && (BW * 8) % 32 == 0, "sector alignment of the staged segments");
+constexpr int RD = 3;                       // staged rows in flight per gather warp
+constexpr int GW = 1;                       // warps per CTA of the gather (the warps are independent; shared memory sets how many fit an SM)
+static_assert((VROW * 8) % 32 == 0 && (PROW * 8) % 32 == 0 && (BW * 8) % 32 == 0 && (CSEG * 8) % 32 == 0, "sector alignment of the staged segments");
+static_assert(ACC0 % 2 == 0 && L01 % 2 == 0, "16-byte alignment of the ring slots");
 
-// ---- stage: contraction + constraint epilogue, coalesced write of the cell record ---------------------------------
+// ---- stage: contraction + constraint epilogue, coalesced write of the staged rows --------------------------------
 // The DMMA accumulator layout does the transposition: lane (frow = lane / 4, fk = lane % 4) holds the 3x3 blocks of
-// (row node 8 ta + frow, column nodes 8 tb + 2 fk + {0,1}).  Direct orientation: for every r = 3c+d the warp writes
+// (row node 8 ta + frow, column nodes 8 tb + 2 fk + {0,1}).  Direct orientation: for every (c, d) the warp writes
 // 8 rows x 64 contiguous bytes with one 16-byte store per lane; transposed orientation (row node b, column node a,
-// entry [d][c]): for every (r, jj) 4 rows x 64 contiguous bytes with one 8-byte store per lane.  All segments start
+// entry [d][c]): for every (c, d, jj) 4 rows x 64 contiguous bytes with one 8-byte store per lane.  All segments start
 // on 32-byte sector boundaries (BW = 28).
 __constant__ unsigned char c_task_ta[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
 __constant__ unsigned char c_task_tb[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
 
-// `sched` names the cells of this CTA (cell(k, w, slot): its k-th plan cell and staging slot) and, in the persistent
-// kernel, waits for the slot to be free (wait_slot) and publishes the finished record (signal).
-template <class Sched>
-__device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, const double* __restrict__ dphi_lane, double* __restrict__ stage,
-                                            const Sched sched) {
+struct StageOut {
+  double* vstage;            // velocity-node rows of the chunk
+  double* pstage;            // pressure-node rows of the chunk
+  const unsigned* slots;     // [plan cell][SLOTS]: slot of every local node inside its chunk
+};
+
+__global__ void __launch_bounds__(MTHREADS, 4)
+th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, StageOut so, long long w_begin, long long w_end) {
   extern __shared__ __align__(16) double smem[];
   double* X = smem;                     // KQ * LDB
   double* wq = X + KQ * LDB;            // KQ (+4)
@@ -75,7 +79,8 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
   unsigned char* snm2 = (unsigned char*)(sGU + NQ * 12);       // 2 x MSTR
   int* sidx2 = (int*)(snm2 + 2 * MSTR);                        // 2 x IDS
   int* sidt2 = sidx2 + 2 * IDS;                                // 2 x 28
-  int* sys_u = sidt2 + 2 * 28;                                 // 3*NU
+  unsigned* sslot2 = (unsigned*)(sidt2 + 2 * 28);              // 2 x SLOTS
+  int* sys_u = (int*)(sslot2 + 2 * SLOTS);                     // 3*NU
   int* sys_p = sys_u + 3 * NU;                                 // NP
   unsigned char* skc = (unsigned char*)(sys_p + NP);           // 28
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -93,47 +98,43 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
   for (int i = tid; i < NQ * NP; i += nt) X[(i / NP) * LDB + PSI0 + (i % NP)] = __ldg(a.phi_p + i);
   const double nu = a.prm.dt * a.prm.inv_re;
   const bool do_rhs = a.rhs != nullptr;
-  const double* sgeo = sgeo2;
-  const unsigned char* snm = snm2;
-  const int* sidx = sidx2;
-  const int* sidt = sidt2;
-  // mapping record, masks and dof indices of a cell, copied asynchronously into buffer `b`
+  // mapping record, masks, dof indices and staging slots of a cell, copied asynchronously into buffer `b`
   auto issue_raw = [&](long long w, int b) {
     const long long cell = a.cells[w];
     const double* g = a.geom + cell * GS;
     for (int i = tid; i < GS; i += nt) cp_async8(sgeo2 + b * (GS + 1) + i, g + i);
     if (tid < MSTR / 8) cp_async8(snm2 + b * MSTR + 8 * tid, a.nmask + w * MSTR + 8 * tid);
+    if (tid >= 32 && tid - 32 < SLOTS / 2) cp_async8(sslot2 + b * SLOTS + 2 * (tid - 32), so.slots + w * SLOTS + 2 * (tid - 32));
     for (int i = tid; i < ND; i += nt) cp_async4(sidx2 + b * IDS + i, a.l2g + cell * ND + i);
     if (do_rhs)
       for (int i = tid; i < a.ndt; i += nt) cp_async4(sidt2 + b * 28 + i, a.l2g_t + cell * a.ndt + i);
   };
-  auto node_cs = [&](int n) {
-    NodeCs c;
-    c.mask = snm[n];
-    c.k = skc[n];
-    c.w0 = swt[3 * n];
-    c.w1 = swt[3 * n + 1];
-    c.w2 = swt[3 * n + 2];
-    return c;
-  };
   const int frow = lane >> 2, fk = lane & 3;
 
-  int buf = 0, k = 0;
-  long long w = 0, w_next = 0;
-  int slot = 0, slot_next = 0;
-  bool have = sched.cell(0, w, slot), have_next = false;
-  if (have) issue_raw(w, 0);
+  int buf = 0;
+  long long w = w_begin + blockIdx.x;
+  if (w < w_end) issue_raw(w, 0);
   cp_async_commit();
-  for (; have; ++k, buf ^= 1, w = w_next, slot = slot_next, have = have_next) {
-    have_next = sched.cell(k + 1, w_next, slot_next);
-    double* S = stage + (size_t)slot * REC;
-    sgeo = sgeo2 + buf * (GS + 1);
-    snm = snm2 + buf * MSTR;
-    sidx = sidx2 + buf * IDS;
-    sidt = sidt2 + buf * 28;
+  for (; w < w_end; w += gridDim.x, buf ^= 1) {
+    const long long w_next = w + gridDim.x;
+    const double* sgeo = sgeo2 + buf * (GS + 1);
+    const unsigned char* snm = snm2 + buf * MSTR;
+    const int* sidx = sidx2 + buf * IDS;
+    const int* sidt = sidt2 + buf * 28;
+    const unsigned* sslot = sslot2 + buf * SLOTS;
+    auto node_cs = [&](int n) {
+      NodeCs c;
+      c.mask = snm[n];
+      c.k = skc[n];
+      c.w0 = swt[3 * n];
+      c.w1 = swt[3 * n + 1];
+      c.w2 = swt[3 * n + 2];
+      return c;
+    };
+    auto vrow = [&](int n) { return so.vstage + (size_t)sslot[n] * VROW; };
+    auto prow = [&](int pn) { return so.pstage + (size_t)sslot[NU + pn] * PROW; };
     cp_async_wait<0>();
     __syncthreads();   // this cell's raw inputs have landed; every warp is done with the previous cell
-    if (Sched::FUSED && k > 0 && tid == 0) sched.signal(k - 1);   // ... and has fenced its stores of that cell
     if (do_rhs) {
       for (int i = tid; i < 3 * NU; i += nt) {
         const int c = i / NU, n = i - c * NU;
@@ -142,7 +143,7 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
       for (int i = tid; i < a.ndt; i += nt) cp_async8(sTn + i, a.old_temp + sidt[i]);
     }
     cp_async_commit();
-    if (have_next) issue_raw(w_next, buf ^ 1);   // the CTA's next cell, while this one is computed
+    if (w_next < w_end) issue_raw(w_next, buf ^ 1);   // the CTA's next cell, while this one is computed
     cp_async_commit();
     const int cflag = snm[35];
     if (tid >= 96 && tid - 96 < NU) {   // warp 3 (the table build below keeps warps 0..3 busy with tid < 108 only partly)
@@ -189,7 +190,6 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
         for (int d = 0; d < 3; ++d) x[32 * d + j] = kinv[0][d] * r0 + kinv[1][d] * r1 + kinv[2][d] * r2;
       }
     }
-    if (Sched::FUSED && tid == 0) sched.wait_slot(k);   // the gather pass is done with the record this cell overwrites
     cp_async_wait<1>();   // the gathered old solution (the next cell's raw inputs may still be in flight)
     __syncthreads();
 
@@ -207,7 +207,7 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
               const double pv = X[q * LDB + PSI0 + frow];
               dmma(c0, c1, wq[q] * pv, pv);
             }
-            __stcg(reinterpret_cast<double2*>(S + OFF_PP + frow * NP + 2 * fk), make_double2(c0, c1));
+            __stcg(reinterpret_cast<double2*>(prow(frow) + 3 * BW + 2 * fk), make_double2(c0, c1));
           }
           break;
         }
@@ -283,10 +283,13 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
         }
         // direct orientation: row 8ta + frow, columns 8tb + 2fk + {0,1} (padding nodes contribute exact zeros)
         if (na < NU && 8 * tb_ + 2 * fk < BW) {
-          double* row = S + na * VROW + 8 * tb_ + 2 * fk;
+          double* row = vrow(na) + 8 * tb_ + 2 * fk;
+          __stcg(reinterpret_cast<double2*>(row), make_double2(dgj[0], dgj[1]));
 #pragma unroll
-          for (int r9 = 0; r9 < 9; ++r9) __stcg(reinterpret_cast<double2*>(row + r9 * BW), make_double2(Fj[0][r9], Fj[1][r9]));
-          __stcg(reinterpret_cast<double2*>(S + OFF_DG + na * BW + 8 * tb_ + 2 * fk), make_double2(dgj[0], dgj[1]));
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              __stcg(reinterpret_cast<double2*>(row + BW + c * CSEG + d * BW), make_double2(Fj[0][c * 3 + d], Fj[1][c * 3 + d]));
         }
         if (ta != tb_) {
           // transposed orientation: row node b, column node a, entry [d][c] = F[c][d]
@@ -294,12 +297,12 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
           for (int jj = 0; jj < 2; ++jj) {
             const int nb = 8 * tb_ + 2 * fk + jj;
             if (nb < NU) {   // column 8ta + frow <= 23 is always a real node here (ta < tb)
-              double* row = S + nb * VROW + 8 * ta + frow;
+              double* row = vrow(nb) + 8 * ta + frow;
+              __stcg(row, dgj[jj]);
 #pragma unroll
               for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) __stcg(row + (d * 3 + c) * BW, Fj[jj][c * 3 + d]);
-              __stcg(S + OFF_DG + nb * BW + 8 * ta + frow, dgj[jj]);
+                for (int d = 0; d < 3; ++d) __stcg(row + BW + d * CSEG + c * BW, Fj[jj][c * 3 + d]);
             }
           }
         }
@@ -336,12 +339,15 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
               }
             }
           }
+          double* vr = vrow(na) + BW + 3 * BW + 2 * fk;
+          double* p0 = prow(2 * fk) + na;
+          double* p1 = prow(2 * fk + 1) + na;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            // velocity-node row: [c][p]; pressure-node rows: [c][a]
-            __stcg(reinterpret_cast<double2*>(S + na * VROW + VPRS + c * 8 + 2 * fk), make_double2(sv[0][c], sv[1][c]));
-            __stcg(S + NU * VROW + (2 * fk) * PROW + c * BW + na, sv[0][c]);
-            __stcg(S + NU * VROW + (2 * fk + 1) * PROW + c * BW + na, sv[1][c]);
+            // velocity-node row: component c, pressure columns; pressure-node rows: [c][a]
+            __stcg(reinterpret_cast<double2*>(vr + c * CSEG), make_double2(sv[0][c], sv[1][c]));
+            __stcg(p0 + c * BW, sv[0][c]);
+            __stcg(p1 + c * BW, sv[1][c]);
           }
         }
       }
@@ -421,34 +427,7 @@ __device__ __forceinline__ void stage_cells(const MmaArgs& a, const CsView& cs, 
         }
       }
     }
-    if (Sched::FUSED) __threadfence();   // staged record visible device-wide before the barrier that precedes signal()
   }
-  if (Sched::FUSED) {
-    __syncthreads();
-    if (tid == 0 && k > 0) sched.signal(k - 1);
-  }
-}
-
-// one launch per chunk: the CTAs stride over the chunk's cells
-struct LaunchSched {
-  static constexpr bool FUSED = false;
-  long long w_begin, w_end;
-  int slot_begin, ring;
-  __device__ __forceinline__ bool cell(int k, long long& w, int& slot) const {
-    w = w_begin + blockIdx.x + (long long)k * gridDim.x;
-    if (w >= w_end) return false;
-    slot = slot_begin + (int)(w - w_begin);
-    if (slot >= ring) slot -= ring;
-    return true;
-  }
-  __device__ __forceinline__ void wait_slot(int) const {}
-  __device__ __forceinline__ void signal(int) const {}
-};
-
-__global__ void __launch_bounds__(MTHREADS, 4)
-th_stage_kernel(MmaArgs a, CsView cs, const double* __restrict__ dphi_lane, double* __restrict__ stage, long long w_begin, long long w_end,
-                int slot_begin, int ring) {
-  stage_cells(a, cs, dphi_lane, stage, LaunchSched{w_begin, w_end, slot_begin, ring});
 }
 
 // reference gradients in the order the table build reads them: [node of the group j][e][thread = 4 q + group]
@@ -462,219 +441,61 @@ __global__ void dphi_lane_kernel(const double* __restrict__ dphi_u, double* __re
 
 constexpr size_t stage_smem_bytes() {
   return sizeof(double) * (KQ * LDB + 32 + 2 * (GS + 1) + 3 * NU + 1 + NQ * 3 + 3 * BW + 32 + 28 + NQ * 12) + 2 * MSTR +
-         sizeof(int) * (2 * IDS + 2 * 28 + 3 * NU + NP) + 28 + 36;
+         sizeof(int) * (2 * IDS + 2 * 28 + 2 * SLOTS + 3 * NU + NP) + 28 + 36;
 }
 
-// ---- gather: one warp per (chunk, node) -------------------------------------------------------------------------
+// ---- gather: one warp per (chunk, node) ---------------------------------------------------------------------------
+// Everything an item needs arrives through one sequential stream per kind: the staged rows of its incidences (written
+// by the stage pass) and, in the same order, a static record per incidence (built once with the plan): a 16-byte
+// header, the positions of the incidence's column nodes inside the rows of nse_matrix and inside the rows of the
+// preconditioner.  A warp owns a contiguous run of items; one lane feeds a ring of RD slots with two bulk copies per
+// incidence (staged row, static record), all lanes add a landed slot into shared-memory accumulators and write the rows
+// of a finished item.
+struct IncHdr {
+  unsigned e;    // (cell inside the chunk << 5) | local node, bit 31: the cell holds constrained velocity dofs
+  int wp;        // index of the cell in the preconditioner's plan; -1: not gathered for that matrix
+  unsigned hi;   // bit 0: that plan's cell holds constrained dofs, bits 1..27: index of its wide table + 1, bit 29: the item has
+                 // such cells (general path for the preconditioner), bit 30: first chunk that touches the node, bit 31: last
+                 // incidence of the item
+  int g0n;       // first dof / row of the next item (-1: none): its row starts are fetched one item ahead
+};
+constexpr unsigned HI_NP = 1u << 29, HI_FIRST = 1u << 30, HI_LAST = 1u << 31, HI_WIDE = 0x0ffffffeu;
+constexpr int META = 18;                    // doubles per static record: header (16 B), positions (72 B), preconditioner positions (56 B)
+constexpr int MPOS = 8, MPPOS = 8 + 36;     // u16 offsets of the two position rows inside the record
+constexpr int VSLOT = VROW + META;          // ring slot (322 doubles): a velocity-node row or a pressure-node row, then the record
+
 struct GatherArgs {
   const int* v_g0;
   const unsigned* v_incptr;
-  const unsigned char* v_flag;
-  const unsigned* v_inc;
+  const double* v_meta;                      // [incidence][META]
   const int* p_g0;
   const unsigned* p_incptr;
-  const unsigned char* p_flag;
-  const unsigned* p_inc;
+  const double* p_meta;
   long long v_begin, v_end, p_begin, p_end;  // item ranges of this chunk
   long long w_base;                          // first plan cell of the chunk
-  int slot_base, ring;                       // its staging slot; slots wrap at `ring`
-  const unsigned short* pos;
   const unsigned char* nmask;
-  const double* stage;
+  const double* vstage;                      // the chunk's staged velocity-node rows, in incidence order
+  const double* pstage;                      // ... pressure-node rows
+  // fused preconditioner: masks and per-component positions of the cells on the general path
+  const unsigned char* pnmask;
+  const unsigned short* ppos_wide;
+  int pstr;                                  // length of the accumulator of one preconditioner row (even)
+  int wb;                                    // items per block: a warp takes blocks round-robin
 };
 
 constexpr unsigned INC_CS = 0x80000000u;     // incidence word: the cell holds constrained velocity dofs
-
-// what one incidence (cell of the chunk, local node) contributes to a velocity node: loaded one incidence ahead
-// (positions and masks keep their 16- / 8-bit types until they are used: a widening right after the load would make the
-// prefetch wait for it)
-struct VInc {
-  double v[9];   // lane = column node b: staged [r][b]
-  double vp;     // lanes < 24: staged [c][p]
-  unsigned short ob, op;
-  unsigned char mb, maskA;
-  int a;
-};
-
-__device__ __forceinline__ void load_vinc(VInc& I, const GatherArgs& g, unsigned e, int lane) {
-  const int a = e & 31;
-  const unsigned wl = (e & ~INC_CS) >> 5;
-  const size_t w = (size_t)g.w_base + wl;
-  int slot = g.slot_base + (int)wl;
-  if (slot >= g.ring) slot -= g.ring;
-  const unsigned short* prow = g.pos + w * PSTR + a * NE;
-  const double* S = g.stage + (size_t)slot * REC + a * VROW;
-  I.a = a;
-  I.ob = 0;
-  I.op = 0;
-  if (lane < NU) I.ob = prow[lane];
-  if (lane < NP) I.op = prow[NU + lane];
-  I.mb = 7;
-  I.maskA = 7;
-  if (e & INC_CS) {
-    const unsigned char* mrow = g.nmask + w * MSTR;
-    I.mb = 0;
-    if (lane < NU) I.mb = mrow[lane];
-    I.maskA = mrow[a];
-  }
-#pragma unroll
-  for (int r = 0; r < 9; ++r) I.v[r] = lane < NU ? __ldcg(S + r * BW + lane) : 0.0;
-  I.vp = lane < 24 ? __ldcg(S + VPRS + lane) : 0.0;
-}
-
-// add one incidence into the warp's accumulators (the nine targets of a lane are distinct: load all, then store all)
-__device__ __forceinline__ void add_vinc(const VInc& I, double* acc, double* acc01, double* accd, int lane) {
-  const int ob = I.ob, mb = I.mb;
-  if (I.maskA == 7 && __all_sync(0xffffffffu, lane >= NU || mb == 7)) {
-    if (lane < NU) {
-      double tv[9];
-#pragma unroll
-      for (int r = 0; r < 9; ++r) tv[r] = acc[(r / 3) * ASTR + ob + (r % 3)];
-#pragma unroll
-      for (int r = 0; r < 9; ++r) acc[(r / 3) * ASTR + ob + (r % 3)] = tv[r] + I.v[r];
-    }
-    const int o = __shfl_sync(0xffffffffu, (int)I.op, lane & 7);
-    if (lane < 24) acc01[(lane >> 3) * L01 + o] += I.vp;
-  } else {
-    const int maskA = I.maskA;
-    if (lane < NU) {
-      int idx[9];
-      double tv[9];
-#pragma unroll
-      for (int r = 0; r < 9; ++r) {
-        const int c = r / 3, d = r - 3 * c;
-        const bool on = ((maskA >> c) & 1) && ((mb >> d) & 1);
-        idx[r] = on ? c * ASTR + ob + __popc(mb & ((1 << d) - 1)) : -1;
-      }
-#pragma unroll
-      for (int r = 0; r < 9; ++r) tv[r] = idx[r] >= 0 ? acc[idx[r]] : 0.0;
-#pragma unroll
-      for (int r = 0; r < 9; ++r)
-        if (idx[r] >= 0) acc[idx[r]] = tv[r] + I.v[r];
-      if (lane == I.a && maskA != 7) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (!((maskA >> c) & 1)) accd[c] += I.v[4 * c];
-      }
-    }
-    const int c = lane >> 3;
-    const int o = __shfl_sync(0xffffffffu, (int)I.op, lane & 7);
-    if (lane < 24 && ((maskA >> c) & 1)) acc01[c * L01 + o] += I.vp;
-  }
-  __syncwarp();
-}
-
-// write `len` accumulated entries to the row at `out` (store, or add to what earlier chunks left there) and leave the
-// accumulators zero for the next item
-__device__ __forceinline__ void flush_row(double* __restrict__ out, double* acc, int len, bool first, int lane) {
-  if (first) {
-#pragma unroll 4
-    for (int k = lane; k < len; k += 32) {
-      out[k] = acc[k];
-      acc[k] = 0.0;
-    }
-  } else {
-    for (int k0 = lane; k0 < len; k0 += 128) {
-      double old[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) old[u] = k0 + 32 * u < len ? __ldcg(out + k0 + 32 * u) : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + 32 * u;
-        if (k < len) {
-          out[k] = old[u] + acc[k];
-          acc[k] = 0.0;
-        }
-      }
-    }
-  }
-}
-
 constexpr unsigned FULLM = 0xffffffffu;
-constexpr int WB = 32;   // items per block: a warp takes blocks round-robin, so expensive items (rows that earlier chunks
-                         // already touched are read-modify-written) spread over all warps
 
-// Walk the items [begin, end) block-cyclically.  Per block: the 32 item headers are read at once (lane t <-> item t);
-// the incidence words of the block are read 32 at a time, one batch ahead; the loads of incidence i + 1 (`load`) and
-// the row starts of item t + 1 (`rows`) are in flight while incidence i / item t are processed (`add`, `flush`).
-// `aux` maps an incidence word to a second index that is fetched together with the words.
-template <class Inc, int WBT, class AuxF, class RowF, class LoadF, class AddF, class FlushF>
-__device__ __forceinline__ void walk_items(const int* __restrict__ g0s, const unsigned char* __restrict__ flags, const unsigned* __restrict__ incptr,
-                                           const unsigned* __restrict__ incs, long long begin, long long end, long long gw, long long nw, int lane,
-                                           AuxF aux, RowF rows, LoadF load, AddF add, FlushF flush) {
-  for (long long j_lo = begin + gw * WBT; j_lo < end; j_lo += nw * WBT) {
-    const int n_it = (int)((j_lo + WBT < end ? j_lo + WBT : end) - j_lo);
-    int h_g0 = 0, h_first = 0;
-    unsigned h_iend = 0;
-    if (lane < n_it) {
-      h_g0 = g0s[j_lo + lane];
-      h_first = flags[j_lo + lane] & 1;
-      h_iend = incptr[j_lo + lane + 1];
-    }
-    const unsigned i_lo = incptr[j_lo], i_hi = __shfl_sync(FULLM, h_iend, n_it - 1);
-    unsigned ec = 0, en = 0, ib = i_lo;
-    long long ac = -1, an = -1;
-    if (ib + lane < i_hi) { ec = incs[ib + lane]; ac = aux(ec); }
-    if (ib + 32 + lane < i_hi) { en = incs[ib + 32 + lane]; an = aux(en); }
-    auto rotate = [&]() {
-      ib += 32;
-      ec = en; ac = an;
-      en = 0; an = -1;
-      if (ib + 32 + lane < i_hi) { en = incs[ib + 32 + lane]; an = aux(en); }
-    };
-    auto word = [&](unsigned i) {
-      const unsigned k = i - ib;
-      return k < 32 ? __shfl_sync(FULLM, ec, (int)k) : __shfl_sync(FULLM, en, (int)(k - 32));
-    };
-    auto auxw = [&](unsigned i) {
-      const unsigned k = i - ib;
-      return k < 32 ? __shfl_sync(FULLM, ac, (int)k) : __shfl_sync(FULLM, an, (int)(k - 32));
-    };
-    long long rnext = rows(__shfl_sync(FULLM, h_g0, 0));
-    Inc bufA, bufB;
-    unsigned i = i_lo;
-    load(bufA, word(i), auxw(i));
-    for (int t = 0; t < n_it; ++t) {
-      const unsigned it_end = __shfl_sync(FULLM, h_iend, t);
-      const bool first = __shfl_sync(FULLM, h_first, t) != 0;
-      const long long rcur = rnext;
-      if (t + 1 < n_it) rnext = rows(__shfl_sync(FULLM, h_g0, t + 1));
-      // incidences of the item, two per trip: one buffer is consumed while the other one's loads are in flight
-      while (i < it_end) {
-        if (i - ib >= 32) rotate();
-        if (i + 1 < i_hi) load(bufB, word(i + 1), auxw(i + 1));
-        add(bufA);
-        ++i;
-        if (i < it_end) {
-          if (i - ib >= 32) rotate();
-          if (i + 1 < i_hi) load(bufA, word(i + 1), auxw(i + 1));
-          add(bufB);
-          ++i;
-        } else {
-          bufA = bufB;   // the prefetched incidence belongs to the next item
-          break;
-        }
-      }
-      flush(rcur, first);
-    }
-  }
-}
-
-// (A register ring with 3-4 incidences in flight per warp was measured slower than the two-buffer walk above: 1.5 ms
-// against 1.16 ms per 65 536 cells for the preconditioner's gather -- these passes are bound by the DRAM efficiency of
-// their 2 kB-granular accesses, not by the depth of the prefetch.)
-
-// ---- TMA bulk copies into a per-warp ring ---------------------------------------------------------------------------
-// A staged velocity-node row is one regular 2 208-byte tile: one elected lane fetches it with cp.async.bulk (SASS UBLKCP),
-// completion is counted on an mbarrier of the slot.  GD rows are in flight per warp while one is added -- the gather is
-// bound by the latency of these loads, not by their bytes.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void bulk_load_row(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned bytes) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's previous readers (generic proxy) come first
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one regular tile of a stream -> shared memory (SASS UBLKCP); completion is counted on the slot's mbarrier
+__device__ __forceinline__ void bulk_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                "r"(bytes), "r"(smem_u32(bar))
                : "memory");
@@ -693,529 +514,355 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// velocity items of one chunk through the ring (same item / incidence walk as walk_items)
-template <int WBT>
-__device__ __forceinline__ void gather_system_velocity_bulk(const GatherArgs& g, const BlockView& A, double* acc, double* ring,
-                                                            unsigned long long* bars, long long gw, long long nw, int lane) {
-  double* acc01 = acc + 3 * ASTR;
-  double* accd = acc01 + 3 * L01;
-  const long long* rp00 = A.rowptr[0][0];
-  const long long* rp01 = A.rowptr[0][1];
-  double* v00 = A.val[0][0];
-  double* v01 = A.val[0][1];
-  unsigned phases = 0;   // parity of every slot's next completion
-  for (long long j_lo = g.v_begin + gw * WBT; j_lo < g.v_end; j_lo += nw * WBT) {
-    const int n_it = (int)((j_lo + WBT < g.v_end ? j_lo + WBT : g.v_end) - j_lo);
-    int h_g0 = 0, h_first = 0;
-    unsigned h_iend = 0;
-    if (lane < n_it) {
-      h_g0 = g.v_g0[j_lo + lane];
-      h_first = g.v_flag[j_lo + lane] & 1;
-      h_iend = g.v_incptr[j_lo + lane + 1];
+// write `len` accumulated entries to the row at `out` (store, or add to what earlier chunks left there); ZERO: leave the
+// accumulators zero for the next item.  Rows longer than `cap` (preconditioner rows of nodes with no-normal-flux lines:
+// their cells are not gathered, nothing was accumulated beyond cap): the tail is stored as zeros by the first chunk.
+template <bool ZERO>
+__device__ __forceinline__ void flush_row(double* __restrict__ out, double* acc, int len, int cap, bool first, int lane) {
+  const int n = len < cap ? len : cap;
+  if (first) {
+    int k = lane;
+    for (; k + 96 < n; k += 128) {
+      const double v0 = acc[k], v1 = acc[k + 32], v2 = acc[k + 64], v3 = acc[k + 96];
+      __stcs(out + k, v0);
+      __stcs(out + k + 32, v1);
+      __stcs(out + k + 64, v2);
+      __stcs(out + k + 96, v3);
+      if (ZERO) acc[k] = acc[k + 32] = acc[k + 64] = acc[k + 96] = 0.0;
     }
-    const unsigned i_lo = g.v_incptr[j_lo], i_hi = __shfl_sync(FULLM, h_iend, n_it - 1);
-    unsigned ec = 0, en = 0, ib = i_lo;
-    if (ib + lane < i_hi) ec = g.v_inc[ib + lane];
-    if (ib + 32 + lane < i_hi) en = g.v_inc[ib + 32 + lane];
-    auto word = [&](unsigned i) {
-      const unsigned k = i - ib;
-      return k < 32 ? __shfl_sync(FULLM, ec, (int)k) : __shfl_sync(FULLM, en, (int)(k - 32));
-    };
-    auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : (lane < 8 ? rp01[g0 + lane - 4] : 0ll); };
-    // per-slot metadata (registers; the slot index is a compile-time constant everywhere below)
-    unsigned short m_ob[GD], m_op[GD];
-    unsigned char m_mb[GD], m_maskA[GD];
-    int m_a[GD];
-    auto issue = [&](unsigned i, int u, unsigned short& ob, unsigned char& mb, unsigned short& op, int& aa, unsigned char& maskA) {
-      const unsigned e = word(i);
-      const int a = e & 31;
-      const unsigned wl = (e & ~INC_CS) >> 5;
-      const size_t w = (size_t)g.w_base + wl;
-      int slot = g.slot_base + (int)wl;
-      if (slot >= g.ring) slot -= g.ring;
-      if (lane == 0) bulk_load_row(ring + u * VROW, g.stage + (size_t)slot * REC + a * VROW, VROW * 8, bars + u);
-      const unsigned short* prow = g.pos + w * PSTR + a * NE;
-      aa = a;
-      ob = 0;
-      op = 0;
-      if (lane < NU) ob = prow[lane];
-      if (lane < NP) op = prow[NU + lane];
-      mb = 7;
-      maskA = 7;
-      if (e & INC_CS) {
-        const unsigned char* mrow = g.nmask + w * MSTR;
-        mb = 0;
-        if (lane < NU) mb = mrow[lane];
-        maskA = mrow[a];
-      }
-    };
-    long long rnext = rows(__shfl_sync(FULLM, h_g0, 0));
+    for (; k < n; k += 32) {
+      __stcs(out + k, acc[k]);
+      if (ZERO) acc[k] = 0.0;
+    }
+    for (k = cap + lane; k < len; k += 32) __stcs(out + k, 0.0);
+  } else {
+    for (int k0 = lane; k0 < n; k0 += 128) {
+      double old[4];
 #pragma unroll
-    for (int u = 0; u < GD; ++u)
-      if (i_lo + u < i_hi) issue(i_lo + u, u, m_ob[u], m_mb[u], m_op[u], m_a[u], m_maskA[u]);
-    unsigned i = i_lo;
-    int t = 0, maskA_item = 7;
-    unsigned it_end = __shfl_sync(FULLM, h_iend, 0);
-    bool first = __shfl_sync(FULLM, h_first, 0) != 0;
-    long long rcur = rnext;
-    if (n_it > 1) rnext = rows(__shfl_sync(FULLM, h_g0, 1));
-    while (i < i_hi) {
+      for (int u = 0; u < 4; ++u) old[u] = k0 + 32 * u < n ? __ldcs(out + k0 + 32 * u) : 0.0;
 #pragma unroll
-      for (int u = 0; u < GD; ++u) {
-        if (i < i_hi) {
-          mbar_wait(bars + u, (phases >> u) & 1u);
-          phases ^= 1u << u;
-          VInc I;
-          const double* S = ring + u * VROW;
-#pragma unroll
-          for (int r = 0; r < 9; ++r) I.v[r] = lane < NU ? S[r * BW + lane] : 0.0;
-          I.vp = lane < 24 ? S[VPRS + lane] : 0.0;
-          I.ob = m_ob[u];
-          I.mb = m_mb[u];
-          I.op = m_op[u];
-          I.a = m_a[u];
-          I.maskA = m_maskA[u];
-          maskA_item = I.maskA;
-          add_vinc(I, acc, acc01, accd, lane);   // ends with __syncwarp: every lane has read the slot
-          if (i - ib >= 32) {   // keep the word window ahead of the prefetch distance
-            ib += 32;
-            ec = en;
-            en = 0;
-            if (ib + 32 + lane < i_hi) en = g.v_inc[ib + 32 + lane];
-          }
-          if (i + GD < i_hi) issue(i + GD, u, m_ob[u], m_mb[u], m_op[u], m_a[u], m_maskA[u]);
-          ++i;
-          if (i == it_end) {   // the item is complete: write its rows, move to the next item
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
-              const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
-              if ((maskA_item >> c) & 1) {
-                flush_row(v00 + rs, acc + c * ASTR, len, first, lane);
-                flush_row(v01 + rs01, acc01 + c * L01, len01, first, lane);
-              } else if (lane == 0) {
-                double* out = v00 + rs;   // constrained dof: the row holds its diagonal only
-                if (first) {
-                  out[0] = accd[c];
-                  for (int k = 1; k < len; ++k) out[k] = 0.0;
-                  for (int k = 0; k < len01; ++k) v01[rs01 + k] = 0.0;
-                } else
-                  out[0] = __ldcg(out) + accd[c];
-                accd[c] = 0.0;
-              }
-            }
-            __syncwarp();
-            maskA_item = 7;
-            ++t;
-            if (t < n_it) {
-              it_end = __shfl_sync(FULLM, h_iend, t);
-              first = __shfl_sync(FULLM, h_first, t) != 0;
-              rcur = rnext;
-              if (t + 1 < n_it) rnext = rows(__shfl_sync(FULLM, h_g0, t + 1));
-            }
-          }
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        if (k < n) {
+          __stcs(out + k, old[u] + acc[k]);
+          if (ZERO) acc[k] = 0.0;
         }
       }
     }
   }
 }
 
-struct PInc {
-  double v[3];
-  unsigned short ob;
-  unsigned char mb;
+// Per-warp shared memory: acc [3][ACC0] (rows of block(0,0) / one row of block(1,0)), acc01 [3][L01], accP [pstr] (one
+// preconditioner row), accd [4] (diagonals of constrained rows), the ring and its mbarriers.
+struct WarpMem {
+  double *acc, *acc01, *accP, *accd, *ring;
+  unsigned long long* bars;
 };
 
-// the items of one chunk, system matrix: `acc` = this warp's zeroed accumulators [3][ASTR] + [3][L01] + diagonals
-template <int WBT, bool VELOCITY = true>
-__device__ __forceinline__ void gather_system(const GatherArgs& g, const BlockView& A, double* acc, long long gw, long long nw, int lane) {
-  double* acc01 = acc + 3 * ASTR;           // [3][L01]
-  double* accd = acc01 + 3 * L01;           // [3] constrained diagonals
-  const long long* rp00 = A.rowptr[0][0];
-  const long long* rp01 = A.rowptr[0][1];
-  const long long* rp10 = A.rowptr[1][0];
-  double* v00 = A.val[0][0];
-  double* v01 = A.val[0][1];
-  double* v10 = A.val[1][0];
-  auto no_aux = [](unsigned) { return 0ll; };
-
-  // velocity nodes: rows (g0 + c) of block(0,0) and block(0,1)
-  if (VELOCITY) {
+// Walk this warp's blocks of items.  VEL: velocity nodes -- rows (g0 + c) of block(0,0), block(0,1) and of the
+// preconditioner's block(0,0); else pressure nodes -- a row of block(1,0) and of the preconditioner's block(1,1).
+template <bool VEL, bool PRE>
+__device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockView& A, const BlockView& Ap, const WarpMem& m, unsigned& phases,
+                                             long long gw, long long nw, int lane) {
+  constexpr int ROWD = VEL ? VROW : PROW;
+  const int* __restrict__ g0s = VEL ? g.v_g0 : g.p_g0;
+  const unsigned* __restrict__ incptr = VEL ? g.v_incptr : g.p_incptr;
+  const double* __restrict__ meta = VEL ? g.v_meta : g.p_meta;
+  const double* __restrict__ stage = VEL ? g.vstage : g.pstage;
+  const long long begin = VEL ? g.v_begin : g.p_begin, end = VEL ? g.v_end : g.p_end;
+  const long long i0 = (long long)(VEL ? NU : NP) * g.w_base;   // first incidence of the chunk: staging slot = incidence - i0
+  const long long* rpa = VEL ? A.rowptr[0][0] : A.rowptr[1][0];
+  const long long* rpb = A.rowptr[0][1];
+  const long long* rpq = VEL ? Ap.rowptr[0][0] : Ap.rowptr[1][1];
+  double* va = VEL ? A.val[0][0] : A.val[1][0];
+  double* vb = A.val[0][1];
+  double* vq = VEL ? Ap.val[0][0] : Ap.val[1][1];
+  double* acc = m.acc;
+  double* acc01 = m.acc01;
+  double* accP = m.accP;
+  double* accd = m.accd;
+  // row starts of an item: lanes 0..3 block(0,0) (or 0..1 block(1,0)), 4..7 block(0,1), 8..11 the preconditioner's block
+  auto rows = [&](int g0) {
+    if (VEL) return lane < 4 ? rpa[g0 + lane] : (lane < 8 ? rpb[g0 + lane - 4] : (PRE && lane < 12 ? rpq[g0 + lane - 8] : 0ll));
+    return lane < 2 ? rpa[g0 + lane] : (PRE && lane >= 8 && lane < 10 ? rpq[g0 + lane - 8] : 0ll);
+  };
+  auto issue = [&](unsigned i, int u) {
+    if (lane == 0) {
+      double* slot = m.ring + u * VSLOT;
+      mbar_expect(m.bars + u, (ROWD + META) * 8);
+      bulk_load(slot, stage + (size_t)((long long)i - i0) * ROWD, ROWD * 8, m.bars + u);
+      bulk_load(slot + ROWD, meta + (size_t)i * META, META * 8, m.bars + u);
+    }
+  };
+  for (long long j_lo = begin + gw * g.wb; j_lo < end; j_lo += nw * g.wb) {
+    const long long j_hi = j_lo + g.wb < end ? j_lo + g.wb : end;
+    const unsigned i_lo = incptr[j_lo], i_hi = incptr[j_hi];
+    unsigned pi = i_lo;
+    int u = 0;
+    for (; u < RD && pi < i_hi; ++u, ++pi) issue(pi, u);
+    u = 0;
+    long long rcur = rows(g0s[j_lo]), rnext = 0;
+    bool item_start = true;
     int maskA = 7;
-    auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : (lane < 8 ? rp01[g0 + lane - 4] : 0ll); };
-    auto load = [&](VInc& I, unsigned e, long long) { load_vinc(I, g, e, lane); };
-    auto add = [&](const VInc& I) {
-      maskA = I.maskA;
-      add_vinc(I, acc, acc01, accd, lane);
-    };
-    auto flush = [&](long long rcur, bool first) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
-        const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
-        if ((maskA >> c) & 1) {
-          flush_row(v00 + rs, acc + c * ASTR, len, first, lane);
-          flush_row(v01 + rs01, acc01 + c * L01, len01, first, lane);
-        } else if (lane == 0) {
-          // constrained dof: the row holds its diagonal only
-          double* out = v00 + rs;
-          if (first) {
-            out[0] = accd[c];
-            for (int k = 1; k < len; ++k) out[k] = 0.0;
-            for (int k = 0; k < len01; ++k) v01[rs01 + k] = 0.0;
-          } else
-            out[0] = __ldcg(out) + accd[c];
-          accd[c] = 0.0;
+    for (unsigned ci = i_lo; ci < i_hi; ++ci) {
+      mbar_wait(m.bars + u, (phases >> u) & 1u);
+      phases ^= 1u << u;
+      const double* S = m.ring + u * VSLOT;
+      const uint4 hw = *reinterpret_cast<const uint4*>(S + ROWD);
+      const unsigned short* spos = reinterpret_cast<const unsigned short*>(S + ROWD) + MPOS;
+      const unsigned short* sppos = reinterpret_cast<const unsigned short*>(S + ROWD) + MPPOS;
+      const unsigned e = hw.x, hi = hw.z;
+      const int wp = (int)hw.y;
+      const bool first = (hi & HI_FIRST) != 0, np = PRE && (hi & HI_NP) != 0;
+      const int a = e & 31;
+      if (item_start) {
+        item_start = false;
+        const int g0n = (int)hw.w;
+        if (g0n >= 0) rnext = rows(g0n);
+        if (VEL && np && first) {
+          // general path of the preconditioner: its rows are updated in place, so the first chunk clears them first
+          const long long ps = __shfl_sync(FULLM, rcur, 8), pe = __shfl_sync(FULLM, rcur, 11);
+          for (long long k = ps + lane; k < pe; k += 32) vq[k] = 0.0;
+          __syncwarp();
         }
       }
-      maskA = 7;
-      __syncwarp();
-    };
-    walk_items<VInc, WBT>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, no_aux, rows, load, add, flush);
-  }
-
-  // pressure nodes: row of block(1,0)
-  {
-    auto rows = [&](int pr) { return lane < 2 ? rp10[pr + lane] : 0ll; };
-    auto load = [&](PInc& I, unsigned e, long long) {
-      const int pn = e & 31;
-      const unsigned wl = (e & ~INC_CS) >> 5;
-      const size_t w = (size_t)g.w_base + wl;
-      int slot = g.slot_base + (int)wl;
-      if (slot >= g.ring) slot -= g.ring;
-      I.ob = 0;
-      I.mb = 0;
-      I.v[0] = I.v[1] = I.v[2] = 0.0;
-      if (lane < NU) {
-        I.ob = g.pos[w * PSTR + (NU + pn) * NE + lane];
-        I.mb = 7;
-        if (e & INC_CS) I.mb = g.nmask[w * MSTR + lane];
-        const double* S = g.stage + (size_t)slot * REC + NU * VROW + pn * PROW;
+      if (VEL) {
+        int mb = 7, mA = 7;
+        if (e & INC_CS) {
+          const unsigned char* mrow = g.nmask + ((size_t)g.w_base + ((e & ~INC_CS) >> 5)) * MSTR;
+          mb = lane < NU ? mrow[lane] : 0;
+          mA = mrow[a];
+        }
+        maskA = mA;
+        if (mA == 7 && __all_sync(FULLM, lane >= NU || mb == 7)) {
+          if (lane < NU) {
+            double* t = acc + spos[lane];
+            const double* s = S + BW + lane;
+            double tv[9];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) I.v[c] = __ldcg(S + c * BW + lane);
+            for (int r = 0; r < 9; ++r) tv[r] = t[(r / 3) * ACC0 + (r % 3)];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) t[(r / 3) * ACC0 + (r % 3)] = tv[r] + s[(r / 3) * CSEG + (r % 3) * BW];
+          }
+          if (lane < 3 * NP) {
+            const int c = lane >> 3, p = lane & 7;
+            acc01[c * L01 + spos[NU + p]] += S[BW + c * CSEG + 3 * BW + p];
+          }
+        } else {
+          if (lane < NU) {
+            const int ob = spos[lane];
+            int idx[9];
+            double tv[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+              const int c = r / 3, d = r - 3 * c;
+              const bool on = ((mA >> c) & 1) && ((mb >> d) & 1);
+              idx[r] = on ? c * ACC0 + ob + __popc(mb & ((1 << d) - 1)) : -1;
+            }
+#pragma unroll
+            for (int r = 0; r < 9; ++r) tv[r] = idx[r] >= 0 ? acc[idx[r]] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 9; ++r)
+              if (idx[r] >= 0) acc[idx[r]] = tv[r] + S[BW + (r / 3) * CSEG + (r % 3) * BW + lane];
+            if (lane == a && mA != 7) {   // constrained dof: |L_ii| staged in the slot [c][c] of the node's own column
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                if (!((mA >> c) & 1)) accd[c] += S[BW + c * CSEG + c * BW + a];
+            }
+          }
+          if (lane < 3 * NP) {
+            const int c = lane >> 3, p = lane & 7;
+            if ((mA >> c) & 1) acc01[c * L01 + spos[NU + p]] += S[BW + c * CSEG + 3 * BW + p];
+          }
+        }
+        if (PRE && wp >= 0) {
+          const double dg = lane < NU ? S[lane] : 0.0;
+          if (!np) {
+            if (lane < NU) {
+              const unsigned o = sppos[lane];
+              if (o != 0xffff) accP[o] += dg;
+            }
+          } else {
+            // cells with masks or per-component positions (boundary): read-modify-write of the rows in global memory
+            const int wide = (int)((hi & HI_WIDE) >> 1) - 1;
+            int pmb = 7, pa = 7;
+            if (hi & 1u) {
+              const unsigned char* nm = g.pnmask + (size_t)wp * MSTR;
+              pmb = lane < NU ? nm[lane] : 0;
+              pa = nm[a];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              double* row = vq + __shfl_sync(FULLM, rcur, 8 + c);
+              if (lane < NU) {
+                unsigned o = sppos[lane];
+                if (wide >= 0) o = g.ppos_wide[(size_t)wide * (3 * NU * NU) + c * (NU * NU) + a * NU + lane];
+                if ((((pa & pmb) >> c) & 1) && o != 0xffff) row[o] += dg;
+                if (lane == a && !((pa >> c) & 1)) row[0] += fabs(dg);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      } else {
+        if (lane < NU) {
+          int mb = 7;
+          if (e & INC_CS) mb = g.nmask[((size_t)g.w_base + ((e & ~INC_CS) >> 5)) * MSTR + lane];
+          const int ob = spos[lane];
+          int idx[3];
+          double tv[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) idx[c] = ((mb >> c) & 1) ? ob + __popc(mb & ((1 << c) - 1)) : -1;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tv[c] = idx[c] >= 0 ? acc[idx[c]] : 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (idx[c] >= 0) acc[idx[c]] = tv[c] + S[c * BW + lane];
+        }
+        if (PRE && wp >= 0 && lane < NP) {
+          const unsigned o = sppos[lane];
+          if (o != 0xffff) accP[o] += S[3 * BW + lane];
+        }
       }
-    };
-    auto add = [&](const PInc& I) {
-      if (lane < NU) {
-        int idx[3];
-        double tv[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) idx[c] = ((I.mb >> c) & 1) ? (int)I.ob + __popc((int)I.mb & ((1 << c) - 1)) : -1;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tv[c] = idx[c] >= 0 ? acc[idx[c]] : 0.0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (idx[c] >= 0) acc[idx[c]] = tv[c] + I.v[c];
+      __syncwarp();   // every lane has read the slot and updated the accumulators
+      if (pi < i_hi) {
+        issue(pi, u);
+        ++pi;
       }
-      __syncwarp();
-    };
-    auto flush = [&](long long rcur, bool first) {
-      const long long rs = __shfl_sync(FULLM, rcur, 0);
-      const int len = (int)(__shfl_sync(FULLM, rcur, 1) - rs);
-      flush_row(v10 + rs, acc, len, first, lane);
-      __syncwarp();
-    };
-    walk_items<PInc, WBT>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, no_aux, rows, load, add, flush);
+      u = u + 1 == RD ? 0 : u + 1;
+      if (hi & HI_LAST) {
+        if (VEL) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
+            const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
+            if ((maskA >> c) & 1) {
+              flush_row<true>(va + rs, acc + c * ACC0, len, ACC0, first, lane);
+              flush_row<true>(vb + rs01, acc01 + c * L01, len01, L01, first, lane);
+            } else if (lane == 0) {
+              // constrained dof: the row holds its diagonal only
+              double* out = va + rs;
+              if (first) {
+                out[0] = accd[c];
+                for (int k = 1; k < len; ++k) out[k] = 0.0;
+                for (int k = 0; k < len01; ++k) vb[rs01 + k] = 0.0;
+              } else
+                out[0] = __ldcg(out) + accd[c];
+              accd[c] = 0.0;
+            }
+          }
+          if (PRE && !np) {
+            // the three component rows of the node are equal: accumulated once, stored three times
+            const long long p0 = __shfl_sync(FULLM, rcur, 8), p1 = __shfl_sync(FULLM, rcur, 9), p2 = __shfl_sync(FULLM, rcur, 10),
+                            p3 = __shfl_sync(FULLM, rcur, 11);
+            flush_row<false>(vq + p0, accP, (int)(p1 - p0), g.pstr, first, lane);
+            flush_row<false>(vq + p1, accP, (int)(p2 - p1), g.pstr, first, lane);
+            flush_row<false>(vq + p2, accP, (int)(p3 - p2), g.pstr, first, lane);
+            int lm = (int)(p1 - p0) > (int)(p2 - p1) ? (int)(p1 - p0) : (int)(p2 - p1);
+            if ((int)(p3 - p2) > lm) lm = (int)(p3 - p2);
+            if (lm > g.pstr) lm = g.pstr;
+            for (int k = lane; k < lm; k += 32) accP[k] = 0.0;
+          }
+        } else {
+          const long long rs = __shfl_sync(FULLM, rcur, 0);
+          flush_row<true>(va + rs, acc, (int)(__shfl_sync(FULLM, rcur, 1) - rs), ACC0, first, lane);
+          if (PRE) {
+            const long long ps = __shfl_sync(FULLM, rcur, 8);
+            flush_row<true>(vq + ps, accP, (int)(__shfl_sync(FULLM, rcur, 9) - ps), g.pstr, first, lane);
+          }
+        }
+        __syncwarp();
+        rcur = rnext;
+        item_start = true;
+        maskA = 7;
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(GWARPS * 32, 2) th_gather_kernel(GatherArgs g, BlockView A) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = smem + warp * GACC;
-  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;   // invariant: all accumulators are zero between items
-  __syncwarp();
-  gather_system<WB>(g, A, acc, (long long)blockIdx.x * GWARPS + warp, (long long)gridDim.x * GWARPS, lane);
-}
+__host__ __device__ constexpr int gather_warp_doubles(int pstr) { return 3 * ACC0 + 3 * L01 + pstr + 4 + RD * VSLOT + RD + (RD & 1); }
 
-// The same pass with the staged rows fetched by TMA bulk copies into a ring of GD rows per warp (DCP_GATHER_BULK=1).
-// Measured slower than the register pipeline above (2.7 ms against 1.9 ms per 65 536 cells: the ring costs a quarter of
-// the resident warps and the pass is bound by DRAM efficiency, not by the depth of the prefetch); kept selectable.
-__global__ void __launch_bounds__(GSW * 32, 2) th_gather_bulk_kernel(GatherArgs g, BlockView A) {
+template <bool PRE>
+__global__ void __launch_bounds__(GW * 32) th_gather_kernel(GatherArgs g, BlockView A, BlockView Ap) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = smem + warp * GSWARP;
-  double* ring = acc + GACC;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + GD * VROW);
-  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;   // invariant: all accumulators are zero between items
+  const int nacc = 3 * ACC0 + 3 * L01 + g.pstr + 4;
+  WarpMem m;
+  m.acc = smem + warp * gather_warp_doubles(g.pstr);
+  m.acc01 = m.acc + 3 * ACC0;
+  m.accP = m.acc01 + 3 * L01;
+  m.accd = m.accP + g.pstr;
+  m.ring = m.acc + nacc;
+  m.bars = reinterpret_cast<unsigned long long*>(m.ring + RD * VSLOT);
+  for (int k = lane; k < nacc; k += 32) m.acc[k] = 0.0;   // invariant: all accumulators are zero between items
   if (lane == 0) {
-    for (int u = 0; u < GD; ++u) mbar_init(bars + u, 1);
+    for (int u = 0; u < RD; ++u) mbar_init(m.bars + u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  const long long gw = (long long)blockIdx.x * GSW + warp, nw = (long long)gridDim.x * GSW;
-  gather_system_velocity_bulk<WB>(g, A, acc, ring, bars, gw, nw, lane);
-  gather_system<WB, false>(g, A, acc, gw, nw, lane);
+  unsigned phases = 0;   // parity of every slot's next completion
+  const long long gw = (long long)blockIdx.x * GW + warp, nw = (long long)gridDim.x * GW;
+  gather_items<true, PRE>(g, A, Ap, m, phases, gw, nw, lane);
+  gather_items<false, PRE>(g, A, Ap, m, phases, gw, nw, lane);
 }
 
-// ---- fused preconditioner: second gather over the same (chunk, node) items ---------------------------------------
-// nse_preconditioner_matrix (include/core/boussinesq_model.tpp:421-476): velocity rows hold m + nu k on the same
-// component only, pressure rows the pressure mass matrix.  Positions and masks come from the preconditioner's own plan
-// (pre_w: its index of a system-plan cell).  Cells with no-normal-flux lines -- their C^T (dg I) C spreads over other
-// component pairs -- and cells outside that plan are skipped here and added afterwards by the reduction kernels; the
-// first chunk that touches a node stores its whole rows, so those later additions start from a defined state.
-struct PreArgs {
-  const long long* pre_w;           // per system-plan cell: low word = index in the preconditioner plan (-1: skipped here),
-                                    // high word = (index of its wide table + 1) << 1 | cell has constrained dofs
+// The static records of all incidences, in incidence order: one warp per item.
+struct MetaArgs {
+  long long n_items;
+  const int* g0s;
+  const unsigned* incptr;
+  const unsigned* incs;
+  const unsigned char* flags;
+  const long long* pre_w;          // nullptr: no fused preconditioner
   const unsigned short* pos;
-  const unsigned char* nmask;
-  const unsigned short* pos_wide;
+  const unsigned short* ppos;
+  long long chunk;                 // cells per chunk
+  double* meta;
 };
-
-struct PVInc {
-  double v;
-  unsigned short o0, o1, o2;
-  unsigned char mb, maskA;
-  int a, skip;
-};
-struct PPInc {
-  double v;
-  unsigned short o;
-  int skip;
-};
-
-// Accumulators of the preconditioner's gather: [3][PSTRIDE] + 3 diagonals.  The gathered contributions land on the
-// same component only (at most 125 entries per row; checked when the plan is attached); rows of nodes with
-// no-normal-flux lines are longer, but all their cells are skipped here, so the tail beyond PSTRIDE is stored as zeros.
-constexpr int PSTRIDE = 131;                   // 131 mod 16 == 3
-constexpr int PACC = 3 * PSTRIDE + 7;          // 400 doubles per warp
-
-template <int WBT>
-__device__ __forceinline__ void flush_row_capped(double* __restrict__ out, double* acc, int len, int cap, bool first, int lane) {
-  const int n = len < cap ? len : cap;
-  flush_row(out, acc, n, first, lane);
-  if (first)
-    for (int k = cap + lane; k < len; k += 32) out[k] = 0.0;
-}
-
-template <int WBT, int PS = PSTRIDE>
-__device__ __forceinline__ void gather_pre(const GatherArgs& g, const PreArgs& pa, const BlockView& A, double* acc, long long gw, long long nw, int lane) {
-  double* accd = acc + 3 * PS;
-  const long long* rp00 = A.rowptr[0][0];
-  const long long* rp11 = A.rowptr[1][1];
-  double* v00 = A.val[0][0];
-  double* v11 = A.val[1][1];
-  auto aux = [&](unsigned e) { return pa.pre_w[(size_t)g.w_base + ((e & ~INC_CS) >> 5)]; };
-  auto slot_of = [&](unsigned e) {
-    int slot = g.slot_base + (int)((e & ~INC_CS) >> 5);
-    return slot >= g.ring ? slot - g.ring : slot;
-  };
-  // velocity nodes
-  {
-    int maskA_item = 7;
-    auto rows = [&](int g0) { return lane < 4 ? rp00[g0 + lane] : 0ll; };
-    auto load = [&](PVInc& I, unsigned e, long long ax) {
-      const int wp = (int)(ax & 0xffffffffll), hi = (int)(ax >> 32);
-      I.skip = wp < 0;
-      I.a = e & 31;
-      I.v = 0.0;
-      I.o0 = I.o1 = I.o2 = 0xffff;
-      I.mb = I.maskA = 7;
-      if (wp < 0) return;
-      const unsigned char* nm = pa.nmask + (size_t)wp * MSTR;
-      const int cflag = hi & 1, wide = (hi >> 1) - 1;
-      if (lane < NU) {
-        I.v = __ldcg(g.stage + (size_t)slot_of(e) * REC + OFF_DG + I.a * BW + lane);
-        if (wide >= 0) {
-          const unsigned short* b = pa.pos_wide + (size_t)wide * (3 * NU * NU) + I.a * NU + lane;
-          I.o0 = b[0];
-          I.o1 = b[NU * NU];
-          I.o2 = b[2 * NU * NU];
-        } else {
-          const unsigned short o = pa.pos[(size_t)wp * PSTR + I.a * NE + lane];
-          I.o0 = o;
-          I.o1 = o;
-          I.o2 = o;
-        }
-        if (cflag) I.mb = nm[lane];
-      }
-      if (cflag) I.maskA = nm[I.a];
-    };
-    auto add = [&](const PVInc& I) {
-      if (!I.skip) {
-        maskA_item = I.maskA;
-        if (lane < NU) {
-          const int mm = I.maskA & I.mb;
-          if ((mm & 1) && I.o0 != 0xffff) acc[I.o0] += I.v;
-          if ((mm & 2) && I.o1 != 0xffff) acc[PS + I.o1] += I.v;
-          if ((mm & 4) && I.o2 != 0xffff) acc[2 * PS + I.o2] += I.v;
-          if (lane == I.a && I.maskA != 7) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              if (!((I.maskA >> c) & 1)) accd[c] += fabs(I.v);
-          }
-        }
-      }
-      __syncwarp();
-    };
-    auto flush = [&](long long rcur, bool first) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const long long rs = __shfl_sync(FULLM, rcur, c);
-        const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs);
-        if ((maskA_item >> c) & 1)
-          flush_row_capped<WBT>(v00 + rs, acc + c * PS, len, PS, first, lane);
-        else if (lane == 0) {
-          double* out = v00 + rs;
-          if (first) {
-            out[0] = accd[c];
-            for (int k = 1; k < len; ++k) out[k] = 0.0;
-          } else
-            out[0] = __ldcg(out) + accd[c];
-          accd[c] = 0.0;
-        }
-      }
-      maskA_item = 7;
-      __syncwarp();
-    };
-    walk_items<PVInc, WBT>(g.v_g0, g.v_flag, g.v_incptr, g.v_inc, g.v_begin, g.v_end, gw, nw, lane, aux, rows, load, add, flush);
+template <bool VEL>
+__global__ void gather_meta_kernel(MetaArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= a.n_items) return;
+  constexpr long long NL = VEL ? NU : NP;
+  const unsigned ib = a.incptr[j], ie = a.incptr[j + 1];
+  const long long ch = (long long)ib / (NL * a.chunk), w_base = ch * a.chunk;
+  int g0n = -1;
+  if (j + 1 < a.n_items && (long long)a.incptr[j + 1] / (NL * a.chunk) == ch) g0n = a.g0s[j + 1];
+  unsigned e = 0;
+  long long ax = -1;
+  if (ib + lane < ie) {
+    e = a.incs[ib + lane];
+    if (a.pre_w) ax = a.pre_w[w_base + ((e & ~INC_CS) >> 5)];
   }
-  // pressure nodes: rows of block(1,1)
-  {
-    auto rows = [&](int pr) { return lane < 2 ? rp11[pr + lane] : 0ll; };
-    auto load = [&](PPInc& I, unsigned e, long long ax) {
-      const int wp = (int)(ax & 0xffffffffll);
-      I.skip = wp < 0;
-      I.v = 0.0;
-      I.o = 0xffff;
-      if (wp < 0 || lane >= NP) return;
-      const int pn = e & 31;
-      I.v = __ldcg(g.stage + (size_t)slot_of(e) * REC + OFF_PP + pn * NP + lane);
-      I.o = pa.pos[(size_t)wp * PSTR + (NU + pn) * NE + NU + lane];
-    };
-    auto add = [&](const PPInc& I) {
-      if (!I.skip && lane < NP && I.o != 0xffff) acc[I.o] += I.v;
-      __syncwarp();
-    };
-    auto flush = [&](long long rcur, bool first) {
-      const long long rs = __shfl_sync(FULLM, rcur, 0);
-      const int len = (int)(__shfl_sync(FULLM, rcur, 1) - rs);
-      flush_row_capped<WBT>(v11 + rs, acc, len, PS, first, lane);
-      __syncwarp();
-    };
-    walk_items<PPInc, WBT>(g.p_g0, g.p_flag, g.p_incptr, g.p_inc, g.p_begin, g.p_end, gw, nw, lane, aux, rows, load, add, flush);
-  }
-}
-
-__global__ void __launch_bounds__(GWARPS * 32, 3) th_pre_gather_kernel(GatherArgs g, PreArgs pa, BlockView A) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = smem + warp * PACC;
-  for (int k = lane; k < PACC; k += 32) acc[k] = 0.0;
-  __syncwarp();
-  gather_pre<WB>(g, pa, A, acc, (long long)blockIdx.x * GWARPS + warp, (long long)gridDim.x * GWARPS, lane);
-}
-
-// ---- persistent kernel: staging ring in L2 ------------------------------------------------------------------------
-// One cooperative launch for the whole pass.  The first n_stage CTAs stage cells (chunk k = the k-th cell of every
-// stage CTA), the other CTAs gather: chunk by chunk, as soon as all its records are staged.  The ring holds `ring_chunks`
-// chunks (a few tens of MB: it lives in L2, the records never travel to HBM and back); a stage CTA overwrites a slot
-// once every gather warp has finished the chunk that used it.  Gather warps finish chunk c before any of them starts
-// c + 1, so the rows a node shares between chunks are read-modify-written in chunk order without atomics.
-// Dependencies: stage(k) <- gathered(k - ring_chunks) <- staged(k - ring_chunks): no cycle; the launch is cooperative, so
-// all CTAs are resident.  Every wait gives up after about a second and raises the abort flag (d_err[1]) instead of
-// hanging the device.
-struct FusedSync {
-  unsigned* staged;    // [n_chunks] records published
-  unsigned* gdone;     // [n_chunks] gather warps finished
-  int* err;            // d_err: [1] = abort
-};
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void spin_until(const unsigned* p, unsigned target, int* err) {
-  for (unsigned it = 0; it < (1u << 23); ++it) {
-    if (ld_acquire_u32(p) >= target) return;
-    if ((it & 1023) == 1023 && *reinterpret_cast<volatile int*>(err + 1) != 0) return;
-    __nanosleep(100);
-  }
-  atomicExch(err + 1, 1);   // give up: the results are invalid, the host reports it (dcp_check_device_errors)
-}
-
-struct FusedSched {
-  static constexpr bool FUSED = true;
-  long long n_cells;
-  int n_stage, ring_chunks, n_gather_warps, rank;
-  FusedSync sy;
-  __device__ __forceinline__ bool cell(int k, long long& w, int& slot) const {
-    w = (long long)k * n_stage + rank;
-    if (w >= n_cells) return false;
-    slot = (k % ring_chunks) * n_stage + rank;
-    return true;
-  }
-  __device__ __forceinline__ void wait_slot(int k) const {
-    if (k >= ring_chunks) spin_until(sy.gdone + (k - ring_chunks), (unsigned)n_gather_warps, sy.err);
-  }
-  __device__ __forceinline__ void signal(int k) const {
-    __threadfence();
-    atomicAdd(sy.staged + k, 1u);
-  }
-};
-
-struct FusedArgs {
-  MmaArgs a;
-  CsView cs;
-  const double* dphi_lane;
-  double* stage;
-  GatherArgs g;            // item arrays, plan, staging (per-chunk fields are set in the kernel)
-  PreArgs pa;
-  const long long* v_chunk_ptr;
-  const long long* p_chunk_ptr;
-  long long n_cells, n_chunks;
-  int n_stage, n_gather_ctas, ring_chunks, fuse_pre;
-  FusedSync sy;
-};
-
-constexpr size_t fused_smem_bytes() {
-  return stage_smem_bytes() > sizeof(double) * GACC * (MTHREADS / 32) ? stage_smem_bytes() : sizeof(double) * GACC * (MTHREADS / 32);
-}
-
-constexpr int WBF = 2;   // items per block in the persistent kernel (a chunk has about 8 items per gather warp)
-
-__global__ void __launch_bounds__(MTHREADS, 4) th_fused_kernel(const __grid_constant__ FusedArgs f, const __grid_constant__ BlockView A,
-                                                               const __grid_constant__ BlockView Apre) {
-  if ((int)blockIdx.x < f.n_stage) {
-    FusedSched sc;
-    sc.n_cells = f.n_cells;
-    sc.n_stage = f.n_stage;
-    sc.ring_chunks = f.ring_chunks;
-    sc.n_gather_warps = f.n_gather_ctas * (MTHREADS / 32);
-    sc.rank = (int)blockIdx.x;
-    sc.sy = f.sy;
-    stage_cells(f.a, f.cs, f.dphi_lane, f.stage, sc);
-    return;
-  }
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* acc = smem + warp * GACC;
-  for (int k = lane; k < GACC; k += 32) acc[k] = 0.0;
-  __syncwarp();
-  const long long gw = (long long)((int)blockIdx.x - f.n_stage) * (MTHREADS / 32) + warp, nw = (long long)f.n_gather_ctas * (MTHREADS / 32);
-  GatherArgs g = f.g;
-  g.ring = f.ring_chunks * f.n_stage;
-  for (long long c = 0; c < f.n_chunks; ++c) {
-    const long long w0 = c * f.n_stage;
-    const unsigned cells = (unsigned)(f.n_cells - w0 < f.n_stage ? f.n_cells - w0 : f.n_stage);
+  const bool np_item = __ballot_sync(FULLM, (int)ax >= 0 && (int)(ax >> 32) != 0) != 0;
+  const unsigned item_bits = (VEL && np_item ? HI_NP : 0u) | ((a.flags[j] & 1) ? HI_FIRST : 0u);
+  for (unsigned i = ib; i < ie; ++i) {
+    const unsigned ei = __shfl_sync(FULLM, e, (int)(i - ib));
+    const long long axi = __shfl_sync(FULLM, ax, (int)(i - ib));
+    const int wp = (int)axi, hi = (int)(axi >> 32);
+    const size_t w = (size_t)w_base + ((ei & ~INC_CS) >> 5);
+    const int ln = ei & 31;
+    double* rec = a.meta + (size_t)i * META;
     if (lane == 0) {
-      if (c > 0) spin_until(f.sy.gdone + (c - 1), (unsigned)nw, f.sy.err);   // rows shared with the previous chunk are final
-      spin_until(f.sy.staged + c, cells, f.sy.err);
+      IncHdr h;
+      h.e = ei;
+      h.wp = wp;
+      h.hi = (wp >= 0 ? ((unsigned)hi & (HI_WIDE | 1u)) : 0u) | item_bits | (i + 1 == ie ? HI_LAST : 0u);
+      h.g0n = g0n;
+      *reinterpret_cast<IncHdr*>(rec) = h;
     }
-    __syncwarp();
-    g.v_begin = f.v_chunk_ptr[c];
-    g.v_end = f.v_chunk_ptr[c + 1];
-    g.p_begin = f.p_chunk_ptr[c];
-    g.p_end = f.p_chunk_ptr[c + 1];
-    g.w_base = w0;
-    g.slot_base = (int)(c % f.ring_chunks) * f.n_stage;
-    gather_system<WBF>(g, A, acc, gw, nw, lane);
-    if (f.fuse_pre) gather_pre<WBF, ASTR>(g, f.pa, Apre, acc, gw, nw, lane);
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence();
-      atomicAdd(f.sy.gdone + c, 1u);
+    unsigned short* r16 = reinterpret_cast<unsigned short*>(rec);
+    const unsigned short* prow = a.pos + w * PSTR + (VEL ? ln : NU + ln) * NE;
+    for (int t = lane; t < 36; t += 32) r16[MPOS + t] = t < (VEL ? NE : NU) ? prow[t] : (unsigned short)0xffff;
+    if (lane < 28) {
+      unsigned short v = 0xffff;
+      if (wp >= 0) {
+        const unsigned short* pprow = a.ppos + (size_t)wp * PSTR + (VEL ? ln : NU + ln) * NE;
+        if (VEL ? lane < NU : lane < NP) v = VEL ? pprow[lane] : pprow[NU + lane];
+      }
+      r16[MPPOS + lane] = v;
     }
   }
 }
@@ -1244,24 +891,20 @@ void dcp_gather_plan_free(GatherPlan* p) {
   cudaFree(p->p_incptr);
   cudaFree(p->p_flag);
   cudaFree(p->p_inc);
+  cudaFree(p->slots);
+  cudaFree(p->v_meta);
+  cudaFree(p->p_meta);
   cudaFree(p->staging);
   cudaFree(p->dphi_lane);
   cudaFree(p->pre_w);
   cudaFree(p->pre_rest);
-  if (p->stream2) cudaStreamDestroy(p->stream2);
-  for (int i = 0; i < 2; ++i) {
-    if (p->ev_staged[i]) cudaEventDestroy(p->ev_staged[i]);
-    if (p->ev_gathered[i]) cudaEventDestroy(p->ev_gathered[i]);
-  }
-  cudaFree(p->d_v_chunk_ptr);
-  cudaFree(p->d_p_chunk_ptr);
-  cudaFree(p->sync);
   delete p;
 }
 
-// Items (chunk, node) with their incidences (cell of the chunk, local node) for the gather pass.  `cells` is the plan
-// order of the masked plan.  Returns DCP_OK with *out == nullptr when the model does not qualify (row longer than the
-// accumulators): the caller keeps the reduction path.
+// Items (chunk, node) with their incidences (cell of the chunk, local node) for the gather pass, and the staging slot
+// of every (cell, local node).  `cells` is the plan order of the masked plan.  Returns DCP_OK with *out == nullptr when
+// the model does not qualify (row longer than the accumulators, more than 8 cells of a chunk at one node): the caller
+// keeps the reduction path.
 int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vector<int32_t>& cells,
                           const std::vector<uint8_t>& cell_has_constraints, GatherPlan** out) {
   *out = nullptr;
@@ -1275,44 +918,10 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     return mx;
   };
   if (max_len(pat[0][0]) > LROW || max_len(pat[1][0]) > LROW || max_len(pat[0][1]) > L01) return DCP_OK;
-  // Default: one stage + gather launch pair per chunk of DCP_GATHER_CHUNK cells (65 536), staging in HBM.
-  // DCP_STAGED_MODE=persistent: one cooperative launch, chunk = one cell per staging CTA, the ring of `ring_chunks`
-  // chunks stays in L2.  Measured 7x slower than the launch pairs at refine 5 and 6 (the gather needs two thirds of the
-  // SMs at equal occupancy, and blocks of two items expose every load latency); kept as an experiment.
+  // one stage + gather launch pair per chunk of DCP_GATHER_CHUNK cells (default 65 536)
   int64_t chunk = 65536;
-  bool fused = false;
-  if (const char* e = std::getenv("DCP_STAGED_MODE")) fused = std::string(e) == "persistent";
-  int n_stage = 0, n_gather_ctas = 0, ring_chunks = 2;
-  if (const char* e = std::getenv("DCP_GATHER_CHUNK")) {
-    chunk = std::max<int64_t>(1, std::atoll(e));
-    fused = false;
-  }
-  if (fused) {
-    int coop = 0, per_sm = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->ctx->device);
-    const size_t smem_f = fused_smem_bytes();
-    const cudaError_t e1 = cudaFuncSetAttribute(th_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-    const cudaError_t e2 = e1 == cudaSuccess ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, th_fused_kernel, MTHREADS, smem_f) : e1;
-    if (!coop || e2 != cudaSuccess || per_sm < 2) {
-      if (std::getenv("DCP_VERBOSE"))
-        std::fprintf(stderr, "[dcp] persistent assembly kernel not used: cooperative launch %d, %s, %d CTAs per SM, %zu B shared memory\n", coop,
-                     cudaGetErrorString(e2), per_sm, smem_f);
-      cudaGetLastError();
-      fused = false;
-    } else {
-      const int total = per_sm * m->ctx->sm_count;
-      double frac = 0.25;   // share of the CTAs that gather
-      if (const char* e = std::getenv("DCP_FUSED_GATHER_FRACTION")) frac = std::min(0.75, std::max(0.05, std::atof(e)));
-      if (const char* e = std::getenv("DCP_FUSED_RING_CHUNKS")) ring_chunks = std::min(8, std::max(2, std::atoi(e)));
-      n_gather_ctas = std::max(1, (int)(total * frac + 0.5));
-      n_stage = total - n_gather_ctas;
-      chunk = n_stage;
-    }
-  }
+  if (const char* e = std::getenv("DCP_GATHER_CHUNK")) chunk = std::max<int64_t>(1, std::atoll(e));
   chunk = std::min<int64_t>(chunk, n);
-  if (fused && chunk < n_stage) {   // fewer cells than staging CTAs: one chunk
-    n_stage = (int)chunk;
-  }
   if (chunk >= (int64_t(1) << 26)) return DCP_OK;
   const int64_t n_chunks = (n + chunk - 1) / chunk;
   std::vector<int> sys_u(3 * NU), sys_p(NP);
@@ -1340,6 +949,7 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     std::vector<uint8_t> flag;
   };
   std::vector<ChunkItems> V((size_t)n_chunks), P((size_t)n_chunks);
+  std::vector<uint32_t> slots((size_t)n * SLOTS, 0u);
   bool too_many = false;   // the gather walks at most 8 incidences per item (hexahedral meshes without extraordinary edges)
 #pragma omp parallel
   {
@@ -1365,7 +975,10 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
           const uint32_t g0 = (uint32_t)(keys[k] >> 32);
           size_t e = k;
           while (e < keys.size() && (uint32_t)(keys[e] >> 32) == g0) {
-            I.inc.push_back((uint32_t)(keys[e] & 0xffffffffu));
+            const uint32_t word = (uint32_t)(keys[e] & 0xffffffffu);
+            I.inc.push_back(word);
+            // the staged row of this (cell, node) goes to the slot of its incidence: the rows of one node are consecutive
+            slots[(size_t)(w0 + ((word & ~INC_CS) >> 5)) * SLOTS + (pass == 0 ? 0 : NU) + (word & 31)] = (uint32_t)e;
             ++e;
           }
           I.g0.push_back((int32_t)g0);
@@ -1382,14 +995,8 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
   G->chunk = chunk;
   G->n_chunks = n_chunks;
   G->n_cells = n;
-  G->fused = fused;
-  G->n_stage = n_stage;
-  G->n_gather_ctas = n_gather_ctas;
-  G->ring_chunks = ring_chunks;
   if (std::getenv("DCP_VERBOSE"))
-    std::fprintf(stderr, "[dcp] staged assembly: %s, %lld cells in %lld chunks of %lld, %d staging + %d gathering CTAs, ring of %d chunks\n",
-                 fused ? "persistent kernel" : "one launch pair per chunk", (long long)n, (long long)n_chunks, (long long)chunk, n_stage,
-                 n_gather_ctas, ring_chunks);
+    std::fprintf(stderr, "[dcp] staged assembly: %lld cells in %lld chunks of %lld\n", (long long)n, (long long)n_chunks, (long long)chunk);
   dcp_ctx* ctx = m->ctx;
   int rc = DCP_OK;
   for (int pass = 0; pass < 2 && rc == DCP_OK; ++pass) {
@@ -1432,6 +1039,7 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     if (rc == DCP_OK) rc = upg(ctx, pass == 0 ? &G->v_flag : &G->p_flag, flag);
     cudaStreamSynchronize(ctx->stream);
   }
+  if (rc == DCP_OK) rc = upg(ctx, &G->slots, slots);
   if (rc == DCP_OK) {
     if (cudaMalloc((void**)&G->dphi_lane, sizeof(double) * 7 * 3 * 4 * NQ) != cudaSuccess) {
       cudaGetLastError();
@@ -1442,33 +1050,7 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
       if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = DCP_ERR_CUDA;
     }
   }
-  if (rc == DCP_OK && fused) {
-    rc = upg(ctx, reinterpret_cast<int64_t**>(&G->d_v_chunk_ptr), G->v_chunk_ptr);
-    if (rc == DCP_OK) rc = upg(ctx, reinterpret_cast<int64_t**>(&G->d_p_chunk_ptr), G->p_chunk_ptr);
-    if (rc == DCP_OK && cudaMalloc((void**)&G->sync, sizeof(unsigned) * 2 * (size_t)n_chunks) != cudaSuccess) rc = DCP_ERR_CUDA;
-    cudaStreamSynchronize(ctx->stream);
-  }
-  // DCP_STAGED_OVERLAP=1: two streams (see dcp_launch_th_staged).  Measured slower at refine 5 for every split of the SMs
-  // (19.2 ms with 2 + 1 CTAs per SM, 15.1 ms with full grids on both streams, against 14.1 ms on one stream): both sides
-  // are occupancy-starved already, halving their resident warps costs more than the overlap returns.
-  bool overlap = false;
-  if (const char* e = std::getenv("DCP_STAGED_OVERLAP")) overlap = !fused && n_chunks > 1 && std::atoi(e) != 0;
-  if (overlap) {
-    if (const char* e = std::getenv("DCP_OVERLAP_STAGE_CTAS")) G->overlap_stage_ctas = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("DCP_OVERLAP_GATHER_CTAS")) G->overlap_gather_ctas = std::max(1, std::atoi(e));
-    bool ok = cudaStreamCreateWithFlags(&G->stream2, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; ++i)
-      ok = cudaEventCreateWithFlags(&G->ev_staged[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&G->ev_gathered[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) {
-      cudaGetLastError();
-      if (G->stream2) cudaStreamDestroy(G->stream2);
-      G->stream2 = nullptr;
-      overlap = false;
-    }
-  }
-  const size_t staging_cells = fused ? (size_t)ring_chunks * (size_t)n_stage : (size_t)chunk * (overlap ? 2 : 1);
-  if (rc == DCP_OK && cudaMalloc((void**)&G->staging, sizeof(double) * (size_t)REC * staging_cells) != cudaSuccess) {
+  if (rc == DCP_OK && cudaMalloc((void**)&G->staging, sizeof(double) * (size_t)REC * (size_t)chunk) != cudaSuccess) {
     cudaGetLastError();
     dcp_set_error("gather plan: staging allocation failed");
     rc = DCP_ERR_CUDA;
@@ -1481,54 +1063,99 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
   return DCP_OK;
 }
 
-// Fused preconditioner: map the system plan's cells to the preconditioner plan.  Not attached (the preconditioner keeps
-// its own pass) when a row of that matrix is longer than the accumulators.
-int dcp_gather_plan_attach_pre(dcp_model* m, const dcp_model_desc* d, GatherPlan* G, const MaskedPlan* nse_plan, const MaskedPlan* pre_plan) {
-  if (!G || !nse_plan || !pre_plan || std::getenv("DCP_NO_FUSED_PRECONDITIONER")) return DCP_OK;
-  const dcp_csr_desc(*pat)[DCP_MAX_BLOCKS] = d->pre_pattern;
-  for (const dcp_csr_desc* P : {&pat[0][0], &pat[1][1]}) {
-    int64_t mx = 0;
-#pragma omp parallel for reduction(max : mx)
-    for (int64_t r = 0; r < P->n_rows; ++r) mx = std::max(mx, P->rowptr[r + 1] - P->rowptr[r]);
-    if (mx > LROW) return DCP_OK;
-  }
-  if (pre_plan->max_off_plain >= PSTRIDE) return DCP_OK;   // a gathered entry would not fit the compact accumulators
-  {
-    int64_t mx = 0;   // pressure mass rows go through the same accumulators
-    const dcp_csr_desc& P11 = pat[1][1];
-#pragma omp parallel for reduction(max : mx)
-    for (int64_t r = 0; r < P11.n_rows; ++r) mx = std::max(mx, P11.rowptr[r + 1] - P11.rowptr[r]);
-    if (mx > PSTRIDE) return DCP_OK;
-  }
-  std::vector<int32_t> of_cell((size_t)d->n_cells, -1);
-  for (size_t i = 0; i < pre_plan->h_cells.size(); ++i) of_cell[pre_plan->h_cells[i]] = (int32_t)i;
-  std::vector<long long> pre_w(nse_plan->h_cells.size(), -1ll);
-  std::vector<int32_t> rest;
-  for (size_t w = 0; w < nse_plan->h_cells.size(); ++w) {
-    const int32_t wp = of_cell[nse_plan->h_cells[w]];
-    if (wp >= 0 && pre_plan->h_nnf_idx[wp] < 0) {
-      const long long hi = ((long long)(pre_plan->h_wide_idx[wp] + 1) << 1) | (pre_plan->h_cflag[wp] ? 1 : 0);
-      pre_w[w] = (hi << 32) | (unsigned)wp;
-    }
-  }
-  for (size_t i = 0; i < pre_plan->h_cells.size(); ++i)
-    if (pre_plan->h_nnf_idx[i] >= 0) rest.push_back((int32_t)i);
+// The static record stream of the gather (header + positions per incidence, in incidence order), built on the device
+// from the item lists and the two plans; the item lists' incidence words and flags are not needed afterwards.
+static int gather_meta_build(dcp_model* m, GatherPlan* G, const MaskedPlan* nse_plan, const MaskedPlan* pre_plan) {
   dcp_ctx* ctx = m->ctx;
-  int rc = upg(ctx, &G->pre_w, pre_w);
-  if (rc == DCP_OK) rc = upg(ctx, &G->pre_rest, rest);
-  if (rc != DCP_OK) return rc;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int64_t n_items = pass == 0 ? G->v_chunk_ptr.back() : G->p_chunk_ptr.back();
+    const int64_t n_inc = (int64_t)(pass == 0 ? NU : NP) * G->n_cells;
+    double** dst = pass == 0 ? &G->v_meta : &G->p_meta;
+    if (cudaMalloc((void**)dst, sizeof(double) * META * (size_t)n_inc) != cudaSuccess) {
+      cudaGetLastError();
+      dcp_set_error("gather plan: allocation of the record stream failed");
+      return DCP_ERR_CUDA;
+    }
+    MetaArgs a;
+    a.n_items = n_items;
+    a.g0s = pass == 0 ? G->v_g0 : G->p_g0;
+    a.incptr = pass == 0 ? G->v_incptr : G->p_incptr;
+    a.incs = pass == 0 ? G->v_inc : G->p_inc;
+    a.flags = pass == 0 ? G->v_flag : G->p_flag;
+    a.pre_w = G->has_pre ? G->pre_w : nullptr;
+    a.pos = nse_plan->pos;
+    a.ppos = G->has_pre ? pre_plan->pos : nullptr;
+    a.chunk = G->chunk;
+    a.meta = *dst;
+    const unsigned grid = (unsigned)((n_items + 7) / 8);
+    if (pass == 0)
+      gather_meta_kernel<true><<<grid, 256, 0, ctx->stream>>>(a);
+    else
+      gather_meta_kernel<false><<<grid, 256, 0, ctx->stream>>>(a);
+  }
   DCP_CUDA(cudaStreamSynchronize(ctx->stream));
-  G->n_pre_rest = (int64_t)rest.size();
-  G->has_pre = true;
+  DCP_CUDA(cudaGetLastError());
+  cudaFree(G->v_inc);
+  cudaFree(G->p_inc);
+  cudaFree(G->v_flag);
+  cudaFree(G->p_flag);
+  cudaFree(G->pre_w);
+  G->v_inc = G->p_inc = nullptr;
+  G->v_flag = G->p_flag = nullptr;
+  G->pre_w = nullptr;
   return DCP_OK;
 }
 
-// NSE system, write-once: per chunk of plan cells, stage then gather (stream-ordered).
+// Finish the gather plan: map the system plan's cells to the preconditioner plan (fused preconditioner; not attached --
+// the preconditioner keeps its own pass -- when a row of that matrix that the gather has to accumulate is longer than the
+// accumulators), then build the record stream.
+int dcp_gather_plan_attach_pre(dcp_model* m, const dcp_model_desc* d, GatherPlan* G, const MaskedPlan* nse_plan, const MaskedPlan* pre_plan) {
+  if (!G || !nse_plan) return DCP_OK;
+  bool fuse = pre_plan != nullptr && !std::getenv("DCP_NO_FUSED_PRECONDITIONER");
+  if (fuse) {
+    // accumulator of one preconditioner row: the largest offset a gathered cell writes to (rows of nodes with
+    // no-normal-flux lines are longer, but their cells are not gathered), and the longest pressure-mass row
+    int64_t need = (int64_t)pre_plan->max_off_plain + 1;
+    const dcp_csr_desc& P11 = d->pre_pattern[1][1];
+    int64_t mx = 0;
+#pragma omp parallel for reduction(max : mx)
+    for (int64_t r = 0; r < P11.n_rows; ++r) mx = std::max(mx, P11.rowptr[r + 1] - P11.rowptr[r]);
+    need = std::max(need, mx);
+    if (need > LROW) fuse = false;
+    else G->pstr = (int)((need + 3) / 4 * 4);
+  }
+  if (fuse) {
+    std::vector<int32_t> of_cell((size_t)d->n_cells, -1);
+    for (size_t i = 0; i < pre_plan->h_cells.size(); ++i) of_cell[pre_plan->h_cells[i]] = (int32_t)i;
+    std::vector<long long> pre_w(nse_plan->h_cells.size(), -1ll);
+    std::vector<int32_t> rest;
+    for (size_t w = 0; w < nse_plan->h_cells.size(); ++w) {
+      const int32_t wp = of_cell[nse_plan->h_cells[w]];
+      if (wp >= 0 && pre_plan->h_nnf_idx[wp] < 0) {
+        const long long hi = ((long long)(pre_plan->h_wide_idx[wp] + 1) << 1) | (pre_plan->h_cflag[wp] ? 1 : 0);
+        pre_w[w] = (hi << 32) | (unsigned)wp;
+      }
+    }
+    for (size_t i = 0; i < pre_plan->h_cells.size(); ++i)
+      if (pre_plan->h_nnf_idx[i] >= 0) rest.push_back((int32_t)i);
+    dcp_ctx* ctx = m->ctx;
+    int rc = upg(ctx, &G->pre_w, pre_w);
+    if (rc == DCP_OK) rc = upg(ctx, &G->pre_rest, rest);
+    if (rc != DCP_OK) return rc;
+    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+    G->n_pre_rest = (int64_t)rest.size();
+    G->has_pre = true;
+  }
+  return gather_meta_build(m, G, nse_plan, pre_plan);
+}
+
+// NSE system (and, fused, its preconditioner), write-once: per chunk of plan cells, stage then gather (stream-ordered).
 int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* plan, const double* old_nse, const double* old_temp) {
   dcp_ctx* ctx = m->ctx;
   const GatherPlan* G = plan->gather;
   MmaArgs a;
   a.n_fast = plan->n;
+  a.wlist = nullptr;
   a.cells = plan->cells;
   a.pos = plan->pos;
   a.nmask = plan->nmask;
@@ -1549,144 +1176,69 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   a.rhs = m->nse_rhs;
   a.n_u = m->nse.start[1];
   a.prm = p;
-  const size_t smem_s = stage_smem_bytes(), smem_g = sizeof(double) * GACC * GWARPS, smem_gs = sizeof(double) * GSWARP * GSW,
-               smem_p = sizeof(double) * PACC * GWARPS;
+  const bool fuse_pre = G->has_pre && m->masked_pre;
+  const int pstr = fuse_pre ? G->pstr : 4;
+  const size_t smem_s = stage_smem_bytes(), smem_g = sizeof(double) * (size_t)gather_warp_doubles(pstr) * GW;
+  auto gather_fn = fuse_pre ? th_gather_kernel<true> : th_gather_kernel<false>;
   DCP_CUDA(cudaFuncSetAttribute(th_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-  const bool bulk = std::getenv("DCP_GATHER_BULK") != nullptr;
-  DCP_CUDA(cudaFuncSetAttribute(th_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  DCP_CUDA(cudaFuncSetAttribute(th_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gs));
-  int per_sm_s = 1, per_sm_g = 1, per_sm_p = 1;
+  DCP_CUDA(cudaFuncSetAttribute(gather_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  int per_sm_s = 1, per_sm_g = 1;
   DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, th_stage_kernel, MTHREADS, smem_s));
-  if (bulk)
-    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_bulk_kernel, GSW * 32, smem_gs));
-  else
-    DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, th_gather_kernel, GWARPS * 32, smem_g));
-  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, th_pre_gather_kernel, GWARPS * 32, smem_p));
+  DCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, gather_fn, GW * 32, smem_g));
   per_sm_s = std::max(per_sm_s, 1);
   per_sm_g = std::max(per_sm_g, 1);
-  per_sm_p = std::max(per_sm_p, 1);
-  GatherArgs g;
+  if (const char* e = std::getenv("DCP_GATHER_CTAS")) per_sm_g = std::max(1, std::min(per_sm_g, std::atoi(e)));
+  GatherArgs g{};
   g.v_g0 = G->v_g0;
   g.v_incptr = G->v_incptr;
-  g.v_flag = G->v_flag;
-  g.v_inc = G->v_inc;
+  g.v_meta = G->v_meta;
   g.p_g0 = G->p_g0;
   g.p_incptr = G->p_incptr;
-  g.p_flag = G->p_flag;
-  g.p_inc = G->p_inc;
-  g.ring = (int)G->chunk;
-  g.pos = plan->pos;
+  g.p_meta = G->p_meta;
   g.nmask = plan->nmask;
-  g.stage = G->staging;
-  const BlockView A = make_view(m->nse);
-  const CsView cs = make_view(m->nse_cs);
-  const bool fuse_pre = G->has_pre && m->masked_pre;
-  if (G->fused) {
-    FusedArgs f{};
-    f.a = a;
-    f.cs = cs;
-    f.dphi_lane = G->dphi_lane;
-    f.stage = G->staging;
-    f.g = g;
-    f.g.w_base = 0;
-    f.g.slot_base = 0;
-    f.g.v_begin = f.g.v_end = f.g.p_begin = f.g.p_end = 0;
-    if (fuse_pre) {
-      f.pa.pre_w = G->pre_w;
-      f.pa.pos = m->masked_pre->pos;
-      f.pa.nmask = m->masked_pre->nmask;
-      f.pa.pos_wide = m->masked_pre->pos_wide;
-    }
-    f.v_chunk_ptr = G->d_v_chunk_ptr;
-    f.p_chunk_ptr = G->d_p_chunk_ptr;
-    f.n_cells = plan->n;
-    f.n_chunks = G->n_chunks;
-    f.n_stage = G->n_stage;
-    f.n_gather_ctas = G->n_gather_ctas;
-    f.ring_chunks = G->ring_chunks;
-    f.fuse_pre = fuse_pre ? 1 : 0;
-    f.sy.staged = G->sync;
-    f.sy.gdone = G->sync + G->n_chunks;
-    f.sy.err = ctx->d_err;
-    BlockView Av = A, Apv = make_view(m->pre);
-    DCP_CUDA(cudaMemsetAsync(G->sync, 0, sizeof(unsigned) * 2 * (size_t)G->n_chunks, ctx->stream));
-    const size_t smem_f = fused_smem_bytes();
-    DCP_CUDA(cudaFuncSetAttribute(th_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-    void* params[] = {(void*)&f, (void*)&Av, (void*)&Apv};
-    DCP_CUDA(cudaLaunchCooperativeKernel((const void*)th_fused_kernel, dim3((unsigned)(G->n_stage + G->n_gather_ctas)), dim3(MTHREADS), params,
-                                         smem_f, ctx->stream));
-    ctx->launches++;
-    if (fuse_pre) {
-      if (G->n_pre_rest > 0) DCP_TRY(dcp_launch_th_mma(m, p, false, m->masked_pre, nullptr, nullptr, G->pre_rest, G->n_pre_rest));
-      if (m->masked_pre->n_other > 0)
-        DCP_TRY(dcp_launch_th_cells(m, p, false, nullptr, nullptr, m->masked_pre->other_cells, m->masked_pre->n_other, false));
-      m->pre_fused_valid = true;
-      m->pre_fused_dt = p.dt;
-      m->pre_fused_inv_re = p.inv_re;
-    }
-    DCP_CUDA(cudaGetLastError());
-    return DCP_OK;
-  }
-  PreArgs pa{};
-  BlockView Apre = make_view(m->pre);
+  g.wb = 16;
+  if (const char* e = std::getenv("DCP_GATHER_BLOCK")) g.wb = std::max(1, std::atoi(e));
+  g.vstage = G->staging;
+  g.pstage = G->staging + (size_t)NU * VROW * (size_t)G->chunk;
+  g.pstr = pstr;
   if (fuse_pre) {
-    pa.pre_w = G->pre_w;
-    pa.pos = m->masked_pre->pos;
-    pa.nmask = m->masked_pre->nmask;
-    pa.pos_wide = m->masked_pre->pos_wide;
-    DCP_CUDA(cudaFuncSetAttribute(th_pre_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    g.pnmask = m->masked_pre->nmask;
+    g.ppos_wide = m->masked_pre->pos_wide;
   }
-  // Two streams: the stage pass of chunk c + 1 (tensor / LSU bound, writes) runs next to the gather passes of chunk c
-  // (DRAM bound, reads and writes).  Both kernels stride over their work with a fixed grid, so the grids set the split
-  // of the SMs: 2 staging CTAs + 1 gathering CTA per SM fit together (registers, shared memory).  The staging buffer has
-  // two halves; events order reuse.  Opt-in (DCP_STAGED_OVERLAP=1): measured slower than one stream with full grids.
-  const bool overlap = G->stream2 != nullptr && G->n_chunks > 1;
-  cudaStream_t s_stage = ctx->stream, s_gather = overlap ? G->stream2 : ctx->stream;
-  const int stage_per_sm = overlap ? std::min(per_sm_s, G->overlap_stage_ctas) : per_sm_s;
-  const int gather_per_sm = overlap ? std::min(per_sm_g, G->overlap_gather_ctas) : per_sm_g;
-  const int pre_per_sm = overlap ? std::min(per_sm_p, G->overlap_gather_ctas) : per_sm_p;
+  StageOut so;
+  so.vstage = G->staging;
+  so.pstage = G->staging + (size_t)NU * VROW * (size_t)G->chunk;
+  so.slots = G->slots;
+  const BlockView A = make_view(m->nse);
+  const BlockView Apre = make_view(m->pre);
+  const CsView cs = make_view(m->nse_cs);
+  const bool debug_sync = std::getenv("DCP_DEBUG_SYNC") != nullptr;   // name the kernel that faults
+  auto checkpoint = [&](const char* what, long long ch) {
+    if (!debug_sync) return DCP_OK;
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) return DCP_OK;
+    dcp_set_error(std::string("staged assembly, ") + what + " of chunk " + std::to_string(ch) + ": " + cudaGetErrorString(e));
+    return DCP_ERR_CUDA;
+  };
   for (int64_t ch = 0; ch < G->n_chunks; ++ch) {
-    const int half = overlap ? (int)(ch & 1) : 0;
     const long long w0 = ch * G->chunk, w1 = std::min<long long>(plan->n, w0 + G->chunk);
-    long long grid = std::min<long long>((long long)ctx->sm_count * stage_per_sm, w1 - w0);
-    if (overlap && ch >= 2) DCP_CUDA(cudaStreamWaitEvent(s_stage, G->ev_gathered[half], 0));   // the half is free again
-    double* half_base = G->staging + (size_t)half * (size_t)G->chunk * REC;
-    th_stage_kernel<<<(unsigned)grid, MTHREADS, smem_s, s_stage>>>(a, cs, G->dphi_lane, half_base, w0, w1, 0, (int)G->chunk);
-    if (overlap) {
-      DCP_CUDA(cudaEventRecord(G->ev_staged[half], s_stage));
-      DCP_CUDA(cudaStreamWaitEvent(s_gather, G->ev_staged[half], 0));
-    }
-    g.stage = half_base;
+    long long grid = std::min<long long>((long long)ctx->sm_count * per_sm_s, w1 - w0);
+    th_stage_kernel<<<(unsigned)grid, MTHREADS, smem_s, ctx->stream>>>(a, cs, G->dphi_lane, so, w0, w1);
+    DCP_TRY(checkpoint("stage kernel", ch));
     g.v_begin = G->v_chunk_ptr[ch];
     g.v_end = G->v_chunk_ptr[ch + 1];
     g.p_begin = G->p_chunk_ptr[ch];
     g.p_end = G->p_chunk_ptr[ch + 1];
     g.w_base = w0;
-    g.slot_base = 0;
-    const long long items = (g.v_end - g.v_begin) + (g.p_end - g.p_begin);
-    const long long blocks = (items + WB - 1) / WB;   // a warp takes blocks of WB items
-    const int gwarps = bulk ? GSW : GWARPS;
-    grid = std::min<long long>((long long)ctx->sm_count * gather_per_sm, (blocks + gwarps - 1) / gwarps);
-    if (grid > 0) {
-      if (bulk)
-        th_gather_bulk_kernel<<<(unsigned)grid, GSW * 32, smem_gs, s_gather>>>(g, A);
-      else
-        th_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_g, s_gather>>>(g, A);
-    }
+    const long long items = std::max(g.v_end - g.v_begin, g.p_end - g.p_begin);
+    const long long blocks = (items + g.wb - 1) / g.wb;   // a warp takes blocks of g.wb items
+    grid = std::min<long long>((long long)ctx->sm_count * per_sm_g, (blocks + GW - 1) / GW);
+    if (grid > 0) gather_fn<<<(unsigned)grid, GW * 32, smem_g, ctx->stream>>>(g, A, Apre);
+    DCP_TRY(checkpoint("gather kernel", ch));
     ctx->launches += 2;
-    grid = std::min<long long>((long long)ctx->sm_count * pre_per_sm, (blocks + GWARPS - 1) / GWARPS);
-    if (fuse_pre && grid > 0) {
-      th_pre_gather_kernel<<<(unsigned)grid, GWARPS * 32, smem_p, s_gather>>>(g, pa, Apre);
-      ctx->launches++;
-    }
-    if (overlap) DCP_CUDA(cudaEventRecord(G->ev_gathered[half], s_gather));
-  }
-  if (overlap) {   // the context's stream continues after the last gathers
-    DCP_CUDA(cudaStreamWaitEvent(s_stage, G->ev_gathered[0], 0));
-    DCP_CUDA(cudaStreamWaitEvent(s_stage, G->ev_gathered[1], 0));
   }
   if (fuse_pre) {
-    // the cells the second gather skipped: no-normal-flux cells through the reduction kernel, cells outside the
+    // the cells the gather skipped: no-normal-flux cells through the reduction kernel, cells outside the
     // preconditioner's plan through the general kernel -- both add to rows the gather has already stored
     if (G->n_pre_rest > 0) DCP_TRY(dcp_launch_th_mma(m, p, false, m->masked_pre, nullptr, nullptr, G->pre_rest, G->n_pre_rest));
     if (m->masked_pre->n_other > 0)

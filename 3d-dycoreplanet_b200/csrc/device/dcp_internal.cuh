@@ -125,25 +125,19 @@ struct GatherPlan {
   uint32_t *v_incptr = nullptr, *p_incptr = nullptr;   // per item: range in *_inc
   uint32_t *v_inc = nullptr, *p_inc = nullptr;         // (cell index inside the chunk << 5) | local node
   uint8_t *v_flag = nullptr, *p_flag = nullptr;        // bit 0: first chunk that touches the node (store, else accumulate)
+  double *v_meta = nullptr, *p_meta = nullptr;         // per incidence, in incidence order: header + row positions (18 doubles)
+  uint32_t* slots = nullptr;                           // [plan cell][36]: staging slot of every local node = index of its incidence in the chunk
   std::vector<int64_t> v_chunk_ptr, p_chunk_ptr;       // host: item range of every chunk
-  double* staging = nullptr;                           // [chunk][8124]
+  double* staging = nullptr;                           // node-major: [27 chunk][304] velocity-node rows, then [8 chunk][92] pressure-node rows
   double* dphi_lane = nullptr;                         // reference gradients in table-build order [7][3][108]
-  // fused preconditioner (the system pass also stages m + nu k and the pressure mass block; a second gather writes
-  // nse_preconditioner_matrix): index of every system-plan cell in the preconditioner plan (-1: the cell is assembled by
-  // the reduction kernels afterwards), and those cells as a list of preconditioner-plan indices
+  // fused preconditioner (the system pass also stages m + nu k and the pressure mass block; the gather writes
+  // nse_preconditioner_matrix, too): index of every system-plan cell in the preconditioner plan (-1: the cell is
+  // assembled by the reduction kernels afterwards), and those cells as a list of preconditioner-plan indices
   long long* pre_w = nullptr;
   int32_t* pre_rest = nullptr;
   int64_t n_pre_rest = 0;
   bool has_pre = false;
-  // two-stream overlap of the stage pass of chunk c + 1 with the gather passes of chunk c (staging has two halves)
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_gathered[2] = {nullptr, nullptr};
-  int overlap_stage_ctas = 2, overlap_gather_ctas = 1;   // CTAs per SM of each side while both run
-  // persistent kernel (staging ring in L2): chunk == n_stage cells, one per staging CTA
-  bool fused = false;
-  int n_stage = 0, n_gather_ctas = 0, ring_chunks = 0;
-  long long *d_v_chunk_ptr = nullptr, *d_p_chunk_ptr = nullptr;
-  unsigned* sync = nullptr;                            // [2][n_chunks]: records staged, gather warps done
+  int pstr = 4;                                        // accumulator length of one preconditioner row
 };
 
 // masked position tables for the DMMA path (assemble_th_mma.cu): every node-blocked cell, constrained or not

@@ -36,8 +36,7 @@ int dcp_check_device_errors(dcp_ctx* ctx, const char* what) {
   }
   if (ctx->h_err[1] != 0) {
     cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
-    dcp_set_error(std::string(what) + ": the persistent assembly kernel gave up waiting for a staging-ring dependency; the matrices of that "
-                  "pass are invalid (DCP_STAGED_MODE=persistent is an experiment; unset it to use the per-chunk launches)");
+    dcp_set_error(std::string(what) + ": a device-side wait was abandoned; the matrices of that pass are invalid");
     return DCP_ERR_STATE;
   }
   return DCP_OK;

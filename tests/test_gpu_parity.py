@@ -35,7 +35,7 @@ def _params(spec):
 
 @pytest.mark.parametrize("spec", CASES, ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
 @pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4, 5, 6],
-                         ids=["search", "positions", "owner", "staged", "staged-chunk37", "staged-persistent", "staged-bulk"])
+                         ids=["search", "positions", "owner", "staged", "staged-chunk37", "staged-unfused", "staged-chunk1000"])
 def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy, monkeypatch):
     from dycore_b200 import device
     from oracle import oracle as orc
@@ -50,10 +50,10 @@ def test_classic_assembly_matches_oracle(ctx, problem_factory, spec, strategy, m
     u, T = synthetic_fields(P)
     if strategy == 4:   # many small chunks: nodes are visited by several chunks (store first, accumulate later)
         monkeypatch.setenv("DCP_GATHER_CHUNK", "37")
-    if strategy == 5:   # the cooperative kernel with the staging ring (an experiment)
-        monkeypatch.setenv("DCP_STAGED_MODE", "persistent")
-    if strategy == 6:   # staged rows fetched with TMA bulk copies into a per-warp ring (slower, kept selectable)
-        monkeypatch.setenv("DCP_GATHER_BULK", "1")
+    if strategy == 5:   # the preconditioner in its own pass: the gather writes nse_matrix only
+        monkeypatch.setenv("DCP_NO_FUSED_PRECONDITIONER", "1")
+    if strategy == 6:   # a few chunks with a ragged last one
+        monkeypatch.setenv("DCP_GATHER_CHUNK", "1000")
     model = device.BoussinesqModel.from_problem(ctx, P, mp, owner_plan=(strategy == 2))
     if spec["geometry"] == "shell":
         assert model.strategy == device.STRATEGY_STAGED, "the shell qualifies for the write-once path by default"
