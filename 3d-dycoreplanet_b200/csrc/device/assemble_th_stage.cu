@@ -462,7 +462,7 @@ struct IncHdr {
 constexpr unsigned HI_NP = 1u << 29, HI_FIRST = 1u << 30, HI_LAST = 1u << 31, HI_WIDE = 0x0ffffffeu;
 constexpr int META = 18;                    // doubles per static record: header (16 B), positions (72 B), preconditioner positions (56 B)
 constexpr int MPOS = 8, MPPOS = 8 + 36;     // u16 offsets of the two position rows inside the record
-constexpr int VSLOT = VROW + META;          // ring slot (322 doubles): a velocity-node row or a pressure-node row, then the record
+constexpr int GSLOT = BW + CSEG + META;     // ring slot (138 doubles): [m + nu k][one component segment or a pressure-node row][record]
 
 struct GatherArgs {
   const int* v_g0;
@@ -552,19 +552,24 @@ __device__ __forceinline__ void flush_row(double* __restrict__ out, double* acc,
   }
 }
 
-// Per-warp shared memory: acc [3][ACC0] (rows of block(0,0) / one row of block(1,0)), acc01 [3][L01], accP [pstr] (one
-// preconditioner row), accd [4] (diagonals of constrained rows), the ring and its mbarriers.
+// Per-warp shared memory: acc [ACC0] (one row of block(0,0) / block(1,0)), acc01 [L01], accP [pstr] (one
+// preconditioner row), accd [4] (diagonal of a constrained row), the ring and its mbarriers.
 struct WarpMem {
   double *acc, *acc01, *accP, *accd, *ring;
   unsigned long long* bars;
 };
 
 // Walk this warp's blocks of items.  VEL: velocity nodes -- rows (g0 + c) of block(0,0), block(0,1) and of the
-// preconditioner's block(0,0); else pressure nodes -- a row of block(1,0) and of the preconditioner's block(1,1).
+// preconditioner's block(0,0): an item is swept three times over its incidences, sweep c accumulates row component c
+// from the component's segment of the staged rows (the accumulators hold one row: three times as many warps fit an SM
+// as with all three rows at once, and the pass is bound by how many warps work on it).  The three preconditioner rows of
+// a node are equal unless a cell has masks or per-component positions: they are accumulated in sweep 0 and stored
+// three times.  Else pressure nodes: one sweep, a row of block(1,0) and of the preconditioner's block(1,1).
 template <bool VEL, bool PRE>
 __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockView& A, const BlockView& Ap, const WarpMem& m, unsigned& phases,
                                              long long gw, long long nw, int lane) {
   constexpr int ROWD = VEL ? VROW : PROW;
+  constexpr int NSWEEP = VEL ? 3 : 1;
   const int* __restrict__ g0s = VEL ? g.v_g0 : g.p_g0;
   const unsigned* __restrict__ incptr = VEL ? g.v_incptr : g.p_incptr;
   const double* __restrict__ meta = VEL ? g.v_meta : g.p_meta;
@@ -586,31 +591,55 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
     if (VEL) return lane < 4 ? rpa[g0 + lane] : (lane < 8 ? rpb[g0 + lane - 4] : (PRE && lane < 12 ? rpq[g0 + lane - 8] : 0ll));
     return lane < 2 ? rpa[g0 + lane] : (PRE && lane >= 8 && lane < 10 ? rpq[g0 + lane - 8] : 0ll);
   };
-  auto issue = [&](unsigned i, int u) {
+  // sweep c of incidence i into ring slot u: the component's segment (sweep 0 of a velocity node: with m + nu k in front
+  // of it) and the static record
+  auto issue = [&](unsigned i, int c, int u) {
     if (lane == 0) {
-      double* slot = m.ring + u * VSLOT;
-      mbar_expect(m.bars + u, (ROWD + META) * 8);
-      bulk_load(slot, stage + (size_t)((long long)i - i0) * ROWD, ROWD * 8, m.bars + u);
-      bulk_load(slot + ROWD, meta + (size_t)i * META, META * 8, m.bars + u);
+      double* slot = m.ring + u * GSLOT;
+      const double* src = stage + (size_t)((long long)i - i0) * ROWD;
+      if (VEL && PRE && c == 0) {
+        mbar_expect(m.bars + u, (BW + CSEG + META) * 8);
+        bulk_load(slot, src, (BW + CSEG) * 8, m.bars + u);
+      } else {
+        mbar_expect(m.bars + u, (CSEG + META) * 8);
+        bulk_load(slot + BW, VEL ? src + BW + c * CSEG : src, CSEG * 8, m.bars + u);
+      }
+      bulk_load(slot + BW + CSEG, meta + (size_t)i * META, META * 8, m.bars + u);
     }
   };
   for (long long j_lo = begin + gw * g.wb; j_lo < end; j_lo += nw * g.wb) {
-    const long long j_hi = j_lo + g.wb < end ? j_lo + g.wb : end;
-    const unsigned i_lo = incptr[j_lo], i_hi = incptr[j_hi];
-    unsigned pi = i_lo;
+    const int n_it = (int)((j_lo + g.wb < end ? j_lo + g.wb : end) - j_lo);   // <= 32
+    const unsigned h_iend = lane < n_it ? incptr[j_lo + lane + 1] : 0u;
+    const unsigned i_lo = incptr[j_lo];
+    // producer cursor: item pt, sweep pc, incidence pi of [pb, pe)
+    int pt = 0, pc = 0;
+    unsigned pb = i_lo, pe = __shfl_sync(FULLM, h_iend, 0), pi = i_lo;
+    auto produce = [&](int u) {
+      issue(pi, pc, u);
+      if (++pi == pe) {
+        pi = pb;
+        if (++pc == NSWEEP) {
+          pc = 0;
+          pb = pe;
+          pi = pb;
+          if (++pt < n_it) pe = __shfl_sync(FULLM, h_iend, pt);
+        }
+      }
+    };
     int u = 0;
-    for (; u < RD && pi < i_hi; ++u, ++pi) issue(pi, u);
+    for (; u < RD && pt < n_it; ++u) produce(u);
     u = 0;
     long long rcur = rows(g0s[j_lo]), rnext = 0;
     bool item_start = true;
-    int maskA = 7;
-    for (unsigned ci = i_lo; ci < i_hi; ++ci) {
+    int maskA = 7, c = 0, ct = 0;
+    while (ct < n_it) {
       mbar_wait(m.bars + u, (phases >> u) & 1u);
       phases ^= 1u << u;
-      const double* S = m.ring + u * VSLOT;
-      const uint4 hw = *reinterpret_cast<const uint4*>(S + ROWD);
-      const unsigned short* spos = reinterpret_cast<const unsigned short*>(S + ROWD) + MPOS;
-      const unsigned short* sppos = reinterpret_cast<const unsigned short*>(S + ROWD) + MPPOS;
+      const double* S = m.ring + u * GSLOT;
+      const double* seg = S + BW;
+      const uint4 hw = *reinterpret_cast<const uint4*>(S + BW + CSEG);
+      const unsigned short* spos = reinterpret_cast<const unsigned short*>(S + BW + CSEG) + MPOS;
+      const unsigned short* sppos = reinterpret_cast<const unsigned short*>(S + BW + CSEG) + MPPOS;
       const unsigned e = hw.x, hi = hw.z;
       const int wp = (int)hw.y;
       const bool first = (hi & HI_FIRST) != 0, np = PRE && (hi & HI_NP) != 0;
@@ -621,8 +650,8 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
         if (g0n >= 0) rnext = rows(g0n);
         if (VEL && np && first) {
           // general path of the preconditioner: its rows are updated in place, so the first chunk clears them first
-          const long long ps = __shfl_sync(FULLM, rcur, 8), pe = __shfl_sync(FULLM, rcur, 11);
-          for (long long k = ps + lane; k < pe; k += 32) vq[k] = 0.0;
+          const long long ps = __shfl_sync(FULLM, rcur, 8), pe2 = __shfl_sync(FULLM, rcur, 11);
+          for (long long k = ps + lane; k < pe2; k += 32) vq[k] = 0.0;
           __syncwarp();
         }
       }
@@ -634,48 +663,30 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
           mA = mrow[a];
         }
         maskA = mA;
-        if (mA == 7 && __all_sync(FULLM, lane >= NU || mb == 7)) {
+        if ((mA >> c) & 1) {
           if (lane < NU) {
             double* t = acc + spos[lane];
-            const double* s = S + BW + lane;
-            double tv[9];
+            if (mb == 7) {
+              const double t0 = t[0], t1 = t[1], t2 = t[2];
+              t[0] = t0 + seg[lane];
+              t[1] = t1 + seg[BW + lane];
+              t[2] = t2 + seg[2 * BW + lane];
+            } else {
+              int idx[3];
+              double tv[3];
 #pragma unroll
-            for (int r = 0; r < 9; ++r) tv[r] = t[(r / 3) * ACC0 + (r % 3)];
+              for (int d = 0; d < 3; ++d) idx[d] = ((mb >> d) & 1) ? __popc(mb & ((1 << d) - 1)) : -1;
 #pragma unroll
-            for (int r = 0; r < 9; ++r) t[(r / 3) * ACC0 + (r % 3)] = tv[r] + s[(r / 3) * CSEG + (r % 3) * BW];
-          }
-          if (lane < 3 * NP) {
-            const int c = lane >> 3, p = lane & 7;
-            acc01[c * L01 + spos[NU + p]] += S[BW + c * CSEG + 3 * BW + p];
-          }
-        } else {
-          if (lane < NU) {
-            const int ob = spos[lane];
-            int idx[9];
-            double tv[9];
+              for (int d = 0; d < 3; ++d) tv[d] = idx[d] >= 0 ? t[idx[d]] : 0.0;
 #pragma unroll
-            for (int r = 0; r < 9; ++r) {
-              const int c = r / 3, d = r - 3 * c;
-              const bool on = ((mA >> c) & 1) && ((mb >> d) & 1);
-              idx[r] = on ? c * ACC0 + ob + __popc(mb & ((1 << d) - 1)) : -1;
-            }
-#pragma unroll
-            for (int r = 0; r < 9; ++r) tv[r] = idx[r] >= 0 ? acc[idx[r]] : 0.0;
-#pragma unroll
-            for (int r = 0; r < 9; ++r)
-              if (idx[r] >= 0) acc[idx[r]] = tv[r] + S[BW + (r / 3) * CSEG + (r % 3) * BW + lane];
-            if (lane == a && mA != 7) {   // constrained dof: |L_ii| staged in the slot [c][c] of the node's own column
-#pragma unroll
-              for (int c = 0; c < 3; ++c)
-                if (!((mA >> c) & 1)) accd[c] += S[BW + c * CSEG + c * BW + a];
+              for (int d = 0; d < 3; ++d)
+                if (idx[d] >= 0) t[idx[d]] = tv[d] + seg[d * BW + lane];
             }
           }
-          if (lane < 3 * NP) {
-            const int c = lane >> 3, p = lane & 7;
-            if ((mA >> c) & 1) acc01[c * L01 + spos[NU + p]] += S[BW + c * CSEG + 3 * BW + p];
-          }
-        }
-        if (PRE && wp >= 0) {
+          if (lane < NP) acc01[spos[NU + lane]] += seg[3 * BW + lane];
+        } else if (lane == a)
+          accd[0] += seg[c * BW + a];   // constrained dof: |L_ii| staged in the slot [c][c] of the node's own column
+        if (PRE && c == 0 && wp >= 0) {
           const double dg = lane < NU ? S[lane] : 0.0;
           if (!np) {
             if (lane < NU) {
@@ -692,14 +703,14 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
               pa = nm[a];
             }
             __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              double* row = vq + __shfl_sync(FULLM, rcur, 8 + c);
+#pragma unroll 1
+            for (int c2 = 0; c2 < 3; ++c2) {
+              double* row = vq + __shfl_sync(FULLM, rcur, 8 + c2);
               if (lane < NU) {
                 unsigned o = sppos[lane];
-                if (wide >= 0) o = g.ppos_wide[(size_t)wide * (3 * NU * NU) + c * (NU * NU) + a * NU + lane];
-                if ((((pa & pmb) >> c) & 1) && o != 0xffff) row[o] += dg;
-                if (lane == a && !((pa >> c) & 1)) row[0] += fabs(dg);
+                if (wide >= 0) o = g.ppos_wide[(size_t)wide * (3 * NU * NU) + c2 * (NU * NU) + a * NU + lane];
+                if ((((pa & pmb) >> c2) & 1) && o != 0xffff) row[o] += dg;
+                if (lane == a && !((pa >> c2) & 1)) row[0] += fabs(dg);
               }
               __syncwarp();
             }
@@ -709,50 +720,44 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
         if (lane < NU) {
           int mb = 7;
           if (e & INC_CS) mb = g.nmask[((size_t)g.w_base + ((e & ~INC_CS) >> 5)) * MSTR + lane];
-          const int ob = spos[lane];
+          double* t = acc + spos[lane];
           int idx[3];
           double tv[3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) idx[c] = ((mb >> c) & 1) ? ob + __popc(mb & ((1 << c) - 1)) : -1;
+          for (int d = 0; d < 3; ++d) idx[d] = ((mb >> d) & 1) ? __popc(mb & ((1 << d) - 1)) : -1;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) tv[c] = idx[c] >= 0 ? acc[idx[c]] : 0.0;
+          for (int d = 0; d < 3; ++d) tv[d] = idx[d] >= 0 ? t[idx[d]] : 0.0;
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            if (idx[c] >= 0) acc[idx[c]] = tv[c] + S[c * BW + lane];
+          for (int d = 0; d < 3; ++d)
+            if (idx[d] >= 0) t[idx[d]] = tv[d] + seg[d * BW + lane];
         }
         if (PRE && wp >= 0 && lane < NP) {
           const unsigned o = sppos[lane];
-          if (o != 0xffff) accP[o] += S[3 * BW + lane];
+          if (o != 0xffff) accP[o] += seg[3 * BW + lane];
         }
       }
       __syncwarp();   // every lane has read the slot and updated the accumulators
-      if (pi < i_hi) {
-        issue(pi, u);
-        ++pi;
-      }
+      if (pt < n_it) produce(u);
       u = u + 1 == RD ? 0 : u + 1;
-      if (hi & HI_LAST) {
+      if (hi & HI_LAST) {   // the sweep is complete: write its rows
         if (VEL) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
-            const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
-            if ((maskA >> c) & 1) {
-              flush_row<true>(va + rs, acc + c * ACC0, len, ACC0, first, lane);
-              flush_row<true>(vb + rs01, acc01 + c * L01, len01, L01, first, lane);
-            } else if (lane == 0) {
-              // constrained dof: the row holds its diagonal only
-              double* out = va + rs;
-              if (first) {
-                out[0] = accd[c];
-                for (int k = 1; k < len; ++k) out[k] = 0.0;
-                for (int k = 0; k < len01; ++k) vb[rs01 + k] = 0.0;
-              } else
-                out[0] = __ldcg(out) + accd[c];
-              accd[c] = 0.0;
-            }
+          const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
+          const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
+          if ((maskA >> c) & 1) {
+            flush_row<true>(va + rs, acc, len, ACC0, first, lane);
+            flush_row<true>(vb + rs01, acc01, len01, L01, first, lane);
+          } else if (lane == 0) {
+            // constrained dof: the row holds its diagonal only
+            double* out = va + rs;
+            if (first) {
+              out[0] = accd[0];
+              for (int k = 1; k < len; ++k) out[k] = 0.0;
+              for (int k = 0; k < len01; ++k) vb[rs01 + k] = 0.0;
+            } else
+              out[0] = __ldcg(out) + accd[0];
+            accd[0] = 0.0;
           }
-          if (PRE && !np) {
+          if (PRE && c == 0 && !np) {
             // the three component rows of the node are equal: accumulated once, stored three times
             const long long p0 = __shfl_sync(FULLM, rcur, 8), p1 = __shfl_sync(FULLM, rcur, 9), p2 = __shfl_sync(FULLM, rcur, 10),
                             p3 = __shfl_sync(FULLM, rcur, 11);
@@ -773,29 +778,33 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
           }
         }
         __syncwarp();
-        rcur = rnext;
-        item_start = true;
         maskA = 7;
+        if (++c == NSWEEP) {   // next item
+          c = 0;
+          ++ct;
+          rcur = rnext;
+          item_start = true;
+        }
       }
     }
   }
 }
 
-__host__ __device__ constexpr int gather_warp_doubles(int pstr) { return 3 * ACC0 + 3 * L01 + pstr + 4 + RD * VSLOT + RD + (RD & 1); }
+__host__ __device__ constexpr int gather_warp_doubles(int pstr) { return ACC0 + L01 + pstr + 4 + RD * GSLOT + RD + (RD & 1); }
 
 template <bool PRE>
 __global__ void __launch_bounds__(GW * 32) th_gather_kernel(GatherArgs g, BlockView A, BlockView Ap) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nacc = 3 * ACC0 + 3 * L01 + g.pstr + 4;
+  const int nacc = ACC0 + L01 + g.pstr + 4;
   WarpMem m;
   m.acc = smem + warp * gather_warp_doubles(g.pstr);
-  m.acc01 = m.acc + 3 * ACC0;
-  m.accP = m.acc01 + 3 * L01;
+  m.acc01 = m.acc + ACC0;
+  m.accP = m.acc01 + L01;
   m.accd = m.accP + g.pstr;
   m.ring = m.acc + nacc;
-  m.bars = reinterpret_cast<unsigned long long*>(m.ring + RD * VSLOT);
-  for (int k = lane; k < nacc; k += 32) m.acc[k] = 0.0;   // invariant: all accumulators are zero between items
+  m.bars = reinterpret_cast<unsigned long long*>(m.ring + RD * GSLOT);
+  for (int k = lane; k < nacc; k += 32) m.acc[k] = 0.0;   // invariant: all accumulators are zero between sweeps
   if (lane == 0) {
     for (int u = 0; u < RD; ++u) mbar_init(m.bars + u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1197,7 +1206,7 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   g.p_meta = G->p_meta;
   g.nmask = plan->nmask;
   g.wb = 16;
-  if (const char* e = std::getenv("DCP_GATHER_BLOCK")) g.wb = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("DCP_GATHER_BLOCK")) g.wb = std::min(32, std::max(1, std::atoi(e)));   // <= 32: one item per lane in a block
   g.vstage = G->staging;
   g.pstage = G->staging + (size_t)NU * VROW * (size_t)G->chunk;
   g.pstr = pstr;
