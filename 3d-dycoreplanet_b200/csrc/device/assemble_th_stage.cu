@@ -514,46 +514,66 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// write `len` accumulated entries to the row at `out` (store, or add to what earlier chunks left there); ZERO: leave the
-// accumulators zero for the next item.  Rows longer than `cap` (preconditioner rows of nodes with no-normal-flux lines:
-// their cells are not gathered, nothing was accumulated beyond cap): the tail is stored as zeros by the first chunk.
+// ---- writing a finished row -----------------------------------------------------------------------------------------
+// Small rows and the odd cases go through the lanes (flush_row); a long row leaves shared memory as ONE bulk copy
+// (cp.async.bulk shared -> global; rows that earlier chunks already touched: cp.reduce.async.bulk .add.f64, the addition
+// happens at the L2).  Bulk copies need 16-byte aligned ends on both sides: the accumulator row starts at index
+// (row start & 1), so element k of the row is acc[par + k] and the 16-byte phase of the two sides agree; a leading /
+// trailing single element is written by a lane.
 template <bool ZERO>
 __device__ __forceinline__ void flush_row(double* __restrict__ out, double* acc, int len, int cap, bool first, int lane) {
   const int n = len < cap ? len : cap;
   if (first) {
-    int k = lane;
-    for (; k + 96 < n; k += 128) {
-      const double v0 = acc[k], v1 = acc[k + 32], v2 = acc[k + 64], v3 = acc[k + 96];
-      __stcs(out + k, v0);
-      __stcs(out + k + 32, v1);
-      __stcs(out + k + 64, v2);
-      __stcs(out + k + 96, v3);
-      if (ZERO) acc[k] = acc[k + 32] = acc[k + 64] = acc[k + 96] = 0.0;
-    }
-    for (; k < n; k += 32) {
+    for (int k = lane; k < n; k += 32) {
       __stcs(out + k, acc[k]);
       if (ZERO) acc[k] = 0.0;
     }
-    for (k = cap + lane; k < len; k += 32) __stcs(out + k, 0.0);
+    for (int k = cap + lane; k < len; k += 32) __stcs(out + k, 0.0);
   } else {
-    for (int k0 = lane; k0 < n; k0 += 128) {
-      double old[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) old[u] = k0 + 32 * u < n ? __ldcs(out + k0 + 32 * u) : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + 32 * u;
-        if (k < n) {
-          __stcs(out + k, old[u] + acc[k]);
-          if (ZERO) acc[k] = 0.0;
-        }
-      }
+    for (int k = lane; k < n; k += 32) {
+      __stcs(out + k, __ldcs(out + k) + acc[k]);
+      if (ZERO) acc[k] = 0.0;
     }
   }
 }
+__device__ __forceinline__ void bulk_store(double* dst, unsigned src_s, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_add(double* dst, unsigned src_s, unsigned bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(bytes) : "memory");
+}
+// `acc` (shared-memory address acc_s) holds the row from index par = (row start & 1) on; n = number of accumulated entries
+// (<= len; the rest of the row, if any, is stored as zeros by the first chunk).  Issued by lane 0; the caller waits
+// (bulk_wait_read) before the accumulators are cleared.
+__device__ __forceinline__ void bulk_row(double* __restrict__ out, const double* acc, unsigned acc_s, int par, int n, bool first, int lane) {
+  if (lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' accumulator updates come first
+    const int nb = (n - par) & ~1;
+    if (par && n > 0) out[0] = first ? acc[1] : out[0] + acc[1];
+    if (nb > 0) {
+      if (first)
+        bulk_store(out + par, acc_s + 16 * par, 8 * nb);
+      else
+        bulk_add(out + par, acc_s + 16 * par, 8 * nb);
+    }
+    if (par + nb < n) out[n - 1] = first ? acc[par + n - 1] : out[n - 1] + acc[par + n - 1];
+  }
+}
+__device__ __forceinline__ void bulk_wait_read(int lane) {
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  __syncwarp();
+}
+// clear acc[0 .. n) (n rounded up to 2), 16 bytes per lane
+__device__ __forceinline__ void clear_acc(double* acc, int n, int lane) {
+  for (int k = 2 * lane; k < n; k += 64) *reinterpret_cast<double2*>(acc + k) = make_double2(0.0, 0.0);
+}
 
-// Per-warp shared memory: acc [ACC0] (one row of block(0,0) / block(1,0)), acc01 [L01], accP [pstr] (one
-// preconditioner row), accd [4] (diagonal of a constrained row), the ring and its mbarriers.
+// Per-warp shared memory: acc [ACC0] (one row of block(0,0) / block(1,0); the last three entries absorb the idle lanes'
+// updates), acc01 [L01] (likewise its last entry), accP [pstr] (one preconditioner row, likewise), accd [4] (diagonal of a
+// constrained row), the ring and its mbarriers.
 struct WarpMem {
   double *acc, *acc01, *accP, *accd, *ring;
   unsigned long long* bars;
@@ -573,9 +593,9 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
   const int* __restrict__ g0s = VEL ? g.v_g0 : g.p_g0;
   const unsigned* __restrict__ incptr = VEL ? g.v_incptr : g.p_incptr;
   const double* __restrict__ meta = VEL ? g.v_meta : g.p_meta;
-  const double* __restrict__ stage = VEL ? g.vstage : g.pstage;
+  // the chunk's staged rows start at incidence i0: staging slot = incidence - i0
+  const double* __restrict__ stage = (VEL ? g.vstage : g.pstage) - (size_t)((long long)(VEL ? NU : NP) * g.w_base) * ROWD;
   const long long begin = VEL ? g.v_begin : g.p_begin, end = VEL ? g.v_end : g.p_end;
-  const long long i0 = (long long)(VEL ? NU : NP) * g.w_base;   // first incidence of the chunk: staging slot = incidence - i0
   const long long* rpa = VEL ? A.rowptr[0][0] : A.rowptr[1][0];
   const long long* rpb = A.rowptr[0][1];
   const long long* rpq = VEL ? Ap.rowptr[0][0] : Ap.rowptr[1][1];
@@ -586,6 +606,8 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
   double* acc01 = m.acc01;
   double* accP = m.accP;
   double* accd = m.accd;
+  const unsigned ring_s = smem_u32(m.ring), bars_s = smem_u32(m.bars), acc_s = smem_u32(m.acc), accP_s = smem_u32(m.accP);
+  const int ptrash = g.pstr - 1;
   // row starts of an item: lanes 0..3 block(0,0) (or 0..1 block(1,0)), 4..7 block(0,1), 8..11 the preconditioner's block
   auto rows = [&](int g0) {
     if (VEL) return lane < 4 ? rpa[g0 + lane] : (lane < 8 ? rpb[g0 + lane - 4] : (PRE && lane < 12 ? rpq[g0 + lane - 8] : 0ll));
@@ -595,16 +617,18 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
   // of it) and the static record
   auto issue = [&](unsigned i, int c, int u) {
     if (lane == 0) {
-      double* slot = m.ring + u * GSLOT;
-      const double* src = stage + (size_t)((long long)i - i0) * ROWD;
-      if (VEL && PRE && c == 0) {
-        mbar_expect(m.bars + u, (BW + CSEG + META) * 8);
-        bulk_load(slot, src, (BW + CSEG) * 8, m.bars + u);
-      } else {
-        mbar_expect(m.bars + u, (CSEG + META) * 8);
-        bulk_load(slot + BW, VEL ? src + BW + c * CSEG : src, CSEG * 8, m.bars + u);
-      }
-      bulk_load(slot + BW + CSEG, meta + (size_t)i * META, META * 8, m.bars + u);
+      const unsigned slot_s = ring_s + u * (GSLOT * 8), bar_s = bars_s + u * 8;
+      const double* src = stage + (size_t)i * ROWD;
+      const bool with_dg = VEL && PRE && c == 0;
+      const unsigned bytes = with_dg ? (BW + CSEG) * 8 : CSEG * 8;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's previous readers (generic proxy) come first
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes + META * 8) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(with_dg ? slot_s : slot_s + BW * 8),
+                   "l"(with_dg || !VEL ? src : src + BW + c * CSEG), "r"(bytes), "r"(bar_s)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot_s + (BW + CSEG) * 8),
+                   "l"(meta + (size_t)i * META), "r"(META * 8), "r"(bar_s)
+                   : "memory");
     }
   };
   for (long long j_lo = begin + gw * g.wb; j_lo < end; j_lo += nw * g.wb) {
@@ -632,6 +656,8 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
     long long rcur = rows(g0s[j_lo]), rnext = 0;
     bool item_start = true;
     int maskA = 7, c = 0, ct = 0;
+    int par = (int)__shfl_sync(FULLM, rcur, 0) & 1;                   // 16-byte phase of the row of this sweep
+    int parP = PRE ? (int)__shfl_sync(FULLM, rcur, 8) & 1 : 0;        // ... of the first preconditioner row
     while (ct < n_it) {
       mbar_wait(m.bars + u, (phases >> u) & 1u);
       phases ^= 1u << u;
@@ -643,7 +669,6 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
       const unsigned e = hw.x, hi = hw.z;
       const int wp = (int)hw.y;
       const bool first = (hi & HI_FIRST) != 0, np = PRE && (hi & HI_NP) != 0;
-      const int a = e & 31;
       if (item_start) {
         item_start = false;
         const int g0n = (int)hw.w;
@@ -656,22 +681,25 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
         }
       }
       if (VEL) {
-        int mb = 7, mA = 7;
-        if (e & INC_CS) {
+        if (!(e & INC_CS)) {
+          // no constrained dof in the cell (all but the boundary cells): every lane updates -- the idle ones a spare entry
+          double* t = acc + (lane < NU ? par + spos[lane] : ACC0 - 3);
+          const double t0 = t[0], t1 = t[1], t2 = t[2];
+          const double s0 = seg[lane], s1 = seg[BW + lane], s2 = seg[2 * BW + lane];
+          double* t01 = acc01 + (lane < NP ? (int)spos[NU + (lane & 7)] : L01 - 1);
+          const double t3 = *t01, s3 = seg[3 * BW + (lane & 7)];
+          t[0] = t0 + s0;
+          t[1] = t1 + s1;
+          t[2] = t2 + s2;
+          *t01 = t3 + s3;
+        } else {
+          const int a = e & 31;
           const unsigned char* mrow = g.nmask + ((size_t)g.w_base + ((e & ~INC_CS) >> 5)) * MSTR;
-          mb = lane < NU ? mrow[lane] : 0;
-          mA = mrow[a];
-        }
-        maskA = mA;
-        if ((mA >> c) & 1) {
-          if (lane < NU) {
-            double* t = acc + spos[lane];
-            if (mb == 7) {
-              const double t0 = t[0], t1 = t[1], t2 = t[2];
-              t[0] = t0 + seg[lane];
-              t[1] = t1 + seg[BW + lane];
-              t[2] = t2 + seg[2 * BW + lane];
-            } else {
+          const int mb = lane < NU ? mrow[lane] : 0, mA = mrow[a];
+          maskA = mA;
+          if ((mA >> c) & 1) {
+            if (lane < NU) {
+              double* t = acc + par + spos[lane];
               int idx[3];
               double tv[3];
 #pragma unroll
@@ -682,19 +710,19 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
               for (int d = 0; d < 3; ++d)
                 if (idx[d] >= 0) t[idx[d]] = tv[d] + seg[d * BW + lane];
             }
-          }
-          if (lane < NP) acc01[spos[NU + lane]] += seg[3 * BW + lane];
-        } else if (lane == a)
-          accd[0] += seg[c * BW + a];   // constrained dof: |L_ii| staged in the slot [c][c] of the node's own column
+            if (lane < NP) acc01[spos[NU + lane]] += seg[3 * BW + lane];
+          } else if (lane == a)
+            accd[0] += seg[c * BW + a];   // constrained dof: |L_ii| staged in the slot [c][c] of the node's own column
+        }
         if (PRE && c == 0 && wp >= 0) {
-          const double dg = lane < NU ? S[lane] : 0.0;
+          const double dg = S[lane & 31];   // lanes >= 27: the first entries of the segment, added to the spare entry
           if (!np) {
-            if (lane < NU) {
-              const unsigned o = sppos[lane];
-              if (o != 0xffff) accP[o] += dg;
-            }
+            const unsigned o = lane < NU ? (unsigned)sppos[lane] : 0xffffu;
+            double* t = accP + (o != 0xffffu ? parP + (int)o : ptrash);
+            *t += dg;
           } else {
             // cells with masks or per-component positions (boundary): read-modify-write of the rows in global memory
+            const int a = e & 31;
             const int wide = (int)((hi & HI_WIDE) >> 1) - 1;
             int pmb = 7, pa = 7;
             if (hi & 1u) {
@@ -720,7 +748,7 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
         if (lane < NU) {
           int mb = 7;
           if (e & INC_CS) mb = g.nmask[((size_t)g.w_base + ((e & ~INC_CS) >> 5)) * MSTR + lane];
-          double* t = acc + spos[lane];
+          double* t = acc + par + spos[lane];
           int idx[3];
           double tv[3];
 #pragma unroll
@@ -743,8 +771,11 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
         if (VEL) {
           const long long rs = __shfl_sync(FULLM, rcur, c), rs01 = __shfl_sync(FULLM, rcur, 4 + c);
           const int len = (int)(__shfl_sync(FULLM, rcur, c + 1) - rs), len01 = (int)(__shfl_sync(FULLM, rcur, 5 + c) - rs01);
+          const bool plain_pre = PRE && c == 0 && !np;
+          long long p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+          int nq = 0;
           if ((maskA >> c) & 1) {
-            flush_row<true>(va + rs, acc, len, ACC0, first, lane);
+            bulk_row(va + rs, acc, acc_s, par, len, first, lane);
             flush_row<true>(vb + rs01, acc01, len01, L01, first, lane);
           } else if (lane == 0) {
             // constrained dof: the row holds its diagonal only
@@ -757,25 +788,37 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
               out[0] = __ldcg(out) + accd[0];
             accd[0] = 0.0;
           }
-          if (PRE && c == 0 && !np) {
-            // the three component rows of the node are equal: accumulated once, stored three times
-            const long long p0 = __shfl_sync(FULLM, rcur, 8), p1 = __shfl_sync(FULLM, rcur, 9), p2 = __shfl_sync(FULLM, rcur, 10),
-                            p3 = __shfl_sync(FULLM, rcur, 11);
-            flush_row<false>(vq + p0, accP, (int)(p1 - p0), g.pstr, first, lane);
-            flush_row<false>(vq + p1, accP, (int)(p2 - p1), g.pstr, first, lane);
-            flush_row<false>(vq + p2, accP, (int)(p3 - p2), g.pstr, first, lane);
-            int lm = (int)(p1 - p0) > (int)(p2 - p1) ? (int)(p1 - p0) : (int)(p2 - p1);
-            if ((int)(p3 - p2) > lm) lm = (int)(p3 - p2);
-            if (lm > g.pstr) lm = g.pstr;
-            for (int k = lane; k < lm; k += 32) accP[k] = 0.0;
+          if (plain_pre) {
+            // the three component rows of the node are equal: accumulated once, stored three times -- as bulk copies
+            // where the row's 16-byte phase is the accumulator's, through the lanes otherwise
+            p0 = __shfl_sync(FULLM, rcur, 8), p1 = __shfl_sync(FULLM, rcur, 9), p2 = __shfl_sync(FULLM, rcur, 10), p3 = __shfl_sync(FULLM, rcur, 11);
+            const int cap = g.pstr - 2;
+            const long long ps[4] = {p0, p1, p2, p3};
+#pragma unroll
+            for (int c2 = 0; c2 < 3; ++c2) {
+              const int plen = (int)(ps[c2 + 1] - ps[c2]), n = plen < cap ? plen : cap;
+              if (n > nq) nq = n;
+              if (((int)ps[c2] & 1) == parP)
+                bulk_row(vq + ps[c2], accP, accP_s, parP, n, first, lane);
+              else
+                flush_row<false>(vq + ps[c2], accP + parP, n, n, first, lane);
+              if (first)
+                for (int k = cap + lane; k < plen; k += 32) __stcs(vq + ps[c2] + k, 0.0);
+            }
           }
+          bulk_wait_read(lane);   // the bulk copies have read the accumulators (also orders the lanes' own reads)
+          if ((maskA >> c) & 1) clear_acc(acc, len + par, lane);
+          if (plain_pre) clear_acc(accP, nq + parP, lane);
         } else {
           const long long rs = __shfl_sync(FULLM, rcur, 0);
-          flush_row<true>(va + rs, acc, (int)(__shfl_sync(FULLM, rcur, 1) - rs), ACC0, first, lane);
+          const int len = (int)(__shfl_sync(FULLM, rcur, 1) - rs);
+          bulk_row(va + rs, acc, acc_s, par, len, first, lane);
           if (PRE) {
             const long long ps = __shfl_sync(FULLM, rcur, 8);
-            flush_row<true>(vq + ps, accP, (int)(__shfl_sync(FULLM, rcur, 9) - ps), g.pstr, first, lane);
+            flush_row<true>(vq + ps, accP, (int)(__shfl_sync(FULLM, rcur, 9) - ps), g.pstr - 2, first, lane);
           }
+          bulk_wait_read(lane);
+          clear_acc(acc, len + par, lane);
         }
         __syncwarp();
         maskA = 7;
@@ -784,7 +827,9 @@ __device__ __forceinline__ void gather_items(const GatherArgs& g, const BlockVie
           ++ct;
           rcur = rnext;
           item_start = true;
+          parP = PRE ? (int)__shfl_sync(FULLM, rcur, 8) & 1 : 0;
         }
+        par = (int)__shfl_sync(FULLM, rcur, c) & 1;
       }
     }
   }
@@ -814,6 +859,7 @@ __global__ void __launch_bounds__(GW * 32) th_gather_kernel(GatherArgs g, BlockV
   const long long gw = (long long)blockIdx.x * GW + warp, nw = (long long)gridDim.x * GW;
   gather_items<true, PRE>(g, A, Ap, m, phases, gw, nw, lane);
   gather_items<false, PRE>(g, A, Ap, m, phases, gw, nw, lane);
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the rows are in global memory
 }
 
 // The static records of all incidences, in incidence order: one warp per item.
@@ -926,7 +972,7 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     for (int64_t r = 0; r < P.n_rows; ++r) mx = std::max(mx, P.rowptr[r + 1] - P.rowptr[r]);
     return mx;
   };
-  if (max_len(pat[0][0]) > LROW || max_len(pat[1][0]) > LROW || max_len(pat[0][1]) > L01) return DCP_OK;
+  if (max_len(pat[0][0]) > LROW || max_len(pat[1][0]) > LROW || max_len(pat[0][1]) > L01 - 1) return DCP_OK;   // (the last entry of acc01 is the spare one)
   // one stage + gather launch pair per chunk of DCP_GATHER_CHUNK cells (default 65 536)
   int64_t chunk = 65536;
   if (const char* e = std::getenv("DCP_GATHER_CHUNK")) chunk = std::max<int64_t>(1, std::atoll(e));
@@ -1131,7 +1177,7 @@ int dcp_gather_plan_attach_pre(dcp_model* m, const dcp_model_desc* d, GatherPlan
     for (int64_t r = 0; r < P11.n_rows; ++r) mx = std::max(mx, P11.rowptr[r + 1] - P11.rowptr[r]);
     need = std::max(need, mx);
     if (need > LROW) fuse = false;
-    else G->pstr = (int)((need + 3) / 4 * 4);
+    else G->pstr = (int)((need + 2 + 3) / 4 * 4);   // + the parity shift and the spare entry
   }
   if (fuse) {
     std::vector<int32_t> of_cell((size_t)d->n_cells, -1);
