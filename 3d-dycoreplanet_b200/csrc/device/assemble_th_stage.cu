@@ -568,6 +568,7 @@ __device__ __forceinline__ void bulk_wait_read(int lane) {
 }
 // clear acc[0 .. n) (n rounded up to 2), 16 bytes per lane
 __device__ __forceinline__ void clear_acc(double* acc, int n, int lane) {
+#pragma unroll 1
   for (int k = 2 * lane; k < n; k += 64) *reinterpret_cast<double2*>(acc + k) = make_double2(0.0, 0.0);
 }
 
@@ -1251,7 +1252,7 @@ int dcp_launch_th_staged(dcp_model* m, const dcp_params& p, const MaskedPlan* pl
   g.p_incptr = G->p_incptr;
   g.p_meta = G->p_meta;
   g.nmask = plan->nmask;
-  g.wb = 16;
+  g.wb = 8;
   if (const char* e = std::getenv("DCP_GATHER_BLOCK")) g.wb = std::min(32, std::max(1, std::atoi(e)));   // <= 32: one item per lane in a block
   g.vstage = G->staging;
   g.pstage = G->staging + (size_t)NU * VROW * (size_t)G->chunk;
