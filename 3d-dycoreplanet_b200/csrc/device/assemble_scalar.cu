@@ -463,11 +463,58 @@ __global__ void q2_tab_kernel(const double* __restrict__ phi, const double* __re
 constexpr int TQ_LDB = 132;   // 132 mod 16 == 4: conflict-free fragment loads
 constexpr int TQ_HALF = 32;
 
-__global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArgs a, BlockView Mass, BlockView Stiff) {
+// operand table of 32 points of one cell: thread = (point, group of 7 nodes)
+__device__ __forceinline__ void q2_build_table(const ScalarArgs& a, const double* g, int half, double* X, double* wq, int tid) {
+  const int ql = tid >> 2, bg = tid & 3, q = half * TQ_HALF + ql;
+  double kinv[3][3];
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) kinv[e][d] = g[a.nq * (1 + 3 * e + d) + q];
+  if (bg == 0) wq[ql] = g[q];
+  double* x = X + ql * TQ_LDB + bg * 7;
+  const int nb = bg == 3 ? 6 : 7;
+  const double* tb = a.q2_tab + (size_t)half * (7 * 4 * 128) + tid;   // [half][j][e][thread]: coalesced
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    if (j >= nb) break;
+    const double r0 = __ldg(tb + (j * 4) * 128), r1 = __ldg(tb + (j * 4 + 1) * 128), r2 = __ldg(tb + (j * 4 + 2) * 128);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[32 * d + j] = kinv[0][d] * r0 + kinv[1][d] * r1 + kinv[2][d] * r2;
+    x[96 + j] = __ldg(tb + (j * 4 + 3) * 128);
+  }
+}
+
+// the warp's node-block pairs t = warp, warp + 4, warp + 8 (< 10) over the 32 points of the table
+__device__ __forceinline__ void q2_mma_half(const double* X, const double* wq, int warp, int frow, int fk, double (&am)[3][2], double (&ak)[3][2]) {
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const int t = warp + 4 * s;
+    if (t < 10) {
+      int ta = 0, r = t;
+      while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
+      const int tb = ta + r;
+#pragma unroll
+      for (int ks = 0; ks < TQ_HALF / 4; ++ks) {
+        const int ql = 4 * ks + fk;
+        const double* xr = X + ql * TQ_LDB;
+        const double wv = wq[ql];
+#pragma unroll
+        for (int al = 0; al < 4; ++al) {
+          const double af = wv * xr[32 * al + 8 * ta + frow], bf = xr[32 * al + 8 * tb + frow];
+          if (al < 3) dmma_m8n8k4(ak[s][0], ak[s][1], af, bf); else dmma_m8n8k4(am[s][0], am[s][1], af, bf);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArgs a, CsView cs, BlockView Mass, BlockView Stiff, int* err) {
   extern __shared__ __align__(16) double smem_d[];
-  double* X = smem_d;                      // [32][TQ_LDB]
+  double* X = smem_d;                      // [32][TQ_LDB]; after the contraction: the two local matrices of a cell with constrained dofs
   double* wq = X + TQ_HALF * TQ_LDB;       // [32]
   int* idx = reinterpret_cast<int*>(wq + TQ_HALF);   // [28]
+  int* lines = idx + 28;                             // [28]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frow = lane >> 2, fk = lane & 3;
   constexpr int ND2 = 27;
@@ -487,27 +534,15 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
     for (int s = 0; s < 3; ++s) am[s][0] = am[s][1] = ak[s][0] = ak[s][1] = 0.0;
     for (int half = 0; half < 2; ++half) {
       if (half) __syncthreads();
-      // operand table of 32 points: thread = (point, group of 7 nodes)
-      {
-        const int ql = tid >> 2, bg = tid & 3, q = half * TQ_HALF + ql;
-        double kinv[3][3];
-#pragma unroll
-        for (int e = 0; e < 3; ++e)
-#pragma unroll
-          for (int d = 0; d < 3; ++d) kinv[e][d] = g[a.nq * (1 + 3 * e + d) + q];
-        if (bg == 0) wq[ql] = g[q];
-        double* x = X + ql * TQ_LDB + bg * 7;
-        const int nb = bg == 3 ? 6 : 7;
-        const double* tb = a.q2_tab + (size_t)half * (7 * 4 * 128) + tid;   // [half][j][e][thread]: coalesced
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          if (j >= nb) break;
-          const double r0 = __ldg(tb + (j * 4) * 128), r1 = __ldg(tb + (j * 4 + 1) * 128), r2 = __ldg(tb + (j * 4 + 2) * 128);
-#pragma unroll
-          for (int d = 0; d < 3; ++d) x[32 * d + j] = kinv[0][d] * r0 + kinv[1][d] * r1 + kinv[2][d] * r2;
-          x[96 + j] = __ldg(tb + (j * 4 + 3) * 128);
-        }
-      }
+      q2_build_table(a, g, half, X, wq, tid);
+      __syncthreads();
+      q2_mma_half(X, wq, warp, frow, fk, am, ak);
+    }
+    if (tp[0] == 0xffffu) {
+      // the cell holds constrained dofs: the local matrices go through shared memory (in place of the operand table) and
+      // the full distribute_local_to_global
+      double* A = X;
+      double* B = X + ND2 * ND2 + 1;
       __syncthreads();
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
@@ -516,19 +551,26 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
           int ta = 0, r = t;
           while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
           const int tb = ta + r;
+          const int na = 8 * ta + frow;
 #pragma unroll
-          for (int ks = 0; ks < TQ_HALF / 4; ++ks) {
-            const int ql = 4 * ks + fk;
-            const double* xr = X + ql * TQ_LDB;
-            const double wv = wq[ql];
-#pragma unroll
-            for (int al = 0; al < 4; ++al) {
-              const double af = wv * xr[32 * al + 8 * ta + frow], bf = xr[32 * al + 8 * tb + frow];
-              if (al < 3) dmma_m8n8k4(ak[s][0], ak[s][1], af, bf); else dmma_m8n8k4(am[s][0], am[s][1], af, bf);
-            }
+          for (int jj = 0; jj < 2; ++jj) {
+            const int nb = 8 * tb + 2 * fk + jj;
+            if (na >= ND2 || nb >= ND2) continue;
+            const double mv = am[s][jj], kv = ak[s][jj] * a.prm.inv_pe;
+            A[na * ND2 + nb] = mv;
+            B[na * ND2 + nb] = kv;
+            A[nb * ND2 + na] = mv;
+            B[nb * ND2 + na] = kv;
           }
         }
       }
+      __syncthreads();
+      distribute_local_matrix<false>(cs, ND2, ND2, A, nullptr, idx, lines, Mass, nullptr, tid, 128, false, err);
+      __syncthreads();
+      distribute_local_matrix<false>(cs, ND2, ND2, B, nullptr, idx, lines, Stiff, nullptr, tid, 128, false, err);
+      __syncthreads();
+      for (int i = tid; i < 2 * ND2 * ND2 + 2; i += 128) X[i] = 0.0;   // the padding columns of the table are zero again
+      continue;
     }
     // scatter: lane holds (na, nb = 8 tb + 2 fk + jj); the transposed pair comes from the same registers
 #pragma unroll
@@ -558,6 +600,120 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
   }
 }
 
+// ---- Q2 temperature in 3-D, classic family: right-hand side of the cells with inhomogeneously constrained dofs ------
+// (boussinesq_model.tpp:928-963).  matrix_for_bc = M_local + tau/Pe K_local is the same Gram contraction as the matrices
+// above, so it runs on the tensor cores (the DFMA loop of temperature_rhs_kernel spends 729 entries x 64 points x 8
+// shared-memory loads per cell -- 1.7 ms for the 6 % boundary cells of the refine-5 shell against 1.5 ms for all the
+// others); the local vector comes from the same operand table.
+__global__ void __launch_bounds__(128, 4) temperature_rhs_bc_q2_kernel(ScalarArgs a, CsView cs) {
+  extern __shared__ __align__(16) double smem_d[];
+  double* X = smem_d;                      // [32][TQ_LDB]; after the contraction: matrix_for_bc
+  double* wq = X + TQ_HALF * TQ_LDB;       // [32]
+  int* idx = reinterpret_cast<int*>(wq + TQ_HALF);   // [28]
+  int* lines = idx + 28;                             // [28]
+  double* cq = reinterpret_cast<double*>(lines + 28);   // [32] rhs coefficient of the points
+  double* sT = cq + 32;                    // [28] old temperature
+  double* sU = sT + 28;                    // [3][28] velocity, component-major
+  double* sl = sU + 3 * 28;                // [28] local vector
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frow = lane >> 2, fk = lane & 3;
+  constexpr int ND2 = 27;
+  const double tau = a.prm.dt / a.prm.nse_interval;
+  for (int i = tid; i < TQ_HALF * TQ_LDB; i += 128) X[i] = 0.0;   // padding nodes 27..31 stay zero
+  for (long long ci = blockIdx.x; ci < a.n_cells; ci += gridDim.x) {
+    const long long cell = a.cell_list ? a.cell_list[ci] : ci;
+    const double* g = a.geom + cell * a.gstride;
+    __syncthreads();   // every warp is done with the previous cell
+    if (tid < ND2) {
+      const int gi = a.l2g[cell * ND2 + tid];
+      idx[tid] = gi;
+      sT[tid] = a.old_temp[gi];
+      sl[tid] = 0.0;
+      lines[tid] = cs.line_of_dof[gi];
+    }
+    for (int k = tid; k < a.nd_nse; k += 128) {
+      const int f = __ldg(a.nse_field + k);
+      if (f < 3) sU[f * 28 + __ldg(a.nse_base + k)] = a.nse_solution[a.l2g_nse[cell * a.nd_nse + k]];
+    }
+    double am[3][2], ak[3][2];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) am[s][0] = am[s][1] = ak[s][0] = ak[s][1] = 0.0;
+    for (int half = 0; half < 2; ++half) {
+      if (half) __syncthreads();
+      q2_build_table(a, g, half, X, wq, tid);
+      __syncthreads();
+      {
+        // old temperature, its gradient and the velocity at the point: the four threads of a point share the nodes
+        const int ql = tid >> 2, part = tid & 3, q = half * TQ_HALF + ql;
+        const double* xr = X + ql * TQ_LDB;
+        double oldT = 0.0, gT[3] = {0.0, 0.0, 0.0}, u[3] = {0.0, 0.0, 0.0};
+        const int k1 = part == 3 ? ND2 : 7 * part + 7;
+        for (int k = 7 * part; k < k1; ++k) {
+          const double Tk = sT[k], ph = __ldg(a.phi_uT + (size_t)k * a.nq + q);
+          oldT += Tk * xr[96 + k];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            gT[d] += Tk * xr[32 * d + k];
+            u[d] += sU[d * 28 + k] * ph;
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          oldT += __shfl_xor_sync(0xffffffffu, oldT, o);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            gT[d] += __shfl_xor_sync(0xffffffffu, gT[d], o);
+            u[d] += __shfl_xor_sync(0xffffffffu, u[d], o);
+          }
+        }
+        const double gamma = 0.0;  // heat source multiplied by literal 0 in the reference (:922-926)
+        if (part == 0) cq[ql] = (oldT - tau * (u[0] * gT[0] + u[1] * gT[1] + u[2] * gT[2]) - tau * gamma) * wq[ql];
+      }
+      q2_mma_half(X, wq, warp, frow, fk, am, ak);
+      __syncthreads();
+      if (tid < ND2) {
+        double s = 0.0;
+        for (int p = 0; p < TQ_HALF; ++p) s += X[p * TQ_LDB + 96 + tid] * cq[p];
+        sl[tid] += s;
+      }
+    }
+    double* A = X;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int t = warp + 4 * s;
+      if (t < 10) {
+        int ta = 0, r = t;
+        while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
+        const int tb = ta + r;
+        const int na = 8 * ta + frow;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int nb = 8 * tb + 2 * fk + jj;
+          if (na >= ND2 || nb >= ND2) continue;
+          const double v = am[s][jj] + tau * a.prm.inv_pe * ak[s][jj];
+          A[na * ND2 + nb] = v;
+          A[nb * ND2 + na] = v;
+        }
+      }
+    }
+    __syncthreads();
+    distribute_local_vector_bc<false>(cs, ND2, ND2, sl, A, idx, lines, a.rhs, tid, 128);
+    __syncthreads();
+    for (int i = tid; i < ND2 * ND2; i += 128) X[i] = 0.0;   // the padding columns of the table are zero again
+  }
+}
+
+constexpr size_t q2_smem_bytes() { return sizeof(double) * (TQ_HALF * TQ_LDB + TQ_HALF + 32 + 28 + 3 * 28 + 28) + sizeof(int) * 56; }
+
+int dcp_q2_table(dcp_model* m) {
+  if (m->temp_q2_tab) return DCP_OK;
+  DCP_CUDA(cudaMalloc((void**)&m->temp_q2_tab, sizeof(double) * 2 * 7 * 4 * 128));
+  q2_tab_kernel<<<(2 * 7 * 4 * 128 + 255) / 256, 256, 0, m->ctx->stream>>>(m->phi_t_qt, m->dphi_t_qt, m->temp_q2_tab);
+  DCP_CUDA(cudaGetLastError());
+  return DCP_OK;
+}
+
 }  // namespace
 
 int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
@@ -582,32 +738,16 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
   a.prm = p;
   if (m->n_cells == 0) return DCP_OK;
   if (m->dim == 3 && a.nd == 27 && a.nq == 64 && !std::getenv("DCP_NO_Q2_DMMA")) {
-    // Q2 temperature: tensor-core kernel on the cells with a position row, general kernel on the others
-    if (m->n_temp_fast > 0) {
-      if (!m->temp_q2_tab) {
-        DCP_CUDA(cudaMalloc((void**)&m->temp_q2_tab, sizeof(double) * 2 * 7 * 4 * 128));
-        q2_tab_kernel<<<(2 * 7 * 4 * 128 + 255) / 256, 256, 0, ctx->stream>>>(m->phi_t_qt, m->dphi_t_qt, m->temp_q2_tab);
-      }
-      a.q2_tab = m->temp_q2_tab;
-      ScalarArgs f = a;
-      f.cell_list = m->temp_fast_cells;
-      f.n_cells = m->n_temp_fast;
-      const size_t smem = sizeof(double) * (TQ_HALF * TQ_LDB + TQ_HALF) + sizeof(int) * 28;
-      DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const long long grid = std::min<long long>((long long)ctx->sm_count * 4, f.n_cells);
-      temperature_matrix_q2_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(f, make_view(m->tmass), make_view(m->tstiff));
-      ctx->launches++;
-    }
-    if (m->n_temp_general > 0) {
-      ScalarArgs gn = a;
-      gn.cell_list = m->temp_general_cells;
-      gn.n_cells = m->n_temp_general;
-      const ScalarLaunch sg = scalar_launch(ctx, gn.n_cells, a.nd, 0);
-      DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg.smem));
-      temperature_matrix_kernel<3><<<sg.grid, 32 * sg.warps, sg.smem, ctx->stream>>>(
-          gn, make_view(m->temp_cs), make_view(m->tmass), make_view(m->tstiff), ctx->d_err);
-      ctx->launches++;
-    }
+    // Q2 temperature: tensor-core kernel; cells without a position row (constrained dofs) end in the general scatter
+    DCP_TRY(dcp_q2_table(m));
+    a.q2_tab = m->temp_q2_tab;
+    a.cell_list = nullptr;
+    const size_t smem = q2_smem_bytes();
+    DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = std::min<long long>((long long)ctx->sm_count * 4, a.n_cells);
+    temperature_matrix_q2_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(a, make_view(m->temp_cs), make_view(m->tmass), make_view(m->tstiff),
+                                                                           ctx->d_err);
+    ctx->launches++;
     DCP_CUDA(cudaGetLastError());
     return DCP_OK;
   }
@@ -673,6 +813,17 @@ int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* 
   a.cell_list = m->temp_bc_cells;
   a.bc_flag = nullptr;
   a.n_cells = m->n_temp_bc_cells;
+  if (m->dim == 3 && !a.feec && a.nd == 27 && a.nq == 64 && a.ndu == 27 && !std::getenv("DCP_NO_Q2_DMMA")) {
+    DCP_TRY(dcp_q2_table(m));
+    a.q2_tab = m->temp_q2_tab;
+    const size_t smem = q2_smem_bytes();
+    DCP_CUDA(cudaFuncSetAttribute(temperature_rhs_bc_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = std::min<long long>((long long)ctx->sm_count * 4, a.n_cells);
+    temperature_rhs_bc_q2_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(a, make_view(m->temp_cs));
+    ctx->launches++;
+    DCP_CUDA(cudaGetLastError());
+    return DCP_OK;
+  }
   const ScalarLaunch s = scalar_launch(ctx, a.n_cells, a.nd, a.nd_nse);
   if (m->dim == 3) {
     DCP_CUDA(cudaFuncSetAttribute(temperature_rhs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
