@@ -68,6 +68,8 @@ struct DevCsr {
   double* val = nullptr;
   bool owns_pattern = true;  // mass/stiffness/temperature matrices share one pattern
   int lanes = 32;            // lanes per row chosen for the SpMV kernel
+  mutable int triple = -1;   // SpMV: most groups of three consecutive rows share one pattern (-1: not tested yet)
+  mutable unsigned char* triple_same = nullptr;   // ... per group: 1 = shared pattern
 };
 
 struct BlockMat {

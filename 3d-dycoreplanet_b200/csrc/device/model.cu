@@ -153,6 +153,8 @@ static int share_csr_pattern(dcp_ctx* ctx, const DevCsr& src, DevCsr& A) {
 }
 
 static void free_csr(DevCsr& A) {
+  cudaFree(A.triple_same);
+  A.triple_same = nullptr;
   if (A.owns_pattern) {
     cudaFree(A.rowptr);
     cudaFree(A.col);
