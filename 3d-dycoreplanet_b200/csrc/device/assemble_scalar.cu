@@ -485,28 +485,42 @@ __device__ __forceinline__ void q2_build_table(const ScalarArgs& a, const double
   }
 }
 
-// the warp's node-block pairs t = warp, warp + 4, warp + 8 (< 10) over the 32 points of the table
-__device__ __forceinline__ void q2_mma_half(const double* X, const double* wq, int warp, int frow, int fk, double (&am)[3][2], double (&ak)[3][2]) {
+// The 10 node-block pairs (ta <= tb) of a cell are grouped so that the pairs of one warp share operand fragments:
+// warp 0: (0,0) (0,1) (0,2); warp 1: (0,3) (1,3) (2,3); warp 2: (1,1) (1,2); warp 3: (2,2) (3,3) -- 11 fragment loads per
+// 10 DMMA and product instead of 20 (the kernel was bound by the LSU pipe: one pair of loads per DMMA).
+__constant__ unsigned char c_q2_ta[4][3] = {{0, 0, 0}, {0, 1, 2}, {1, 1, 9}, {2, 3, 9}};
+__constant__ unsigned char c_q2_tb[4][3] = {{0, 1, 2}, {3, 3, 3}, {1, 2, 9}, {2, 3, 9}};
+
+template <int W>
+__device__ __forceinline__ void q2_mma_half_w(const double* X, const double* wq, int frow, int fk, double (&am)[3][2], double (&ak)[3][2]) {
+  constexpr int NT = W < 2 ? 3 : 2;
+  constexpr int TA[4][3] = {{0, 0, 0}, {0, 1, 2}, {1, 1, 9}, {2, 3, 9}};
+  constexpr int TB[4][3] = {{0, 1, 2}, {3, 3, 3}, {1, 2, 9}, {2, 3, 9}};
+  constexpr int T0 = W == 0 ? 0 : (W == 1 ? 0 : (W == 2 ? 1 : 2));   // first operand tile this warp reads
+  constexpr int NTILE = W == 0 ? 3 : (W == 1 ? 4 : 2);               // ... and how many consecutive ones
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    const int t = warp + 4 * s;
-    if (t < 10) {
-      int ta = 0, r = t;
-      while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
-      const int tb = ta + r;
+  for (int ks = 0; ks < TQ_HALF / 4; ++ks) {
+    const int ql = 4 * ks + fk;
+    const double* xr = X + ql * TQ_LDB + frow;
+    const double wv = wq[ql];
 #pragma unroll
-      for (int ks = 0; ks < TQ_HALF / 4; ++ks) {
-        const int ql = 4 * ks + fk;
-        const double* xr = X + ql * TQ_LDB;
-        const double wv = wq[ql];
+    for (int al = 0; al < 4; ++al) {
+      double xt[4];
 #pragma unroll
-        for (int al = 0; al < 4; ++al) {
-          const double af = wv * xr[32 * al + 8 * ta + frow], bf = xr[32 * al + 8 * tb + frow];
-          if (al < 3) dmma_m8n8k4(ak[s][0], ak[s][1], af, bf); else dmma_m8n8k4(am[s][0], am[s][1], af, bf);
-        }
+      for (int t = 0; t < NTILE; ++t) xt[t] = xr[32 * al + 8 * (T0 + t)];
+#pragma unroll
+      for (int s = 0; s < NT; ++s) {
+        const double af = wv * xt[TA[W][s] - T0], bf = xt[TB[W][s] - T0];
+        if (al < 3) dmma_m8n8k4(ak[s][0], ak[s][1], af, bf); else dmma_m8n8k4(am[s][0], am[s][1], af, bf);
       }
     }
   }
+}
+__device__ __forceinline__ void q2_mma_half(const double* X, const double* wq, int warp, int frow, int fk, double (&am)[3][2], double (&ak)[3][2]) {
+  if (warp == 0) q2_mma_half_w<0>(X, wq, frow, fk, am, ak);
+  else if (warp == 1) q2_mma_half_w<1>(X, wq, frow, fk, am, ak);
+  else if (warp == 2) q2_mma_half_w<2>(X, wq, frow, fk, am, ak);
+  else q2_mma_half_w<3>(X, wq, frow, fk, am, ak);
 }
 
 __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArgs a, CsView cs, BlockView Mass, BlockView Stiff, int* err) {
@@ -515,6 +529,7 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
   double* wq = X + TQ_HALF * TQ_LDB;       // [32]
   int* idx = reinterpret_cast<int*>(wq + TQ_HALF);   // [28]
   int* lines = idx + 28;                             // [28]
+  long long* rstart = reinterpret_cast<long long*>(lines + 28);   // [28] row starts of the cell's dofs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frow = lane >> 2, fk = lane & 3;
   constexpr int ND2 = 27;
@@ -527,8 +542,12 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
     const double* g = a.geom + cell * a.gstride;
     const unsigned short* tp = a.tpos + cell * (long long)(ND2 * ND2);
     __syncthreads();   // every warp is done with the previous cell
-    if (tid < ND2) idx[tid] = a.l2g[cell * ND2 + tid];
-    // tasks of this warp: t = warp, warp + 4, warp + 8 (< 10)
+    if (tid < ND2) {
+      const int gi = a.l2g[cell * ND2 + tid];
+      idx[tid] = gi;
+      rstart[tid] = rp[gi];
+    }
+    // pairs of this warp: c_q2_ta / c_q2_tb
     double am[3][2], ak[3][2];
 #pragma unroll
     for (int s = 0; s < 3; ++s) am[s][0] = am[s][1] = ak[s][0] = ak[s][1] = 0.0;
@@ -546,11 +565,8 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
       __syncthreads();
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const int t = warp + 4 * s;
-        if (t < 10) {
-          int ta = 0, r = t;
-          while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
-          const int tb = ta + r;
+        const int ta = c_q2_ta[warp][s], tb = c_q2_tb[warp][s];
+        if (ta < 4) {
           const int na = 8 * ta + frow;
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
@@ -572,25 +588,35 @@ __global__ void __launch_bounds__(128, 4) temperature_matrix_q2_kernel(ScalarArg
       for (int i = tid; i < 2 * ND2 * ND2 + 2; i += 128) X[i] = 0.0;   // the padding columns of the table are zero again
       continue;
     }
-    // scatter: lane holds (na, nb = 8 tb + 2 fk + jj); the transposed pair comes from the same registers
+    // scatter: lane holds (na, nb = 8 tb + 2 fk + jj); the transposed pair comes from the same registers.  All positions
+    // are fetched before the first reduction (the reductions order memory: a load behind one would wait for its turn).
+    unsigned short pd[3][2], pt[3][2];
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      const int t = warp + 4 * s;
-      if (t < 10) {
-        int ta = 0, r = t;
-        while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
-        const int tb = ta + r;
+      const int ta = c_q2_ta[warp][s], tb = c_q2_tb[warp][s];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int na = 8 * ta + frow, nb = 8 * tb + 2 * fk + jj;
+        const bool on = ta < 4 && na < ND2 && nb < ND2;
+        pd[s][jj] = on ? tp[na * ND2 + nb] : (unsigned short)0;
+        pt[s][jj] = on && ta != tb ? tp[nb * ND2 + na] : (unsigned short)0;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ta = c_q2_ta[warp][s], tb = c_q2_tb[warp][s];
+      if (ta < 4) {
         const int na = 8 * ta + frow;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int nb = 8 * tb + 2 * fk + jj;
           if (na >= ND2 || nb >= ND2) continue;
           const double mv = am[s][jj], kv = ak[s][jj] * a.prm.inv_pe;
-          const long long at = rp[idx[na]] + tp[na * ND2 + nb];
+          const long long at = rstart[na] + pd[s][jj];
           red_add_f64(vm + at, mv);
           red_add_f64(vk + at, kv);
           if (ta != tb) {
-            const long long at2 = rp[idx[nb]] + tp[nb * ND2 + na];
+            const long long at2 = rstart[nb] + pt[s][jj];
             red_add_f64(vm + at2, mv);
             red_add_f64(vk + at2, kv);
           }
@@ -681,11 +707,8 @@ __global__ void __launch_bounds__(128, 4) temperature_rhs_bc_q2_kernel(ScalarArg
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      const int t = warp + 4 * s;
-      if (t < 10) {
-        int ta = 0, r = t;
-        while (r >= 4 - ta) { r -= 4 - ta; ++ta; }
-        const int tb = ta + r;
+      const int ta = c_q2_ta[warp][s], tb = c_q2_tb[warp][s];
+      if (ta < 4) {
         const int na = 8 * ta + frow;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
@@ -704,7 +727,7 @@ __global__ void __launch_bounds__(128, 4) temperature_rhs_bc_q2_kernel(ScalarArg
   }
 }
 
-constexpr size_t q2_smem_bytes() { return sizeof(double) * (TQ_HALF * TQ_LDB + TQ_HALF + 32 + 28 + 3 * 28 + 28) + sizeof(int) * 56; }
+constexpr size_t q2_smem_bytes() { return sizeof(double) * (TQ_HALF * TQ_LDB + TQ_HALF + 32 + 28 + 3 * 28 + 28 + 28) + sizeof(int) * 56; }
 
 int dcp_q2_table(dcp_model* m) {
   if (m->temp_q2_tab) return DCP_OK;
