@@ -1,8 +1,7 @@
 #!/usr/bin/env python
 """Sum dram__bytes_read.sum + dram__bytes_write.sum over the launches of one bench step from an ncu CSV
 (`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file <csv> python bench.py ...`) and record the
-NSE system pass (th_stage_kernel + th_gather_kernel + th_pre_gather_kernel, or th_mma_kernel<1> for the reduction
-strategy) in profiles/traffic.json, which bench.py reads for `roofline.traffic`.
+NSE system pass (th_stage_kernel + th_gather_kernel, or th_mma_kernel<1> for the reduction strategy) in profiles/traffic.json, which bench.py reads for `roofline.traffic`.
 
     python profiles/extract_traffic.py <csv> <strategy> <refine> <steps captured> [<commit>]
 """
@@ -32,8 +31,9 @@ def main():
         unit = d["Metric Unit"].lower()
         scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1.0)
         name = d["Kernel Name"].replace("<unnamed>::", "").replace("void ", "")
-        name = name.split("(thmma")[0].split("(GatherArgs")[0].split("(<unnamed>")[0].strip()
-        per_kernel[name][0] += 1
+        name = name.split("(thmma")[0].split("(GatherArgs")[0].split("(<unnamed>")[0].split("(MmaArgs")[0].strip()
+        if d["Metric Name"] == "dram__bytes_read.sum":
+            per_kernel[name][0] += 1
         per_kernel[name][1] += v * scale
     def in_system_pass(n):
         if any(k in n for k in ("th_stage_kernel", "th_gather", "th_pre_gather", "th_fused_kernel")):
@@ -44,7 +44,7 @@ def main():
     data = json.load(open(out_path)) if os.path.exists(out_path) else {}
     data[f"{strategy}:r{refine}"] = {
         "dram_bytes_per_step": total / steps,
-        "kernels": {n: {"launches_per_step": c / 2 / steps, "dram_bytes_per_step": b / steps} for n, (c, b) in sorted(per_kernel.items())},
+        "kernels": {n: {"launches_per_step": c / steps, "dram_bytes_per_step": b / steps} for n, (c, b) in sorted(per_kernel.items())},
         "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of `python bench.py --refine {refine}` "
                   f"({os.path.basename(path)}, {steps} step(s) captured" + (f", commit {commit}" if commit else "") + ")",
     }
