@@ -86,7 +86,7 @@ EXPORTS = [
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
     "dcp_vmult_add", "dcp_block_vmult", "dcp_vmult_rows", "dcp_block_vmult_rows", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
-    "dcp_vec_scale", "dcp_vec_copy", "dcp_vec_fill", "dcp_vec_shift", "dcp_comm_unique_id", "dcp_comm_create", "dcp_comm_adopt", "dcp_comm_info",
+    "dcp_vec_scale", "dcp_vec_copy", "dcp_vec_fill", "dcp_vec_shift", "dcp_cg_solve", "dcp_comm_unique_id", "dcp_comm_create", "dcp_comm_adopt", "dcp_comm_info",
     "dcp_comm_destroy", "dcp_halo_create", "dcp_halo_destroy", "dcp_halo_exchange", "dcp_halo_block_vmult",
     "dcp_vec_dot_allreduce", "dcp_allreduce_max", "dcp_velocity_extrema", "dcp_constraints_distribute",
     "dcp_geometry_create", "dcp_ilu_create", "dcp_ilu_refactor", "dcp_ilu_vmult", "dcp_ilu_levels", "dcp_ilu_destroy",
@@ -144,6 +144,9 @@ def lib():
         L.dcp_block_vmult_rows.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_jacobi_vmult.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_vec_dot.argtypes = [vp, ctypes.c_int64, vp, vp, c_dp]
+        L.dcp_cg_solve.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp,
+                                   ctypes.c_double, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                   ctypes.POINTER(ctypes.c_double)]
         L.dcp_vec_axpy.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp, vp]
         L.dcp_vec_sadd.argtypes = [vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, vp, vp]
         L.dcp_vec_scale.argtypes = [vp, ctypes.c_int64, ctypes.c_double, vp]
@@ -258,6 +261,14 @@ class SparseMatrix:
         check(lib().dcp_matrix_info(model._h, which, bi, bj, ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(nz)))
         self._nr, self._nc, self.nnz = nr.value, nc.value, nz.value
 
+    @property
+    def n_rows(self):
+        return self._nr
+
+    @property
+    def n_cols(self):
+        return self._nc
+
     def m(self):
         return self._nr
 
@@ -322,6 +333,32 @@ class BlockSparseMatrix:
 
 
 ROWS_ALL, ROWS_INTERIOR, ROWS_GHOSTED = 0, 1, 2
+
+
+PRECOND_IDENTITY, PRECOND_JACOBI, PRECOND_ILU = 0, 1, 2
+ERR_NO_CONVERGENCE = 5
+
+
+def cg_solve(matrix, x, b, tol, max_steps, preconditioner=None, check_every=8):
+    """dcp_cg_solve: SolverCG on the device without a host synchronisation per iteration.  `matrix`: SparseMatrix (a
+    square block), `preconditioner`: None (identity), PreconditionJacobi or PreconditionILU; x, b: device tensors.
+    Returns (converged, last_step, last_residual)."""
+    kind, which_p, bp, ilu = PRECOND_IDENTITY, 0, 0, None
+    if isinstance(preconditioner, PreconditionJacobi):
+        kind, which_p, bp = PRECOND_JACOBI, preconditioner.which, preconditioner.bi
+    elif isinstance(preconditioner, PreconditionILU):
+        kind, ilu = PRECOND_ILU, preconditioner._h
+    elif preconditioner is not None:
+        raise TypeError("cg_solve: identity, Jacobi or ILU(0) preconditioners only")
+    xd, mx = _vec_arg(x)
+    bd, mb = _vec_arg(b)
+    assert mx == DEVICE and mb == DEVICE, "cg_solve works on device vectors"
+    step, res = ctypes.c_int64(), ctypes.c_double()
+    rc = lib().dcp_cg_solve(matrix._m._h, matrix.which, matrix.bi, matrix.bj, kind, which_p, bp, ilu, xd, bd, float(tol),
+                            int(min(max_steps, 2 ** 62)), int(check_every), ctypes.byref(step), ctypes.byref(res))
+    if rc not in (0, ERR_NO_CONVERGENCE):
+        check(rc, "dcp_cg_solve")
+    return rc == 0, step.value, res.value
 
 
 class PreconditionJacobi:

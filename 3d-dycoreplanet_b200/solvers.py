@@ -78,6 +78,7 @@ class DeviceBackend:
         from . import device
         self.torch, self.dv, self.ctx = torch, device, ctx
         self._res = ctypes.c_double()
+        self.resident_cg = True      # SolverCG inside the library where the operands allow (dcp_cg_solve)
         # the library's own stream is non-blocking: run it on torch's current stream so that tensor creation
         # (torch.zeros, .cuda()) and the library's kernels on the same memory are ordered
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -155,8 +156,33 @@ class Wrap:
 
 
 # ---- deal.II solvers -----------------------------------------------------------------------------------------
+def _device_cg_operands(B, A, P):
+    """(device SparseMatrix, device preconditioner or None) when the whole solve can run inside libdcp (dcp_cg_solve:
+    a square block of a device matrix, preconditioned by the identity, a Jacobi sweep or ILU(0)); else None."""
+    if not isinstance(B, DeviceBackend) or not B.resident_cg:
+        return None
+    dv = B.dv
+    mat = A.op if isinstance(A, Wrap) else A
+    if not isinstance(mat, dv.SparseMatrix) or mat.n_rows != mat.n_cols:
+        return None
+    pre = P.op if isinstance(P, Wrap) else P
+    if isinstance(pre, Identity):
+        pre = None
+    elif not isinstance(pre, (dv.PreconditionJacobi, dv.PreconditionILU)):
+        return None
+    return mat, pre
+
+
 def solver_cg(B, A, x, b, P, tol, max_steps):
-    """SolverCG<Vector>::solve(A, x, b, P) with SolverControl(max_steps, tol).  Returns last_step."""
+    """SolverCG<Vector>::solve(A, x, b, P) with SolverControl(max_steps, tol).  Returns last_step.  On the device
+    backend, with a plain matrix block and an identity / Jacobi / ILU(0) preconditioner, the whole loop runs inside the
+    library (no host synchronisation per iteration); every other combination uses the loop below."""
+    ops = _device_cg_operands(B, A, P)
+    if ops is not None:
+        ok, step, res = B.dv.cg_solve(ops[0], x, b, tol, max_steps, ops[1])
+        if not ok:
+            raise NoConvergence(step, res)
+        return step
     n = len(b) if hasattr(b, "__len__") else b.numel()
     r, z, p, Ap = B.zeros(n), B.zeros(n), B.zeros(n), B.zeros(n)
     A.vmult(r, x, B)

@@ -47,7 +47,8 @@ enum {
   DCP_ERR_CUDA = 1,     /* CUDA runtime error or no device */
   DCP_ERR_ARG = 2,      /* invalid argument */
   DCP_ERR_PATTERN = 3,  /* a scatter target is not in the sparsity pattern */
-  DCP_ERR_STATE = 4     /* call order (e.g. rhs before matrices) */
+  DCP_ERR_STATE = 4,    /* call order (e.g. rhs before matrices) */
+  DCP_ERR_NO_CONVERGENCE = 5  /* dcp_cg_solve: SolverControl::NoConvergence (last step / residual are reported) */
 };
 
 enum { DCP_HOST = 0, DCP_DEVICE = 1 }; /* where a caller-provided vector lives */
@@ -316,6 +317,18 @@ int dcp_vec_axpy(dcp_ctx* ctx, int64_t n, double a, const double* x_dev, double*
 int dcp_vec_sadd(dcp_ctx* ctx, int64_t n, double s, double a, const double* x_dev, double* y_dev);
 int dcp_vec_scale(dcp_ctx* ctx, int64_t n, double a, double* y_dev);
 int dcp_vec_copy(dcp_ctx* ctx, int64_t n, const double* x_dev, double* y_dev);
+/* SolverCG<Vector>::solve(A, x, b, P) with SolverControl(max_steps, tol), resident on the device: A = block (bi, bj) of
+ * matrix `which`, P = identity, the Jacobi diagonal of block (bp, bp) of matrix `which_p`, or an ILU(0) handle.  alpha, beta
+ * and the residual norm stay in device memory; the host reads the convergence flag once per `check_every` iterations
+ * (<= 0: 8) and iterations enqueued behind the converged one are no-ops, so x, *last_step and *last_residual are those
+ * of the reference's loop (inner products: the tree of dcp_vec_dot).  x_dev holds the start vector.  Returns
+ * DCP_ERR_NO_CONVERGENCE after max_steps steps (x_dev = last iterate, like the exception the reference catches).
+ * Replaces the SolverCG loops of LinearAlgebra::InverseMatrix::vmult (include/linear_algebra/inverse_matrix.hpp:90-121),
+ * ApproximateInverseMatrix::vmult (approximate_inverse.hpp:97-128) and solve_temperature
+ * (include/core/boussinesq_model.tpp:1426-1440).  Single-rank models (row-distributed: DCP_ERR_STATE). */
+enum { DCP_PRECOND_IDENTITY = 0, DCP_PRECOND_JACOBI = 1, DCP_PRECOND_ILU = 2 };
+int dcp_cg_solve(dcp_model* m, int which, int bi, int bj, int precond, int which_p, int bp, dcp_ilu* ilu, double* x_dev,
+                 const double* b_dev, double tol, int64_t max_steps, int check_every, int64_t* last_step, double* last_residual);
 /* y = value (deal.II `dst = 0`: an assignment, so NaN / Inf in an uninitialised destination do not survive) */
 int dcp_vec_fill(dcp_ctx* ctx, int64_t n, double value, double* y_dev);
 /* y += a in every entry (Vector::add(a): the zero-mean correction of the FEEC pressure, nested_schur_complement.hpp:180-182) */

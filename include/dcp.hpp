@@ -133,6 +133,10 @@ class SparseMatrix {
   int64_t m() const { return rows_; }
   int64_t n() const { return cols_; }
   int64_t n_nonzero_elements() const { return nnz_; }
+  dcp_model* model() const { return m_; }
+  int which() const { return which_; }
+  int block_row() const { return bi_; }
+  int block_col() const { return bj_; }
   template <class Dst, class Src>
   void vmult(Dst& dst, const Src& src) const {
     auto d = detail::arg(dst);
@@ -195,6 +199,8 @@ class PreconditionJacobi {
  public:
   PreconditionJacobi() = default;
   PreconditionJacobi(dcp_model* m, int which, int bi) : m_(m), which_(which), bi_(bi) {}
+  int which() const { return which_; }
+  int block() const { return bi_; }
   template <class Dst, class Src>
   void vmult(Dst& dst, const Src& src) const {
     auto d = detail::arg(dst);
@@ -207,6 +213,22 @@ class PreconditionJacobi {
   dcp_model* m_ = nullptr;
   int which_ = 0, bi_ = 0;
 };
+
+// SolverCG<LA::MPI::Vector>(SolverControl(max_steps, tol)).solve(A, x, b, P) on device vectors, P = PreconditionJacobi (or
+// the identity with `preconditioner == nullptr`): the loop of LinearAlgebra::InverseMatrix::vmult
+// (include/linear_algebra/inverse_matrix.hpp:90-121) and of solve_temperature (boussinesq_model.tpp:1426-1440), resident on
+// the device (dcp_cg_solve).  Returns the last step; throws like SolverControl::NoConvergence when the limit is reached.
+inline int64_t solve_cg(const SparseMatrix& A, DeviceVector& x, const DeviceVector& b, const PreconditionJacobi* preconditioner, double tol,
+                        int64_t max_steps, double* last_residual = nullptr) {
+  int64_t step = 0;
+  double res = 0.0;
+  const int rc = dcp_cg_solve(A.model(), A.which(), A.block_row(), A.block_col(), preconditioner ? DCP_PRECOND_JACOBI : DCP_PRECOND_IDENTITY,
+                              preconditioner ? preconditioner->which() : 0, preconditioner ? preconditioner->block() : 0, nullptr, x.data(),
+                              b.data(), tol, max_steps, 0, &step, &res);
+  if (last_residual) *last_residual = res;
+  if (rc != DCP_OK) throw Error(rc, "dcp_cg_solve");
+  return step;
+}
 
 // Device-side state of Standard::BoussinesqModel<dim> / ExteriorCalculus::BoussinesqModel<3> for one mesh.
 class BoussinesqModel {

@@ -92,3 +92,54 @@ def test_feec_block_preconditioned_step(problem_factory, refine):
         err = np.abs(got["nse"][sl] - ref["nse"][sl]).max() / np.abs(ref["nse"][sl]).max()
         assert err <= 1e-5, (name, err)
     assert np.abs(got["nse"] - ref["nse"]).max() / np.abs(ref["nse"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("precond", ["identity", "jacobi", "ilu"])
+def test_resident_cg_equals_the_host_driven_loop(problem_factory, precond):
+    """dcp_cg_solve (alpha, beta, residual in device memory, convergence flag read every 8 iterations) against the same
+    SolverCG driven from the host with one dcp_vec_dot round trip per inner product: same inner-product tree and the
+    same update formulas, so step counts are equal and the iterates agree to rounding; also the step limit
+    (SolverControl::NoConvergence) and the zero-step exit."""
+    import torch
+    from dycore_b200 import device, params, solvers as S
+    mp = params.NAMED["shell_3d_classic"]
+    P = problem_factory(geometry="shell", refine=2)
+    ctx = device.Context(0)
+    model = device.BoussinesqModel.from_problem(ctx, P, mp)
+    B = S.DeviceBackend(ctx)
+    u, T = K.synthetic_state(P) if hasattr(K, "synthetic_state") else (np.zeros(P.scalar("nse.n_dofs")), K.initial_temperature(P, mp))
+    model.assemble_nse_system(torch.from_numpy(u).cuda(), torch.from_numpy(T).cuda())
+    model.assemble_nse_preconditioner()
+    model.assemble_temperature_matrix()
+    model.assemble_temperature_rhs(torch.from_numpy(T).cuda(), torch.from_numpy(u).cuda())
+    if precond == "ilu":
+        mat = model.nse_preconditioner_matrix.block(0, 0)          # the velocity block the reference inverts with ILU + CG
+        pre = device.PreconditionILU(model, device.MAT_NSE_PRECOND, 0)
+    else:
+        mat = model.temperature_matrix
+        mat = mat.block(0, 0) if hasattr(mat, "block") else mat
+        pre = device.PreconditionJacobi(model, device.MAT_TEMP, 0) if precond == "jacobi" else None
+    n = mat.n_rows
+    rng = np.random.default_rng(7)
+    b = B.from_numpy(rng.standard_normal(n))
+    tol = 1e-10 * float(np.sqrt(B.dot(b, b)))
+    P_op = S.Wrap(pre) if pre is not None else S.Identity()
+    results = []
+    for resident in (True, False):
+        B.resident_cg = resident
+        x = B.zeros(n)
+        its = S.solver_cg(B, S.Wrap(mat), x, b, P_op, tol, 10 * n)
+        results.append((its, B.to_numpy(x)))
+    (it_a, xa), (it_b, xb) = results
+    assert it_a == it_b and it_a > 3, (it_a, it_b)
+    assert np.abs(xa - xb).max() <= 1e-12 * np.abs(xb).max()
+    # step limit: NoConvergence with the step count of the limit
+    B.resident_cg = True
+    with pytest.raises(S.NoConvergence) as e:
+        S.solver_cg(B, S.Wrap(mat), B.zeros(n), b, P_op, 1e-300, 5)
+    assert e.value.last_step == 5
+    # a start vector that already solves the system: zero steps
+    x = B.from_numpy(xa)
+    assert S.solver_cg(B, S.Wrap(mat), x, b, P_op, 1e-6 * float(np.sqrt(B.dot(b, b))), 100) == 0
+    model.close()
+    ctx.close()
