@@ -42,6 +42,8 @@ struct dcp_ctx {
   int64_t stage_cap[3] = {0, 0, 0};
   double* dot_scratch = nullptr;  // partial sums of dcp_vec_dot
   double* dot_host = nullptr;     // pinned result
+  cudaStream_t copy_stream = nullptr;   // dcp_memcpy_*_async (created on first use)
+  cudaEvent_t copy_event = nullptr;
 };
 
 // constraint lines on the device

@@ -262,6 +262,11 @@ int dcp_ctx_destroy(dcp_ctx* ctx) {
   cudaFree(ctx->dot_scratch);
   cudaFreeHost(ctx->dot_host);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->copy_event);
+  }
   delete ctx;
   return DCP_OK;
 }
@@ -310,6 +315,41 @@ int dcp_memcpy_d2h(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t by
   if (!ctx) return DCP_ERR_ARG;
   DCP_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
   DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DCP_OK;
+}
+
+// ---- asynchronous host <-> device copies on the context's copy stream ---------------------------------------------
+static int copy_stream(dcp_ctx* ctx) {
+  if (ctx->copy_stream) return DCP_OK;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  DCP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  DCP_CUDA(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+  return DCP_OK;
+}
+int dcp_memcpy_h2d_async(dcp_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes) {
+  if (!ctx || bytes < 0) return DCP_ERR_ARG;
+  DCP_TRY(copy_stream(ctx));
+  DCP_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  return DCP_OK;
+}
+int dcp_memcpy_d2h_async(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
+  if (!ctx || bytes < 0) return DCP_ERR_ARG;
+  DCP_TRY(copy_stream(ctx));
+  DCP_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  return DCP_OK;
+}
+int dcp_copy_fence(dcp_ctx* ctx, int direction) {
+  if (!ctx || (direction != DCP_COMPUTE_WAITS_FOR_COPIES && direction != DCP_COPIES_WAIT_FOR_COMPUTE)) return DCP_ERR_ARG;
+  DCP_TRY(copy_stream(ctx));
+  cudaStream_t from = direction == DCP_COMPUTE_WAITS_FOR_COPIES ? ctx->copy_stream : ctx->stream;
+  cudaStream_t to = direction == DCP_COMPUTE_WAITS_FOR_COPIES ? ctx->stream : ctx->copy_stream;
+  DCP_CUDA(cudaEventRecord(ctx->copy_event, from));
+  DCP_CUDA(cudaStreamWaitEvent(to, ctx->copy_event, 0));
+  return DCP_OK;
+}
+int dcp_copy_synchronize(dcp_ctx* ctx) {
+  if (!ctx) return DCP_ERR_ARG;
+  if (ctx->copy_stream) DCP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   return DCP_OK;
 }
 

@@ -81,7 +81,7 @@ class MappingDesc(ctypes.Structure):
 
 EXPORTS = [
     "dcp_ctx_create", "dcp_ctx_destroy", "dcp_ctx_set_stream", "dcp_ctx_synchronize", "dcp_last_error",
-    "dcp_ctx_launch_count", "dcp_malloc", "dcp_free", "dcp_memcpy_h2d", "dcp_memcpy_d2h", "dcp_model_create",
+    "dcp_ctx_launch_count", "dcp_malloc", "dcp_free", "dcp_memcpy_h2d", "dcp_memcpy_d2h", "dcp_memcpy_h2d_async", "dcp_memcpy_d2h_async", "dcp_copy_fence", "dcp_copy_synchronize", "dcp_model_create",
     "dcp_model_destroy", "dcp_model_set_strategy", "dcp_model_get_strategy", "dcp_model_set_owned", "dcp_gather_f64", "dcp_scatter_f64", "dcp_assemble_nse_system", "dcp_assemble_nse_preconditioner",
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
@@ -120,6 +120,10 @@ def lib():
         L.dcp_free.argtypes = [vp, vp]
         L.dcp_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_int64]
         L.dcp_memcpy_d2h.argtypes = [vp, vp, vp, ctypes.c_int64]
+        L.dcp_memcpy_h2d_async.argtypes = [vp, vp, vp, ctypes.c_int64]
+        L.dcp_memcpy_d2h_async.argtypes = [vp, vp, vp, ctypes.c_int64]
+        L.dcp_copy_fence.argtypes = [vp, ctypes.c_int]
+        L.dcp_copy_synchronize.argtypes = [vp]
         L.dcp_model_create.argtypes = [vp, ctypes.POINTER(ModelDesc), ctypes.POINTER(vp)]
         L.dcp_model_destroy.argtypes = [vp]
         L.dcp_model_set_strategy.argtypes = [vp, ctypes.c_int]

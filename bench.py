@@ -5,8 +5,9 @@ One "step" = one pass of the hot path over one mesh: the four assemblers of the 
 (assemble_nse_system, assemble_nse_preconditioner, assemble_temperature_matrix, assemble_temperature_rhs;
 /root/reference/include/core/boussinesq_model.tpp:1867-1884) followed by the SpMVs one outer Krylov iteration
 makes (full nse_matrix block vmult + temperature_matrix vmult).  `value` = DoFs (n_u+n_p+n_T) / step time with
-all inputs resident in HBM; `e2e` = the same step through the C ABI with HOST buffers (H2D of the solution
-vectors and SpMV sources, D2H of the right-hand sides and SpMV results inside the timed region).
+all inputs resident in HBM; `e2e` = the same step through the C ABI with pinned HOST buffers (H2D of the solution
+vectors and SpMV sources, D2H of the right-hand sides and SpMV results inside the timed region, moved with the
+library's asynchronous copies behind the kernels; DCP_NO_ASYNC_E2E=1: the blocking DCP_HOST path of the entry points).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--refine R] [--temperature-degree D]
   python bench.py --impl reference ...   # the restated CPU path (oracle, OpenMP) on the host cores
@@ -374,28 +375,53 @@ def main():
 
     L = device.lib()
 
+    COMPUTE_WAITS, COPIES_WAIT = 0, 1
+    rhs_ptr, trhs_ptr = ctypes.c_void_p(), ctypes.c_void_p()
+    _n = ctypes.c_int64()
+    device.check(L.dcp_vector_device(model._h, device.VEC_NSE_RHS, ctypes.byref(rhs_ptr), ctypes.byref(_n)), "dcp_vector_device")
+    device.check(L.dcp_vector_device(model._h, device.VEC_TEMP_RHS, ctypes.byref(trhs_ptr), ctypes.byref(_n)), "dcp_vector_device")
+
     def step_host():
-        # the same step for a caller whose vectors live in HOST memory, through the C ABI's DCP_HOST path: the assemblers
-        # and (single rank) the products take host pointers, the library stages them in and out (H2D of the solution
-        # vectors and SpMV sources, D2H of the right-hand sides and SpMV results inside the call).  Row-distributed
-        # products take device vectors (the ghost exchange lives there), so with several ranks the sources go up and the
-        # results come down through dcp_memcpy_h2d / dcp_memcpy_d2h around dcp_halo_block_vmult.
-        model.assemble_nse_system(h_u, h_T)
-        model.assemble_nse_preconditioner()
-        model.assemble_temperature_matrix()
-        model.assemble_temperature_rhs(h_T, h_u)
-        device.check(L.dcp_vector_download(model._h, device.VEC_NSE_RHS, hp(h_rhs)), "dcp_vector_download")
-        device.check(L.dcp_vector_download(model._h, device.VEC_TEMP_RHS, hp(h_trhs)), "dcp_vector_download")
-        if halo_nse is not None:
-            device.check(L.dcp_memcpy_h2d(ctx._h, hp(d_x), hp(h_x), 8 * n_nse))
-            device.check(L.dcp_memcpy_h2d(ctx._h, hp(d_xt), hp(h_xt), 8 * n_t))
-            op_nse.vmult(d_y, d_x)
-            op_t.vmult(d_yt, d_xt)
-            device.check(L.dcp_memcpy_d2h(ctx._h, hp(h_y), hp(d_y), 8 * n_nse))
-            device.check(L.dcp_memcpy_d2h(ctx._h, hp(h_yt), hp(d_yt), 8 * n_t))
-        else:
+        # the same step for a caller whose vectors live in (pinned) HOST memory, through the C ABI: every input comes up and
+        # every result goes down inside the timed region, with the library's asynchronous copies (dcp_memcpy_*_async on
+        # the context's copy stream, ordered by dcp_copy_fence) so that the SpMV sources travel while the assemblers run
+        # and the right-hand sides while the products run -- what a deal.II host does with the vectors of the next /
+        # previous operator call.  (DCP_NO_ASYNC_E2E=1: the blocking host-pointer path of the entry points, DCP_HOST.)
+        if os.environ.get("DCP_NO_ASYNC_E2E") and halo_nse is None:
+            model.assemble_nse_system(h_u, h_T)
+            model.assemble_nse_preconditioner()
+            model.assemble_temperature_matrix()
+            model.assemble_temperature_rhs(h_T, h_u)
+            device.check(L.dcp_vector_download(model._h, device.VEC_NSE_RHS, hp(h_rhs)), "dcp_vector_download")
+            device.check(L.dcp_vector_download(model._h, device.VEC_TEMP_RHS, hp(h_trhs)), "dcp_vector_download")
             model.nse_matrix.vmult(h_y, h_x)
             model.temperature_matrix.vmult(h_yt, h_xt)
+            return
+        c = ctx._h
+        device.check(L.dcp_copy_fence(c, COPIES_WAIT))                         # the previous step is done with d_u, d_T, d_x
+        device.check(L.dcp_memcpy_h2d_async(c, hp(d_u), hp(h_u), 8 * n_nse))   # old solution
+        device.check(L.dcp_memcpy_h2d_async(c, hp(d_T), hp(h_T), 8 * n_t))
+        device.check(L.dcp_copy_fence(c, COMPUTE_WAITS))
+        device.check(L.dcp_memcpy_h2d_async(c, hp(d_x), hp(h_x), 8 * n_nse))   # SpMV sources: behind the assemblers
+        device.check(L.dcp_memcpy_h2d_async(c, hp(d_xt), hp(h_xt), 8 * n_t))
+        model.assemble_nse_system(d_u, d_T)
+        model.assemble_nse_preconditioner()
+        model.assemble_temperature_matrix()
+        model.assemble_temperature_rhs(d_T, d_u)
+        device.check(L.dcp_copy_fence(c, COMPUTE_WAITS))                       # sources are up
+        device.check(L.dcp_copy_fence(c, COPIES_WAIT))                         # right-hand sides are assembled
+        device.check(L.dcp_memcpy_d2h_async(c, hp(h_rhs), rhs_ptr, 8 * n_nse))  # ... and go down behind the products
+        device.check(L.dcp_memcpy_d2h_async(c, hp(h_trhs), trhs_ptr, 8 * n_t))
+        if halo_nse is not None:
+            op_nse.vmult(d_y, d_x)
+            op_t.vmult(d_yt, d_xt)
+        else:
+            model.nse_matrix.vmult(d_y, d_x)
+            model.temperature_matrix.vmult(d_yt, d_xt)
+        device.check(L.dcp_copy_fence(c, COPIES_WAIT))
+        device.check(L.dcp_memcpy_d2h_async(c, hp(h_y), hp(d_y), 8 * n_nse))
+        device.check(L.dcp_memcpy_d2h_async(c, hp(h_yt), hp(d_yt), 8 * n_t))
+        device.check(L.dcp_copy_fence(c, COMPUTE_WAITS))                       # the step ends when the results are on the host
 
     def barrier():
         if world > 1:

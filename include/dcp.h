@@ -222,6 +222,17 @@ int dcp_malloc(dcp_ctx* ctx, int64_t bytes, void** out);
 int dcp_free(dcp_ctx* ctx, void* p);
 int dcp_memcpy_h2d(dcp_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
 int dcp_memcpy_d2h(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+/* The same copies on the context's own copy stream, so that vectors travel while kernels run (host memory should be
+ * pinned).  Ordering against the work of the context's stream is explicit: dcp_copy_fence(DCP_COMPUTE_WAITS_FOR_COPIES)
+ * makes everything enqueued on the context's stream afterwards wait for the copies enqueued so far (an uploaded vector is
+ * used), dcp_copy_fence(DCP_COPIES_WAIT_FOR_COMPUTE) makes later copies wait for the kernels enqueued so far (a result
+ * is downloaded); dcp_copy_synchronize blocks the host until the copy stream is idle.  A deal.II host uses these to move
+ * LA::MPI::Vector data of the next / previous operator call behind the current one. */
+enum { DCP_COMPUTE_WAITS_FOR_COPIES = 0, DCP_COPIES_WAIT_FOR_COMPUTE = 1 };
+int dcp_memcpy_h2d_async(dcp_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+int dcp_memcpy_d2h_async(dcp_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+int dcp_copy_fence(dcp_ctx* ctx, int direction);
+int dcp_copy_synchronize(dcp_ctx* ctx);
 
 /* ---- mapping data on the device ------------------------------------------------------- */
 /* Evaluates the records of one quadrature rule for all cells into a new device buffer (*geom_dev).  Hand it to
