@@ -37,14 +37,17 @@ def _rand(torch, n, seed):
 
 
 def test_strategies_agree_through_checksums(setup):
-    """SEARCH (general AffineConstraints scatter, parity-checked against the oracle at small sizes) and POSITIONS
-    (DMMA kernel with position tables) must assemble the same matrices: compare A x for random x, and the rhs."""
+    """SEARCH (general AffineConstraints scatter, parity-checked against the oracle at small sizes), POSITIONS (DMMA
+    kernel with position tables, reductions) and STAGED (write-once: node-major staging + TMA gather, the default on the
+    shell; the preconditioner comes out of the system pass) must assemble the same matrices: compare A x for random x,
+    and the rhs."""
     s, torch, device = setup, setup["torch"], setup["device"]
     m = s["model"]
     n = m.n_nse
     x = _rand(torch, n, 1)
     out = {}
-    for name, strat in (("search", device.STRATEGY_SEARCH), ("positions", device.STRATEGY_POSITIONS)):
+    assert m.strategy == device.STRATEGY_STAGED, "the shell qualifies for the write-once path"
+    for name, strat in (("search", device.STRATEGY_SEARCH), ("positions", device.STRATEGY_POSITIONS), ("staged", device.STRATEGY_STAGED)):
         m.set_strategy(strat)
         m.assemble_nse_system(s["u"], s["T"])
         m.assemble_nse_preconditioner()
@@ -53,8 +56,9 @@ def test_strategies_agree_through_checksums(setup):
         m.nse_preconditioner_matrix.vmult(z, x)
         torch.cuda.synchronize()
         out[name] = (y.clone(), z.clone(), torch.from_numpy(m.nse_rhs))
-    for a, b, what in zip(out["search"], out["positions"], ("nse_matrix x", "preconditioner x", "nse_rhs")):
-        assert float((a - b).abs().max() / b.abs().max()) <= TOL, what
+    for other in ("positions", "staged"):
+        for a, b, what in zip(out["search"], out[other], ("nse_matrix x", "preconditioner x", "nse_rhs")):
+            assert float((a - b).abs().max() / b.abs().max()) <= TOL, (other, what)
 
 
 def test_nse_matrix_is_symmetric(setup):
