@@ -974,7 +974,7 @@ int dcp_gather_plan_build(dcp_model* m, const dcp_model_desc* d, const std::vect
     return mx;
   };
   if (max_len(pat[0][0]) > LROW || max_len(pat[1][0]) > LROW || max_len(pat[0][1]) > L01 - 1) return DCP_OK;   // (the last entry of acc01 is the spare one)
-  // one stage + gather launch pair per chunk of DCP_GATHER_CHUNK cells (default 65 536)
+  // one stage + gather launch pair per chunk of DCP_GATHER_CHUNK cells (default 65 536; 131 072 was measured equal at refine 6 and costs 4.7 GB more)
   int64_t chunk = 65536;
   if (const char* e = std::getenv("DCP_GATHER_CHUNK")) chunk = std::max<int64_t>(1, std::atoll(e));
   chunk = std::min<int64_t>(chunk, n);

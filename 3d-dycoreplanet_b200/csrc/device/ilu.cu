@@ -12,6 +12,7 @@
 // level, one warp per row.  The same levels order the forward substitution; the backward substitution uses the
 // levels of the upper triangle.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "dcp_internal.cuh"
@@ -25,6 +26,14 @@ struct dcp_ilu {
   int32_t *rows_l = nullptr, *rows_u = nullptr;  // rows sorted by level (lower / upper dependencies)
   std::vector<int64_t> lvl_l, lvl_u;             // level start offsets into rows_l / rows_u
   double* tmp = nullptr;          // intermediate vector of the two substitutions
+  // the level launches of one application, captured once per (source, destination) pair: a Krylov loop applies the
+  // preconditioner to the same two vectors every iteration, so hundreds of launches become one graph launch
+  cudaGraphExec_t solve_graph = nullptr;
+  const double* graph_src = nullptr;
+  double* graph_dst = nullptr;
+  const double* last_src = nullptr;   // operands of the previous application: a pair is captured when it comes twice in a row
+  double* last_dst = nullptr;
+  int64_t graph_nodes = 0;
 };
 
 namespace {
@@ -102,6 +111,7 @@ int dcp_ilu_destroy(dcp_ilu* p) {
   cudaFree(p->rows_l);
   cudaFree(p->rows_u);
   cudaFree(p->tmp);
+  if (p->solve_graph) cudaGraphExecDestroy(p->solve_graph);
   delete p;
   return DCP_OK;
 }
@@ -216,20 +226,53 @@ int dcp_ilu_vmult(dcp_ilu* p, double* dst, const double* src, int mem) {
   DCP_TRY(dcp_stage_in(ctx, 0, src, p->n, mem, &dx));
   DCP_TRY(dcp_stage_out_alloc(ctx, 1, dst, p->n, mem, &dy));
   constexpr int LANES = 8;
-  for (size_t l = 0; l + 1 < p->lvl_l.size(); ++l) {
-    const int nr = (int)(p->lvl_l[l + 1] - p->lvl_l[l]);
-    if (nr == 0) continue;
-    ilu_solve_level<false><<<(nr * LANES + 127) / 128, 128, 0, ctx->stream>>>(p->rows_l + p->lvl_l[l], nr, p->n, (const long long*)A.rowptr, A.col,
-                                                                            (const long long*)p->diag, p->lu, dx, p->tmp);
-    ++ctx->launches;
+  auto enqueue = [&](cudaStream_t st) {
+    int64_t nodes = 0;
+    for (size_t l = 0; l + 1 < p->lvl_l.size(); ++l) {
+      const int nr = (int)(p->lvl_l[l + 1] - p->lvl_l[l]);
+      if (nr == 0) continue;
+      ilu_solve_level<false><<<(nr * LANES + 127) / 128, 128, 0, st>>>(p->rows_l + p->lvl_l[l], nr, p->n, (const long long*)A.rowptr, A.col,
+                                                                      (const long long*)p->diag, p->lu, dx, p->tmp);
+      ++nodes;
+    }
+    for (size_t l = 0; l + 1 < p->lvl_u.size(); ++l) {
+      const int nr = (int)(p->lvl_u[l + 1] - p->lvl_u[l]);
+      if (nr == 0) continue;
+      ilu_solve_level<true><<<(nr * LANES + 127) / 128, 128, 0, st>>>(p->rows_u + p->lvl_u[l], nr, p->n, (const long long*)A.rowptr, A.col,
+                                                                     (const long long*)p->diag, p->lu, p->tmp, dy);
+      ++nodes;
+    }
+    return nodes;
+  };
+  static const bool use_graph = std::getenv("DCP_NO_ILU_GRAPH") == nullptr;
+  if (use_graph && mem == DCP_DEVICE) {
+    const bool have = p->solve_graph && p->graph_src == dx && p->graph_dst == dy;
+    const bool repeated = p->last_src == dx && p->last_dst == dy;
+    p->last_src = dx;
+    p->last_dst = dy;
+    if (!have && repeated) {
+      if (p->solve_graph) cudaGraphExecDestroy(p->solve_graph);
+      p->solve_graph = nullptr;
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        p->graph_nodes = enqueue(ctx->stream);
+        if (cudaStreamEndCapture(ctx->stream, &g) == cudaSuccess && g &&
+            cudaGraphInstantiate(&p->solve_graph, g, nullptr, nullptr, 0) == cudaSuccess) {
+          p->graph_src = dx;
+          p->graph_dst = dy;
+        } else
+          p->solve_graph = nullptr;
+        if (g) cudaGraphDestroy(g);
+      }
+      cudaGetLastError();
+    }
+    if (p->solve_graph && p->graph_src == dx && p->graph_dst == dy) {
+      DCP_CUDA(cudaGraphLaunch(p->solve_graph, ctx->stream));
+      ctx->launches += p->graph_nodes;
+      return DCP_OK;
+    }
   }
-  for (size_t l = 0; l + 1 < p->lvl_u.size(); ++l) {
-    const int nr = (int)(p->lvl_u[l + 1] - p->lvl_u[l]);
-    if (nr == 0) continue;
-    ilu_solve_level<true><<<(nr * LANES + 127) / 128, 128, 0, ctx->stream>>>(p->rows_u + p->lvl_u[l], nr, p->n, (const long long*)A.rowptr, A.col,
-                                                                           (const long long*)p->diag, p->lu, p->tmp, dy);
-    ++ctx->launches;
-  }
+  ctx->launches += enqueue(ctx->stream);
   DCP_CUDA(cudaGetLastError());
   return dcp_stage_out_finish(ctx, 1, dst, p->n, mem);
 }
