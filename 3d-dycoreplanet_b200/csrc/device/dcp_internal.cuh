@@ -42,6 +42,8 @@ struct dcp_ctx {
   int64_t stage_cap[3] = {0, 0, 0};
   double* dot_scratch = nullptr;  // partial sums of dcp_vec_dot
   double* dot_host = nullptr;     // pinned result
+  double* mgs_scalars = nullptr;  // dcp_vec_mgs: Hessenberg column + partial sums (device), pinned mirror
+  double* mgs_host = nullptr;
   cudaStream_t copy_stream = nullptr;   // dcp_memcpy_*_async (created on first use)
   cudaEvent_t copy_event = nullptr;
 };

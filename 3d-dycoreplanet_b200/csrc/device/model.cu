@@ -261,6 +261,8 @@ int dcp_ctx_destroy(dcp_ctx* ctx) {
   cudaFreeHost(ctx->h_err);
   cudaFree(ctx->dot_scratch);
   cudaFreeHost(ctx->dot_host);
+  cudaFree(ctx->mgs_scalars);
+  cudaFreeHost(ctx->mgs_host);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);

@@ -50,6 +50,12 @@ __global__ void scale_kernel(long long n, double a, double* __restrict__ y) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] *= a;
 }
+// y += sign * (*a) * x with the scalar in device memory
+__global__ void axpy_dev_kernel(long long n, const double* __restrict__ a_dev, double sign, const double* __restrict__ x, double* __restrict__ y) {
+  const double a = sign * *a_dev;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] += a * x[i];
+}
 inline unsigned vgrid(dcp_ctx* ctx, long long n) {
   long long b = (n + 255) / 256, cap = (long long)ctx->sm_count * 8;
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -74,6 +80,33 @@ int dcp_vec_dot(dcp_ctx* ctx, int64_t n, const double* x_dev, const double* y_de
   DCP_CUDA(cudaMemcpyAsync(ctx->dot_host, ctx->dot_scratch + DOT_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DCP_CUDA(cudaStreamSynchronize(ctx->stream));
   *result_host = *ctx->dot_host;
+  return DCP_OK;
+}
+
+int dcp_vec_mgs(dcp_ctx* ctx, int64_t n, int k, const double* const* v_dev, double* w_dev, double* h_host) {
+  if (!ctx || n < 0 || k < 0 || k > DCP_MGS_MAX || (k > 0 && !v_dev) || !w_dev || !h_host) return DCP_ERR_ARG;
+  DCP_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->mgs_scalars) {
+    DCP_CUDA(cudaMalloc((void**)&ctx->mgs_scalars, sizeof(double) * (DCP_MGS_MAX + 1 + DOT_BLOCKS)));
+    DCP_CUDA(cudaMallocHost((void**)&ctx->mgs_host, sizeof(double) * (DCP_MGS_MAX + 1)));
+  }
+  if (n == 0) {
+    for (int i = 0; i <= k; ++i) h_host[i] = 0.0;
+    return DCP_OK;
+  }
+  double* sc = ctx->mgs_scalars;
+  double* partial = sc + DCP_MGS_MAX + 1;
+  for (int i = 0; i < k; ++i) {
+    dot_stage1<<<DOT_BLOCKS, DOT_THREADS, 0, ctx->stream>>>(n, w_dev, v_dev[i], partial);
+    dot_stage2<<<1, DOT_THREADS, 0, ctx->stream>>>(DOT_BLOCKS, partial, sc + i);
+    axpy_dev_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, sc + i, -1.0, v_dev[i], w_dev);
+  }
+  dot_stage1<<<DOT_BLOCKS, DOT_THREADS, 0, ctx->stream>>>(n, w_dev, w_dev, partial);
+  dot_stage2<<<1, DOT_THREADS, 0, ctx->stream>>>(DOT_BLOCKS, partial, sc + k);
+  ctx->launches += 3 * k + 2;
+  DCP_CUDA(cudaMemcpyAsync(ctx->mgs_host, sc, sizeof(double) * (size_t)(k + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i <= k; ++i) h_host[i] = ctx->mgs_host[i];
   return DCP_OK;
 }
 

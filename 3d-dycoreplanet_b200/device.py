@@ -86,7 +86,7 @@ EXPORTS = [
     "dcp_assemble_temperature_matrix", "dcp_assemble_temperature_rhs", "dcp_matrix_info", "dcp_matrix_values_device",
     "dcp_matrix_download", "dcp_matrix_upload", "dcp_vector_device", "dcp_vector_download", "dcp_vmult",
     "dcp_vmult_add", "dcp_block_vmult", "dcp_vmult_rows", "dcp_block_vmult_rows", "dcp_jacobi_vmult", "dcp_vec_dot", "dcp_vec_axpy", "dcp_vec_sadd",
-    "dcp_vec_scale", "dcp_vec_copy", "dcp_vec_fill", "dcp_vec_shift", "dcp_cg_solve", "dcp_comm_unique_id", "dcp_comm_create", "dcp_comm_adopt", "dcp_comm_info",
+    "dcp_vec_scale", "dcp_vec_copy", "dcp_vec_fill", "dcp_vec_shift", "dcp_vec_mgs", "dcp_cg_solve", "dcp_comm_unique_id", "dcp_comm_create", "dcp_comm_adopt", "dcp_comm_info",
     "dcp_comm_destroy", "dcp_halo_create", "dcp_halo_destroy", "dcp_halo_exchange", "dcp_halo_block_vmult",
     "dcp_vec_dot_allreduce", "dcp_allreduce_max", "dcp_velocity_extrema", "dcp_constraints_distribute",
     "dcp_geometry_create", "dcp_ilu_create", "dcp_ilu_refactor", "dcp_ilu_vmult", "dcp_ilu_levels", "dcp_ilu_destroy",
@@ -148,6 +148,7 @@ def lib():
         L.dcp_block_vmult_rows.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_jacobi_vmult.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
         L.dcp_vec_dot.argtypes = [vp, ctypes.c_int64, vp, vp, c_dp]
+        L.dcp_vec_mgs.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(vp), vp, c_dp]
         L.dcp_cg_solve.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp,
                                    ctypes.c_double, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
                                    ctypes.POINTER(ctypes.c_double)]

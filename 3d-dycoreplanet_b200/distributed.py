@@ -261,6 +261,9 @@ class DistributedDeviceBackend:
     owned_by_length: {local vector length: [(begin, end), ...]} -- which entries of a vector of that length are
     owned (the full block vector and every block sub-vector a solver chain takes dots of)."""
 
+    supports_mgs = False      # inner products need the owned ranges and the all-reduce: the Arnoldi loop stays in solvers.py
+    resident_cg = False
+
     def __init__(self, ctx, comm, owned_by_length):
         from . import solvers
         self._b = solvers.DeviceBackend(ctx)

@@ -79,6 +79,7 @@ class DeviceBackend:
         self.torch, self.dv, self.ctx = torch, device, ctx
         self._res = ctypes.c_double()
         self.resident_cg = True      # SolverCG inside the library where the operands allow (dcp_cg_solve)
+        self.supports_mgs = True     # Arnoldi orthogonalisation with one synchronisation (dcp_vec_mgs)
         # the library's own stream is non-blocking: run it on torch's current stream so that tensor creation
         # (torch.zeros, .cuda()) and the library's kernels on the same memory are ordered
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -104,6 +105,15 @@ class DeviceBackend:
         self.dv.check(self.dv.lib().dcp_vec_dot(self.ctx._h, x.numel(), self._p(x), self._p(y), ctypes.byref(self._res)),
                       "dcp_vec_dot")
         return self._res.value
+
+    def mgs(self, w, basis):
+        """Modified Gram-Schmidt of w against `basis` on the device (dcp_vec_mgs): returns [w.v_0, ..., w.v_{k-1}, w.w]
+        with one host synchronisation; w is updated in place."""
+        k = len(basis)
+        ptrs = (ctypes.c_void_p * max(k, 1))(*[b.data_ptr() for b in basis])
+        h = (ctypes.c_double * (k + 1))()
+        self.dv.check(self.dv.lib().dcp_vec_mgs(self.ctx._h, w.numel(), k, ptrs, self._p(w), h), "dcp_vec_mgs")
+        return list(h)
 
     def axpy(self, a, x, y):
         self.dv.check(self.dv.lib().dcp_vec_axpy(self.ctx._h, x.numel(), float(a), self._p(x), self._p(y)), "dcp_vec_axpy")
@@ -263,11 +273,15 @@ def solver_gmres(B, A, x, b, P, tol, max_steps, restart=28, flexible=False):
             else:
                 A.vmult(t, V[k], B)
                 P.vmult(w, t, B)
-            h = [0.0] * (k + 2)
-            for i in range(k + 1):               # modified Gram-Schmidt
-                h[i] = B.dot(w, V[i])
-                B.axpy(-h[i], V[i], w)
-            h[k + 1] = math.sqrt(B.dot(w, w))
+            if getattr(B, "supports_mgs", False) and k + 1 <= 256:   # the whole orthogonalisation with one host synchronisation
+                h = B.mgs(w, V[:k + 1])
+                h[k + 1] = math.sqrt(h[k + 1])
+            else:
+                h = [0.0] * (k + 2)
+                for i in range(k + 1):               # modified Gram-Schmidt
+                    h[i] = B.dot(w, V[i])
+                    B.axpy(-h[i], V[i], w)
+                h[k + 1] = math.sqrt(B.dot(w, w))
             if h[k + 1] != 0.0:
                 B.assign(V[k + 1], w)
                 B.scale(1.0 / h[k + 1], V[k + 1])

@@ -328,6 +328,13 @@ int dcp_vec_axpy(dcp_ctx* ctx, int64_t n, double a, const double* x_dev, double*
 int dcp_vec_sadd(dcp_ctx* ctx, int64_t n, double s, double a, const double* x_dev, double* y_dev);
 int dcp_vec_scale(dcp_ctx* ctx, int64_t n, double a, double* y_dev);
 int dcp_vec_copy(dcp_ctx* ctx, int64_t n, const double* x_dev, double* y_dev);
+/* Arnoldi orthogonalisation step of SolverGMRES / SolverFGMRES (modified Gram-Schmidt, deal.II's default; e.g. the outer
+ * solve boussinesq_model.tpp:1191-1199): for i < k: h[i] = w . v_i, w -= h[i] v_i; then h[k] = w . w.  The inner products
+ * stay in device memory between the updates; the k + 1 scalars come back with ONE synchronisation instead of k + 1.
+ * v_dev: host array of k device pointers; k <= DCP_MGS_MAX.  Same kernels as dcp_vec_dot / dcp_vec_axpy: bit-identical
+ * to the loop that calls them. */
+enum { DCP_MGS_MAX = 256 };
+int dcp_vec_mgs(dcp_ctx* ctx, int64_t n, int k, const double* const* v_dev, double* w_dev, double* h_host);
 /* SolverCG<Vector>::solve(A, x, b, P) with SolverControl(max_steps, tol), resident on the device: A = block (bi, bj) of
  * matrix `which`, P = identity, the Jacobi diagonal of block (bp, bp) of matrix `which_p`, or an ILU(0) handle.  alpha, beta
  * and the residual norm stay in device memory; the host reads the convergence flag once per `check_every` iterations
