@@ -222,6 +222,97 @@ __global__ void __launch_bounds__(128) temperature_matrix_kernel(ScalarArgs a, C
   }
 }
 
+// ---- Q1 temperature in 3-D: the two 8x8 Gram matrices on DMMA, with the cell's loads one cell ahead ---------------
+// Same arithmetic as the Q1 branch of temperature_matrix_kernel.  That kernel was bound by the latency of its loads
+// (ncu: long-scoreboard 6.5 of 13 stall cycles per issue, 17 warps per SM): mapping record -> table -> DMMA -> dof
+// indices -> row starts -> reductions form one dependent chain per cell.  Here a warp keeps the next cell's mapping
+// data and dof indices in registers while it works on the current one, and fetches the row starts / positions of the
+// current cell before the table build.
+__global__ void __launch_bounds__(128) temperature_matrix_q1_kernel(ScalarArgs a, CsView cs, BlockView Mass, BlockView Stiff, int* err) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int nd = 8;
+  const ScalarLayout L = scalar_layout(nd, 0);
+  double* base = smem_d + (size_t)wid * L.doubles;
+  double* S = base + L.o_S;
+  double* A = base + L.o_A;
+  double* B = base + L.o_B;
+  double* wq = base + L.o_c;
+  int* idx = reinterpret_cast<int*>(base + L.o_idx);
+  int* lines = idx + MAX_ND + 1;
+  const int frow = lane >> 2, fk = lane & 3, e0 = frow * 8 + 2 * fk, nq = a.nq;
+  const long long stride = (long long)gridDim.x * nwarps;
+  long long ci = (long long)blockIdx.x * nwarps + wid;
+  auto load_cell = [&](long long c, double (&gq)[10], int& iv) {
+    const double* g = a.geom + c * a.gstride;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) gq[k] = lane < nq ? g[nq * k + lane] : 0.0;
+    iv = lane < nd ? a.l2g[c * nd + lane] : 0;
+  };
+  double gc[10];
+  int ic = 0;
+  if (ci < a.n_cells) load_cell(ci, gc, ic);
+  for (; ci < a.n_cells; ci += stride) {
+    double gn[10];
+    int in = 0;
+    if (ci + stride < a.n_cells) load_cell(ci + stride, gn, in);   // in flight while this cell is worked on
+    const unsigned short* tp = a.tpos + ci * (long long)(nd * nd);
+    const unsigned short t00 = tp[0], tpa = tp[e0], tpb = tp[e0 + 1];
+    const long long r0 = Mass.rowptr[0][0][__shfl_sync(0xffffffffu, ic, frow)];
+    if (lane < 28) {
+      double* row = S + lane * L.sv;
+      if (lane < nq) {
+        for (int k = 0; k < nd; ++k) {
+          const double r0d = __ldg(a.dphiT + (size_t)(k * 3) * nq + lane), r1d = __ldg(a.dphiT + (size_t)(k * 3 + 1) * nq + lane),
+                       r2d = __ldg(a.dphiT + (size_t)(k * 3 + 2) * nq + lane);
+          row[k * 4] = __ldg(a.phiT + (size_t)k * nq + lane);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) row[k * 4 + 1 + d] = gc[1 + d] * r0d + gc[4 + d] * r1d + gc[7 + d] * r2d;
+        }
+        wq[lane] = gc[0];
+      } else {
+        for (int k = 0; k < 32; ++k) row[k] = 0.0;
+        wq[lane] = 0.0;
+      }
+    }
+    __syncwarp();
+    double m0 = 0.0, m1 = 0.0, k0 = 0.0, k1 = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 7; ++ks) {
+      const int q = 4 * ks + fk;
+      const double* sp = S + q * L.sv + frow * 4;
+      const double w = wq[q], x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3];
+      dmma_m8n8k4(m0, m1, w * x0, x0);
+      dmma_m8n8k4(k0, k1, w * x1, x1);
+      dmma_m8n8k4(k0, k1, w * x2, x2);
+      dmma_m8n8k4(k0, k1, w * x3, x3);
+    }
+    k0 *= a.prm.inv_pe;
+    k1 *= a.prm.inv_pe;
+    if (t00 != 0xffffu) {
+      const long long at0 = r0 + tpa, at1 = r0 + tpb;
+      red_add_f64(Mass.val[0][0] + at0, m0);
+      red_add_f64(Mass.val[0][0] + at1, m1);
+      red_add_f64(Stiff.val[0][0] + at0, k0);
+      red_add_f64(Stiff.val[0][0] + at1, k1);
+    } else {
+      if (lane < nd) idx[lane] = ic;
+      A[e0] = m0;
+      A[e0 + 1] = m1;
+      B[e0] = k0;
+      B[e0 + 1] = k1;
+      __syncwarp();
+      distribute_local_matrix<true>(cs, nd, nd, A, nullptr, idx, lines, Mass, nullptr, lane, 32, false, err);
+      __syncwarp();
+      distribute_local_matrix<true>(cs, nd, nd, B, nullptr, idx, lines, Stiff, nullptr, lane, 32, false, err);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 10; ++k) gc[k] = gn[k];
+    ic = in;
+  }
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(128) temperature_rhs_kernel(ScalarArgs a, CsView cs) {
   extern __shared__ double smem_d[];
@@ -420,6 +511,112 @@ __global__ void __launch_bounds__(128, 8) temperature_rhs_plain_kernel(ScalarArg
       }
       __syncwarp();
     }
+    distribute_local_vector_bc<true>(cs, nd, nd, l, nullptr, idx, lines, a.rhs, lane, 32);
+    __syncwarp();
+  }
+}
+
+// ---- Q1 temperature in 3-D, classic family: the plain right-hand side with its two dense contractions on DMMA ------
+// Same integrand as temperature_rhs_plain_kernel (boussinesq_model.tpp:928-937).  ncu on that kernel: 56 % of the issue
+// slots, of which 29 % interpolate the velocity at the quadrature points (27 points x 27 Q2 nodes x 3 components, a lane
+// per point looping over the nodes) and 19 % contract the point coefficients with the 8 test functions on 8 lanes.
+// Both are small GEMMs with a constant operand: u[p][c] = sum_n phi_u[p][n] U[n][c] (4 x 7 DMMA) and
+// l[i] = sum_p phi_t[p][i] cq[p] (7 DMMA); the constant tables sit in shared memory once per CTA.
+constexpr int RQ_LD = 28;   // 27 points / nodes padded to 28 (k-steps of 4)
+__global__ void __launch_bounds__(128, 8) temperature_rhs_plain_q1_kernel(ScalarArgs a, CsView cs) {
+  extern __shared__ __align__(16) double smem_d[];
+  constexpr int nd = 8, NDU = 27, NQ1 = 27;
+  double* tabU = smem_d;                      // [28 points][28 nodes] phi_u, zero padded
+  double* tabT = tabU + RQ_LD * RQ_LD;        // [28 points][8] phi_t
+  double* wbase = tabT + RQ_LD * nd;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int PER_WARP = 32 + 8 + 3 * RQ_LD + RQ_LD * 4 + 8 + 12;
+  double* cq = wbase + (size_t)wid * PER_WARP;   // [32] rhs coefficient of the points (28..31 zero)
+  double* T = cq + 32;                           // [8]
+  double* U = T + 8;                             // [3][28] velocity, component-major, entry 27 zero
+  double* su = U + 3 * RQ_LD;                    // [28 points][4] velocity at the points
+  double* l = su + RQ_LD * 4;                    // [8]
+  int* idx = reinterpret_cast<int*>(l + 8);      // [8]
+  int* lines = idx + 8;                          // [8]
+  const int frow = lane >> 2, fk = lane & 3;
+  for (int i = threadIdx.x; i < RQ_LD * RQ_LD; i += blockDim.x) {
+    const int pnt = i / RQ_LD, n = i - pnt * RQ_LD;
+    tabU[i] = pnt < NQ1 && n < NDU ? __ldg(a.phi_uT + (size_t)n * a.nq + pnt) : 0.0;
+  }
+  for (int i = threadIdx.x; i < RQ_LD * nd; i += blockDim.x) {
+    const int pnt = i / nd, k = i - pnt * nd;
+    tabT[i] = pnt < NQ1 ? __ldg(a.phi + (size_t)pnt * nd + k) : 0.0;
+  }
+  for (int i = lane; i < 32; i += 32) cq[i] = 0.0;
+  for (int i = lane; i < 3 * RQ_LD; i += 32) U[i] = 0.0;
+  __syncthreads();
+  const double tau = a.prm.dt / a.prm.nse_interval;
+  for (long long cell = (long long)blockIdx.x * nwarps + wid; cell < a.n_cells; cell += (long long)gridDim.x * nwarps) {
+    if (a.bc_flag[cell]) continue;
+    const double* g = a.geom + cell * a.gstride;
+    if (lane < nd) {
+      const int gi = a.l2g[cell * nd + lane];
+      idx[lane] = gi;
+      T[lane] = a.old_temp[gi];
+      lines[lane] = cs.line_of_dof[gi];
+    }
+    for (int k = lane; k < a.nd_nse; k += 32) {
+      const int f = __ldg(a.nse_field + k);
+      if (f < 3) U[f * RQ_LD + __ldg(a.nse_base + k)] = a.nse_solution[a.l2g_nse[cell * a.nd_nse + k]];
+    }
+    // the lane's quadrature point: d xi / d x and the weight (in flight during the velocity interpolation)
+    double K[3][3], w = 0.0;
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) K[e][d] = lane < NQ1 ? g[NQ1 * (1 + e * 3 + d) + lane] : 0.0;
+    if (lane < NQ1) w = g[lane];
+    __syncwarp();
+    // u[p][c] = sum_n phi_u[p][n] U[n][c]
+    {
+      double bfr[7];
+#pragma unroll
+      for (int ks = 0; ks < 7; ++ks) bfr[ks] = frow < 3 ? U[frow * RQ_LD + 4 * ks + fk] : 0.0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        double c0 = 0.0, c1 = 0.0;
+        const int pnt = 8 * t + frow;
+#pragma unroll
+        for (int ks = 0; ks < 7; ++ks) dmma_m8n8k4(c0, c1, pnt < RQ_LD ? tabU[pnt * RQ_LD + 4 * ks + fk] : 0.0, bfr[ks]);
+        if (pnt < RQ_LD && fk < 2) {
+          su[pnt * 4 + 2 * fk] = c0;
+          su[pnt * 4 + 2 * fk + 1] = c1;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane < NQ1) {
+      double oldT = 0.0, gT[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < nd; ++k) {
+        const double Tk = T[k];
+        oldT += Tk * tabT[lane * nd + k];
+        const double r0 = __ldg(a.dphiT + (size_t)(k * 3) * a.nq + lane), r1 = __ldg(a.dphiT + (size_t)(k * 3 + 1) * a.nq + lane),
+                     r2 = __ldg(a.dphiT + (size_t)(k * 3 + 2) * a.nq + lane);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gT[d] += Tk * (K[0][d] * r0 + K[1][d] * r1 + K[2][d] * r2);
+      }
+      const double ugT = su[lane * 4] * gT[0] + su[lane * 4 + 1] * gT[1] + su[lane * 4 + 2] * gT[2];
+      const double gamma = 0.0;  // heat source multiplied by literal 0 in the reference (:922-926)
+      cq[lane] = (oldT - tau * ugT - tau * gamma) * w;
+    }
+    __syncwarp();
+    // l[i] = sum_p phi_t[p][i] cq[p]
+    {
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 7; ++ks) {
+        const int pnt = 4 * ks + fk;
+        dmma_m8n8k4(c0, c1, tabT[pnt * nd + frow], frow == 0 ? cq[pnt] : 0.0);
+      }
+      if (fk == 0) l[frow] = c0;
+    }
+    __syncwarp();
     distribute_local_vector_bc<true>(cs, nd, nd, l, nullptr, idx, lines, a.rhs, lane, 32);
     __syncwarp();
   }
@@ -775,6 +972,14 @@ int dcp_launch_temperature_matrix(dcp_model* m, const dcp_params& p) {
     return DCP_OK;
   }
   const ScalarLaunch s = scalar_launch(ctx, m->n_cells, a.nd, 0);
+  if (m->dim == 3 && a.nd == 8 && a.nq <= 28 && !std::getenv("DCP_NO_Q1_PREFETCH")) {
+    DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_q1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
+    temperature_matrix_q1_kernel<<<s.grid, 32 * s.warps, s.smem, ctx->stream>>>(a, make_view(m->temp_cs), make_view(m->tmass), make_view(m->tstiff),
+                                                                               ctx->d_err);
+    ctx->launches++;
+    DCP_CUDA(cudaGetLastError());
+    return DCP_OK;
+  }
   if (m->dim == 3) {
     DCP_CUDA(cudaFuncSetAttribute(temperature_matrix_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
     temperature_matrix_kernel<3><<<s.grid, 32 * s.warps, s.smem, ctx->stream>>>(
@@ -824,7 +1029,11 @@ int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* 
     long long b = (m->n_cells + warps - 1) / warps;
     const long long cap = (long long)ctx->sm_count * 16;
     const unsigned grid = (unsigned)(b > cap ? cap : b);
-    if (m->dim == 3)
+    if (m->dim == 3 && !a.feec && a.nd == 8 && a.nq == 27 && a.ndu == 27 && !std::getenv("DCP_NO_Q1_DMMA_RHS")) {
+      const size_t smem_q = sizeof(double) * (size_t)(RQ_LD * RQ_LD + RQ_LD * 8 + warps * (32 + 8 + 3 * RQ_LD + RQ_LD * 4 + 8 + 12));
+      const unsigned grid_q = (unsigned)std::min<long long>(b, (long long)ctx->sm_count * 8);
+      temperature_rhs_plain_q1_kernel<<<grid_q, 32 * warps, smem_q, ctx->stream>>>(a, make_view(m->temp_cs));
+    } else if (m->dim == 3)
       temperature_rhs_plain_kernel<3><<<grid, 32 * warps, smem, ctx->stream>>>(a, make_view(m->temp_cs));
     else
       temperature_rhs_plain_kernel<2><<<grid, 32 * warps, smem, ctx->stream>>>(a, make_view(m->temp_cs));
