@@ -464,21 +464,21 @@ __global__ void __launch_bounds__(128, 8) temperature_rhs_plain_kernel(ScalarArg
         for (int e = 0; e < DIM; ++e)
 #pragma unroll
           for (int d = 0; d < DIM; ++d) K[e][d] = g[a.nq * (1 + e * DIM + d) + q];
-        double oldT = 0.0, gT[3] = {0.0, 0.0, 0.0}, u[3] = {0.0, 0.0, 0.0};
+        // grad T = K^T (sum_k T_k grad_ref phi_k): the reference gradient is summed over the nodes first, the mapping is
+        // applied once per point (9 multiply-adds per node less than mapping every shape function)
+        double oldT = 0.0, gT[3] = {0.0, 0.0, 0.0}, u[3] = {0.0, 0.0, 0.0}, gr[DIM];
+#pragma unroll
+        for (int e = 0; e < DIM; ++e) gr[e] = 0.0;
         for (int k = 0; k < nd; ++k) {
           const double Tk = T[k];
           oldT += Tk * __ldg(a.phiT + (size_t)k * a.nq + q);
-          double r[DIM];
 #pragma unroll
-          for (int e = 0; e < DIM; ++e) r[e] = __ldg(a.dphiT + (size_t)(k * DIM + e) * a.nq + q);
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) {
-            double v = 0.0;
-#pragma unroll
-            for (int e = 0; e < DIM; ++e) v += K[e][d] * r[e];
-            gT[d] += Tk * v;
-          }
+          for (int e = 0; e < DIM; ++e) gr[e] += Tk * __ldg(a.dphiT + (size_t)(k * DIM + e) * a.nq + q);
         }
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+          for (int e = 0; e < DIM; ++e) gT[d] += K[e][d] * gr[e];
         if (a.feec) {
           const double det = g[a.nq * 22 + q];
           for (int k = 0; k < 6; ++k) {
@@ -591,16 +591,17 @@ __global__ void __launch_bounds__(128, 8) temperature_rhs_plain_q1_kernel(Scalar
     }
     __syncwarp();
     if (lane < NQ1) {
-      double oldT = 0.0, gT[3] = {0.0, 0.0, 0.0};
+      // grad T = K^T (sum_k T_k grad_ref phi_k): reference gradient first, the mapping once per point
+      double oldT = 0.0, gT[3], gr[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int k = 0; k < nd; ++k) {
         const double Tk = T[k];
         oldT += Tk * tabT[lane * nd + k];
-        const double r0 = __ldg(a.dphiT + (size_t)(k * 3) * a.nq + lane), r1 = __ldg(a.dphiT + (size_t)(k * 3 + 1) * a.nq + lane),
-                     r2 = __ldg(a.dphiT + (size_t)(k * 3 + 2) * a.nq + lane);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) gT[d] += Tk * (K[0][d] * r0 + K[1][d] * r1 + K[2][d] * r2);
+        for (int e = 0; e < 3; ++e) gr[e] += Tk * __ldg(a.dphiT + (size_t)(k * 3 + e) * a.nq + lane);
       }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) gT[d] = K[0][d] * gr[0] + K[1][d] * gr[1] + K[2][d] * gr[2];
       const double ugT = su[lane * 4] * gT[0] + su[lane * 4 + 1] * gT[1] + su[lane * 4 + 2] * gT[2];
       const double gamma = 0.0;  // heat source multiplied by literal 0 in the reference (:922-926)
       cq[lane] = (oldT - tau * ugT - tau * gamma) * w;
