@@ -516,46 +516,59 @@ __global__ void __launch_bounds__(128, 8) temperature_rhs_plain_kernel(ScalarArg
   }
 }
 
-// ---- Q1 temperature in 3-D, classic family: the plain right-hand side with its two dense contractions on DMMA ------
-// Same integrand as temperature_rhs_plain_kernel (boussinesq_model.tpp:928-937).  ncu on that kernel: 56 % of the issue
-// slots, of which 29 % interpolate the velocity at the quadrature points (27 points x 27 Q2 nodes x 3 components, a lane
-// per point looping over the nodes) and 19 % contract the point coefficients with the 8 test functions on 8 lanes.
-// Both are small GEMMs with a constant operand: u[p][c] = sum_n phi_u[p][n] U[n][c] (4 x 7 DMMA) and
-// l[i] = sum_p phi_t[p][i] cq[p] (7 DMMA); the constant tables sit in shared memory once per CTA.
-constexpr int RQ_LD = 28;   // 27 points / nodes padded to 28 (k-steps of 4)
-__global__ void __launch_bounds__(128, 8) temperature_rhs_plain_q1_kernel(ScalarArgs a, CsView cs) {
+// ---- Q1 / Q2 temperature in 3-D, classic family: the plain right-hand side with its two dense contractions on DMMA --
+// Same integrand as temperature_rhs_plain_kernel (boussinesq_model.tpp:928-937).  ncu on that kernel (Q1): 56 % of the
+// issue slots, of which 29 % interpolate the velocity at the quadrature points (a lane per point looping over the 27 Q2
+// nodes) and 19 % contract the point coefficients with the test functions on a few lanes; with runtime sizes its index
+// arithmetic costs as much again (Q2: 4 600 warp instructions per cell).  Both are small GEMMs with a constant operand:
+//   u[p][c] = sum_n phi_u[p][n] U[n][c]  (4 row tiles of points x 7 k-steps per batch of 32 points)
+//   l[i]    = sum_p phi_t[p][i] cq[p]    (row tiles of test functions x 8 k-steps per batch)
+// with the constant tables in shared memory once per CTA and compile-time sizes (ND dofs, NQ points per cell).
+constexpr int RQ_LD = 28;   // 27 velocity nodes padded to 28 (k-steps of 4)
+template <int ND, int NQ>
+struct RhsDmma {
+  static constexpr int NB = (NQ + 31) / 32;          // batches of 32 points
+  static constexpr int NQP = NB * 32;                // padded points
+  static constexpr int NT = (ND + 7) / 8;            // row tiles of test functions
+  static constexpr int NDP = NT * 8 + 4;             // row stride of the phi_t table: padded test functions + 4 (the fragment
+                                                     // loads "lane = (test function, point)" then fall on distinct banks)
+  static constexpr int PER_WARP = 32 + 28 + 3 * RQ_LD + 32 * 4 + 28 + 28;   // cq, T, U, su, l, (idx, lines)
+  static constexpr size_t smem_bytes(int warps) { return sizeof(double) * (size_t)(NQP * RQ_LD + NQP * NDP + warps * PER_WARP); }
+};
+
+template <int ND, int NQ>
+__global__ void __launch_bounds__(128, ND == 8 ? 8 : 5) temperature_rhs_plain_dmma_kernel(ScalarArgs a, CsView cs) {
+  using C = RhsDmma<ND, NQ>;
   extern __shared__ __align__(16) double smem_d[];
-  constexpr int nd = 8, NDU = 27, NQ1 = 27;
-  double* tabU = smem_d;                      // [28 points][28 nodes] phi_u, zero padded
-  double* tabT = tabU + RQ_LD * RQ_LD;        // [28 points][8] phi_t
-  double* wbase = tabT + RQ_LD * nd;
+  constexpr int NDU = 27;
+  double* tabU = smem_d;                      // [NQP points][28 nodes] phi_u, zero padded
+  double* tabT = tabU + C::NQP * RQ_LD;       // [NQP points][NDP] phi_t, zero padded
+  double* wbase = tabT + C::NQP * C::NDP;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int PER_WARP = 32 + 8 + 3 * RQ_LD + RQ_LD * 4 + 8 + 12;
-  double* cq = wbase + (size_t)wid * PER_WARP;   // [32] rhs coefficient of the points (28..31 zero)
-  double* T = cq + 32;                           // [8]
-  double* U = T + 8;                             // [3][28] velocity, component-major, entry 27 zero
-  double* su = U + 3 * RQ_LD;                    // [28 points][4] velocity at the points
-  double* l = su + RQ_LD * 4;                    // [8]
-  int* idx = reinterpret_cast<int*>(l + 8);      // [8]
-  int* lines = idx + 8;                          // [8]
+  double* cq = wbase + (size_t)wid * C::PER_WARP;   // [32] rhs coefficient of the batch's points
+  double* T = cq + 32;                              // [28]
+  double* U = T + 28;                               // [3][28] velocity, component-major, entry 27 zero
+  double* su = U + 3 * RQ_LD;                       // [32 points][4] velocity at the batch's points
+  double* l = su + 32 * 4;                          // [28]
+  int* idx = reinterpret_cast<int*>(l + 28);        // [28]
+  int* lines = idx + 28;                            // [28]
   const int frow = lane >> 2, fk = lane & 3;
-  for (int i = threadIdx.x; i < RQ_LD * RQ_LD; i += blockDim.x) {
+  for (int i = threadIdx.x; i < C::NQP * RQ_LD; i += blockDim.x) {
     const int pnt = i / RQ_LD, n = i - pnt * RQ_LD;
-    tabU[i] = pnt < NQ1 && n < NDU ? __ldg(a.phi_uT + (size_t)n * a.nq + pnt) : 0.0;
+    tabU[i] = pnt < NQ && n < NDU ? __ldg(a.phi_uT + (size_t)n * NQ + pnt) : 0.0;
   }
-  for (int i = threadIdx.x; i < RQ_LD * nd; i += blockDim.x) {
-    const int pnt = i / nd, k = i - pnt * nd;
-    tabT[i] = pnt < NQ1 ? __ldg(a.phi + (size_t)pnt * nd + k) : 0.0;
+  for (int i = threadIdx.x; i < C::NQP * C::NDP; i += blockDim.x) {
+    const int pnt = i / C::NDP, k = i - pnt * C::NDP;
+    tabT[i] = pnt < NQ && k < ND ? __ldg(a.phi + (size_t)pnt * ND + k) : 0.0;
   }
-  for (int i = lane; i < 32; i += 32) cq[i] = 0.0;
   for (int i = lane; i < 3 * RQ_LD; i += 32) U[i] = 0.0;
   __syncthreads();
   const double tau = a.prm.dt / a.prm.nse_interval;
   for (long long cell = (long long)blockIdx.x * nwarps + wid; cell < a.n_cells; cell += (long long)gridDim.x * nwarps) {
     if (a.bc_flag[cell]) continue;
     const double* g = a.geom + cell * a.gstride;
-    if (lane < nd) {
-      const int gi = a.l2g[cell * nd + lane];
+    if (lane < ND) {
+      const int gi = a.l2g[cell * ND + lane];
       idx[lane] = gi;
       T[lane] = a.old_temp[gi];
       lines[lane] = cs.line_of_dof[gi];
@@ -564,61 +577,74 @@ __global__ void __launch_bounds__(128, 8) temperature_rhs_plain_q1_kernel(Scalar
       const int f = __ldg(a.nse_field + k);
       if (f < 3) U[f * RQ_LD + __ldg(a.nse_base + k)] = a.nse_solution[a.l2g_nse[cell * a.nd_nse + k]];
     }
-    // the lane's quadrature point: d xi / d x and the weight (in flight during the velocity interpolation)
-    double K[3][3], w = 0.0;
+    double acc[C::NT][2];
 #pragma unroll
-    for (int e = 0; e < 3; ++e)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) K[e][d] = lane < NQ1 ? g[NQ1 * (1 + e * 3 + d) + lane] : 0.0;
-    if (lane < NQ1) w = g[lane];
+    for (int t = 0; t < C::NT; ++t) acc[t][0] = acc[t][1] = 0.0;
     __syncwarp();
-    // u[p][c] = sum_n phi_u[p][n] U[n][c]
-    {
-      double bfr[7];
+    double bfr[7];   // the velocity operand of the interpolation: U[c = frow][node 4 ks + fk]
 #pragma unroll
-      for (int ks = 0; ks < 7; ++ks) bfr[ks] = frow < 3 ? U[frow * RQ_LD + 4 * ks + fk] : 0.0;
+    for (int ks = 0; ks < 7; ++ks) bfr[ks] = frow < 3 ? U[frow * RQ_LD + 4 * ks + fk] : 0.0;
+#pragma unroll 1
+    for (int bt = 0; bt < C::NB; ++bt) {
+      const int q = 32 * bt + lane;
+      const bool on = q < NQ;
+      // the lane's quadrature point: d xi / d x and the weight (in flight during the velocity interpolation)
+      double K[3][3], w = 0.0;
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) K[e][d] = on ? g[NQ * (1 + e * 3 + d) + q] : 0.0;
+      if (on) w = g[q];
+      // u[p][c] = sum_n phi_u[p][n] U[n][c] for the 32 points of the batch
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         double c0 = 0.0, c1 = 0.0;
-        const int pnt = 8 * t + frow;
+        const double* ta = tabU + (size_t)(32 * bt + 8 * t + frow) * RQ_LD + fk;
 #pragma unroll
-        for (int ks = 0; ks < 7; ++ks) dmma_m8n8k4(c0, c1, pnt < RQ_LD ? tabU[pnt * RQ_LD + 4 * ks + fk] : 0.0, bfr[ks]);
-        if (pnt < RQ_LD && fk < 2) {
-          su[pnt * 4 + 2 * fk] = c0;
-          su[pnt * 4 + 2 * fk + 1] = c1;
+        for (int ks = 0; ks < 7; ++ks) dmma_m8n8k4(c0, c1, ta[4 * ks], bfr[ks]);
+        if (fk < 2) {
+          su[(8 * t + frow) * 4 + 2 * fk] = c0;
+          su[(8 * t + frow) * 4 + 2 * fk + 1] = c1;
         }
       }
-    }
-    __syncwarp();
-    if (lane < NQ1) {
-      // grad T = K^T (sum_k T_k grad_ref phi_k): reference gradient first, the mapping once per point
-      double oldT = 0.0, gT[3], gr[3] = {0.0, 0.0, 0.0};
+      __syncwarp();
+      {
+        // grad T = K^T (sum_k T_k grad_ref phi_k): reference gradient first, the mapping once per point
+        double oldT = 0.0, gr[3] = {0.0, 0.0, 0.0};
+        if (on) {
 #pragma unroll
-      for (int k = 0; k < nd; ++k) {
-        const double Tk = T[k];
-        oldT += Tk * tabT[lane * nd + k];
+          for (int k = 0; k < ND; ++k) {
+            const double Tk = T[k];
+            oldT += Tk * __ldg(a.phiT + (size_t)k * NQ + q);   // point-fastest copy: coalesced (the shared table is [point][i])
 #pragma unroll
-        for (int e = 0; e < 3; ++e) gr[e] += Tk * __ldg(a.dphiT + (size_t)(k * 3 + e) * a.nq + lane);
+            for (int e = 0; e < 3; ++e) gr[e] += Tk * __ldg(a.dphiT + (size_t)(k * 3 + e) * NQ + q);
+          }
+        }
+        double ugT = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ugT += su[lane * 4 + d] * (K[0][d] * gr[0] + K[1][d] * gr[1] + K[2][d] * gr[2]);
+        const double gamma = 0.0;  // heat source multiplied by literal 0 in the reference (:922-926)
+        cq[lane] = (oldT - tau * ugT - tau * gamma) * w;   // w = 0 for the padding points
       }
+      __syncwarp();
+      // l[i] += sum_p phi_t[p][i] cq[p]
 #pragma unroll
-      for (int d = 0; d < 3; ++d) gT[d] = K[0][d] * gr[0] + K[1][d] * gr[1] + K[2][d] * gr[2];
-      const double ugT = su[lane * 4] * gT[0] + su[lane * 4 + 1] * gT[1] + su[lane * 4 + 2] * gT[2];
-      const double gamma = 0.0;  // heat source multiplied by literal 0 in the reference (:922-926)
-      cq[lane] = (oldT - tau * ugT - tau * gamma) * w;
-    }
-    __syncwarp();
-    // l[i] = sum_p phi_t[p][i] cq[p]
-    {
-      double c0 = 0.0, c1 = 0.0;
+      for (int ks = 0; ks < 8; ++ks) {
+        const int pl = 4 * ks + fk;
+        const double bq = frow == 0 ? cq[pl] : 0.0;
+        const double* tt = tabT + (size_t)(32 * bt + pl) * C::NDP + frow;
 #pragma unroll
-      for (int ks = 0; ks < 7; ++ks) {
-        const int pnt = 4 * ks + fk;
-        dmma_m8n8k4(c0, c1, tabT[pnt * nd + frow], frow == 0 ? cq[pnt] : 0.0);
+        for (int t = 0; t < C::NT; ++t) dmma_m8n8k4(acc[t][0], acc[t][1], tt[8 * t], bq);
       }
-      if (fk == 0) l[frow] = c0;
+      __syncwarp();
+    }
+    if (fk == 0) {
+#pragma unroll
+      for (int t = 0; t < C::NT; ++t)
+        if (8 * t + frow < ND) l[8 * t + frow] = acc[t][0];
     }
     __syncwarp();
-    distribute_local_vector_bc<true>(cs, nd, nd, l, nullptr, idx, lines, a.rhs, lane, 32);
+    distribute_local_vector_bc<true>(cs, ND, ND, l, nullptr, idx, lines, a.rhs, lane, 32);
     __syncwarp();
   }
 }
@@ -1030,10 +1056,20 @@ int dcp_launch_temperature_rhs(dcp_model* m, const dcp_params& p, const double* 
     long long b = (m->n_cells + warps - 1) / warps;
     const long long cap = (long long)ctx->sm_count * 16;
     const unsigned grid = (unsigned)(b > cap ? cap : b);
-    if (m->dim == 3 && !a.feec && a.nd == 8 && a.nq == 27 && a.ndu == 27 && !std::getenv("DCP_NO_Q1_DMMA_RHS")) {
-      const size_t smem_q = sizeof(double) * (size_t)(RQ_LD * RQ_LD + RQ_LD * 8 + warps * (32 + 8 + 3 * RQ_LD + RQ_LD * 4 + 8 + 12));
-      const unsigned grid_q = (unsigned)std::min<long long>(b, (long long)ctx->sm_count * 8);
-      temperature_rhs_plain_q1_kernel<<<grid_q, 32 * warps, smem_q, ctx->stream>>>(a, make_view(m->temp_cs));
+    if (m->dim == 3 && !a.feec && a.ndu == 27 && ((a.nd == 8 && a.nq == 27) || (a.nd == 27 && a.nq == 64)) && !std::getenv("DCP_NO_DMMA_RHS")) {
+      if (a.nd == 8) {
+        using C = RhsDmma<8, 27>;
+        const size_t smem_q = C::smem_bytes(warps);
+        DCP_CUDA(cudaFuncSetAttribute(temperature_rhs_plain_dmma_kernel<8, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+        const unsigned grid_q = (unsigned)std::min<long long>(b, (long long)ctx->sm_count * 8);
+        temperature_rhs_plain_dmma_kernel<8, 27><<<grid_q, 32 * warps, smem_q, ctx->stream>>>(a, make_view(m->temp_cs));
+      } else {
+        using C = RhsDmma<27, 64>;
+        const size_t smem_q = C::smem_bytes(warps);
+        DCP_CUDA(cudaFuncSetAttribute(temperature_rhs_plain_dmma_kernel<27, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+        const unsigned grid_q = (unsigned)std::min<long long>(b, (long long)ctx->sm_count * 5);
+        temperature_rhs_plain_dmma_kernel<27, 64><<<grid_q, 32 * warps, smem_q, ctx->stream>>>(a, make_view(m->temp_cs));
+      }
     } else if (m->dim == 3)
       temperature_rhs_plain_kernel<3><<<grid, 32 * warps, smem, ctx->stream>>>(a, make_view(m->temp_cs));
     else
