@@ -12,12 +12,12 @@
 //      [m + nu k: 28][component c: [d][28 column nodes] + 8 pressure columns] x 3; pressure-node row (92 doubles):
 //      [c][28] + 8 pressure-mass columns.
 //   2. th_gather_kernel: one warp per (chunk, node) item.  Everything the item needs lies in one contiguous piece of the
-//      staging buffer; the warp streams it with TMA bulk copies (cp.async.bulk + mbarrier) through a ring of RD slots
-//      in shared memory, one component row at a time (three sweeps over the item's incidences), adds the segments at
-//      the plan's row positions into shared-memory accumulators and writes every CSR row of nse_matrix and of
-//      nse_preconditioner_matrix once (first chunk that touches the node: plain store of the whole row, which doubles
-//      as the zero-fill; later chunks: read-modify-write; chunks are stream-ordered and a row belongs to one warp, so
-//      no atomics are needed).
+//      staging buffer and of a static record stream (header + row positions per incidence); the warp streams both with
+//      TMA bulk copies (cp.async.bulk + mbarrier) through a ring of RD slots in shared memory, one component row at a
+//      time (three sweeps over the item's incidences), adds the segments at the row positions into shared-memory
+//      accumulators and writes every CSR row of nse_matrix and of nse_preconditioner_matrix once, as one bulk copy from
+//      shared memory (first chunk that touches the node: store of the whole row, which doubles as the zero-fill; later
+//      chunks: bulk reduce-add at the L2; chunks are stream-ordered and a row belongs to one warp).
 //
 // The cells are processed in chunks of the plan order; a chunk's staging is consumed before the next chunk overwrites
 // it.  Right-hand side: as in assemble_th_mma.cu (reductions into nse_rhs, 81 per cell).
