@@ -241,13 +241,20 @@ int dcp_ctx_create(int device, dcp_ctx** out) {
   DCP_CUDA(cudaSetDevice(device));
   dcp_ctx* ctx = new dcp_ctx;
   ctx->device = device;
-  DCP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   cudaDeviceProp prop;
-  DCP_CUDA(cudaGetDeviceProperties(&prop, device));
+  // a failure after this point releases what has been created so far (dcp_ctx_destroy copes with the unset members)
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&ctx->d_err, 4 * sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(ctx->d_err, 0, 4 * sizeof(int))) != cudaSuccess ||
+      (e = cudaMallocHost((void**)&ctx->h_err, 4 * sizeof(int))) != cudaSuccess) {
+    dcp_set_error(std::string("dcp_ctx_create: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    if (!ctx->stream) ctx->own_stream = false;
+    dcp_ctx_destroy(ctx);
+    return DCP_ERR_CUDA;
+  }
   ctx->sm_count = prop.multiProcessorCount;
-  DCP_CUDA(cudaMalloc((void**)&ctx->d_err, 4 * sizeof(int)));
-  DCP_CUDA(cudaMemset(ctx->d_err, 0, 4 * sizeof(int)));
-  DCP_CUDA(cudaMallocHost((void**)&ctx->h_err, 4 * sizeof(int)));
   *out = ctx;
   return DCP_OK;
 }
@@ -609,7 +616,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     for (int k = 0; k < d->nse_n_local; ++k)
       if (d->nse_local_field[k] < dim) vd[(size_t)d->nse_local_field[k] * d->ndu + d->nse_local_base[k]] = k;
     M_TRY(dcp_upload(ctx, &m->vel_dof, vd.data(), (int64_t)vd.size()));
-    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(DCP_ERR_CUDA);
   }
   // temperature matrices: scatter positions for the cells without constrained temperature dofs
   {
@@ -646,7 +653,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
       m->n_temp_general = (int64_t)general.size();
       if (!fast.empty()) M_TRY(dcp_upload(ctx, &m->temp_fast_cells, fast.data(), (int64_t)fast.size()));
       if (!general.empty()) M_TRY(dcp_upload(ctx, &m->temp_general_cells, general.data(), (int64_t)general.size()));
-      DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(DCP_ERR_CUDA);
     }
     // cells whose right-hand side needs matrix_for_bc: an inhomogeneously constrained temperature dof
     std::vector<uint8_t> flag((size_t)std::max<int64_t>(nc, 1), 0);
@@ -662,7 +669,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     m->n_temp_bc_cells = (int64_t)bc_cells.size();
     M_TRY(dcp_upload(ctx, &m->temp_bc_flag, flag.data(), (int64_t)flag.size()));
     if (!bc_cells.empty()) M_TRY(dcp_upload(ctx, &m->temp_bc_cells, bc_cells.data(), (int64_t)bc_cells.size()));
-    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(DCP_ERR_CUDA);
   }
   // cells holding a constrained NSE dof
   {
@@ -677,7 +684,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
     }
     m->n_nse_constrained_cells = (int64_t)cells.size();
     M_TRY(dcp_upload(ctx, &m->nse_constrained_cells, cells.data(), (int64_t)cells.size()));
-    DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(DCP_ERR_CUDA);
   }
   if (feec) {
     M_TRY(dcp_feec_positions_build(m, d, true, &m->feec_pos_nse));
@@ -708,7 +715,7 @@ int dcp_model_create(dcp_ctx* ctx, const dcp_model_desc* d, dcp_model** out) {
       }
     }
   }
-  DCP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(DCP_ERR_CUDA);
 #undef M_TRY
   *out = m;
   return DCP_OK;

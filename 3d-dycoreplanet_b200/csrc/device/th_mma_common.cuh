@@ -1,5 +1,5 @@
 // Shared definitions of the classic 3-D Taylor-Hood tensor-core kernels (assemble_th_mma.cu: reductions into the CSR
-// values; assemble_th_stage.cu: write-once path through a cell-major staging ring and a row-owner gather).
+// values; assemble_th_stage.cu: write-once path through a node-major staging buffer and a TMA-fed row-owner gather).
 #pragma once
 #include "scatter.cuh"
 

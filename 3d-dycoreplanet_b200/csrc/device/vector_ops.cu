@@ -78,8 +78,12 @@ int dcp_vec_dot(dcp_ctx* ctx, int64_t n, const double* x_dev, const double* y_de
   dot_stage2<<<1, DOT_THREADS, 0, ctx->stream>>>(DOT_BLOCKS, ctx->dot_scratch, ctx->dot_scratch + DOT_BLOCKS);
   ctx->launches += 2;
   DCP_CUDA(cudaMemcpyAsync(ctx->dot_host, ctx->dot_scratch + DOT_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // the scatter-error counters of the assemblers travel with the result: in device-resident mode a dropped matrix entry
+  // is reported by the next synchronising call instead of never (dcp.h, "deferred error reports")
+  DCP_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   DCP_CUDA(cudaStreamSynchronize(ctx->stream));
   *result_host = *ctx->dot_host;
+  if (ctx->h_err[0] != 0 || ctx->h_err[1] != 0) return dcp_check_device_errors(ctx, "an earlier assembly call");
   return DCP_OK;
 }
 

@@ -34,6 +34,11 @@
  * Threading: one context per GPU, calls from one host thread (the rank's main thread, where the
  * reference calls WorkStream::run).  Not re-entrant per context.
  * There is NO CPU fallback: every entry point fails with DCP_ERR_CUDA if no device is present.
+ *
+ * Deferred error reports: with DCP_DEVICE operands the assemblers do not synchronise, so a scatter target that is missing
+ * from the sparsity pattern (DCP_ERR_PATTERN) is counted on the device and reported by the next synchronising entry point
+ * -- dcp_ctx_synchronize, dcp_vec_dot, dcp_matrix_download / dcp_vector_download -- instead of by the assembly call itself
+ * (with DCP_HOST operands the call synchronises and reports directly).
  */
 #ifndef DCP_H
 #define DCP_H
