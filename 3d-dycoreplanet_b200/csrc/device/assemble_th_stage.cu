@@ -490,16 +490,6 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned bytes) {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's previous readers (generic proxy) come first
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// one regular tile of a stream -> shared memory (SASS UBLKCP); completion is counted on the slot's mbarrier
-__device__ __forceinline__ void bulk_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n"
