@@ -224,6 +224,16 @@ int main(int argc, char** argv) {
     model.temperature_matrix.vmult(res, xt);
     res.sadd(-1.0, 1.0, b);
     const double rel_res = std::sqrt(res * res) / std::sqrt(b * b);
+    // the same solve resident on the device (dcp::solve_cg -> dcp_cg_solve): same step count, same iterate
+    dcp::DeviceVector xr(ctx, T);
+    double last_res = 0.0;
+    const int64_t its_r = dcp::solve_cg(model.temperature_matrix, xr, b, &model.T_preconditioner, tol, nT, &last_res);
+    const std::vector<double> xa = xt.download(), xb = xr.download();
+    double dmax = 0.0, xmax = 0.0;
+    for (size_t i = 0; i < xa.size(); ++i) dmax = std::fmax(dmax, std::fabs(xa[i] - xb[i])), xmax = std::fmax(xmax, std::fabs(xa[i]));
+    std::printf("resident CG: %lld iterations, last residual %.3e, max difference to the host-driven loop %.3e\n", (long long)its_r, last_res,
+                dmax / xmax);
+    if (its_r != its || dmax > 1e-12 * xmax || last_res > tol) return 1;
     model.distribute_temperature_constraints(xt);
     const auto vc = model.velocity_extrema(u);
     std::printf("temperature CG: %d iterations, relative residual %.3e; max |u| %.6f, CFL %.6f\n", its, rel_res, vc.first, vc.second);
