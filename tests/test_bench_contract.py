@@ -31,3 +31,22 @@ def test_traffic_record_matches_what_bench_reads():
     traffic, src = bench.ncu_traffic("staged", 6)
     assert traffic == e["dram_bytes_per_step"] and "ncu" in src
     assert bench.ncu_traffic("staged", 99) == (None, None)
+
+
+def test_traffic_record_is_reproducible_from_the_committed_launch_list(tmp_path):
+    """profiles/traffic.json is a sum over profiles/r02_launches_r6_final.csv (ncu launch list with DRAM counters): redo
+    the sum with the committed script and compare."""
+    import shutil
+    work = tmp_path / "profiles"
+    work.mkdir()
+    shutil.copy(os.path.join(ROOT, "profiles", "extract_traffic.py"), work / "extract_traffic.py")
+    csv_path = os.path.join(ROOT, "profiles", "r02_launches_r6_final.csv")
+    r = subprocess.run([sys.executable, str(work / "extract_traffic.py"), csv_path, "staged", "6", "3"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    redone = json.load(open(work / "traffic.json"))["staged:r6"]
+    kept = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["staged:r6"]
+    assert abs(redone["dram_bytes_per_step"] - kept["dram_bytes_per_step"]) <= 1e-9 * kept["dram_bytes_per_step"]
+    per_step = {k: v["launches_per_step"] for k, v in redone["kernels"].items()}
+    assert per_step[[k for k in per_step if k.startswith("th_stage_kernel")][0]] == 24   # 1 572 864 cells in chunks of 65 536
+    assert per_step[[k for k in per_step if k.startswith("th_gather_kernel")][0]] == 24
